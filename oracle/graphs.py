@@ -1,0 +1,242 @@
+"""Functional CPU restatement of the reference model graphs (TEST INFRASTRUCTURE).
+
+Each graph is a plain function `f(sd, x, ...)` over a state dict `sd` whose keys and
+shapes are exactly those of the corresponding reference nn.Module, so the shipped
+.pth files and `module.state_dict()` of the real reference feed it directly.
+Everything runs in fp32 on the CPU through torch.nn.functional, i.e. through the same
+ATen CPU kernels the reference's own CPU path uses; autograd works through it, so
+gradients w.r.t. `sd` entries are the reference's gradients.
+
+Op pins: cross-correlation conv with zero padding, BN eps 1e-5 /
+momentum 0.1 / biased var for normalisation and unbiased for running_var,
+InstanceNorm affine=False, MaxPool floor mode, trilinear align_corners=False.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+# --------------------------------------------------------------------------- helpers
+def _bn(sd, pfx, x, training):
+    """nn.BatchNorm{1,2,3}d forward incl. running-stat side effects."""
+    rm, rv = sd[pfx + ".running_mean"], sd[pfx + ".running_var"]
+    if training:
+        key = pfx + ".num_batches_tracked"
+        if key in sd:
+            sd[key] += 1
+    return F.batch_norm(x, rm, rv, sd[pfx + ".weight"], sd[pfx + ".bias"],
+                        training, BN_MOMENTUM, BN_EPS)
+
+
+def _norm(sd, pfx, x, kind, training):
+    """unet3d.py:8-17 `normalization(planes, norm)`."""
+    if kind == "bn":
+        return _bn(sd, pfx, x, training)
+    if kind == "in":   # nn.InstanceNorm3d(planes): affine=False, no running stats
+        return F.instance_norm(x, eps=BN_EPS)
+    if kind == "gn":   # nn.GroupNorm(4, planes)
+        return F.group_norm(x, 4, sd[pfx + ".weight"], sd[pfx + ".bias"], BN_EPS)
+    raise ValueError(kind)
+
+
+def _conv(sd, pfx, x, stride=1, padding=0, dilation=1):
+    return F.conv3d(x, sd[pfx + ".weight"], sd.get(pfx + ".bias"), stride, padding, dilation)
+
+
+# ----------------------------------------------------------------- unet3d.Unet (a-1)
+def _convd(sd, pfx, x, first, norm, dropout, training):
+    """unet3d.py:39-47 ConvD.forward, including the dead conv2/bn2 branch (:43-45)
+    whose only effects are BN running-stat updates and RNG consumption."""
+    if not first:
+        x = F.max_pool3d(x, 2, 2)                                       # :41
+    x = _norm(sd, pfx + ".bn1", _conv(sd, pfx + ".conv1", x, 1, 1), norm, training)   # :42
+    dead = F.relu(_norm(sd, pfx + ".bn2", _conv(sd, pfx + ".conv2", x, 1, 1), norm, training))  # :43
+    if dropout > 0:
+        dead = F.dropout3d(dead, dropout)                               # :44-45 (always "training")
+    del dead
+    y = _norm(sd, pfx + ".bn3", _conv(sd, pfx + ".conv3", x, 1, 1), norm, training)   # :46
+    return F.relu(x + y)                                                # :47
+
+
+def _convu(sd, pfx, x, prev, first, norm, training):
+    """unet3d.py:68-79 ConvU.forward."""
+    if not first:
+        x = F.relu(_norm(sd, pfx + ".bn1", _conv(sd, pfx + ".conv1", x, 1, 1), norm, training))  # :71
+    y = F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=False)       # :73
+    y = F.relu(_norm(sd, pfx + ".bn2", _conv(sd, pfx + ".conv2", y, 1, 0), norm, training))     # :74
+    y = torch.cat([prev, y], 1)                                                        # :76
+    return F.relu(_norm(sd, pfx + ".bn3", _conv(sd, pfx + ".conv3", y, 1, 1), norm, training))  # :77
+
+
+def unet3d(sd, x, norm="bn", dropout=0.5, training=False):
+    """unet3d.py:110-126 Unet.forward.  `self.upsample` (:85, broken as written) is the
+    upstream BraTS2017 nn.Upsample(scale_factor=2, trilinear, align_corners=False)."""
+    up = lambda t: F.interpolate(t, scale_factor=2, mode="trilinear", align_corners=False)
+    x1 = _convd(sd, "convd1", x, True, norm, dropout, training)
+    x2 = _convd(sd, "convd2", x1, False, norm, dropout, training)
+    x3 = _convd(sd, "convd3", x2, False, norm, dropout, training)
+    x4 = _convd(sd, "convd4", x3, False, norm, dropout, training)
+    x5 = _convd(sd, "convd5", x4, False, norm, dropout, training)
+    y4 = _convu(sd, "convu4", x5, x4, True, norm, training)
+    y3 = _convu(sd, "convu3", y4, x3, False, norm, training)
+    y2 = _convu(sd, "convu2", y3, x2, False, norm, training)
+    y1 = _convu(sd, "convu1", y2, x1, False, norm, training)
+    s3 = _conv(sd, "seg3", y3)                                           # :122
+    s2 = _conv(sd, "seg2", y2) + up(s3)                                  # :123
+    return _conv(sd, "seg1", y1) + up(s2)                                # :124
+
+
+# ------------------------------------------- third-party unet.UNet (a-2, restated)
+def _fp_block(sd, pfx, x, training):
+    """One fepegar ConvolutionalBlock: conv(3^3, pad 1, bias) -> [BatchNorm3d] -> PReLU.
+    The norm is absent on the very first conv (no `norm_layer.*` keys in the checkpoint)."""
+    x = _conv(sd, pfx + ".conv_layer", x, 1, 1)
+    if pfx + ".norm_layer.weight" in sd:
+        x = _bn(sd, pfx + ".norm_layer", x, training)
+        if training and pfx + ".block.1.num_batches_tracked" in sd and \
+                sd[pfx + ".block.1.num_batches_tracked"] is not sd[pfx + ".norm_layer.num_batches_tracked"]:
+            sd[pfx + ".block.1.num_batches_tracked"] += 1    # same module registered twice
+    return F.prelu(x, sd[pfx + ".activation_layer.weight"])
+
+
+def fepegar_unet(sd, x, training=False, num_encoding_blocks=3):
+    """`unet.UNet(in=1, out_classes=2, dimensions=3, num_encoding_blocks=3, normalization='batch',
+    upsampling_type='linear', padding=True, activation='PReLU')` -- call site
+    segmentation/routine.py:346-356.  Encoder has num_encoding_blocks-1 pooled blocks,
+    then the bottom block, then as many decoding blocks; skips are the pre-pool tensors;
+    decoder concatenates (skip, upsampled) and upsamples trilinearly, align_corners=False."""
+    skips = []
+    for i in range(num_encoding_blocks - 1):
+        p = f"encoder.encoding_blocks.{i}"
+        x = _fp_block(sd, p + ".conv1", x, training)
+        x = _fp_block(sd, p + ".conv2", x, training)
+        skips.append(x)
+        x = F.max_pool3d(x, 2)
+    x = _fp_block(sd, "bottom_block.conv1", x, training)
+    x = _fp_block(sd, "bottom_block.conv2", x, training)
+    for i in range(num_encoding_blocks - 1):
+        p = f"decoder.decoding_blocks.{i}"
+        x = F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=False)
+        x = torch.cat((skips[-1 - i], x), dim=1)
+        x = _fp_block(sd, p + ".conv1", x, training)
+        x = _fp_block(sd, p + ".conv2", x, training)
+    return _conv(sd, "classifier.conv_layer", x)
+
+
+# ------------------------------------------------ AE family (a-3, a-4) AE_model.py
+def _act(x, act):
+    # AE_model.py:31-36: 'l_relu' -> nn.LeakyReLU() (slope 0.01), anything else -> nn.ReLU()
+    return F.leaky_relu(x, 0.01) if act == "l_relu" else F.relu(x)
+
+
+def _sep3(sd, pfx, names, x, k, s, p):
+    """The three separable convs (k,1,1) (1,k,1) (1,1,k) -- AE_model.py:9-26."""
+    x = _conv(sd, f"{pfx}.{names[0]}", x, (s, 1, 1), (p, 0, 0))
+    x = _conv(sd, f"{pfx}.{names[1]}", x, (1, s, 1), (0, p, 0))
+    return _conv(sd, f"{pfx}.{names[2]}", x, (1, 1, s), (0, 0, p))
+
+
+def down_block(sd, pfx, x, kw, training):
+    """AE_model.py:45-53: modules run in sorted-key order: convx, convy, convz,
+    MaxPool3d, BatchNorm3d (after the pool), activation."""
+    shape_before = tuple(x.shape[2:])
+    x = _sep3(sd, pfx + ".block", ("1_convx", "2_convy", "3_convz"), x, kw["conv_k"], kw["conv_s"], kw["conv_pad"])
+    x = F.max_pool3d(x, kw["maxpool_k"], kw["maxpool_s"])
+    if kw["batch_norm"]:
+        x = _bn(sd, pfx + ".block.5_batch_norm", x, training)
+    return _act(x, kw["act"]), shape_before
+
+
+def up_block(sd, pfx, x, shape_before, kw, training):
+    """AE_model.py:109-120 (upsample variant; `up='transpose_conv'` uses ConvTranspose3d :62-68)."""
+    if kw["up"] == "transpose_conv":
+        x = F.conv_transpose3d(x, sd[pfx + ".block.1_upsample.weight"], sd[pfx + ".block.1_upsample.bias"],
+                               kw["scale"], kw["t_conv_pad"])
+    else:
+        x = F.interpolate(x, scale_factor=kw["scale"], mode=kw["scale_mode"])
+    if any(a > b for a, b in zip(shape_before, x.shape[2:])):          # :116-119 odd sizes
+        x = F.interpolate(x, tuple(shape_before))
+    x = _sep3(sd, pfx + ".block", ("2_convx", "3_convy", "4_convz"), x, kw["conv_k"], kw["conv_s"], kw["conv_pad"])
+    if kw["batch_norm"]:
+        x = _bn(sd, pfx + ".block.5_batch_norm", x, training)
+    return _act(x, kw["act"])
+
+
+def encoder(sd, x, depth, down_kw, training=False, reduce_size=False, pfx="encode"):
+    """AE_model.py:137-144 Encoder.forward -> (latent, size_list)."""
+    sizes, i0 = [], 0
+    if reduce_size:                                                       # :127-128
+        x = _conv(sd, f"{pfx}.0", x, 4, 0)
+        sizes.append(None)
+        i0 = 1
+    for i in range(depth):
+        x, s = down_block(sd, f"{pfx}.{i + i0}", x, down_kw, training)
+        sizes.append(s)
+    return x, sizes
+
+
+def autoencoder(sd, x, depth, down_kw, up_kw, training=False):
+    """AE_model.py:207-210 AE.forward (reduce_size=False as in train_AE.ipynb [cell 8])."""
+    z, sizes = encoder(sd, x, depth, down_kw, training, pfx="enc.encode")
+    sizes = sizes[::-1]                                                   # :166
+    for i in range(depth):
+        z = up_block(sd, f"dec.decode.{i}", z, sizes[i], up_kw, training)
+    return _conv(sd, "dec.vox", z, 1, 1)                                  # :160-164,169
+
+
+def fader_head(sd, x, kw, training=False, pfx="clf"):
+    """AE_model.py:258-262 / :308-312 Discriminator / Classificator forward (sorted keys):
+    convx, convy, convz, Flatten, Linear, [BatchNorm1d], act, Dropout, Linear."""
+    x = _sep3(sd, pfx, ("1_convx", "2_convy", "3_convz"), x, kw["conv_k"], kw["conv_s"], kw["conv_pad"])
+    x = F.linear(x.flatten(1), sd[pfx + ".5_l1.weight"], sd[pfx + ".5_l1.bias"])
+    if kw["batch_norm"]:
+        x = _bn(sd, pfx + ".6_batch_norm", x, training)
+    x = _act(x, kw["act"])
+    x = F.dropout(x, kw.get("p_drop", 0.5), training)
+    return F.linear(x, sd[pfx + ".9_l_f.weight"], sd[pfx + ".9_l_f.bias"])
+
+
+# --------------------------------------------- detection PatchModel (a-6), 2-D
+def patch_model(sd, x, training=False):
+    """detection/model_utils.py:19-52: 5x [Conv2d 3x3 p0 -> BatchNorm2d -> ReLU], MaxPool2d(2),
+    Flatten, Dropout(0.4), Linear 8448->256, ReLU, Linear 256->2."""
+    for i in range(5):
+        p = f"conv_blocks.{i}"
+        x = F.conv2d(x, sd[p + ".conv.weight"], sd[p + ".conv.bias"])
+        x = F.relu(_bn(sd, p + ".bn", x, training))
+    x = F.max_pool2d(x, 2).flatten(1)
+    x = F.dropout(x, 0.4, training)
+    x = torch.relu(F.linear(x, sd["fc1.weight"], sd["fc1.bias"]))
+    return F.linear(x, sd["fc2.weight"], sd["fc2.bias"])
+
+
+# ------------------------------------------------------- losses on the device path
+def dice_loss_mean(logits, targets, eps=1e-9):
+    """segmentation/routine.py:272-274 with get_dice_score :239-250.  Note the broadcast:
+    probabilities (B,2,...) against targets (B,1,...) -> per-(batch,channel) dice, then mean."""
+    p0 = F.softmax(logits, dim=1)
+    g0 = targets
+    p1, g1 = 1 - p0, 1 - g0
+    tp = (p0 * g0).sum(dim=(2, 3, 4))
+    fp = (p0 * g1).sum(dim=(2, 3, 4))
+    fn = (p1 * g0).sum(dim=(2, 3, 4))
+    return (1 - 2 * tp / (2 * tp + fp + fn + eps)).mean()
+
+
+def adv_loss(domain, pred_logits, n_domains):
+    """classification/train_ENC_CLF.ipynb [cell 14]: -mean((1-onehot) * log_softmax)."""
+    onehot = torch.zeros((domain.shape[0], n_domains), dtype=torch.int32)
+    onehot.scatter_(1, domain.view(-1, 1), 1)
+    return -torch.mean((1 - onehot) * F.log_softmax(pred_logits, dim=1))
+
+
+# kwargs of the shipped fader checkpoints -- classification/train_ENC_CLF.ipynb [cell 17]
+FADER_DOWN = dict(conv_k=6, conv_pad=2, conv_s=2, maxpool_k=2, maxpool_s=2, batch_norm=True, act="l_relu")
+FADER_HEAD = dict(conv_k=3, conv_s=1, conv_pad=0, batch_norm=True, act="relu", p_drop=0.5)
+# kwargs of config 1 -- classification/train_AE.ipynb [cell 8]
+AE_DOWN = dict(conv_k=3, conv_pad=1, conv_s=1, maxpool_k=2, maxpool_s=2, batch_norm=True, act="relu")
+AE_UP = dict(up="upsample", scale=2, scale_mode="nearest", conv_k=3, conv_pad=1, conv_s=1, batch_norm=True, act="relu")

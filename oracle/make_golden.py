@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""Generate tests/golden/* by running the REAL reference modules (TEST INFRASTRUCTURE).
+
+Run in the build container, where /root/reference exists:
+
+    python oracle/make_golden.py
+
+Everything here calls the reference's own classes/functions (through oracle.refload)
+on seeded inputs and deterministic weights from oracle.weights, and freezes the
+results.  The oracle restatement (oracle.graphs / oracle.patches) is then checked
+against these files by the CPU test-suite, and the CUDA path by the GPU suite.
+
+Data fixtures (not source) copied next to the vectors: the three shipped fader
+checkpoints, one shipped segmentation checkpoint and the GM template.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import graphs, patches, refload, weights  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def sha16(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def save(name, **arrs):
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **{k: (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in arrs.items()})
+    print(f"  wrote {name}.npz ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
+def grads_of(model):
+    return {k: p.grad for k, p in model.named_parameters()}
+
+
+def thin(t, cap=32768):
+    """Large tensors are stored as a strided sample of their flattening (tests use the same rule)."""
+    t = t.detach() if torch.is_tensor(t) else torch.as_tensor(t)
+    if t.numel() <= cap:
+        return t
+    flat = t.reshape(-1)
+    return flat[:: flat.numel() // cap]
+
+
+def unet3d_cases():
+    for norm, train in (("bn", True), ("bn", False), ("in", True), ("gn", False)):
+        torch.manual_seed(0)
+        sd = weights.unet3d_state(1, 16, 2, norm, seed=1)
+        net = refload.make_unet3d(c=1, n=16, dropout=0.5, norm=norm, num_classes=2)
+        net.load_state_dict(sd, strict=True)
+        net.train(train)
+        g = torch.Generator().manual_seed(2)
+        x = torch.randn(2, 1, 32, 32, 32, generator=g)
+        t = (torch.rand(2, 1, 32, 32, 32, generator=g) > 0.5).float()
+        out = {}
+        if train:
+            logits = net(x)
+            # loss exactly as segmentation/routine.py:272-274
+            routine = refload.seg_routine_module()
+            loss = routine.get_dice_loss(torch.softmax(logits, dim=1), t).mean()
+            loss.backward()
+            gr = grads_of(net)
+            out["loss"] = loss.detach()
+            for k in ("convd1.conv1.weight", "convd1.conv3.weight", "convd2.conv1.weight", "convd5.conv3.weight",
+                      "convu1.conv3.weight", "convu1.conv2.weight", "seg1.weight", "seg1.bias", "convu3.conv1.weight"):
+                out["grad:" + k] = thin(gr[k])
+            if norm == "bn":
+                out["grad:convd1.bn1.weight"] = gr["convd1.bn1.weight"]
+                out["grad:convu1.bn3.bias"] = gr["convu1.bn3.bias"]
+                out["rm:convd1.bn2"] = net.convd1.bn2.running_mean
+                out["rv:convu1.bn3"] = net.convu1.bn3.running_var
+            out["none_grads"] = np.array(sorted(k for k, v in gr.items() if v is None))
+            out["grad_norms"] = np.array([float(v.norm()) if v is not None else -1.0 for v in gr.values()])
+            out["grad_keys"] = np.array(list(gr.keys()))
+        else:
+            with torch.no_grad():
+                logits = net(x)
+        out["logits"] = logits.detach()
+        out["argmax_sha"] = np.array(sha16(logits.detach().argmax(1).numpy().astype(np.uint8)))
+        save(f"unet3d_{norm}_{'train' if train else 'eval'}", **out)
+
+
+def ae_cases():
+    ae_mod = refload.ae_module()
+    down = dict(graphs.AE_DOWN)
+    up = dict(graphs.AE_UP)
+    kw = dict(c_in=1, is_skip=False, deapth=4, c_base=16, inc_size=2, reduce_size=False,
+              down_block_kwargs=down, up_block_kwargs=up)
+    torch.manual_seed(0)
+    net = ae_mod.AE(**kw)
+    net.load_state_dict(weights.ae_state(depth=4, c_base=16, seed=3), strict=True)
+    net.train()
+    x = weights.synthetic_t1w((2, 1, 32, 32, 32), seed=4)
+    rec = net(x)
+    loss = torch.nn.MSELoss()(rec, x)
+    loss.backward()
+    gr = grads_of(net)
+    save("ae_d4_train", rec=rec.detach(), loss=loss.detach(),
+         **{"grad:" + k: gr[k] for k in ("enc.encode.0.block.1_convx.weight", "enc.encode.0.block.3_convz.weight",
+                                         "enc.encode.3.block.2_convy.weight", "dec.decode.3.block.4_convz.weight",
+                                         "dec.decode.0.block.2_convx.bias", "dec.vox.weight",
+                                         "enc.encode.1.block.5_batch_norm.weight")},
+         grad_norms=np.array([float(v.norm()) for v in gr.values()]), grad_keys=np.array(list(gr.keys())))
+    # odd input size: exercises the nearest-to-size branch AE_model.py:116-119
+    net.eval()
+    xo = weights.synthetic_t1w((1, 1, 36, 28, 20), seed=5)
+    with torch.no_grad():
+        save("ae_d4_eval_odd", rec=net(xo))
+
+
+def fader_cases():
+    ae_mod = refload.ae_module()
+    down = dict(graphs.FADER_DOWN)
+    up = dict(up="upsample", scale=4, scale_mode="nearest", conv_k=3, conv_pad=1, conv_s=1, batch_norm=False, act="l_relu")
+    enc = ae_mod.AE(c_in=1, is_skip=False, deapth=3, c_base=8, inc_size=2, reduce_size=False,
+                    down_block_kwargs=down, up_block_kwargs=up).enc
+    head_kw = dict(c_in=32, c_out=64, conv_k=3, conv_s=1, conv_pad=0, l_in=64, l_out=32, batch_norm=True, act="relu", p_drop=0.5)
+    disc = ae_mod.Discriminator(n_domains=18, **head_kw)
+    clf = ae_mod.Classificator(n_class=2, **head_kw)
+    for m, f in ((enc, "encoder"), (clf, "clf"), (disc, "disc")):
+        m.load_state_dict(torch.load(refload.path(f"classification/{f}_93_6_4.pth"), map_location="cpu", weights_only=True), strict=True)
+        m.eval()
+    # KAT-1
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 1, 192, 192, 192, generator=g)
+    with torch.no_grad():
+        lat, _ = enc(x)
+        save("fader_kat1_eval", latent=lat, clf=clf(lat), disc=disc(lat), x_head=x[0, 0, 0, 0, :3])
+    # one adversarial encoder+clf step at a small size (train_ENC_CLF.ipynb [cell 16] second half)
+    g = torch.Generator().manual_seed(7)
+    xs = torch.randn(4, 1, 96, 96, 96, generator=g)
+    y = torch.tensor([0, 1, 1, 0])
+    dom = torch.tensor([3, 0, 17, 5])
+    # 96^3 -> latent 1^3 would break the p0 k3 heads; use the encoder only + a surrogate loss on the latent
+    enc.train()
+    lat, _ = enc(xs)
+    loss = (lat * torch.linspace(-1, 1, lat.numel()).view_as(lat)).sum() / lat.numel()
+    loss.backward()
+    gr = grads_of(enc)
+    save("fader_encoder_train96", latent=lat.detach(), loss=loss.detach(),
+         **{"grad:" + k: v for k, v in gr.items()},
+         rm0=enc.encode[0].block["5_batch_norm"].running_mean, rv2=enc.encode[2].block["5_batch_norm"].running_var)
+    # heads in train mode on a synthetic latent (B,32,3,3,3), with the notebook's losses
+    clf.train(); disc.eval()
+    torch.manual_seed(11)
+    lat = torch.randn(6, 32, 3, 3, 3, generator=g, requires_grad=True)
+    y = torch.tensor([0, 1, 1, 0, 1, 0]); dom = torch.tensor([3, 0, 17, 5, 9, 9])
+    torch.manual_seed(5)                       # dropout mask
+    pc = clf(lat); pd = disc(lat)
+    ce = torch.nn.CrossEntropyLoss(weight=torch.tensor([1.0, 2.0]))(pc, y)
+    adv = graphs.adv_loss(dom, pd, 18)
+    (ce + 0.05 * adv).backward()
+    save("fader_heads_train", pc=pc.detach(), pd=pd.detach(), ce=ce.detach(), adv=adv.detach(), dlat=lat.grad,
+         **{"grad:" + k: v for k, v in grads_of(clf).items()})
+
+
+def patch_cases():
+    pu = refload.patch_utils_module()
+    gm = patches.read_nifti1_f32(refload.path("detection/MNI152_T1_1mm_brain_gray.nii.gz")).astype(np.float64)
+    img = np.random.default_rng(0).random((182, 218, 182))
+    t0 = time.time()
+    ref = pu.get_only_patches(img, gm, 16, 32)
+    print(f"  reference get_only_patches: {time.time() - t0:.1f}s, {ref.shape}")
+    plan = patches.patch_plan(gm, None, 16, 32)
+    mine = patches.gather_patches(img, plan)
+    assert ref.shape == mine.shape and np.array_equal(ref, mine), "oracle patches != reference"
+    save("patches_kat4", shape=np.array(ref.shape), total=np.array(ref.sum()), sha=np.array(sha16(ref)),
+         plan=plan.astype(np.int16), template_sha=np.array(sha16(gm.astype(np.float32))), first=ref[:4], last=ref[-4:])
+    # labelled variant with a synthetic lesion mask (ellipsoid), incl. the k=1..15 positive-only passes
+    xx, yy, zz = np.meshgrid(np.arange(182), np.arange(218), np.arange(182), indexing="ij")
+    mask = ((xx - 60) / 9.0) ** 2 + ((yy - 120) / 11.0) ** 2 + ((zz - 90) / 7.0) ** 2 < 1
+    t0 = time.time()
+    rp, rl = pu.get_all_patches_and_labels(img, gm, mask, 16, 32)
+    print(f"  reference get_all_patches_and_labels: {time.time() - t0:.1f}s, {rp.shape}, positives {int(rl.sum())}")
+    plan2 = patches.patch_plan(gm, mask, 16, 32)
+    mp = patches.gather_patches(img, plan2)
+    assert np.array_equal(rp, mp) and np.array_equal(rl, plan2[:, patches.LABEL].astype(bool))
+    save("patches_labelled", shape=np.array(rp.shape), total=np.array(rp.sum()), sha=np.array(sha16(rp)),
+         labels=rl, plan=plan2.astype(np.int16), mask_center=np.array([60, 120, 90]), mask_radii=np.array([9.0, 11.0, 7.0]))
+    # patch classifier (2-D) on the first 96 patches, eval and train
+    PatchModel, _ = refload.patch_model_classes()
+    torch.manual_seed(0)
+    net = PatchModel()
+    net.load_state_dict(weights.patch_model_state(seed=9), strict=True)
+    xb = torch.from_numpy(ref[:96]).float()
+    net.eval()
+    with torch.no_grad():
+        ev = net(xb)
+    net.train()
+    torch.manual_seed(3)
+    tr = net(xb)
+    yb = (torch.arange(96) % 2)
+    loss = torch.nn.CrossEntropyLoss()(tr, yb)
+    loss.backward()
+    gr = grads_of(net)
+    save("patch_model", eval_logits=ev, train_logits=tr.detach(), loss=loss.detach(),
+         **{"grad:" + k: gr[k] for k in ("conv_blocks.0.conv.weight", "conv_blocks.4.conv.weight", "conv_blocks.2.bn.weight", "fc2.weight")})
+
+
+def op_pins():
+    """SURVEY section 8 a-9 pins, produced by the same torch calls the reference modules make."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 4, 16, 16, 16, generator=g)
+    y, idx = torch.nn.MaxPool3d(2, 2, return_indices=True)(x)
+    ties = torch.zeros(1, 1, 4, 4, 4)
+    _, tidx = torch.nn.MaxPool3d(2, 2, return_indices=True)(ties)
+    odd = torch.randn(1, 2, 5, 7, 9, generator=g)
+    yo, io = torch.nn.MaxPool3d(2, 2, return_indices=True)(odd)
+    y42, i42 = torch.nn.MaxPool3d(4, 2, return_indices=True)(x)
+    line = torch.arange(4.0).view(1, 1, 1, 1, 4).expand(1, 1, 2, 2, 4)
+    save("op_pins", pool_idx=idx, pool_idx_sum=np.array(int(idx.sum())), pool_sha=np.array(sha16(idx.numpy())),
+         tie_idx=tidx, odd_idx=io, odd_val=yo, k4s2_idx=i42,
+         tri_false=torch.nn.Upsample(scale_factor=2, mode="trilinear", align_corners=False)(line)[0, 0, 0, 0],
+         tri_true=torch.nn.Upsample(scale_factor=2, mode="trilinear", align_corners=True)(line)[0, 0, 0, 0],
+         nearest_3to7=torch.nn.functional.interpolate(torch.arange(3.0).view(1, 1, 1, 1, 3), size=(1, 1, 7))[0, 0, 0, 0])
+
+
+def fepegar_case():
+    """unet.UNet is third-party and absent: these vectors come from the oracle restatement
+    itself (regression anchor, 'parity unpinned'); strict key coverage of every shipped
+    checkpoint is what is pinned."""
+    import glob
+    names = sorted(glob.glob(refload.path("segmentation/weights/*.pth")))
+    want = set(weights.fepegar_unet_state(8).keys())
+    for p in names:
+        sd = torch.load(p, map_location="cpu", weights_only=True)
+        assert set(sd.keys()) == want, p
+        ref_shapes = {k: tuple(v.shape) for k, v in weights.fepegar_unet_state(8).items()}
+        assert all(tuple(sd[k].shape) == ref_shapes[k] for k in want), p
+    sd = torch.load(refload.path("segmentation/weights/whole_im_train_seg_parc_epoch_7.pth"), map_location="cpu", weights_only=True)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 1, 64, 64, 64, generator=g)
+    with torch.no_grad():
+        logits = graphs.fepegar_unet(sd, x)
+    am = logits.argmax(1).numpy().astype(np.uint8)
+    save("fepegar_kat2_eval_UNPINNED", logits_sum=np.array(float(logits.double().sum())), logits_absmean=np.array(float(logits.abs().mean())),
+         fg=np.array(int(am.sum())), argmax_sha=np.array(sha16(am)), logits_slice=logits[0, :, 32], n_checkpoints=np.array(len(names)))
+
+
+def copy_fixtures():
+    for rel in ("classification/encoder_93_6_4.pth", "classification/clf_93_6_4.pth", "classification/disc_93_6_4.pth",
+                "segmentation/weights/whole_im_train_seg_parc_epoch_7.pth", "detection/MNI152_T1_1mm_brain_gray.nii.gz"):
+        dst = os.path.join(OUT, os.path.basename(rel))
+        shutil.copyfile(refload.path(rel), dst)
+        os.chmod(dst, 0o644)
+        print("  copied", rel)
+
+
+if __name__ == "__main__":
+    assert refload.available(), "needs /root/reference"
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    which = sys.argv[1:] or ["fixtures", "ops", "unet3d", "ae", "fader", "fepegar", "patches"]
+    table = dict(fixtures=copy_fixtures, ops=op_pins, unet3d=unet3d_cases, ae=ae_cases, fader=fader_cases,
+                 fepegar=fepegar_case, patches=patch_cases)
+    for w in which:
+        print(w)
+        table[w]()
