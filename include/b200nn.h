@@ -1,0 +1,201 @@
+/*
+ * b200nn.h -- C ABI of libb200nn.so: hand-written sm_100a kernels for the 3-D-convolutional
+ * hot path of kondratevakate/mri-epilepsy-diagnosis.
+ *
+ * The reference has no FFI layer of its own: its operator API *is* torch.nn, bound at import
+ * by `import torch.nn as nn` (segmentation/models/unet3d.py:1, classification/models/AE_model.py:2,
+ * classification/models/cnn_model.py:3, segmentation/models/modified_3dunet.py:1,
+ * detection/model_utils.py:3).  Each entry point below replaces the ATen/cuDNN call that one of
+ * those torch.nn modules issues; the comment on each names the reference call sites.  The Python
+ * drop-in modules (mri_epilepsy_diagnosis_b200.nn) bind these symbols with ctypes; INTEGRATION.md
+ * shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every activation tensor is channels-last: physical N,D,H,W,C contiguous (what
+ *     torch.channels_last_3d gives a logical N,C,D,H,W tensor; 2-D ops are the D=1 case);
+ *   - dtypes are B200_F32 or B200_BF16; accumulation and all statistics are fp32;
+ *   - plain pointers and sizes only; the callee never allocates, frees or retains device memory:
+ *     outputs, workspaces, packed weights, saved statistics and argmax codes are caller-owned;
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*), never synchronises;
+ *   - return 0 on success, non-zero on error with a thread-local message in b200_last_error();
+ *     an unsupported descriptor is an error -- there is no CPU fallback and no cuDNN dispatch.
+ */
+#ifndef B200NN_H
+#define B200NN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200NN_VERSION 100
+
+enum { B200_F32 = 0, B200_BF16 = 1 };
+enum { B200_ACT_NONE = 0, B200_ACT_RELU = 1, B200_ACT_LEAKY = 2 };
+enum { B200_NORM_BATCH = 0, B200_NORM_INSTANCE = 1, B200_NORM_GROUP = 2 };
+enum { B200_UP_NEAREST = 0, B200_UP_TRILINEAR = 1, B200_UP_TRILINEAR_ALIGNED = 2 };
+enum { B200_PASS_FWD = 0, B200_PASS_DGRAD = 1, B200_PASS_WGRAD = 2 };
+enum { B200_ALGO_SIMT = 0, B200_ALGO_UMMA = 1 };
+
+int b200_version(void);
+const char* b200_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+uint64_t b200_launch_count(void);
+
+/* ------------------------------------------------------------------ convolution
+ * nn.Conv3d / nn.Conv2d (cross-correlation, zero padding, groups=1): unet3d.py:30-36,57-63,99-101;
+ * AE_model.py:9-26,74-91,160-164,218-234,268-284; cnn_model.py:14,49-81,212-240; model_utils.py:47;
+ * nn.ConvTranspose3d: AE_model.py:62-68,159 (transposed=1: x is the small tensor, y the large one,
+ * and `Ci`/`Co` still name the channels of x / y).
+ */
+typedef struct {
+    int32_t x_dtype, y_dtype;            /* activation dtypes of the conv's input and output      */
+    int32_t N;
+    int32_t Ci, Di, Hi, Wi;              /* input  (x)                                            */
+    int32_t Co, Do, Ho, Wo;              /* output (y)                                            */
+    int32_t kd, kh, kw;
+    int32_t sd, sh, sw;
+    int32_t pd, ph, pw;
+    int32_t dd, dh, dw;
+    int32_t transposed;                  /* 0: Conv3d, 1: ConvTranspose3d                         */
+    int32_t allow_umma;                  /* 0 forces the SIMT fp32-FMA kernels (tf32-off mode)    */
+} b200_conv_desc;
+
+/* Which kernel family the library will use for (desc, pass): B200_ALGO_SIMT or B200_ALGO_UMMA. */
+int b200_conv_algo(const b200_conv_desc* d, int pass);
+/* Packed-weight size for (desc, pass in {FWD, DGRAD}); layout is private to the library. */
+size_t b200_conv_packed_bytes(const b200_conv_desc* d, int pass);
+/* Pack the fp32 PyTorch-layout parameter (Conv: Co,Ci,kd,kh,kw; ConvTranspose: Ci,Co,kd,kh,kw). */
+int b200_conv_pack_weights(const b200_conv_desc* d, int pass, const float* w, void* packed, void* stream);
+size_t b200_conv_workspace_bytes(const b200_conv_desc* d, int pass);
+/* y = conv(x, w) + bias.  `bias` is fp32 [Co] or NULL. */
+int b200_conv_fwd(const b200_conv_desc* d, const void* x, const void* w_packed, const float* bias, void* y,
+                  void* workspace, size_t ws_bytes, void* stream);
+/* dx = d(loss)/dx given dy (dtypes: dy has y_dtype, dx has x_dtype). */
+int b200_conv_dgrad(const b200_conv_desc* d, const void* dy, const void* w_packed_dgrad, void* dx,
+                    void* workspace, size_t ws_bytes, void* stream);
+/* dw (fp32, PyTorch parameter layout) and optionally dbias (fp32 [Co], may be NULL); overwritten, not accumulated. */
+int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias,
+                    void* workspace, size_t ws_bytes, void* stream);
+
+/* --------------------------------------------------- normalisation (+ fused activation / residual)
+ * nn.BatchNorm3d/2d (unet3d.py:10; AE_model.py:30,94; cnn_model.py; model_utils.py:48), nn.InstanceNorm3d
+ * (unet3d.py:14; modified_3dunet.py:20-43), nn.GroupNorm(4,C) (unet3d.py:12).  eps/momentum are the
+ * module's; statistics are fp32 with a shifted two-pass-free formulation.
+ *
+ *   stats : per-group mean and biased variance from x; when `running_mean` is given also the
+ *           BatchNorm running update (momentum, UNBIASED variance) -- torch.nn semantics.
+ *   apply : y = act( (x-mean)*rstd*gamma + beta [+ residual] )
+ *   bwd   : dx, dgamma, dbeta (act' folded in through the saved OUTPUT y when act != NONE)
+ * groups: BATCH -> C groups; INSTANCE -> N*C; GROUP -> N*G.  `mean`/`rstd` are fp32 [groups].
+ */
+typedef struct {
+    int32_t dtype;
+    int32_t N, C;
+    int64_t S;                 /* D*H*W */
+    int32_t kind;              /* B200_NORM_*                       */
+    int32_t G;                 /* GROUP only                        */
+    float eps, momentum;
+    int32_t act;               /* B200_ACT_* fused into apply / bwd */
+    float slope;               /* LEAKY                              */
+} b200_norm_desc;
+
+size_t b200_norm_workspace_bytes(const b200_norm_desc* d);
+int b200_norm_stats(const b200_norm_desc* d, const void* x, float* mean, float* rstd,
+                    float* running_mean, float* running_var, void* workspace, size_t ws_bytes, void* stream);
+/* eval-mode BatchNorm: mean/rstd derived from the running statistics */
+int b200_norm_stats_from_running(const b200_norm_desc* d, const float* running_mean, const float* running_var,
+                                 float* mean, float* rstd, void* stream);
+int b200_norm_apply(const b200_norm_desc* d, const void* x, const float* mean, const float* rstd,
+                    const float* gamma, const float* beta, const void* residual, void* y, void* stream);
+/* training=1: batch statistics take part in the gradient; 0: eval-mode BN (mean/rstd are constants) */
+int b200_norm_bwd(const b200_norm_desc* d, int training, const void* x, const void* y, const void* dy,
+                  const float* mean, const float* rstd, const float* gamma,
+                  void* dx, void* dresidual, float* dgamma, float* dbeta,
+                  void* workspace, size_t ws_bytes, void* stream);
+
+/* The same backward split in two so that a data-parallel caller can all-reduce `sums` (fp32 [NB*C*2]: sum dy',
+ * sum dy'*xhat per (reduce-batch, channel); NB = 1 for BATCH, N otherwise) between the steps -- SyncBN.
+ * `world` multiplies the BATCH element count (number of ranks whose sums were added). */
+int b200_norm_bwd_reduce(const b200_norm_desc* d, const void* x, const void* y, const void* dy,
+                         const float* mean, const float* rstd, float* sums,
+                         void* workspace, size_t ws_bytes, void* stream);
+int b200_norm_bwd_apply(const b200_norm_desc* d, int training, int world, const void* x, const void* y, const void* dy,
+                        const float* mean, const float* rstd, const float* gamma, const float* sums,
+                        void* dx, void* dresidual, float* dgamma, float* dbeta,
+                        void* workspace, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ activations
+ * nn.ReLU(inplace) unet3d.py:28,66; nn.LeakyReLU() AE_model.py:32; nn.PReLU(1) unet.UNet (routine.py:355).
+ * y may alias x (inplace).  bwd for RELU/LEAKY reads the OUTPUT y; PReLU reads the input x. */
+int b200_act_fwd(int dtype, int act, float slope, int64_t n, const void* x, void* y, void* stream);
+int b200_act_bwd(int dtype, int act, float slope, int64_t n, const void* y, const void* dy, void* dx, void* stream);
+int b200_prelu_fwd(int dtype, int64_t n, const void* x, const float* a, void* y, void* stream);
+size_t b200_prelu_workspace_bytes(int64_t n);
+int b200_prelu_bwd(int dtype, int64_t n, const void* x, const float* a, const void* dy, void* dx, float* da,
+                   void* workspace, size_t ws_bytes, void* stream);
+/* y = act(a + b) -- residual joins unet3d.py:47, cnn_model.py:37-38 */
+int b200_add_act_fwd(int dtype, int act, float slope, int64_t n, const void* a, const void* b, void* y, void* stream);
+
+/* ------------------------------------------------------------------ max pooling
+ * nn.MaxPool3d(k, s) no padding, floor mode: unet3d.py:25; AE_model.py:27; cnn_model.py:115-148,221,232;
+ * nn.MaxPool2d(2) model_utils.py:29.  Ties -> first in (d,h,w) raster order; NaN wins.
+ * `code` (uint8, one per output element) is the window-local argmax used by the backward pass;
+ * `indices` (int64, optional) are torch's flat offsets inside the input D*H*W plane. */
+typedef struct {
+    int32_t dtype;
+    int32_t N, C, Di, Hi, Wi, Do, Ho, Wo;
+    int32_t kd, kh, kw, sd, sh, sw;
+} b200_pool_desc;
+int b200_maxpool_fwd(const b200_pool_desc* d, const void* x, void* y, uint8_t* code, int64_t* indices, void* stream);
+int b200_maxpool_bwd(const b200_pool_desc* d, const void* dy, const uint8_t* code, void* dx, void* stream);
+
+/* ------------------------------------------------------------------ upsample (+ skip concat)
+ * F.upsample/nn.Upsample trilinear align_corners=False (unet3d.py:73,85; unet.UNet), =True
+ * (3d_bayes_layers.py:65), nearest (AE_model.py:70-73,119; modified_3dunet.py:13).  The result is written
+ * into channels [c_off, c_off+C) of an output whose channel count is Ctot, so `torch.cat([skip, up], 1)`
+ * (unet3d.py:76) costs no extra pass: the skip is copied by b200_copy_channels. */
+typedef struct {
+    int32_t dtype;
+    int32_t mode;              /* B200_UP_*               */
+    int32_t N, C, Di, Hi, Wi, Do, Ho, Wo;
+    int32_t Ctot, c_off;       /* output channel stride and offset */
+} b200_up_desc;
+int b200_upsample_fwd(const b200_up_desc* d, const void* x, void* y, void* stream);
+int b200_upsample_bwd(const b200_up_desc* d, const void* dy, void* dx, void* stream);
+/* dst[v, dst_off:dst_off+C] = src[v, src_off:src_off+C] for V voxels (concat / split along channels) */
+int b200_copy_channels(int dtype, int64_t V, int32_t C, const void* src, int32_t src_ctot, int32_t src_off,
+                       void* dst, int32_t dst_ctot, int32_t dst_off, void* stream);
+
+/* ------------------------------------------------------------------ layout / dtype
+ * NCDHW <-> NDHWC transposes with dtype conversion (first layer reads the loader's fp32 NCDHW batch,
+ * segmentation/routine.py:190). */
+int b200_to_channels_last(int src_dtype, int dst_dtype, int32_t N, int32_t C, int64_t S, const void* src, void* dst, void* stream);
+int b200_from_channels_last(int src_dtype, int dst_dtype, int32_t N, int32_t C, int64_t S, const void* src, void* dst, void* stream);
+
+/* ------------------------------------------------------------------ sliding-window patch gather
+ * detection/patch_utils.py: get_only_patches :142-191, get_all_patches_and_labels :17-140.
+ * Volumes are C-order (X,Y,Z) float64 exactly as the reference holds them.  Two steps:
+ *   plan  : per (slice, strip) decisions + order-preserving compaction -> int32 plan rows
+ *           {slice, row0, c0, c1, label}; *count receives the number of rows; error flags in *status
+ *           (bit0: start_idx==0 assertion, bit1: ragged strip would be emitted).
+ *   gather: copy the planned (2,h,w) windows (channel 1 mirrored) -> out (P,2,h,w) float64 or float32.
+ */
+typedef struct {
+    int32_t X, Y, Z, h, w;
+    int32_t with_mask;         /* labels from a uint8 mask volume            */
+    int32_t upsample_passes;   /* 1: also the k=1..h-1 positive-only passes  */
+} b200_patch_desc;
+size_t b200_patch_workspace_bytes(const b200_patch_desc* d);
+int64_t b200_patch_max_rows(const b200_patch_desc* d);
+int b200_patch_plan(const b200_patch_desc* d, const double* gmpm, const uint8_t* mask, int32_t* plan,
+                    int32_t* count, int32_t* status, void* workspace, size_t ws_bytes, void* stream);
+int b200_patch_gather(const b200_patch_desc* d, const double* target, const int32_t* plan, int64_t rows,
+                      int out_dtype_is_f32, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200NN_H */

@@ -1,0 +1,595 @@
+// libb200nn.so -- C-ABI entry points (include/b200nn.h) and kernel dispatch.  sm_100a only.
+#include <cstdarg>
+
+#include "common.cuh"
+#include "conv_simt.cuh"
+#include "conv_umma.cuh"
+#include "elementwise.cuh"
+#include "norm.cuh"
+#include "patches.cuh"
+#include "pool_upsample.cuh"
+
+using namespace b200;
+
+extern "C" {
+
+int b200_version(void) { return B200NN_VERSION; }
+const char* b200_last_error(void) { return err_slot().c_str(); }
+uint64_t b200_launch_count(void) { return launch_counter().load(); }
+
+}  // extern "C"
+
+// ============================================================================ convolution
+namespace {
+
+struct ConvPlan {
+    GatherGeom g;          // geometry of the gather for this pass
+    int in_dtype, out_dtype;
+    int param_is_ci_major; // ConvTranspose parameter layout (Ci, Co, taps)
+    int pass_swaps;        // packed weight gathers Co and produces Ci
+    int gathered_is_ci;    // wgrad: gathered tensor carries Ci
+    int taps;
+};
+
+int conv_validate(const b200_conv_desc* d) {
+    B200_REQUIRE(d != nullptr, "null conv descriptor");
+    B200_REQUIRE(d->N > 0 && d->Ci > 0 && d->Co > 0 && d->Di > 0 && d->Hi > 0 && d->Wi > 0, "conv: non-positive input dims");
+    B200_REQUIRE(d->kd > 0 && d->kh > 0 && d->kw > 0 && d->sd > 0 && d->sh > 0 && d->sw > 0 && d->dd > 0 && d->dh > 0 && d->dw > 0,
+                 "conv: non-positive kernel/stride/dilation");
+    B200_REQUIRE(d->pd >= 0 && d->ph >= 0 && d->pw >= 0, "conv: negative padding");
+    B200_REQUIRE((d->x_dtype == B200_F32 || d->x_dtype == B200_BF16) && (d->y_dtype == B200_F32 || d->y_dtype == B200_BF16), "conv: bad dtype");
+    int eD, eH, eW;
+    if (!d->transposed) {
+        eD = (d->Di + 2 * d->pd - d->dd * (d->kd - 1) - 1) / d->sd + 1;
+        eH = (d->Hi + 2 * d->ph - d->dh * (d->kh - 1) - 1) / d->sh + 1;
+        eW = (d->Wi + 2 * d->pw - d->dw * (d->kw - 1) - 1) / d->sw + 1;
+    } else {
+        eD = (d->Di - 1) * d->sd - 2 * d->pd + d->dd * (d->kd - 1) + 1;
+        eH = (d->Hi - 1) * d->sh - 2 * d->ph + d->dh * (d->kh - 1) + 1;
+        eW = (d->Wi - 1) * d->sw - 2 * d->pw + d->dw * (d->kw - 1) + 1;
+    }
+    B200_REQUIRE(eD == d->Do && eH == d->Ho && eW == d->Wo && eD > 0 && eH > 0 && eW > 0,
+                 "conv: output size (%d,%d,%d) does not match the expected (%d,%d,%d)", d->Do, d->Ho, d->Wo, eD, eH, eW);
+    return 0;
+}
+
+ConvPlan conv_plan(const b200_conv_desc* d, int pass) {
+    ConvPlan p{};
+    GatherGeom& g = p.g;
+    g.N = d->N;
+    g.kd = d->kd; g.kh = d->kh; g.kw = d->kw; g.sd = d->sd; g.sh = d->sh; g.sw = d->sw;
+    g.pd = d->pd; g.ph = d->ph; g.pw = d->pw; g.dd = d->dd; g.dh = d->dh; g.dw = d->dw;
+    p.taps = d->kd * d->kh * d->kw;
+    p.param_is_ci_major = d->transposed;
+    const bool gather_from_x = (pass == B200_PASS_FWD) || (pass == B200_PASS_WGRAD && !d->transposed);
+    if (gather_from_x) {
+        g.IC = d->Ci; g.ID = d->Di; g.IH = d->Hi; g.IW = d->Wi;
+        g.OC = d->Co; g.OD = d->Do; g.OH = d->Ho; g.OW = d->Wo;
+        p.in_dtype = d->x_dtype; p.out_dtype = d->y_dtype;
+    } else {
+        g.IC = d->Co; g.ID = d->Do; g.IH = d->Ho; g.IW = d->Wo;
+        g.OC = d->Ci; g.OD = d->Di; g.OH = d->Hi; g.OW = d->Wi;
+        p.in_dtype = d->y_dtype; p.out_dtype = d->x_dtype;
+    }
+    if (pass == B200_PASS_FWD) g.transposed = d->transposed;
+    else if (pass == B200_PASS_DGRAD) g.transposed = !d->transposed;
+    else g.transposed = 0;
+    p.pass_swaps = pass == B200_PASS_DGRAD;
+    p.gathered_is_ci = gather_from_x;
+    g.OCp = (g.OC + 3) & ~3;
+    return p;
+}
+
+template <typename TI, typename TO>
+int launch_gather(const ConvPlan& p, const void* in, const float* w, const float* bias, void* out, void* stream) {
+    const GatherGeom& g = p.g;
+    const int64_t V = (int64_t)g.N * g.OD * g.OH * g.OW;
+    if (g.OC > 16) {
+        dim3 grid((unsigned)ceil_div(V, 64), (unsigned)ceil_div(g.OC, 64));
+        B200_LAUNCH((conv_gather_kernel<TI, TO, 64, 64>), grid, 256, 0, stream, g, (const TI*)in, w, bias, (TO*)out);
+    } else {
+        dim3 grid((unsigned)ceil_div(V, 128), 1);
+        B200_LAUNCH((conv_gather_kernel<TI, TO, 128, 16>), grid, 256, 0, stream, g, (const TI*)in, w, bias, (TO*)out);
+    }
+    return 0;
+}
+
+int dispatch_gather(const ConvPlan& p, const void* in, const float* w, const float* bias, void* out, void* stream) {
+    if (p.in_dtype == B200_F32 && p.out_dtype == B200_F32) return launch_gather<float, float>(p, in, w, bias, out, stream);
+    if (p.in_dtype == B200_BF16 && p.out_dtype == B200_BF16) return launch_gather<__nv_bfloat16, __nv_bfloat16>(p, in, w, bias, out, stream);
+    if (p.in_dtype == B200_BF16 && p.out_dtype == B200_F32) return launch_gather<__nv_bfloat16, float>(p, in, w, bias, out, stream);
+    return launch_gather<float, __nv_bfloat16>(p, in, w, bias, out, stream);
+}
+
+struct WgradSplit { int splits; int64_t vox_per_split; int bias_chunks; int64_t bias_rows_per_chunk; size_t partial_bytes, bias_bytes; };
+
+WgradSplit wgrad_split(const b200_conv_desc* d, const ConvPlan& p) {
+    WgradSplit s;
+    const GatherGeom& g = p.g;
+    const int64_t K = (int64_t)p.taps * g.IC;
+    const int64_t V = (int64_t)g.N * g.OD * g.OH * g.OW;
+    const int TN = g.OC > 16 ? 64 : 16;
+    const int64_t base = ceil_div(K, 64) * ceil_div(g.OCp, TN);
+    int64_t splits = ceil_div(4 * kNumSMs, base);
+    const int64_t max_by_vox = ceil_div(V, 256);
+    if (splits > max_by_vox) splits = max_by_vox;
+    const int64_t per_split_bytes = K * g.OCp * 4;
+    const int64_t max_by_mem = ((int64_t)512 << 20) / (per_split_bytes > 0 ? per_split_bytes : 1);
+    if (splits > max_by_mem) splits = max_by_mem;
+    if (splits < 1) splits = 1;
+    s.splits = (int)splits;
+    s.vox_per_split = ceil_div(ceil_div(V, splits), 16) * 16;
+    s.partial_bytes = (size_t)(splits * per_split_bytes);
+    const int64_t Vy = (int64_t)d->N * d->Do * d->Ho * d->Wo;
+    int64_t chunks = ceil_div(Vy, 4096);
+    if (chunks > 2 * kNumSMs) chunks = 2 * kNumSMs;
+    if (chunks < 1) chunks = 1;
+    s.bias_chunks = (int)chunks;
+    s.bias_rows_per_chunk = ceil_div(Vy, chunks);
+    s.bias_bytes = (size_t)chunks * d->Co * 4;
+    return s;
+}
+
+template <typename TI, typename TG>
+int launch_wgrad(const ConvPlan& p, const WgradSplit& s, const void* in, const void* grad, float* partial, void* stream) {
+    const GatherGeom& g = p.g;
+    const int64_t K = (int64_t)p.taps * g.IC;
+    if (g.OC > 16) {
+        dim3 grid((unsigned)ceil_div(K, 64), (unsigned)ceil_div(g.OCp, 64), (unsigned)s.splits);
+        B200_LAUNCH((conv_wgrad_kernel<TI, TG, 64>), grid, 256, 0, stream, g, (const TI*)in, (const TG*)grad, s.vox_per_split, partial);
+    } else {
+        dim3 grid((unsigned)ceil_div(K, 64), 1, (unsigned)s.splits);
+        B200_LAUNCH((conv_wgrad_kernel<TI, TG, 16>), grid, 256, 0, stream, g, (const TI*)in, (const TG*)grad, s.vox_per_split, partial);
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200_conv_algo(const b200_conv_desc* d, int pass) {
+    if (d == nullptr || conv_validate(d) != 0) return B200_ALGO_SIMT;
+    return umma_conv_supported(d, pass) ? B200_ALGO_UMMA : B200_ALGO_SIMT;
+}
+
+size_t b200_conv_packed_bytes(const b200_conv_desc* d, int pass) {
+    if (d == nullptr || pass == B200_PASS_WGRAD) return 0;
+    if (b200_conv_algo(d, pass) == B200_ALGO_UMMA) return umma_packed_bytes(d, pass);
+    const ConvPlan p = conv_plan(d, pass);
+    return (size_t)p.taps * p.g.IC * p.g.OCp * sizeof(float);
+}
+
+int b200_conv_pack_weights(const b200_conv_desc* d, int pass, const float* w, void* packed, void* stream) {
+    if (conv_validate(d)) return 1;
+    B200_REQUIRE(pass == B200_PASS_FWD || pass == B200_PASS_DGRAD, "pack: pass must be FWD or DGRAD");
+    B200_REQUIRE(w != nullptr && packed != nullptr, "pack: null pointer");
+    if (b200_conv_algo(d, pass) == B200_ALGO_UMMA) return umma_pack_weights(d, pass, w, packed, stream);
+    const ConvPlan p = conv_plan(d, pass);
+    const int64_t total = (int64_t)p.taps * p.g.IC * p.g.OCp;
+    B200_LAUNCH(pack_weights_simt_kernel, stream_grid(total, 256), 256, 0, stream, d->Ci, d->Co, p.taps, p.param_is_ci_major, p.pass_swaps,
+                p.g.OCp, w, (float*)packed);
+    return 0;
+}
+
+size_t b200_conv_workspace_bytes(const b200_conv_desc* d, int pass) {
+    if (d == nullptr || conv_validate(d)) return 0;
+    if (b200_conv_algo(d, pass) == B200_ALGO_UMMA) return umma_workspace_bytes(d, pass);
+    if (pass != B200_PASS_WGRAD) return 0;
+    const ConvPlan p = conv_plan(d, pass);
+    const WgradSplit s = wgrad_split(d, p);
+    return s.partial_bytes + s.bias_bytes + 256;
+}
+
+int b200_conv_fwd(const b200_conv_desc* d, const void* x, const void* w_packed, const float* bias, void* y,
+                  void* workspace, size_t ws_bytes, void* stream) {
+    if (conv_validate(d)) return 1;
+    B200_REQUIRE(x && w_packed && y, "conv_fwd: null pointer");
+    if (b200_conv_algo(d, B200_PASS_FWD) == B200_ALGO_UMMA) return umma_conv_run(d, B200_PASS_FWD, x, w_packed, bias, y, workspace, ws_bytes, stream);
+    const ConvPlan p = conv_plan(d, B200_PASS_FWD);
+    return dispatch_gather(p, x, (const float*)w_packed, bias, y, stream);
+}
+
+int b200_conv_dgrad(const b200_conv_desc* d, const void* dy, const void* w_packed_dgrad, void* dx,
+                    void* workspace, size_t ws_bytes, void* stream) {
+    if (conv_validate(d)) return 1;
+    B200_REQUIRE(dy && w_packed_dgrad && dx, "conv_dgrad: null pointer");
+    if (b200_conv_algo(d, B200_PASS_DGRAD) == B200_ALGO_UMMA)
+        return umma_conv_run(d, B200_PASS_DGRAD, dy, w_packed_dgrad, nullptr, dx, workspace, ws_bytes, stream);
+    const ConvPlan p = conv_plan(d, B200_PASS_DGRAD);
+    return dispatch_gather(p, dy, (const float*)w_packed_dgrad, nullptr, dx, stream);
+}
+
+int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias,
+                    void* workspace, size_t ws_bytes, void* stream) {
+    if (conv_validate(d)) return 1;
+    B200_REQUIRE(x && dy && dw, "conv_wgrad: null pointer");
+    B200_REQUIRE(ws_bytes >= b200_conv_workspace_bytes(d, B200_PASS_WGRAD) && workspace != nullptr, "conv_wgrad: workspace too small");
+    if (b200_conv_algo(d, B200_PASS_WGRAD) == B200_ALGO_UMMA) return umma_wgrad_run(d, x, dy, dw, dbias, workspace, ws_bytes, stream);
+    const ConvPlan p = conv_plan(d, B200_PASS_WGRAD);
+    const WgradSplit s = wgrad_split(d, p);
+    float* partial = (float*)workspace;
+    const void* gathered = d->transposed ? dy : x;
+    const void* second = d->transposed ? x : dy;
+    int rc;
+    // p.in_dtype is the gathered tensor's dtype, p.out_dtype the second operand's
+    if (p.in_dtype == B200_F32 && p.out_dtype == B200_F32) rc = launch_wgrad<float, float>(p, s, gathered, second, partial, stream);
+    else if (p.in_dtype == B200_BF16 && p.out_dtype == B200_BF16) rc = launch_wgrad<__nv_bfloat16, __nv_bfloat16>(p, s, gathered, second, partial, stream);
+    else if (p.in_dtype == B200_BF16 && p.out_dtype == B200_F32) rc = launch_wgrad<__nv_bfloat16, float>(p, s, gathered, second, partial, stream);
+    else rc = launch_wgrad<float, __nv_bfloat16>(p, s, gathered, second, partial, stream);
+    if (rc) return rc;
+    const int64_t total = (int64_t)p.taps * p.g.IC * p.g.OC;
+    B200_LAUNCH(conv_wgrad_reduce_kernel, stream_grid(total, 256), 256, 0, stream, s.splits, p.taps, p.g.IC, p.g.OC, p.g.OCp, d->Ci, d->Co,
+                p.param_is_ci_major, p.gathered_is_ci, partial, dw);
+    if (dbias != nullptr) {
+        float* bpart = (float*)((char*)workspace + ((s.partial_bytes + 255) & ~(size_t)255));
+        const int64_t Vy = (int64_t)d->N * d->Do * d->Ho * d->Wo;
+        const size_t smem = (size_t)(d->Co <= 256 ? (256 / d->Co) * d->Co : 1) * sizeof(float);
+        if (d->y_dtype == B200_F32)
+            B200_LAUNCH(colsum_partial_kernel<float>, s.bias_chunks, 256, smem, stream, (const float*)dy, d->Co, Vy, s.bias_rows_per_chunk, bpart);
+        else
+            B200_LAUNCH(colsum_partial_kernel<__nv_bfloat16>, s.bias_chunks, 256, smem, stream, (const __nv_bfloat16*)dy, d->Co, Vy, s.bias_rows_per_chunk, bpart);
+        B200_LAUNCH(colsum_final_kernel, (int)ceil_div(d->Co, 128), 128, 0, stream, s.bias_chunks, d->Co, bpart, dbias);
+    }
+    return 0;
+}
+
+// ============================================================================ normalisation
+static int norm_validate(const b200_norm_desc* d, NormGeom* g, std::initializer_list<const void*> ptrs) {
+    B200_REQUIRE(d != nullptr, "null norm descriptor");
+    B200_REQUIRE(d->N > 0 && d->C > 0 && d->S > 0, "norm: non-positive dims");
+    B200_REQUIRE(d->dtype == B200_F32 || d->dtype == B200_BF16, "norm: bad dtype");
+    B200_REQUIRE(d->kind >= B200_NORM_BATCH && d->kind <= B200_NORM_GROUP, "norm: bad kind");
+    B200_REQUIRE(d->kind != B200_NORM_GROUP || (d->G > 0 && d->C % d->G == 0), "norm: C=%d not divisible by G=%d", d->C, d->G);
+    bool vec_ok = true;
+    for (const void* p : ptrs) vec_ok = vec_ok && (p == nullptr || aligned16(p));
+    B200_REQUIRE(norm_geom(d, vec_ok, g), "norm: C=%d too large for this kernel", d->C);
+    return 0;
+}
+
+size_t b200_norm_workspace_bytes(const b200_norm_desc* d) {
+    NormGeom g;
+    if (d == nullptr || !norm_geom(d, false, &g)) return 0;
+    // chunks can only shrink when vectors are used; size for the scalar geometry (largest)
+    NormGeom gv;
+    norm_geom(d, true, &gv);
+    const int chunks = g.chunks > gv.chunks ? g.chunks : gv.chunks;
+    const size_t partial = (size_t)g.NB * chunks * 2 * d->C * 4;
+    const size_t ab = (size_t)g.NB * d->C * 2 * 4, coef = (size_t)g.NB * d->C * 3 * 4;
+    return partial + ab + coef + 768;
+}
+
+int b200_norm_stats(const b200_norm_desc* d, const void* x, float* mean, float* rstd, float* running_mean, float* running_var,
+                    void* workspace, size_t ws_bytes, void* stream) {
+    NormGeom g;
+    if (norm_validate(d, &g, {x})) return 1;
+    B200_REQUIRE(x && mean && rstd && workspace, "norm_stats: null pointer");
+    B200_REQUIRE(ws_bytes >= b200_norm_workspace_bytes(d), "norm_stats: workspace too small");
+    float* partial = (float*)workspace;
+    dim3 grid(g.chunks, g.NB);
+    const size_t smem = (size_t)2 * g.rpi * d->C * sizeof(float);
+    B200_DISPATCH_T(d->dtype, T, {
+        if (g.V == 1) B200_LAUNCH((norm_stats_partial_kernel<T, 1>), grid, 256, smem, stream, (const T*)x, d->C, g.R, g.rows_per_chunk, partial);
+        else B200_LAUNCH((norm_stats_partial_kernel<T, Vec16<T>::N>), grid, 256, smem, stream, (const T*)x, d->C, g.R, g.rows_per_chunk, partial);
+        B200_LAUNCH(norm_stats_finalize_kernel<T>, (int)ceil_div(g.groups, 128), 128, 0, stream, (const T*)x, d->N, d->C, d->S, d->kind, d->G,
+                    g.chunks, g.R, partial, d->eps, d->momentum, mean, rstd, running_mean, running_var);
+    });
+    return 0;
+}
+
+int b200_norm_stats_from_running(const b200_norm_desc* d, const float* running_mean, const float* running_var, float* mean, float* rstd, void* stream) {
+    B200_REQUIRE(d && d->kind == B200_NORM_BATCH, "stats_from_running: BatchNorm only");
+    B200_REQUIRE(running_mean && running_var && mean && rstd, "stats_from_running: null pointer");
+    B200_LAUNCH(norm_from_running_kernel, (int)ceil_div(d->C, 128), 128, 0, stream, d->C, d->eps, running_mean, running_var, mean, rstd);
+    return 0;
+}
+
+static int apply_grid(const NormGeom& g, int64_t S) {
+    // gx*256 must be a multiple of CV so every thread keeps fixed channels
+    int m = g.CV;
+    int a = 256, b = m;
+    while (b) { int t = a % b; a = b; b = t; }
+    m /= a;                                        // CV / gcd(CV, 256)
+    int gx = stream_grid(S * g.CV, 256, 8);
+    if (g.N > 1) gx = (gx + g.N - 1) / g.N;
+    if (gx < 1) gx = 1;
+    gx = ((gx + m - 1) / m) * m;
+    return gx;
+}
+
+int b200_norm_apply(const b200_norm_desc* d, const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                    const void* residual, void* y, void* stream) {
+    NormGeom g;
+    if (norm_validate(d, &g, {x, y, residual})) return 1;
+    B200_REQUIRE(x && y && mean && rstd, "norm_apply: null pointer");
+    dim3 grid(apply_grid(g, d->S), d->N);
+    B200_DISPATCH_T(d->dtype, T, {
+        if (g.V == 1) B200_LAUNCH((norm_apply_kernel<T, 1>), grid, 256, 0, stream, (const T*)x, mean, rstd, gamma, beta, (const T*)residual, (T*)y,
+                                  d->C, d->S, d->kind, d->G, d->act, d->slope);
+        else B200_LAUNCH((norm_apply_kernel<T, Vec16<T>::N>), grid, 256, 0, stream, (const T*)x, mean, rstd, gamma, beta, (const T*)residual, (T*)y,
+                         d->C, d->S, d->kind, d->G, d->act, d->slope);
+    });
+    return 0;
+}
+
+// workspace layout shared by the backward entry points
+struct NormBwdWs { float* partial; float* AB; float* coef; };
+static NormBwdWs norm_bwd_ws(const b200_norm_desc* d, const NormGeom& g, void* workspace) {
+    NormGeom gs;
+    norm_geom(d, false, &gs);
+    const int max_chunks = g.chunks > gs.chunks ? g.chunks : gs.chunks;
+    NormBwdWs w;
+    w.partial = (float*)workspace;
+    w.AB = w.partial + (((size_t)g.NB * max_chunks * 2 * d->C + 63) & ~(size_t)63);
+    w.coef = w.AB + (((size_t)g.NB * d->C * 2 + 63) & ~(size_t)63);
+    return w;
+}
+
+int b200_norm_bwd_reduce(const b200_norm_desc* d, const void* x, const void* y, const void* dy, const float* mean, const float* rstd,
+                         float* sums, void* workspace, size_t ws_bytes, void* stream) {
+    NormGeom g;
+    if (norm_validate(d, &g, {x, y, dy})) return 1;
+    B200_REQUIRE(x && dy && mean && rstd && sums && workspace, "norm_bwd_reduce: null pointer");
+    B200_REQUIRE(d->act == B200_ACT_NONE || y != nullptr, "norm_bwd: fused activation needs the saved output y");
+    B200_REQUIRE(ws_bytes >= b200_norm_workspace_bytes(d), "norm_bwd_reduce: workspace too small");
+    const NormBwdWs w = norm_bwd_ws(d, g, workspace);
+    dim3 grid(g.chunks, g.NB);
+    const size_t smem = (size_t)2 * g.rpi * d->C * sizeof(float);
+    B200_DISPATCH_T(d->dtype, T, {
+        if (g.V == 1) B200_LAUNCH((norm_bwd_partial_kernel<T, 1>), grid, 256, smem, stream, (const T*)x, (const T*)y, (const T*)dy, mean, rstd, d->C,
+                                  g.R, g.rows_per_chunk, d->kind, d->G, d->act, d->slope, w.partial);
+        else B200_LAUNCH((norm_bwd_partial_kernel<T, Vec16<T>::N>), grid, 256, smem, stream, (const T*)x, (const T*)y, (const T*)dy, mean, rstd, d->C,
+                         g.R, g.rows_per_chunk, d->kind, d->G, d->act, d->slope, w.partial);
+    });
+    B200_LAUNCH(norm_bwd_sum_kernel, (int)ceil_div((int64_t)g.NB * d->C, 128), 128, 0, stream, g.NB, d->C, g.chunks, w.partial, sums);
+    return 0;
+}
+
+int b200_norm_bwd_apply(const b200_norm_desc* d, int training, int world, const void* x, const void* y, const void* dy, const float* mean,
+                        const float* rstd, const float* gamma, const float* sums, void* dx, void* dresidual, float* dgamma, float* dbeta,
+                        void* workspace, size_t ws_bytes, void* stream) {
+    NormGeom g;
+    if (norm_validate(d, &g, {x, y, dy, dx, dresidual})) return 1;
+    B200_REQUIRE(x && dy && dx && mean && rstd && sums && workspace && world >= 1, "norm_bwd_apply: bad arguments");
+    B200_REQUIRE(ws_bytes >= b200_norm_workspace_bytes(d), "norm_bwd_apply: workspace too small");
+    const NormBwdWs w = norm_bwd_ws(d, g, workspace);
+    dim3 agrid(apply_grid(g, d->S), d->N);
+    const int per_sample = d->kind != B200_NORM_BATCH;
+    B200_LAUNCH(norm_bwd_coef_kernel, (int)ceil_div((int64_t)g.NB * d->C, 128), 128, 0, stream, d->N, d->C, d->S, d->kind, d->G, training, world,
+                sums, mean, rstd, gamma, w.coef, dgamma, dbeta);
+    B200_DISPATCH_T(d->dtype, T, {
+        if (g.V == 1) B200_LAUNCH((norm_bwd_apply_kernel<T, 1>), agrid, 256, 0, stream, (const T*)x, (const T*)y, (const T*)dy, w.coef, (T*)dx,
+                                  (T*)dresidual, d->C, d->S, per_sample, d->act, d->slope);
+        else B200_LAUNCH((norm_bwd_apply_kernel<T, Vec16<T>::N>), agrid, 256, 0, stream, (const T*)x, (const T*)y, (const T*)dy, w.coef, (T*)dx,
+                         (T*)dresidual, d->C, d->S, per_sample, d->act, d->slope);
+    });
+    return 0;
+}
+
+int b200_norm_bwd(const b200_norm_desc* d, int training, const void* x, const void* y, const void* dy, const float* mean, const float* rstd,
+                  const float* gamma, void* dx, void* dresidual, float* dgamma, float* dbeta, void* workspace, size_t ws_bytes, void* stream) {
+    NormGeom g;
+    if (norm_validate(d, &g, {x, y, dy, dx, dresidual})) return 1;
+    B200_REQUIRE(workspace != nullptr && ws_bytes >= b200_norm_workspace_bytes(d), "norm_bwd: workspace too small");
+    const NormBwdWs w = norm_bwd_ws(d, g, workspace);
+    if (b200_norm_bwd_reduce(d, x, y, dy, mean, rstd, w.AB, workspace, ws_bytes, stream)) return 1;
+    return b200_norm_bwd_apply(d, training, 1, x, y, dy, mean, rstd, gamma, w.AB, dx, dresidual, dgamma, dbeta, workspace, ws_bytes, stream);
+}
+
+// ============================================================================ activations
+#define B200_ELEMWISE(dtype, n, ptr_ok, KERNEL, ...)                                                        \
+    B200_DISPATCH_T(dtype, T, {                                                                             \
+        constexpr int VF = Vec16<T>::N;                                                                     \
+        if ((ptr_ok) && (n) % VF == 0) { const int64_t nv = (n) / VF; B200_LAUNCH((KERNEL<T, VF>), stream_grid(nv, 256), 256, 0, stream, __VA_ARGS__); } \
+        else { const int64_t nv = (n); B200_LAUNCH((KERNEL<T, 1>), stream_grid(nv, 256), 256, 0, stream, __VA_ARGS__); }                                 \
+    })
+
+int b200_act_fwd(int dtype, int act, float slope, int64_t n, const void* x, void* y, void* stream) {
+    B200_REQUIRE(n >= 0 && (n == 0 || (x && y)), "act_fwd: bad arguments");
+    if (n == 0) return 0;
+    B200_ELEMWISE(dtype, n, aligned16(x) && aligned16(y), act_fwd_kernel, act, slope, nv, (const T*)x, (T*)y);
+    return 0;
+}
+int b200_act_bwd(int dtype, int act, float slope, int64_t n, const void* y, const void* dy, void* dx, void* stream) {
+    B200_REQUIRE(n >= 0 && (n == 0 || (y && dy && dx)), "act_bwd: bad arguments");
+    if (n == 0) return 0;
+    B200_ELEMWISE(dtype, n, aligned16(y) && aligned16(dy) && aligned16(dx), act_bwd_kernel, act, slope, nv, (const T*)y, (const T*)dy, (T*)dx);
+    return 0;
+}
+int b200_prelu_fwd(int dtype, int64_t n, const void* x, const float* a, void* y, void* stream) {
+    B200_REQUIRE(n >= 0 && (n == 0 || (x && y && a)), "prelu_fwd: bad arguments");
+    if (n == 0) return 0;
+    B200_ELEMWISE(dtype, n, aligned16(x) && aligned16(y), prelu_fwd_kernel, nv, (const T*)x, a, (T*)y);
+    return 0;
+}
+size_t b200_prelu_workspace_bytes(int64_t n) { (void)n; return (size_t)kNumSMs * 8 * sizeof(float); }
+int b200_prelu_bwd(int dtype, int64_t n, const void* x, const float* a, const void* dy, void* dx, float* da, void* workspace, size_t ws_bytes,
+                   void* stream) {
+    B200_REQUIRE(n > 0 && x && a && dy && dx && da && workspace, "prelu_bwd: bad arguments");
+    B200_REQUIRE(ws_bytes >= b200_prelu_workspace_bytes(n), "prelu_bwd: workspace too small");
+    float* partial = (float*)workspace;
+    int blocks = 0;
+    B200_DISPATCH_T(dtype, T, {
+        constexpr int VF = Vec16<T>::N;
+        if (aligned16(x) && aligned16(dy) && aligned16(dx) && n % VF == 0) {
+            blocks = stream_grid(n / VF, 256);
+            B200_LAUNCH((prelu_bwd_kernel<T, VF>), blocks, 256, 0, stream, n / VF, (const T*)x, a, (const T*)dy, (T*)dx, partial);
+        } else {
+            blocks = stream_grid(n, 256);
+            B200_LAUNCH((prelu_bwd_kernel<T, 1>), blocks, 256, 0, stream, n, (const T*)x, a, (const T*)dy, (T*)dx, partial);
+        }
+    });
+    B200_LAUNCH(sum_partials_kernel, 1, 32, 0, stream, blocks, partial, da);
+    return 0;
+}
+int b200_add_act_fwd(int dtype, int act, float slope, int64_t n, const void* a, const void* b, void* y, void* stream) {
+    B200_REQUIRE(n >= 0 && (n == 0 || (a && b && y)), "add_act: bad arguments");
+    if (n == 0) return 0;
+    B200_ELEMWISE(dtype, n, aligned16(a) && aligned16(b) && aligned16(y), add_act_kernel, act, slope, nv, (const T*)a, (const T*)b, (T*)y);
+    return 0;
+}
+
+// ============================================================================ pooling
+static int pool_validate(const b200_pool_desc* d) {
+    B200_REQUIRE(d != nullptr, "null pool descriptor");
+    B200_REQUIRE(d->N > 0 && d->C > 0 && d->kd > 0 && d->kh > 0 && d->kw > 0 && d->sd > 0 && d->sh > 0 && d->sw > 0, "pool: bad dims");
+    B200_REQUIRE(d->kd * d->kh * d->kw <= 256, "pool: window too large for the uint8 argmax code");
+    B200_REQUIRE(d->Di >= d->kd && d->Hi >= d->kh && d->Wi >= d->kw, "pool: input smaller than the window");
+    B200_REQUIRE(d->Do == (d->Di - d->kd) / d->sd + 1 && d->Ho == (d->Hi - d->kh) / d->sh + 1 && d->Wo == (d->Wi - d->kw) / d->sw + 1,
+                 "pool: output size mismatch (floor mode, no padding)");
+    return 0;
+}
+int b200_maxpool_fwd(const b200_pool_desc* d, const void* x, void* y, uint8_t* code, int64_t* indices, void* stream) {
+    if (pool_validate(d)) return 1;
+    B200_REQUIRE(x && y, "maxpool_fwd: null pointer");
+    const int64_t nout = (int64_t)d->N * d->Do * d->Ho * d->Wo;
+    B200_DISPATCH_T(d->dtype, T, {
+        constexpr int VF = Vec16<T>::N;
+        if (d->C % VF == 0 && aligned16(x) && aligned16(y))
+            B200_LAUNCH((maxpool_fwd_kernel<T, VF>), stream_grid(nout * (d->C / VF), 256), 256, 0, stream, *d, (const T*)x, (T*)y, code, indices);
+        else
+            B200_LAUNCH((maxpool_fwd_kernel<T, 1>), stream_grid(nout * d->C, 256), 256, 0, stream, *d, (const T*)x, (T*)y, code, indices);
+    });
+    return 0;
+}
+int b200_maxpool_bwd(const b200_pool_desc* d, const void* dy, const uint8_t* code, void* dx, void* stream) {
+    if (pool_validate(d)) return 1;
+    B200_REQUIRE(dy && code && dx, "maxpool_bwd: null pointer");
+    const int64_t nin = (int64_t)d->N * d->Di * d->Hi * d->Wi;
+    B200_DISPATCH_T(d->dtype, T, {
+        constexpr int VF = Vec16<T>::N;
+        if (d->C % VF == 0 && aligned16(dy) && aligned16(dx))
+            B200_LAUNCH((maxpool_bwd_kernel<T, VF>), stream_grid(nin * (d->C / VF), 256), 256, 0, stream, *d, (const T*)dy, code, (T*)dx);
+        else
+            B200_LAUNCH((maxpool_bwd_kernel<T, 1>), stream_grid(nin * d->C, 256), 256, 0, stream, *d, (const T*)dy, code, (T*)dx);
+    });
+    return 0;
+}
+
+// ============================================================================ upsample / concat
+static int up_validate(const b200_up_desc* d) {
+    B200_REQUIRE(d != nullptr, "null upsample descriptor");
+    B200_REQUIRE(d->N > 0 && d->C > 0 && d->Di > 0 && d->Hi > 0 && d->Wi > 0 && d->Do > 0 && d->Ho > 0 && d->Wo > 0, "upsample: bad dims");
+    B200_REQUIRE(d->mode >= B200_UP_NEAREST && d->mode <= B200_UP_TRILINEAR_ALIGNED, "upsample: bad mode");
+    B200_REQUIRE(d->Ctot >= d->C && d->c_off >= 0 && d->c_off + d->C <= d->Ctot, "upsample: bad channel window");
+    B200_REQUIRE(d->Do >= d->Di && d->Ho >= d->Hi && d->Wo >= d->Wi && d->Do <= 4 * d->Di && d->Ho <= 4 * d->Hi && d->Wo <= 4 * d->Wi,
+                 "upsample: only factors in [1,4] are supported");
+    return 0;
+}
+int b200_upsample_fwd(const b200_up_desc* d, const void* x, void* y, void* stream) {
+    if (up_validate(d)) return 1;
+    B200_REQUIRE(x && y, "upsample_fwd: null pointer");
+    const int64_t nout = (int64_t)d->N * d->Do * d->Ho * d->Wo;
+    B200_DISPATCH_T(d->dtype, T, {
+        constexpr int VF = Vec16<T>::N;
+        if (d->C % VF == 0 && d->Ctot % VF == 0 && d->c_off % VF == 0 && aligned16(x) && aligned16(y))
+            B200_LAUNCH((upsample_fwd_kernel<T, VF>), stream_grid(nout * (d->C / VF), 256), 256, 0, stream, *d, (const T*)x, (T*)y);
+        else
+            B200_LAUNCH((upsample_fwd_kernel<T, 1>), stream_grid(nout * d->C, 256), 256, 0, stream, *d, (const T*)x, (T*)y);
+    });
+    return 0;
+}
+int b200_upsample_bwd(const b200_up_desc* d, const void* dy, void* dx, void* stream) {
+    if (up_validate(d)) return 1;
+    B200_REQUIRE(dy && dx, "upsample_bwd: null pointer");
+    const int64_t nin = (int64_t)d->N * d->Di * d->Hi * d->Wi;
+    B200_DISPATCH_T(d->dtype, T, {
+        constexpr int VF = Vec16<T>::N;
+        if (d->C % VF == 0 && d->Ctot % VF == 0 && d->c_off % VF == 0 && aligned16(dy) && aligned16(dx))
+            B200_LAUNCH((upsample_bwd_kernel<T, VF>), stream_grid(nin * (d->C / VF), 256), 256, 0, stream, *d, (const T*)dy, (T*)dx);
+        else
+            B200_LAUNCH((upsample_bwd_kernel<T, 1>), stream_grid(nin * d->C, 256), 256, 0, stream, *d, (const T*)dy, (T*)dx);
+    });
+    return 0;
+}
+int b200_copy_channels(int dtype, int64_t V, int32_t C, const void* src, int32_t src_ctot, int32_t src_off, void* dst, int32_t dst_ctot,
+                       int32_t dst_off, void* stream) {
+    B200_REQUIRE(V >= 0 && C > 0 && src && dst && src_off >= 0 && dst_off >= 0 && src_off + C <= src_ctot && dst_off + C <= dst_ctot,
+                 "copy_channels: bad arguments");
+    if (V == 0) return 0;
+    B200_DISPATCH_T(dtype, T, {
+        constexpr int VF = Vec16<T>::N;
+        if (C % VF == 0 && src_ctot % VF == 0 && dst_ctot % VF == 0 && src_off % VF == 0 && dst_off % VF == 0 && aligned16(src) && aligned16(dst))
+            B200_LAUNCH((copy_channels_kernel<T, VF>), stream_grid(V * (C / VF), 256), 256, 0, stream, V, C / VF, (const T*)src, src_ctot, src_off,
+                        (T*)dst, dst_ctot, dst_off);
+        else
+            B200_LAUNCH((copy_channels_kernel<T, 1>), stream_grid(V * C, 256), 256, 0, stream, V, C, (const T*)src, src_ctot, src_off, (T*)dst,
+                        dst_ctot, dst_off);
+    });
+    return 0;
+}
+
+// ============================================================================ layout
+}  // extern "C"
+template <typename TS, typename TD>
+static int launch_transpose(int N, int C, int64_t S, const void* src, void* dst, bool to_cl, void* stream) {
+    dim3 grid((unsigned)ceil_div(S, 32), (unsigned)ceil_div(C, 32), (unsigned)N);
+    B200_LAUNCH((transpose_cs_kernel<TS, TD>), grid, 256, 0, stream, C, S, (const TS*)src, (TD*)dst, to_cl);
+    return 0;
+}
+static int transpose_dispatch(int sdt, int ddt, int N, int C, int64_t S, const void* src, void* dst, bool to_cl, void* stream) {
+    B200_REQUIRE(N > 0 && C > 0 && S > 0 && src && dst, "layout: bad arguments");
+    B200_REQUIRE(N <= 65535, "layout: N too large");
+    B200_REQUIRE(ceil_div(C, 32) <= 65535 && ceil_div(S, 32) <= 2147483647LL, "layout: too large");
+    if (sdt == B200_F32 && ddt == B200_F32) return launch_transpose<float, float>(N, C, S, src, dst, to_cl, stream);
+    if (sdt == B200_F32 && ddt == B200_BF16) return launch_transpose<float, __nv_bfloat16>(N, C, S, src, dst, to_cl, stream);
+    if (sdt == B200_BF16 && ddt == B200_F32) return launch_transpose<__nv_bfloat16, float>(N, C, S, src, dst, to_cl, stream);
+    if (sdt == B200_BF16 && ddt == B200_BF16) return launch_transpose<__nv_bfloat16, __nv_bfloat16>(N, C, S, src, dst, to_cl, stream);
+    return fail("layout: unsupported dtypes");
+}
+extern "C" {
+int b200_to_channels_last(int sdt, int ddt, int32_t N, int32_t C, int64_t S, const void* src, void* dst, void* stream) {
+    return transpose_dispatch(sdt, ddt, N, C, S, src, dst, true, stream);
+}
+int b200_from_channels_last(int sdt, int ddt, int32_t N, int32_t C, int64_t S, const void* src, void* dst, void* stream) {
+    return transpose_dispatch(sdt, ddt, N, C, S, src, dst, false, stream);
+}
+
+// ============================================================================ patches
+static int patch_validate(const b200_patch_desc* d) {
+    B200_REQUIRE(d != nullptr, "null patch descriptor");
+    B200_REQUIRE(d->X > 0 && d->Y > 0 && d->Z > 0 && d->h > 0 && d->w > 0, "patch: bad dims");
+    B200_REQUIRE(d->X / 2 - d->w >= 0 && 2 * d->w <= d->X, "patch: window wider than half the slice");
+    return 0;
+}
+int64_t b200_patch_max_rows(const b200_patch_desc* d) {
+    if (d == nullptr) return 0;
+    return patch_geom(d).slots * 4;
+}
+size_t b200_patch_workspace_bytes(const b200_patch_desc* d) {
+    if (d == nullptr) return 0;
+    const PatchGeom g = patch_geom(d);
+    return (size_t)g.Y * g.Z * 4 + (size_t)g.slots * 4 * 2 + (size_t)g.slots * 12 * 4 + 1024;
+}
+int b200_patch_plan(const b200_patch_desc* d, const double* gmpm, const uint8_t* mask, int32_t* plan, int32_t* count, int32_t* status,
+                    void* workspace, size_t ws_bytes, void* stream) {
+    if (patch_validate(d)) return 1;
+    B200_REQUIRE(gmpm && plan && count && status && workspace, "patch_plan: null pointer");
+    B200_REQUIRE(!d->with_mask || mask, "patch_plan: with_mask set but mask is null");
+    B200_REQUIRE(ws_bytes >= b200_patch_workspace_bytes(d), "patch_plan: workspace too small");
+    const PatchGeom g = patch_geom(d);
+    int32_t* first_pos = (int32_t*)workspace;
+    int32_t* slot_cnt = first_pos + (((size_t)g.Y * g.Z + 63) & ~(size_t)63);
+    int32_t* offsets = slot_cnt + (((size_t)g.slots + 63) & ~(size_t)63);
+    int32_t* slot_rows = offsets + (((size_t)g.slots + 63) & ~(size_t)63);
+    cudaError_t e = cudaMemsetAsync(status, 0, sizeof(int32_t), (cudaStream_t)stream);
+    B200_REQUIRE(e == cudaSuccess, "patch_plan: memset failed: %s", cudaGetErrorString(e));
+    B200_LAUNCH(patch_first_pos_kernel, (int)ceil_div((int64_t)g.Y * g.Z, 256), 256, 0, stream, g, gmpm, first_pos);
+    const int64_t threads = (int64_t)g.NJ0 * g.Z + (int64_t)(g.passes - 1) * g.NJk * g.Z;
+    B200_LAUNCH(patch_slot_kernel, (int)ceil_div(threads, 128), 128, 0, stream, g, first_pos, d->with_mask ? mask : nullptr, slot_cnt, slot_rows, status);
+    B200_LAUNCH(patch_scan_kernel, 1, 1024, 0, stream, g.slots, slot_cnt, offsets, count);
+    B200_LAUNCH(patch_emit_kernel, (int)ceil_div(g.slots, 256), 256, 0, stream, g, slot_cnt, offsets, slot_rows, plan);
+    return 0;
+}
+int b200_patch_gather(const b200_patch_desc* d, const double* target, const int32_t* plan, int64_t rows, int out_is_f32, void* out, void* stream) {
+    if (patch_validate(d)) return 1;
+    B200_REQUIRE(rows >= 0 && (rows == 0 || (target && plan && out)), "patch_gather: bad arguments");
+    if (rows == 0) return 0;
+    const PatchGeom g = patch_geom(d);
+    const int64_t total = rows * 2 * g.h * g.w;
+    if (out_is_f32) B200_LAUNCH(patch_gather_kernel<float>, stream_grid(total, 256), 256, 0, stream, g, target, plan, rows, (float*)out);
+    else B200_LAUNCH(patch_gather_kernel<double>, stream_grid(total, 256), 256, 0, stream, g, target, plan, rows, (double*)out);
+    return 0;
+}
+
+}  // extern "C"

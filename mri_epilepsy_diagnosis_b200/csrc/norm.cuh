@@ -1,0 +1,309 @@
+// BatchNorm / InstanceNorm / GroupNorm on channels-last tensors: statistics, apply(+act,+residual), backward.
+// HBM-bound: every pass reads each element once with 16-byte vectors; per-channel partial sums are
+// reduced in shared memory per block, then across blocks in a fixed order (deterministic), in double.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+struct NormGeom {
+    int N, C, kind, G;
+    int64_t S;
+    int NB;            // independent reduce-batches: 1 for BATCH, N otherwise
+    int64_t R;         // rows (voxels) per reduce-batch
+    int V;             // channel vector width actually used
+    int CV;            // channel vectors per voxel = C / V
+    int rpi;           // rows per block iteration = 256 / CV
+    int chunks;        // blocks per reduce-batch
+    int64_t rows_per_chunk;
+    int groups;        // number of (mean, rstd) entries
+};
+
+inline bool norm_geom(const b200_norm_desc* d, bool vec_ok, NormGeom* g) {
+    g->N = d->N; g->C = d->C; g->S = d->S; g->kind = d->kind; g->G = d->G;
+    g->NB = d->kind == B200_NORM_BATCH ? 1 : d->N;
+    g->R = d->kind == B200_NORM_BATCH ? (int64_t)d->N * d->S : d->S;
+    int vfull = d->dtype == B200_F32 ? 4 : 8;
+    g->V = (vec_ok && d->C % vfull == 0) ? vfull : 1;
+    g->CV = d->C / g->V;
+    if (g->CV > 256 || g->CV < 1) return false;
+    g->rpi = 256 / g->CV;
+    int64_t want = ceil_div(g->R, (int64_t)g->rpi * 16);
+    int64_t cap = (kNumSMs * 4) / g->NB;
+    if (cap < 1) cap = 1;
+    g->chunks = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+    g->rows_per_chunk = ceil_div(g->R, g->chunks);
+    g->groups = d->kind == B200_NORM_BATCH ? d->C : d->kind == B200_NORM_INSTANCE ? d->N * d->C : d->N * d->G;
+    return true;
+}
+
+__device__ __forceinline__ int norm_group_index(int kind, int n, int c, int C, int G) {
+    return kind == B200_NORM_BATCH ? c : kind == B200_NORM_INSTANCE ? n * C + c : n * G + c / (C / G);
+}
+
+// partial[((nb*chunks + chunk)*2 + {0,1})*C + c] = sum(x-K), sum((x-K)^2) with K = first row of the reduce-batch
+template <typename T, int V>
+__global__ void __launch_bounds__(256) norm_stats_partial_kernel(const T* __restrict__ x, int C, int64_t R, int64_t rows_per_chunk,
+                                                                 float* __restrict__ partial) {
+    extern __shared__ float sm[];                 // [2][rpi][C]
+    const int CV = C / V, rpi = 256 / CV;
+    const int t = threadIdx.x, cv = t % CV, rr = t / CV;
+    const bool active = rr < rpi;
+    const int nb = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+    const T* base = x + (int64_t)nb * R * C;
+    float K[V], s[V], q[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) s[k] = q[k] = 0.f;
+    if (active) {
+        Pack<T, V>::load(base + cv * V, K);
+        const int64_t r_end = min(R, (int64_t)(chunk + 1) * rows_per_chunk);
+        int64_t r = (int64_t)chunk * rows_per_chunk + rr;
+        for (; r + 3 * rpi < r_end; r += 4 * rpi) {
+            float a[4][V];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) Pack<T, V>::load(base + (r + u * rpi) * C + cv * V, a[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int k = 0; k < V; ++k) { float dlt = a[u][k] - K[k]; s[k] += dlt; q[k] += dlt * dlt; }
+        }
+        for (; r < r_end; r += rpi) {
+            float a[V];
+            Pack<T, V>::load(base + r * C + cv * V, a);
+#pragma unroll
+            for (int k = 0; k < V; ++k) { float dlt = a[k] - K[k]; s[k] += dlt; q[k] += dlt * dlt; }
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            sm[rr * C + cv * V + k] = s[k];
+            sm[(rpi + rr) * C + cv * V + k] = q[k];
+        }
+    }
+    __syncthreads();
+    for (int c = t; c < 2 * C; c += 256) {
+        const int which = c / C, ch = c - which * C;
+        float acc = 0.f;
+        for (int j = 0; j < rpi; ++j) acc += sm[(which * rpi + j) * C + ch];
+        partial[(((int64_t)nb * chunks + chunk) * 2 + which) * C + ch] = acc;
+    }
+}
+
+// one thread per (mean, rstd) entry
+template <typename T>
+__global__ void norm_stats_finalize_kernel(const T* __restrict__ x, int N, int C, int64_t S, int kind, int G, int chunks, int64_t R,
+                                           const float* __restrict__ partial, float eps, float momentum,
+                                           float* __restrict__ mean, float* __restrict__ rstd,
+                                           float* __restrict__ running_mean, float* __restrict__ running_var) {
+    const int groups = kind == B200_NORM_BATCH ? C : kind == B200_NORM_INSTANCE ? N * C : N * G;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= groups) return;
+    int nb, c0, c1;
+    if (kind == B200_NORM_BATCH) { nb = 0; c0 = g; c1 = g + 1; }
+    else if (kind == B200_NORM_INSTANCE) { nb = g / C; c0 = g % C; c1 = c0 + 1; }
+    else { nb = g / G; c0 = (g % G) * (C / G); c1 = c0 + C / G; }
+    double m_acc = 0.0, e2_acc = 0.0;
+    for (int c = c0; c < c1; ++c) {
+        double s = 0.0, q = 0.0;
+        for (int k = 0; k < chunks; ++k) {
+            s += (double)partial[(((int64_t)nb * chunks + k) * 2 + 0) * C + c];
+            q += (double)partial[(((int64_t)nb * chunks + k) * 2 + 1) * C + c];
+        }
+        const double K = (double)to_f<T>(x[(int64_t)nb * R * C + c]);
+        const double ms = s / (double)R;
+        const double mc = K + ms;
+        double vc = q / (double)R - ms * ms;
+        if (vc < 0.0) vc = 0.0;
+        m_acc += mc;
+        e2_acc += vc + mc * mc;
+    }
+    const int nc = c1 - c0;
+    const double m = m_acc / nc;
+    double var = e2_acc / nc - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[g] = (float)m;
+    rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+    if (kind == B200_NORM_BATCH && running_mean != nullptr) {
+        const double unbiased = R > 1 ? var * (double)R / (double)(R - 1) : var;
+        running_mean[g] = (float)((1.0 - momentum) * (double)running_mean[g] + momentum * m);
+        running_var[g] = (float)((1.0 - momentum) * (double)running_var[g] + momentum * unbiased);
+    }
+}
+
+__global__ void norm_from_running_kernel(int C, float eps, const float* __restrict__ rm, const float* __restrict__ rv,
+                                         float* __restrict__ mean, float* __restrict__ rstd) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) { mean[c] = rm[c]; rstd[c] = 1.0f / sqrtf(rv[c] + eps); }
+}
+
+// y = act((x - mean) * rstd * gamma + beta [+ residual]); grid (gx, N); gx*256 is a multiple of CV so each thread owns fixed channels
+template <typename T, int V>
+__global__ void __launch_bounds__(256) norm_apply_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         const T* __restrict__ res, T* __restrict__ y,
+                                                         int C, int64_t S, int kind, int G, int act, float slope) {
+    const int CV = C / V, n = blockIdx.y;
+    const int64_t i0 = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int cv = (int)(i0 % CV);
+    float sc[V], sh[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        const int c = cv * V + k;
+        const int g = norm_group_index(kind, n, c, C, G);
+        const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+        sc[k] = rstd[g] * ga;
+        sh[k] = be - mean[g] * sc[k];
+    }
+    const int64_t total = S * CV, stride = (int64_t)gridDim.x * 256, base = (int64_t)n * total;
+    for (int64_t i = i0; i < total; i += stride) {
+        float v[V];
+        Pack<T, V>::load(x + (base + i) * V, v);
+        if (res != nullptr) {
+            float r[V];
+            Pack<T, V>::load(res + (base + i) * V, r);
+#pragma unroll
+            for (int k = 0; k < V; ++k) v[k] = act_apply(fmaf(v[k], sc[k], sh[k]) + r[k], act, slope);
+        } else {
+#pragma unroll
+            for (int k = 0; k < V; ++k) v[k] = act_apply(fmaf(v[k], sc[k], sh[k]), act, slope);
+        }
+        Pack<T, V>::store(y + (base + i) * V, v);
+    }
+}
+
+// partial[((nb*chunks+chunk)*2+{0,1})*C + c] = sum dy', sum dy' * xhat, with dy' = dy * act'(y)
+template <typename T, int V>
+__global__ void __launch_bounds__(256) norm_bwd_partial_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ dy,
+                                                               const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                               int C, int64_t R, int64_t rows_per_chunk, int kind, int G, int act, float slope,
+                                                               float* __restrict__ partial) {
+    extern __shared__ float sm[];
+    const int CV = C / V, rpi = 256 / CV;
+    const int t = threadIdx.x, cv = t % CV, rr = t / CV;
+    const bool active = rr < rpi;
+    const int nb = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+    const int64_t off = (int64_t)nb * R * C;
+    float a[V], b[V], mu[V], rs[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) a[k] = b[k] = 0.f;
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const int g = norm_group_index(kind, nb, cv * V + k, C, G);
+            mu[k] = mean[g]; rs[k] = rstd[g];
+        }
+        const int64_t r_end = min(R, (int64_t)(chunk + 1) * rows_per_chunk);
+        for (int64_t r = (int64_t)chunk * rows_per_chunk + rr; r < r_end; r += rpi) {
+            float xv[V], gv[V];
+            const int64_t p = off + r * C + cv * V;
+            Pack<T, V>::load(x + p, xv);
+            Pack<T, V>::load(dy + p, gv);
+            if (act != B200_ACT_NONE) {
+                float ov[V];
+                Pack<T, V>::load(y + p, ov);
+#pragma unroll
+                for (int k = 0; k < V; ++k) gv[k] *= act_gate(ov[k], act, slope);
+            }
+#pragma unroll
+            for (int k = 0; k < V; ++k) { a[k] += gv[k]; b[k] += gv[k] * (xv[k] - mu[k]) * rs[k]; }
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            sm[rr * C + cv * V + k] = a[k];
+            sm[(rpi + rr) * C + cv * V + k] = b[k];
+        }
+    }
+    __syncthreads();
+    for (int c = t; c < 2 * C; c += 256) {
+        const int which = c / C, ch = c - which * C;
+        float acc = 0.f;
+        for (int j = 0; j < rpi; ++j) acc += sm[(which * rpi + j) * C + ch];
+        partial[(((int64_t)nb * chunks + chunk) * 2 + which) * C + ch] = acc;
+    }
+}
+
+// AB[(nb*C + c)*2 + {0,1}] = sum over chunks
+__global__ void norm_bwd_sum_kernel(int NB, int C, int chunks, const float* __restrict__ partial, float* __restrict__ AB) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NB * C) return;
+    const int nb = i / C, c = i % C;
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < chunks; ++k) {
+        a += (double)partial[(((int64_t)nb * chunks + k) * 2 + 0) * C + c];
+        b += (double)partial[(((int64_t)nb * chunks + k) * 2 + 1) * C + c];
+    }
+    AB[(int64_t)i * 2] = (float)a;
+    AB[(int64_t)i * 2 + 1] = (float)b;
+}
+
+// coef[(nb*C + c)*3 + {0,1,2}] : dx = k1*dy' + k4*x + k5 ; also dgamma/dbeta (thread nb==0 sums over nb)
+__global__ void norm_bwd_coef_kernel(int N, int C, int64_t S, int kind, int G, int training, int world, const float* __restrict__ AB,
+                                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                     float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int NB = kind == B200_NORM_BATCH ? 1 : N;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NB * C) return;
+    const int nb = i / C, c = i % C;
+    const int g = norm_group_index(kind, nb, c, C, G);
+    const double ga = gamma ? (double)gamma[c] : 1.0, rs = rstd[g], mu = mean[g];
+    double k1 = ga * rs, k4 = 0.0, k5 = 0.0;
+    if (training) {
+        double P, Q, M;
+        if (kind == B200_NORM_GROUP) {
+            const int cg = C / G, c0 = (c / cg) * cg;
+            P = Q = 0.0;
+            for (int cc = c0; cc < c0 + cg; ++cc) {
+                const double gg = gamma ? (double)gamma[cc] : 1.0;
+                P += gg * (double)AB[((int64_t)nb * C + cc) * 2];
+                Q += gg * (double)AB[((int64_t)nb * C + cc) * 2 + 1];
+            }
+            M = (double)cg * (double)S;
+            k4 = -rs * rs * Q / M;
+            k5 = -rs * P / M - k4 * mu;
+        } else {
+            M = kind == B200_NORM_BATCH ? (double)N * (double)S * (double)world : (double)S;   // world>1: sums were all-reduced (SyncBN)
+            P = AB[(int64_t)i * 2]; Q = AB[(int64_t)i * 2 + 1];
+            k4 = -ga * rs * rs * Q / M;
+            k5 = -ga * rs * P / M - k4 * mu;
+        }
+    }
+    coef[(int64_t)i * 3] = (float)k1; coef[(int64_t)i * 3 + 1] = (float)k4; coef[(int64_t)i * 3 + 2] = (float)k5;
+    if (nb == 0 && (dgamma != nullptr || dbeta != nullptr)) {
+        double dg = 0.0, db = 0.0;
+        for (int b = 0; b < NB; ++b) { db += (double)AB[((int64_t)b * C + c) * 2]; dg += (double)AB[((int64_t)b * C + c) * 2 + 1]; }
+        if (dgamma) dgamma[c] = (float)dg;
+        if (dbeta) dbeta[c] = (float)db;
+    }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ dy,
+                                                             const float* __restrict__ coef, T* __restrict__ dx, T* __restrict__ dres,
+                                                             int C, int64_t S, int per_sample, int act, float slope) {
+    const int CV = C / V, n = blockIdx.y;
+    const int64_t i0 = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int cv = (int)(i0 % CV);
+    float k1[V], k4[V], k5[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        const int64_t e = ((int64_t)(per_sample ? n : 0) * C + cv * V + k) * 3;
+        k1[k] = coef[e]; k4[k] = coef[e + 1]; k5[k] = coef[e + 2];
+    }
+    const int64_t total = S * CV, stride = (int64_t)gridDim.x * 256, base = (int64_t)n * total;
+    for (int64_t i = i0; i < total; i += stride) {
+        float xv[V], gv[V];
+        Pack<T, V>::load(x + (base + i) * V, xv);
+        Pack<T, V>::load(dy + (base + i) * V, gv);
+        if (act != B200_ACT_NONE) {
+            float ov[V];
+            Pack<T, V>::load(y + (base + i) * V, ov);
+#pragma unroll
+            for (int k = 0; k < V; ++k) gv[k] *= act_gate(ov[k], act, slope);
+        }
+        if (dres != nullptr) Pack<T, V>::store(dres + (base + i) * V, gv);
+#pragma unroll
+        for (int k = 0; k < V; ++k) xv[k] = fmaf(k1[k], gv[k], fmaf(k4[k], xv[k], k5[k]));
+        Pack<T, V>::store(dx + (base + i) * V, xv);
+    }
+}
+
+}  // namespace b200

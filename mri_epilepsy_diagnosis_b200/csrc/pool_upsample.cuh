@@ -1,0 +1,203 @@
+// MaxPool3d (with argmax) and trilinear/nearest upsampling on channels-last tensors.  HBM-bound gathers:
+// one thread per (voxel, 16-byte channel vector), consecutive threads on consecutive channel vectors.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------ max pool
+// Tie/NaN rule of ATen's CPU max_pool3d: `if (val > max || isnan(val)) take` scanning (d,h,w) in raster order.
+template <typename T, int V>
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(b200_pool_desc d, const T* __restrict__ x, T* __restrict__ y,
+                                                          uint8_t* __restrict__ code, int64_t* __restrict__ indices) {
+    const int CV = d.C / V;
+    const int64_t total = (int64_t)d.N * d.Do * d.Ho * d.Wo * CV;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t v = i / CV;
+        const int cv = (int)(i - v * CV);
+        const int xo = (int)(v % d.Wo); v /= d.Wo;
+        const int yo = (int)(v % d.Ho); v /= d.Ho;
+        const int zo = (int)(v % d.Do);
+        const int n = (int)(v / d.Do);
+        float best[V];
+        int bcode[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) { best[k] = -INFINITY; bcode[k] = 0; }
+        const T* xb = x + (int64_t)n * d.Di * d.Hi * d.Wi * d.C + cv * V;
+        int local = 0;
+        for (int a = 0; a < d.kd; ++a)
+            for (int b = 0; b < d.kh; ++b)
+                for (int c = 0; c < d.kw; ++c, ++local) {
+                    const int zi = zo * d.sd + a, yi = yo * d.sh + b, xi = xo * d.sw + c;
+                    float vals[V];
+                    Pack<T, V>::load(xb + (((int64_t)zi * d.Hi + yi) * d.Wi + xi) * d.C, vals);
+#pragma unroll
+                    for (int k = 0; k < V; ++k)
+                        if (vals[k] > best[k] || vals[k] != vals[k]) { best[k] = vals[k]; bcode[k] = local; }
+                }
+        const int64_t o = i * V;
+        Pack<T, V>::store(y + o, best);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            if (code) code[o + k] = (uint8_t)bcode[k];
+            if (indices) {
+                const int a = bcode[k] / (d.kh * d.kw), r = bcode[k] % (d.kh * d.kw);
+                const int zi = zo * d.sd + a, yi = yo * d.sh + r / d.kw, xi = xo * d.sw + r % d.kw;
+                indices[o + k] = ((int64_t)zi * d.Hi + yi) * d.Wi + xi;
+            }
+        }
+    }
+}
+
+// gather form of the scatter: every input voxel sums dy of the windows that cover it and chose it (deterministic, writes all of dx)
+template <typename T, int V>
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(b200_pool_desc d, const T* __restrict__ dy, const uint8_t* __restrict__ code,
+                                                          T* __restrict__ dx) {
+    const int CV = d.C / V;
+    const int64_t total = (int64_t)d.N * d.Di * d.Hi * d.Wi * CV;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t v = i / CV;
+        const int cv = (int)(i - v * CV);
+        const int xi = (int)(v % d.Wi); v /= d.Wi;
+        const int yi = (int)(v % d.Hi); v /= d.Hi;
+        const int zi = (int)(v % d.Di);
+        const int n = (int)(v / d.Di);
+        float acc[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] = 0.f;
+        const int z_lo = max(0, (zi - d.kd + d.sd) / d.sd), z_hi = min(d.Do - 1, zi / d.sd);
+        const int y_lo = max(0, (yi - d.kh + d.sh) / d.sh), y_hi = min(d.Ho - 1, yi / d.sh);
+        const int x_lo = max(0, (xi - d.kw + d.sw) / d.sw), x_hi = min(d.Wo - 1, xi / d.sw);
+        for (int zo = z_lo; zo <= z_hi; ++zo)
+            for (int yo = y_lo; yo <= y_hi; ++yo)
+                for (int xo = x_lo; xo <= x_hi; ++xo) {
+                    const int local = ((zi - zo * d.sd) * d.kh + (yi - yo * d.sh)) * d.kw + (xi - xo * d.sw);
+                    const int64_t o = (((((int64_t)n * d.Do + zo) * d.Ho + yo) * d.Wo + xo) * CV + cv) * V;
+                    float g[V];
+                    Pack<T, V>::load(dy + o, g);
+#pragma unroll
+                    for (int k = 0; k < V; ++k) acc[k] += (code[o + k] == local) ? g[k] : 0.f;
+                }
+        Pack<T, V>::store(dx + i * V, acc);
+    }
+}
+
+// ------------------------------------------------------------------ upsample
+// Source-index rules of ATen (UpSample.h): nearest: min(floor(dst*scale), in-1); linear align_corners=False:
+// max(scale*(dst+0.5)-0.5, 0); align_corners=True: dst*(in-1)/(out-1).
+struct Lin1 { int i0, i1; float w0, w1; };
+__device__ __forceinline__ Lin1 lin_src(int dst, int in, int out, int mode) {
+    Lin1 r;
+    if (mode == B200_UP_NEAREST) {
+        const float scale = (float)in / (float)out;
+        r.i0 = r.i1 = min((int)floorf(dst * scale), in - 1);
+        r.w0 = 1.f; r.w1 = 0.f;
+        return r;
+    }
+    float src;
+    if (mode == B200_UP_TRILINEAR_ALIGNED) {
+        const float scale = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+        src = scale * dst;
+    } else {
+        const float scale = (float)in / (float)out;
+        src = scale * (dst + 0.5f) - 0.5f;
+        if (src < 0.f) src = 0.f;
+    }
+    r.i0 = min((int)src, in - 1);
+    r.i1 = min(r.i0 + 1, in - 1);
+    r.w1 = src - (float)r.i0;
+    r.w0 = 1.f - r.w1;
+    return r;
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) upsample_fwd_kernel(b200_up_desc d, const T* __restrict__ x, T* __restrict__ y) {
+    const int CV = d.C / V;
+    const int64_t total = (int64_t)d.N * d.Do * d.Ho * d.Wo * CV;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t v = i / CV;
+        const int cv = (int)(i - v * CV);
+        const int64_t vox = v;
+        const int xo = (int)(v % d.Wo); v /= d.Wo;
+        const int yo = (int)(v % d.Ho); v /= d.Ho;
+        const int zo = (int)(v % d.Do);
+        const int n = (int)(v / d.Do);
+        const Lin1 lz = lin_src(zo, d.Di, d.Do, d.mode), ly = lin_src(yo, d.Hi, d.Ho, d.mode), lx = lin_src(xo, d.Wi, d.Wo, d.mode);
+        const T* xb = x + (int64_t)n * d.Di * d.Hi * d.Wi * d.C + cv * V;
+        float acc[V];
+        if (d.mode == B200_UP_NEAREST) {
+            Pack<T, V>::load(xb + (((int64_t)lz.i0 * d.Hi + ly.i0) * d.Wi + lx.i0) * d.C, acc);
+        } else {
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] = 0.f;
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const float w = (a ? lz.w1 : lz.w0) * (b ? ly.w1 : ly.w0) * (c ? lx.w1 : lx.w0);
+                        float t[V];
+                        Pack<T, V>::load(xb + (((int64_t)(a ? lz.i1 : lz.i0) * d.Hi + (b ? ly.i1 : ly.i0)) * d.Wi + (c ? lx.i1 : lx.i0)) * d.C, t);
+#pragma unroll
+                        for (int k = 0; k < V; ++k) acc[k] = fmaf(w, t[k], acc[k]);
+                    }
+        }
+        Pack<T, V>::store(y + vox * d.Ctot + d.c_off + cv * V, acc);
+    }
+}
+
+// For input index j along one dimension: the output indices whose interpolation touches j and their weights.
+// Upsampling by an integer factor f touches at most 2f+2 outputs; we support f <= 4 (reference uses 2 and 4).
+constexpr int kMaxTouch = 12;
+struct Touch { int n; int o[kMaxTouch]; float w[kMaxTouch]; };
+__device__ __forceinline__ void touching(int j, int in, int out, int mode, Touch& t) {
+    t.n = 0;
+    const float inv = (float)out / (float)in;
+    int lo = (int)floorf((j - 1) * inv) - 2, hi = (int)ceilf((j + 2) * inv) + 2;
+    lo = max(lo, 0); hi = min(hi, out - 1);
+    for (int o = lo; o <= hi; ++o) {
+        const Lin1 l = lin_src(o, in, out, mode);
+        float w = 0.f;
+        if (l.i0 == j) w += l.w0;
+        if (l.i1 == j && mode != B200_UP_NEAREST) w += l.w1;
+        if (w != 0.f && t.n < kMaxTouch) { t.o[t.n] = o; t.w[t.n] = w; ++t.n; }
+    }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) upsample_bwd_kernel(b200_up_desc d, const T* __restrict__ dy, T* __restrict__ dx) {
+    const int CV = d.C / V;
+    const int64_t total = (int64_t)d.N * d.Di * d.Hi * d.Wi * CV;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t v = i / CV;
+        const int cv = (int)(i - v * CV);
+        const int xi = (int)(v % d.Wi); v /= d.Wi;
+        const int yi = (int)(v % d.Hi); v /= d.Hi;
+        const int zi = (int)(v % d.Di);
+        const int n = (int)(v / d.Di);
+        Touch tz, ty, tx;
+        touching(zi, d.Di, d.Do, d.mode, tz);
+        touching(yi, d.Hi, d.Ho, d.mode, ty);
+        touching(xi, d.Wi, d.Wo, d.mode, tx);
+        float acc[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] = 0.f;
+        const T* gb = dy + (int64_t)n * d.Do * d.Ho * d.Wo * d.Ctot + d.c_off + cv * V;
+        for (int a = 0; a < tz.n; ++a)
+            for (int b = 0; b < ty.n; ++b) {
+                const float wab = tz.w[a] * ty.w[b];
+                const T* row = gb + ((int64_t)tz.o[a] * d.Ho + ty.o[b]) * d.Wo * d.Ctot;
+                for (int c = 0; c < tx.n; ++c) {
+                    float g[V];
+                    Pack<T, V>::load(row + (int64_t)tx.o[c] * d.Ctot, g);
+                    const float w = wab * tx.w[c];
+#pragma unroll
+                    for (int k = 0; k < V; ++k) acc[k] = fmaf(w, g[k], acc[k]);
+                }
+            }
+        Pack<T, V>::store(dx + i * V, acc);
+    }
+}
+
+}  // namespace b200

@@ -1,0 +1,476 @@
+"""torch.autograd.Functions over the C ABI (include/b200nn.h).
+
+One Function per operator of the reference's hot path; tensors are logical (N,C,D,H,W) /
+(N,C,H,W) in channels-last memory format.  PyTorch owns every buffer (outputs, workspaces,
+packed weights, saved statistics); the library only enqueues kernels on the current stream.
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+
+from . import _cabi as cabi
+from ._cabi import ConvDesc, NormDesc, PoolDesc, UpDesc, check, dtype_code, lib, need_cuda, ptr, stream
+
+import ctypes as C
+
+
+# --------------------------------------------------------------------------- helpers
+def _fmt(t):
+    return torch.channels_last_3d if t.dim() == 5 else torch.channels_last
+
+
+def to_cl(t):
+    """Channels-last contiguous view/copy of a 4-D/5-D tensor (no-op when it already is)."""
+    if t.dim() not in (4, 5):
+        raise RuntimeError(f"b200nn: expected a 4-D or 5-D tensor, got {tuple(t.shape)}")
+    return t.contiguous(memory_format=_fmt(t))
+
+
+def _empty_cl(shape, dtype, device):
+    fmt = torch.channels_last_3d if len(shape) == 5 else torch.channels_last
+    return torch.empty(shape, dtype=dtype, device=device, memory_format=fmt)
+
+
+def _dhw(t):
+    """(D,H,W) of a 5-D tensor, (1,H,W) of a 4-D one."""
+    return (1,) + tuple(t.shape[2:]) if t.dim() == 4 else tuple(t.shape[2:])
+
+
+def _triple(v, dim):
+    if isinstance(v, int):
+        return (v,) * 3 if dim == 5 else (1 if False else v,) * 2
+    return tuple(v)
+
+
+def _t3(v, dims, fill):
+    """Normalise a module attribute (int or tuple of len 2/3) to a 3-tuple (d,h,w)."""
+    if isinstance(v, int):
+        v = (v,) * (3 if dims == 5 else 2)
+    v = tuple(int(a) for a in v)
+    return v if len(v) == 3 else (fill,) + v
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------- convolution
+class ConvConfig:
+    """Static configuration of one Conv/ConvTranspose module + its packed-weight cache."""
+
+    def __init__(self, stride, padding, dilation, transposed=False, allow_umma=True):
+        self.stride, self.padding, self.dilation = stride, padding, dilation
+        self.transposed = bool(transposed)
+        self.allow_umma = bool(allow_umma)
+        self._packed = {}
+
+    def desc(self, x, weight, out_dtype):
+        dims = x.dim()
+        k = _t3(tuple(weight.shape[2:]), dims, 1)
+        s, p, d = _t3(self.stride, dims, 1), _t3(self.padding, dims, 0), _t3(self.dilation, dims, 1)
+        N, Ci = x.shape[0], x.shape[1]
+        Di, Hi, Wi = _dhw(x)
+        if not self.transposed:
+            Co = weight.shape[0]
+            if weight.shape[1] != Ci:
+                raise RuntimeError(f"b200nn.conv: expected input with {weight.shape[1]} channels, got {Ci}")
+            out = [(i + 2 * pp - dd * (kk - 1) - 1) // ss + 1 for i, pp, dd, kk, ss in zip((Di, Hi, Wi), p, d, k, s)]
+        else:
+            Co = weight.shape[1]
+            if weight.shape[0] != Ci:
+                raise RuntimeError(f"b200nn.conv_transpose: expected input with {weight.shape[0]} channels, got {Ci}")
+            out = [(i - 1) * ss - 2 * pp + dd * (kk - 1) + 1 for i, pp, dd, kk, ss in zip((Di, Hi, Wi), p, d, k, s)]
+        if min(out) <= 0:
+            raise RuntimeError(f"b200nn.conv: computed output size {tuple(out)} is too small")
+        cd = ConvDesc(dtype_code(x.dtype), dtype_code(out_dtype), N, Ci, Di, Hi, Wi, Co, out[0], out[1], out[2],
+                      k[0], k[1], k[2], s[0], s[1], s[2], p[0], p[1], p[2], d[0], d[1], d[2],
+                      int(self.transposed), int(self.allow_umma))
+        shape = (N, Co) + (tuple(out) if dims == 5 else tuple(out[1:]))
+        return cd, shape
+
+    def packed(self, cd, weight, which):
+        """Packed copy of `weight` for pass `which`; re-derived when the parameter changes (optimizer step / load_state_dict)."""
+        algo = lib().b200_conv_algo(C.byref(cd), which)
+        key = (which, algo, cd.x_dtype, cd.y_dtype, cd.Ci, cd.Co)
+        tag = (weight.data_ptr(), weight._version, weight.device)
+        hit = self._packed.get(key)
+        if hit is not None and hit[0] == tag:
+            return hit[1]
+        nbytes = lib().b200_conv_packed_bytes(C.byref(cd), which)
+        buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=weight.device)
+        w = weight.detach()
+        if w.dtype != torch.float32 or not w.is_contiguous():
+            w = w.float().contiguous()
+        check(lib().b200_conv_pack_weights(C.byref(cd), which, w.data_ptr(), buf.data_ptr(), stream()))
+        self._packed[key] = (tag, buf)
+        return buf
+
+
+class _ConvFn(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, cfg, out_dtype):
+        need_cuda(x, "conv")
+        x = to_cl(x)
+        cd, shape = cfg.desc(x, weight, out_dtype)
+        wp = cfg.packed(cd, weight, cabi.PASS_FWD)
+        y = _empty_cl(shape, out_dtype, x.device)
+        b = None
+        if bias is not None:
+            b = bias.detach()
+            if b.dtype != torch.float32:
+                b = b.float()
+        nws = lib().b200_conv_workspace_bytes(C.byref(cd), cabi.PASS_FWD)
+        ws = _workspace(nws, x.device)
+        check(lib().b200_conv_fwd(C.byref(cd), x.data_ptr(), wp.data_ptr(), ptr(b), y.data_ptr(), ws.data_ptr(), nws, stream()))
+        ctx.save_for_backward(x, weight)
+        ctx.cfg, ctx.cd, ctx.has_bias, ctx.out_dtype = cfg, cd, bias is not None, out_dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        cfg, cd = ctx.cfg, ctx.cd
+        dy = to_cl(dy)
+        if dy.dtype != ctx.out_dtype:
+            dy = dy.to(ctx.out_dtype)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wp = cfg.packed(cd, weight, cabi.PASS_DGRAD)
+            dx = _empty_cl(tuple(x.shape), x.dtype, x.device)
+            nws = lib().b200_conv_workspace_bytes(C.byref(cd), cabi.PASS_DGRAD)
+            ws = _workspace(nws, x.device)
+            check(lib().b200_conv_dgrad(C.byref(cd), dy.data_ptr(), wp.data_ptr(), dx.data_ptr(), ws.data_ptr(), nws, stream()))
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
+            db = torch.empty(weight.shape[1] if cfg.transposed else weight.shape[0], dtype=torch.float32, device=x.device) \
+                if ctx.has_bias else None
+            nws = lib().b200_conv_workspace_bytes(C.byref(cd), cabi.PASS_WGRAD)
+            ws = _workspace(nws, x.device)
+            check(lib().b200_conv_wgrad(C.byref(cd), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ptr(db), ws.data_ptr(), nws, stream()))
+            if weight.dtype != torch.float32:
+                dw = dw.to(weight.dtype)
+            if not ctx.needs_input_grad[1]:
+                dw = None
+        return dx, dw, db, None, None
+
+
+def conv(x, weight, bias, cfg: ConvConfig, out_dtype=None):
+    return _ConvFn.apply(x, weight, bias, cfg, out_dtype or x.dtype)
+
+
+# --------------------------------------------------------------------------- normalisation
+def _norm_desc(x, kind, groups, eps, momentum, act, slope):
+    N, Cc = x.shape[0], x.shape[1]
+    S = 1
+    for v in x.shape[2:]:
+        S *= v
+    return NormDesc(dtype_code(x.dtype), N, Cc, S, kind, groups, float(eps), float(momentum), act, float(slope))
+
+
+def _f32(t):
+    if t is None:
+        return None
+    t = t.detach()
+    return t if t.dtype == torch.float32 else t.float()
+
+
+class _NormFn(Function):
+    """BatchNorm / InstanceNorm / GroupNorm (+ fused ReLU/LeakyReLU and residual add).
+
+    `sync` is an optional (process_group, world_size): batch statistics and the backward sums are
+    all-reduced across ranks (SyncBN), so N ranks x local batch == one device x global batch."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, kind, groups, use_batch_stats, momentum, eps, act, slope, sync):
+        need_cuda(x, "norm")
+        x = to_cl(x)
+        nd = _norm_desc(x, kind, groups, eps, momentum if momentum is not None else 0.0, act, slope)
+        ngroups = {cabi.NORM_BATCH: nd.C, cabi.NORM_INSTANCE: nd.N * nd.C, cabi.NORM_GROUP: nd.N * max(groups, 1)}[kind]
+        mean = torch.empty(ngroups, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        nws = lib().b200_norm_workspace_bytes(C.byref(nd))
+        ws = _workspace(nws, x.device)
+        world = 1
+        if use_batch_stats:
+            if sync is not None and kind == cabi.NORM_BATCH:
+                import torch.distributed as dist
+                pg, world = sync
+                check(lib().b200_norm_stats(C.byref(nd), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), None, None, ws.data_ptr(), nws, stream()))
+                var = rstd.pow(-2) - eps
+                packed = torch.stack([mean, var + mean * mean])
+                dist.all_reduce(packed, group=pg)
+                packed /= world
+                mean = packed[0].contiguous()
+                var = (packed[1] - mean * mean).clamp_min_(0)
+                rstd = (var + eps).rsqrt()
+                if running_mean is not None:
+                    cnt = nd.N * nd.S * world
+                    running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
+                    running_var.mul_(1 - momentum).add_(var * (cnt / max(cnt - 1, 1)), alpha=momentum)
+            else:
+                check(lib().b200_norm_stats(C.byref(nd), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ptr(running_mean), ptr(running_var),
+                                            ws.data_ptr(), nws, stream()))
+        else:
+            check(lib().b200_norm_stats_from_running(C.byref(nd), running_mean.data_ptr(), running_var.data_ptr(), mean.data_ptr(),
+                                                     rstd.data_ptr(), stream()))
+        y = torch.empty_like(x)
+        g32, b32 = _f32(gamma), _f32(beta)
+        res = None
+        if residual is not None:
+            res = to_cl(residual)
+            if res.dtype != x.dtype:
+                res = res.to(x.dtype)
+        check(lib().b200_norm_apply(C.byref(nd), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ptr(g32), ptr(b32), ptr(res), y.data_ptr(), stream()))
+        ctx.save_for_backward(x, y if act != cabi.ACT_NONE else None, mean, rstd, gamma)
+        ctx.nd, ctx.training, ctx.world, ctx.sync = nd, bool(use_batch_stats), world, sync
+        ctx.has_res, ctx.affine = residual is not None, gamma is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, mean, rstd, gamma = ctx.saved_tensors
+        nd = ctx.nd
+        dy = to_cl(dy)
+        if dy.dtype != x.dtype:
+            dy = dy.to(x.dtype)
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if ctx.has_res and ctx.needs_input_grad[3] else None
+        dgamma = dbeta = None
+        if ctx.affine:
+            dgamma = torch.empty(nd.C, dtype=torch.float32, device=x.device)
+            dbeta = torch.empty(nd.C, dtype=torch.float32, device=x.device)
+        g32 = _f32(gamma)
+        nws = lib().b200_norm_workspace_bytes(C.byref(nd))
+        ws = _workspace(nws, x.device)
+        if ctx.world > 1:
+            import torch.distributed as dist
+            sums = torch.empty(nd.C * 2, dtype=torch.float32, device=x.device)
+            check(lib().b200_norm_bwd_reduce(C.byref(nd), x.data_ptr(), ptr(y), dy.data_ptr(), mean.data_ptr(), rstd.data_ptr(), sums.data_ptr(),
+                                             ws.data_ptr(), nws, stream()))
+            local = sums.clone()
+            dist.all_reduce(sums, group=ctx.sync[0])
+            check(lib().b200_norm_bwd_apply(C.byref(nd), 1, ctx.world, x.data_ptr(), ptr(y), dy.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ptr(g32),
+                                            sums.data_ptr(), dx.data_ptr(), ptr(dres), ptr(dgamma), ptr(dbeta), ws.data_ptr(), nws, stream()))
+            if ctx.affine:   # parameter grads stay LOCAL sums (the gradient all-reduce averages them like every other parameter)
+                lv = local.view(nd.C, 2)
+                dbeta, dgamma = lv[:, 0].contiguous(), lv[:, 1].contiguous()
+        else:
+            check(lib().b200_norm_bwd(C.byref(nd), int(ctx.training), x.data_ptr(), ptr(y), dy.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ptr(g32),
+                                      dx.data_ptr(), ptr(dres), ptr(dgamma), ptr(dbeta), ws.data_ptr(), nws, stream()))
+        if ctx.affine and gamma.dtype != torch.float32:
+            dgamma, dbeta = dgamma.to(gamma.dtype), dbeta.to(gamma.dtype)
+        if not ctx.needs_input_grad[0]:
+            dx = None
+        return (dx, dgamma if ctx.needs_input_grad[1] else None, dbeta if ctx.needs_input_grad[2] else None, dres) + (None,) * 10
+
+
+def norm(x, gamma, beta, *, kind, groups=0, running_mean=None, running_var=None, use_batch_stats=True, momentum=0.1, eps=1e-5,
+         act=cabi.ACT_NONE, slope=0.01, residual=None, sync=None):
+    return _NormFn.apply(x, gamma, beta, residual, running_mean, running_var, kind, groups, use_batch_stats, momentum, eps, act, slope, sync)
+
+
+# --------------------------------------------------------------------------- activations
+class _ActFn(Function):
+    @staticmethod
+    def forward(ctx, x, act, slope, inplace):
+        need_cuda(x, "activation")
+        if not (x.is_contiguous() or (x.dim() in (4, 5) and x.is_contiguous(memory_format=_fmt(x)))):
+            x = x.contiguous()
+            inplace = False
+        y = x if inplace else torch.empty_like(x)
+        check(lib().b200_act_fwd(dtype_code(x.dtype), act, float(slope), x.numel(), x.data_ptr(), y.data_ptr(), stream()))
+        if inplace:
+            ctx.mark_dirty(x)
+        ctx.save_for_backward(y)
+        ctx.act, ctx.slope = act, float(slope)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        if dy.stride() != y.stride():
+            dy = dy.contiguous(memory_format=_fmt(y)) if y.dim() in (4, 5) and not y.is_contiguous() else dy.contiguous()
+        if dy.dtype != y.dtype:
+            dy = dy.to(y.dtype)
+        dx = torch.empty_like(y)
+        check(lib().b200_act_bwd(dtype_code(y.dtype), ctx.act, ctx.slope, y.numel(), y.data_ptr(), dy.data_ptr(), dx.data_ptr(), stream()))
+        return dx, None, None, None
+
+
+def relu(x, inplace=False):
+    return _ActFn.apply(x, cabi.ACT_RELU, 0.0, inplace)
+
+
+def leaky_relu(x, negative_slope=0.01, inplace=False):
+    return _ActFn.apply(x, cabi.ACT_LEAKY, negative_slope, inplace)
+
+
+class _PReLUFn(Function):
+    @staticmethod
+    def forward(ctx, x, a):
+        need_cuda(x, "prelu")
+        if a.numel() != 1:
+            raise RuntimeError("b200nn.PReLU supports num_parameters=1 (the reference's unet.UNet activation)")
+        if not (x.is_contiguous() or (x.dim() in (4, 5) and x.is_contiguous(memory_format=_fmt(x)))):
+            x = x.contiguous()
+        y = torch.empty_like(x)
+        a32 = _f32(a)
+        check(lib().b200_prelu_fwd(dtype_code(x.dtype), x.numel(), x.data_ptr(), a32.data_ptr(), y.data_ptr(), stream()))
+        ctx.save_for_backward(x, a)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, a = ctx.saved_tensors
+        if dy.stride() != x.stride():
+            dy = dy.contiguous(memory_format=_fmt(x)) if x.dim() in (4, 5) and not x.is_contiguous() else dy.contiguous()
+        if dy.dtype != x.dtype:
+            dy = dy.to(x.dtype)
+        dx = torch.empty_like(x)
+        da = torch.empty(1, dtype=torch.float32, device=x.device)
+        nws = lib().b200_prelu_workspace_bytes(x.numel())
+        ws = _workspace(nws, x.device)
+        a32 = _f32(a)
+        check(lib().b200_prelu_bwd(dtype_code(x.dtype), x.numel(), x.data_ptr(), a32.data_ptr(), dy.data_ptr(), dx.data_ptr(), da.data_ptr(),
+                                   ws.data_ptr(), nws, stream()))
+        return dx, da.to(a.dtype).view_as(a)
+
+
+def prelu(x, weight):
+    return _PReLUFn.apply(x, weight)
+
+
+# --------------------------------------------------------------------------- max pool
+def _pool_desc(x, kernel, stride):
+    dims = x.dim()
+    k = _t3(kernel, dims, 1)
+    s = _t3(stride if stride is not None else kernel, dims, 1)
+    Di, Hi, Wi = _dhw(x)
+    out = [(i - kk) // ss + 1 for i, kk, ss in zip((Di, Hi, Wi), k, s)]
+    pd = PoolDesc(dtype_code(x.dtype), x.shape[0], x.shape[1], Di, Hi, Wi, out[0], out[1], out[2], k[0], k[1], k[2], s[0], s[1], s[2])
+    shape = (x.shape[0], x.shape[1]) + (tuple(out) if dims == 5 else tuple(out[1:]))
+    return pd, shape
+
+
+class _MaxPoolFn(Function):
+    @staticmethod
+    def forward(ctx, x, kernel, stride, want_indices):
+        need_cuda(x, "max_pool")
+        x = to_cl(x)
+        pd, shape = _pool_desc(x, kernel, stride)
+        if min(shape[2:]) <= 0:
+            raise RuntimeError(f"b200nn.max_pool: input {tuple(x.shape)} is smaller than the window")
+        y = _empty_cl(shape, x.dtype, x.device)
+        code = torch.empty(y.numel(), dtype=torch.uint8, device=x.device)
+        idx = _empty_cl(shape, torch.int64, x.device) if want_indices else None
+        check(lib().b200_maxpool_fwd(C.byref(pd), x.data_ptr(), y.data_ptr(), code.data_ptr(), ptr(idx), stream()))
+        ctx.save_for_backward(code)
+        ctx.pd, ctx.in_shape, ctx.dtype = pd, tuple(x.shape), x.dtype
+        if want_indices:
+            ctx.mark_non_differentiable(idx)
+            return y, idx
+        return y
+
+    @staticmethod
+    def backward(ctx, dy, *unused):
+        (code,) = ctx.saved_tensors
+        dy = to_cl(dy)
+        if dy.dtype != ctx.dtype:
+            dy = dy.to(ctx.dtype)
+        dx = _empty_cl(ctx.in_shape, ctx.dtype, dy.device)
+        check(lib().b200_maxpool_bwd(C.byref(ctx.pd), dy.data_ptr(), code.data_ptr(), dx.data_ptr(), stream()))
+        return dx, None, None, None
+
+
+def max_pool(x, kernel_size, stride=None, return_indices=False):
+    return _MaxPoolFn.apply(x, kernel_size, stride, return_indices)
+
+
+# --------------------------------------------------------------------------- upsample / concat
+_MODES = {("nearest", None): cabi.UP_NEAREST, ("nearest", False): cabi.UP_NEAREST,
+          ("trilinear", None): cabi.UP_TRILINEAR, ("trilinear", False): cabi.UP_TRILINEAR, ("trilinear", True): cabi.UP_TRILINEAR_ALIGNED,
+          ("bilinear", None): cabi.UP_TRILINEAR, ("bilinear", False): cabi.UP_TRILINEAR, ("bilinear", True): cabi.UP_TRILINEAR_ALIGNED,
+          ("linear", None): cabi.UP_TRILINEAR, ("linear", False): cabi.UP_TRILINEAR, ("linear", True): cabi.UP_TRILINEAR_ALIGNED}
+
+
+def _out_size(x, size, scale_factor):
+    sp = tuple(x.shape[2:])
+    if size is not None:
+        size = (size,) * len(sp) if isinstance(size, int) else tuple(int(s) for s in size)
+        return size
+    sf = (scale_factor,) * len(sp) if not isinstance(scale_factor, (tuple, list)) else tuple(scale_factor)
+    for f in sf:
+        if float(f) != int(f):
+            raise RuntimeError("b200nn.upsample supports integer scale factors (the reference uses 2 and 4)")
+    return tuple(int(s * int(f)) for s, f in zip(sp, sf))
+
+
+class _UpsampleFn(Function):
+    """Upsample x and write it into channels [c_off, c_off+C) of `into` (or a fresh tensor)."""
+
+    @staticmethod
+    def forward(ctx, x, out_size, mode, skip):
+        need_cuda(x, "upsample")
+        x = to_cl(x)
+        dims = x.dim()
+        Di, Hi, Wi = _dhw(x)
+        o = (1,) + tuple(out_size) if dims == 4 else tuple(out_size)
+        Cx = x.shape[1]
+        c_off = 0 if skip is None else skip.shape[1]
+        ctot = Cx + c_off
+        y = _empty_cl((x.shape[0], ctot) + tuple(out_size), x.dtype, x.device)
+        ud = UpDesc(dtype_code(x.dtype), mode, x.shape[0], Cx, Di, Hi, Wi, o[0], o[1], o[2], ctot, c_off)
+        check(lib().b200_upsample_fwd(C.byref(ud), x.data_ptr(), y.data_ptr(), stream()))
+        if skip is not None:
+            s = to_cl(skip)
+            if s.dtype != x.dtype:
+                s = s.to(x.dtype)
+            V = s.shape[0] * o[0] * o[1] * o[2]
+            check(lib().b200_copy_channels(dtype_code(x.dtype), V, c_off, s.data_ptr(), c_off, 0, y.data_ptr(), ctot, 0, stream()))
+        ctx.ud, ctx.in_shape, ctx.has_skip, ctx.dtype = ud, tuple(x.shape), skip is not None, x.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        ud = ctx.ud
+        dy = to_cl(dy)
+        if dy.dtype != ctx.dtype:
+            dy = dy.to(ctx.dtype)
+        dx = dskip = None
+        if ctx.needs_input_grad[0]:
+            dx = _empty_cl(ctx.in_shape, ctx.dtype, dy.device)
+            check(lib().b200_upsample_bwd(C.byref(ud), dy.data_ptr(), dx.data_ptr(), stream()))
+        if ctx.has_skip and ctx.needs_input_grad[3]:
+            dskip = _empty_cl((dy.shape[0], ud.c_off) + tuple(dy.shape[2:]), ctx.dtype, dy.device)
+            V = dy.shape[0] * ud.Do * ud.Ho * ud.Wo
+            check(lib().b200_copy_channels(dtype_code(ctx.dtype), V, ud.c_off, dy.data_ptr(), ud.Ctot, 0, dskip.data_ptr(), ud.c_off, 0, stream()))
+        return dx, None, None, dskip
+
+
+def interpolate(x, size=None, scale_factor=None, mode="nearest", align_corners=None):
+    key = (mode, align_corners)
+    if key not in _MODES:
+        raise RuntimeError(f"b200nn.interpolate: unsupported mode={mode!r} align_corners={align_corners}")
+    return _UpsampleFn.apply(x, _out_size(x, size, scale_factor), _MODES[key], None)
+
+
+def upsample_concat(skip, x, scale_factor=2, mode="trilinear", align_corners=False):
+    """torch.cat([skip, upsample(x)], 1) in one pass over the output (unet3d.py:73-76, unet.UNet decoder)."""
+    return _UpsampleFn.apply(x, _out_size(x, None, scale_factor), _MODES[(mode, align_corners)], skip)
+
+
+# --------------------------------------------------------------------------- layout
+def to_channels_last(x, dtype=None):
+    """(N,C,D,H,W) contiguous -> channels-last tensor of `dtype` through the library's transpose kernel."""
+    need_cuda(x, "to_channels_last")
+    dtype = dtype or x.dtype
+    if x.dim() not in (4, 5):
+        raise RuntimeError("b200nn.to_channels_last: 4-D or 5-D tensor expected")
+    if x.shape[1] == 1 or x.is_contiguous(memory_format=_fmt(x)):
+        return to_cl(x).to(dtype)
+    x = x.contiguous()
+    y = _empty_cl(tuple(x.shape), dtype, x.device)
+    S = x.numel() // (x.shape[0] * x.shape[1])
+    check(lib().b200_to_channels_last(dtype_code(x.dtype), dtype_code(dtype), x.shape[0], x.shape[1], S, x.data_ptr(), y.data_ptr(), stream()))
+    return y

@@ -1,0 +1,392 @@
+"""Host-side mirrors of the reference's model interfaces, assembled from the drop-in modules.
+
+The reference checkout is not importable everywhere (and its `unet.UNet` dependency is
+third-party and absent), so the graphs the hot path is benchmarked and tested on are
+restated here with IDENTICAL constructor arguments, attribute names and state_dict keys:
+
+  Unet            segmentation/models/unet3d.py:82-126   (ConvD :20-47, ConvU :50-79)
+  FepegarUNet     `unet.UNet` as called at segmentation/routine.py:346-356; keys of segmentation/weights/*.pth
+  AE/Encoder/...  classification/models/AE_model.py:4-312
+  PatchModel      detection/model_utils.py:19-52
+
+Every shipped checkpoint loads into these with strict=True.  Users of the real reference
+files get the same kernels through `nn.convert(model)` / `nn.patch()`.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as tnn
+
+from . import functional as BF
+from . import nn as bnn
+
+
+# ------------------------------------------------------------------ unet3d.Unet
+def _norm3d(planes, norm):
+    """unet3d.py:8-17"""
+    if norm == "bn":
+        return bnn.BatchNorm3d(planes)
+    if norm == "gn":
+        return bnn.GroupNorm(4, planes)
+    if norm == "in":
+        return bnn.InstanceNorm3d(planes)
+    raise ValueError("normalization type {} is not supported".format(norm))
+
+
+def _c3(cin, cout, k):
+    return bnn.Conv3d(cin, cout, k, 1, k // 2, bias=False)
+
+
+class ConvD(tnn.Module):
+    """Encoder stage (unet3d.py:20-47).  conv2/bn2 feed a branch whose result the reference discards
+    (:43-46); it is still executed so BatchNorm running statistics and the RNG stream match."""
+
+    def __init__(self, inplanes, planes, dropout=0.0, norm="gn", first=False):
+        super().__init__()
+        self.first, self.dropout = first, dropout
+        self.maxpool = bnn.MaxPool3d(2, 2)
+        self.relu = bnn.ReLU(inplace=True)
+        for i, cin in ((1, inplanes), (2, planes), (3, planes)):
+            setattr(self, f"conv{i}", _c3(cin, planes, 3))
+            setattr(self, f"bn{i}", _norm3d(planes, norm))
+
+    def forward(self, x):
+        if not self.first:
+            x = self.maxpool(x)
+        x = self.bn1(self.conv1(x))
+        dead = self.relu(self.bn2(self.conv2(x)))
+        if self.dropout > 0:
+            dead = torch.nn.functional.dropout3d(dead, self.dropout)
+        del dead
+        return self.relu(x + self.bn3(self.conv3(x)))
+
+
+class ConvU(tnn.Module):
+    """Decoder stage (unet3d.py:50-79)."""
+
+    def __init__(self, planes, norm="gn", first=False):
+        super().__init__()
+        self.first = first
+        if not first:
+            self.conv1, self.bn1 = _c3(2 * planes, planes, 3), _norm3d(planes, norm)
+        self.conv2, self.bn2 = _c3(planes, planes // 2, 1), _norm3d(planes // 2, norm)
+        self.conv3, self.bn3 = _c3(planes, planes, 3), _norm3d(planes, norm)
+        self.relu = bnn.ReLU(inplace=True)
+
+    def forward(self, x, prev):
+        if not self.first:
+            x = self.relu(self.bn1(self.conv1(x)))
+        y = BF.interpolate(x, scale_factor=2, mode="trilinear", align_corners=False)
+        y = self.relu(self.bn2(self.conv2(y)))
+        y = torch.cat([prev, y], 1)
+        return self.relu(self.bn3(self.conv3(y)))
+
+
+class Unet(tnn.Module):
+    def __init__(self, c=4, n=16, dropout=0.5, norm="gn", num_classes=5):
+        super().__init__()
+        self.upsample = bnn.Upsample(scale_factor=2, mode="trilinear", align_corners=False)   # intent of unet3d.py:85
+        widths = [c, n, 2 * n, 4 * n, 8 * n, 16 * n]
+        for i in range(1, 6):
+            setattr(self, f"convd{i}", ConvD(widths[i - 1], widths[i], dropout, norm, first=(i == 1)))
+        self.convu4 = ConvU(16 * n, norm, True)
+        self.convu3, self.convu2, self.convu1 = ConvU(8 * n, norm), ConvU(4 * n, norm), ConvU(2 * n, norm)
+        self.seg3, self.seg2, self.seg1 = (bnn.Conv3d(w * n, num_classes, 1) for w in (8, 4, 2))
+        for m in self.modules():                                                              # unet3d.py:103-108
+            if isinstance(m, tnn.Conv3d):
+                tnn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, (tnn.BatchNorm3d, tnn.GroupNorm)):
+                tnn.init.constant_(m.weight, 1)
+                tnn.init.constant_(m.bias, 0)
+
+    def forward(self, x):
+        x1 = self.convd1(x)
+        x2 = self.convd2(x1)
+        x3 = self.convd3(x2)
+        x4 = self.convd4(x3)
+        x5 = self.convd5(x4)
+        y4 = self.convu4(x5, x4)
+        y3 = self.convu3(y4, x3)
+        y2 = self.convu2(y3, x2)
+        y1 = self.convu1(y2, x1)
+        s3 = self.seg3(y3)
+        s2 = self.seg2(y2) + self.upsample(s3)
+        return self.seg1(y1) + self.upsample(s2)
+
+
+# ------------------------------------------------------------------ third-party unet.UNet
+class _FpBlock(tnn.Module):
+    """conv -> [BatchNorm3d] -> PReLU, registered twice (named attributes and `block` Sequential) like the original,
+    so the checkpoint's duplicated keys (`conv_layer.*` and `block.0.*`) both exist and share storage."""
+
+    def __init__(self, cin, cout, k=3, norm=True, act=True):
+        super().__init__()
+        layers = []
+        self.conv_layer = bnn.Conv3d(cin, cout, k, padding=(k + 1) // 2 - 1)
+        layers.append(self.conv_layer)
+        self.norm_layer = None
+        if norm:
+            self.norm_layer = bnn.BatchNorm3d(cout)
+            layers.append(self.norm_layer)
+        self.activation_layer = None
+        if act:
+            self.activation_layer = bnn.PReLU()
+            layers.append(self.activation_layer)
+        self.block = tnn.Sequential(*layers)
+
+    def forward(self, x):
+        return self.block(x)
+
+
+class _FpStage(tnn.Module):
+    def __init__(self, cin, c1, c2, first_norm=True):
+        super().__init__()
+        self.conv1 = _FpBlock(cin, c1, norm=first_norm)
+        self.conv2 = _FpBlock(c1, c2)
+
+    def forward(self, x):
+        return self.conv2(self.conv1(x))
+
+
+class FepegarUNet(tnn.Module):
+    """`unet.UNet(in_channels=1, out_classes=2, dimensions=3, num_encoding_blocks=3, out_channels_first_layer=F,
+    normalization='batch', upsampling_type='linear', padding=True, activation='PReLU')` -- segmentation/routine.py:346-356."""
+
+    def __init__(self, in_channels=1, out_classes=2, num_encoding_blocks=3, out_channels_first_layer=16):
+        super().__init__()
+        F = out_channels_first_layer
+        self.encoder = tnn.Module()
+        self.encoder.encoding_blocks = tnn.ModuleList()
+        cin, skips = in_channels, []
+        for i in range(num_encoding_blocks - 1):
+            c1 = F * 2 ** i
+            self.encoder.encoding_blocks.append(_FpStage(cin, c1, 2 * c1, first_norm=(i > 0)))
+            cin = 2 * c1
+            skips.append(cin)
+        self.bottom_block = _FpStage(cin, cin, 2 * cin)
+        cin *= 2
+        self.decoder = tnn.Module()
+        self.decoder.decoding_blocks = tnn.ModuleList()
+        for skip in reversed(skips):
+            self.decoder.decoding_blocks.append(_FpStage(cin + skip, skip, skip))
+            cin = skip
+        self.classifier = _FpBlock(cin, out_classes, k=1, norm=False, act=False)
+        self.pool = bnn.MaxPool3d(2)
+
+    def forward(self, x):
+        skips = []
+        for stage in self.encoder.encoding_blocks:
+            x = stage(x)
+            skips.append(x)
+            x = self.pool(x)
+        x = self.bottom_block(x)
+        for stage in self.decoder.decoding_blocks:
+            x = BF.upsample_concat(skips.pop(), x, 2, "trilinear", False)     # cat((skip, up(x)), 1), one pass
+            x = stage(x)
+        return self.classifier(x)
+
+
+# ------------------------------------------------------------------ AE family
+def _act(name):
+    return bnn.LeakyReLU() if name == "l_relu" else bnn.ReLU()
+
+
+def _gain(name):
+    return tnn.init.calculate_gain("leaky_relu", 0.01) if name == "l_relu" else tnn.init.calculate_gain("relu")
+
+
+def _sep_convs(names, cin, cout, k, s, p):
+    shapes = (((k, 1, 1), (s, 1, 1), (p, 0, 0)), ((1, k, 1), (1, s, 1), (0, p, 0)), ((1, 1, k), (1, 1, s), (0, 0, p)))
+    chans = ((cin, cout), (cout, cout), (cout, cout))
+    return {n: bnn.Conv3d(ci, co, kernel_size=ks, stride=st, padding=pd) for n, (ci, co), (ks, st, pd) in zip(names, chans, shapes)}
+
+
+def _xavier(block, gain):
+    for m in block.values():                                                  # AE_model.py:39-43
+        if hasattr(m, "weight") and m.weight is not None and m.weight.dim() > 1:
+            tnn.init.xavier_uniform_(m.weight.data, gain=gain)
+            tnn.init.constant_(m.bias.data, 0)
+
+
+class DownBlock(tnn.Module):
+    """AE_model.py:4-53; modules run in sorted-key order (conv x/y/z, pool, BN, act)."""
+
+    def __init__(self, c_in, c_out, skip=False, **kw):
+        super().__init__()
+        self.skip = skip
+        self.block = tnn.ModuleDict(_sep_convs(("1_convx", "2_convy", "3_convz"), c_in, c_out, kw["conv_k"], kw["conv_s"], kw["conv_pad"]))
+        self.block["4_pooling"] = bnn.MaxPool3d(kernel_size=kw["maxpool_k"], stride=kw["maxpool_s"])
+        if kw["batch_norm"]:
+            self.block["5_batch_norm"] = bnn.BatchNorm3d(c_out)
+        self.block["6_act"] = _act(kw["act"])
+        self.init_gain = _gain(kw["act"])
+        _xavier(self.block, self.init_gain)
+
+    def forward(self, x):
+        before = tuple(x.shape[2:])
+        for _, m in sorted(self.block.items()):
+            x = m(x)
+        return x, before
+
+
+class UpBlock(tnn.Module):
+    """AE_model.py:56-120."""
+
+    def __init__(self, c_in, c_out, skip=False, **kw):
+        super().__init__()
+        self.skip = skip
+        self.block = tnn.ModuleDict()
+        if kw["up"] == "transpose_conv":
+            self.block["1_upsample"] = bnn.ConvTranspose3d(c_in, c_out, kernel_size=kw["scale"], stride=kw["scale"], padding=kw["t_conv_pad"])
+        else:
+            self.block["1_upsample"] = bnn.Upsample(scale_factor=kw["scale"], mode=kw["scale_mode"])
+        self.block.update(_sep_convs(("2_convx", "3_convy", "4_convz"), c_in, c_out, kw["conv_k"], kw["conv_s"], kw["conv_pad"]))
+        if kw["batch_norm"]:
+            self.block["5_batch_norm"] = bnn.BatchNorm3d(c_out)
+        self.block["6_act"] = _act(kw["act"])
+        self.init_gain = _gain(kw["act"])
+        _xavier(self.block, self.init_gain)
+
+    def forward(self, x, shape_before_pool=None, x_before_pool=None):
+        for key, m in sorted(self.block.items()):
+            x = m(x)
+            if key == "1_upsample" and any(a > b for a, b in zip(shape_before_pool, x.shape[2:])):
+                x = BF.interpolate(x, size=tuple(shape_before_pool))          # AE_model.py:116-119 (nearest)
+        return x
+
+
+class Encoder(tnn.Module):
+    def __init__(self, **kw):
+        super().__init__()
+        self.encode = tnn.ModuleList()
+        if kw["reduce_size"]:
+            self.encode.append(bnn.Conv3d(1, 1, kernel_size=4, stride=4, padding=0))
+        for i in range(kw["deapth"]):
+            self.encode.append(DownBlock(kw["chanels"][i], kw["chanels"][i + 1], kw["skip_map"][i], **kw["down_block_kwargs"]))
+
+    def forward(self, x):
+        sizes = []
+        for m in self.encode:
+            if isinstance(m, DownBlock):
+                x, s = m(x)
+            else:                                   # reduce_size stem; the reference would fail to unpack here
+                s = tuple(x.shape[2:])
+                x = m(x)
+            sizes.append(s)
+        return x, sizes
+
+
+class Decoder(tnn.Module):
+    def __init__(self, **kw):
+        super().__init__()
+        self.decode = tnn.ModuleList()
+        for i in range(kw["deapth"]):
+            self.decode.append(UpBlock(kw["chanels"][i], kw["chanels"][i + 1], kw["skip_map"][i], **kw["up_block_kwargs"]))
+        if kw["reduce_size"]:
+            self.decode.append(bnn.ConvTranspose3d(1, 1, kernel_size=4, stride=4, padding=0))
+        self.vox = bnn.Conv3d(1, 1, kernel_size=3, stride=1, padding=1)
+
+    def forward(self, x, size_list):
+        size_list.reverse()
+        for i, m in enumerate(self.decode):
+            x = m(x, size_list[i]) if isinstance(m, UpBlock) else m(x)
+        return self.vox(x)
+
+
+class AE(tnn.Module):
+    def __init__(self, **kw):
+        super().__init__()
+        depth = kw["deapth"]
+        skip_map = kw["skip_map"] if kw["is_skip"] else [False] * depth
+        chans = [kw["c_in"]] + [kw["c_base"] * kw["inc_size"] ** i for i in range(depth)]
+        self.enc = Encoder(deapth=depth, chanels=chans, skip_map=skip_map, reduce_size=kw["reduce_size"],
+                           down_block_kwargs=kw["down_block_kwargs"])
+        self.dec = Decoder(deapth=depth, chanels=chans[::-1], skip_map=skip_map[::-1], reduce_size=kw["reduce_size"],
+                           up_block_kwargs=kw["up_block_kwargs"])
+
+    def forward(self, x):
+        z, sizes = self.enc(x)
+        return self.dec(z, sizes)
+
+
+class _FaderHead(tnn.Module):
+    _attr = "clf"
+    _out_key = "n_class"
+
+    def __init__(self, **kw):
+        super().__init__()
+        d = tnn.ModuleDict(_sep_convs(("1_convx", "2_convy", "3_convz"), kw["c_in"], kw["c_out"], kw["conv_k"], kw["conv_s"], kw["conv_pad"]))
+        d["4_flat"] = tnn.Flatten()
+        d["5_l1"] = tnn.Linear(kw["l_in"], kw["l_out"])
+        if kw["batch_norm"]:
+            d["6_batch_norm"] = tnn.BatchNorm1d(kw["l_out"])
+        d["7_act"] = tnn.LeakyReLU() if kw["act"] == "l_relu" else tnn.ReLU()      # 2-D (B, l_out) tensors: stays PyTorch (K14)
+        d["8_drop"] = tnn.Dropout(kw["p_drop"])
+        d["9_l_f"] = tnn.Linear(kw["l_out"], kw[self._out_key])
+        setattr(self, self._attr, d)
+        self.init_gain = _gain(kw["act"])
+        _xavier(d, self.init_gain)
+
+    def forward(self, x):
+        for key, m in sorted(getattr(self, self._attr).items()):
+            x = m(x)
+            if key == "3_convz":
+                x = x.float()        # the fully-connected tail runs in fp32 PyTorch
+        return x
+
+
+class Classificator(_FaderHead):
+    """AE_model.py:264-312"""
+    _attr, _out_key = "clf", "n_class"
+
+
+class Discriminator(_FaderHead):
+    """AE_model.py:213-262"""
+    _attr, _out_key = "disc", "n_domains"
+
+
+# ------------------------------------------------------------------ detection PatchModel (2-D)
+class ConvolutionBlock(tnn.Module):
+    def __init__(self, in_c, out_c, pad=0):
+        super().__init__()
+        self.conv = bnn.Conv2d(in_c, out_c, kernel_size=3, padding=pad)
+        self.bn = bnn.BatchNorm2d(out_c)
+        self.relu = bnn.ReLU()
+
+    def forward(self, x):
+        return self.relu(self.bn(self.conv(x)))
+
+
+class PatchModel(tnn.Module):
+    """detection/model_utils.py:19-42"""
+
+    def __init__(self):
+        super().__init__()
+        widths = (2, 16, 32, 64, 128, 256)
+        self.conv_blocks = tnn.Sequential(*[ConvolutionBlock(a, b) for a, b in zip(widths, widths[1:])], bnn.MaxPool2d(2))
+        self.flatten = tnn.Flatten()
+        self.dropout = tnn.Dropout(p=0.4)
+        self.fc1 = tnn.Linear(3 * 11 * 256, 256)
+        self.fc2 = tnn.Linear(256, 2)
+
+    def forward(self, x):
+        x = self.conv_blocks(x)
+        x = self.flatten(x.float())          # logical NCHW flatten order, as the reference's fc1 expects
+        x = self.dropout(x)
+        return self.fc2(torch.relu(self.fc1(x)))
+
+
+# kwargs used by the reference notebooks
+FADER_DOWN = dict(conv_k=6, conv_pad=2, conv_s=2, maxpool_k=2, maxpool_s=2, batch_norm=True, act="l_relu")        # train_ENC_CLF.ipynb [cell 17]
+FADER_UP = dict(up="upsample", scale=4, scale_mode="nearest", conv_k=3, conv_pad=1, conv_s=1, batch_norm=False, act="l_relu")
+FADER_HEAD = dict(c_in=32, c_out=64, conv_k=3, conv_s=1, conv_pad=0, l_in=64, l_out=32, batch_norm=True, act="relu", p_drop=0.5)
+AE_DOWN = dict(conv_k=3, conv_pad=1, conv_s=1, maxpool_k=2, maxpool_s=2, batch_norm=True, act="relu")              # train_AE.ipynb [cell 8]
+AE_UP = dict(up="upsample", scale=2, scale_mode="nearest", conv_k=3, conv_pad=1, conv_s=1, batch_norm=True, act="relu")
+
+
+def fader_encoder():
+    return AE(c_in=1, is_skip=False, deapth=3, c_base=8, inc_size=2, reduce_size=False, down_block_kwargs=FADER_DOWN, up_block_kwargs=FADER_UP).enc
+
+
+def config1_autoencoder(depth=6, c_base=16):
+    return AE(c_in=1, is_skip=False, deapth=depth, c_base=c_base, inc_size=2, reduce_size=False, down_block_kwargs=AE_DOWN, up_block_kwargs=AE_UP)

@@ -1,0 +1,437 @@
+"""GPU parity tests, operator level: every C-ABI kernel family against the CPU oracle
+(torch fp32 on the host = the reference's own CPU path for these torch.nn operators).
+
+Tolerances (north star): fp32 ("tf32-off") path rel <= 1e-4, bf16 path rel <= 1e-2;
+max-pool indices, patch indices and argmax are bit-exact.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLDEN, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL32, TOL16 = 1e-4, 1e-2
+
+
+@pytest.fixture(scope="module")
+def B():
+    import mri_epilepsy_diagnosis_b200 as pkg
+    pkg._cabi.lib()
+    return pkg
+
+
+def sha16(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+CONV_CASES = [
+    # (name, N, Ci, Co, size, kernel, stride, padding, dilation, bias)
+    ("stem3", 2, 1, 16, (12, 16, 20), 3, 1, 1, 1, False),
+    ("c16", 2, 16, 16, (10, 12, 16), 3, 1, 1, 1, False),
+    ("c16_32", 1, 16, 32, (8, 16, 24), 3, 1, 1, 1, True),
+    ("c48_16", 1, 48, 16, (8, 8, 16), 3, 1, 1, 1, True),
+    ("head1", 2, 32, 2, (8, 8, 8), 1, 1, 0, 1, True),
+    ("pw64_32", 1, 64, 32, (4, 8, 8), 1, 1, 0, 1, False),
+    ("sepx_k6s2", 2, 1, 8, (24, 10, 12), (6, 1, 1), (2, 1, 1), (2, 0, 0), 1, True),
+    ("sepy_k6s2", 2, 8, 8, (12, 20, 12), (1, 6, 1), (1, 2, 1), (0, 2, 0), 1, True),
+    ("sepz_k3p0", 3, 32, 64, (3, 3, 3), (1, 1, 3), 1, 0, 1, True),
+    ("dil3", 1, 4, 8, (14, 14, 14), 3, 1, 0, 3, True),
+    ("k3s2p0", 1, 8, 12, (11, 13, 15), 3, 2, 0, 1, True),
+    ("k4s4", 1, 1, 1, (16, 16, 16), 4, 4, 0, 1, True),
+    ("odd_c", 1, 5, 7, (6, 7, 9), 3, 1, 1, 1, True),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_conv3d_fwd_bwd(B, case, dtype):
+    name, N, Ci, Co, size, k, s, p, d, bias = case
+    g = gen(hash(name) % 1000)
+    x = torch.randn(N, Ci, *size, generator=g)
+    ref = torch.nn.Conv3d(Ci, Co, k, s, p, d, bias=bias)
+    with torch.no_grad():
+        ref.weight.copy_(torch.randn(ref.weight.shape, generator=g) * (2.0 / (Ci * np.prod(ref.kernel_size))) ** 0.5)
+        if bias:
+            ref.bias.copy_(torch.randn(Co, generator=g) * 0.1)
+    mod = B.nn.Conv3d(Ci, Co, k, s, p, d, bias=bias).cuda()
+    mod.load_state_dict(ref.state_dict())
+    mod.compute_dtype = dtype
+    tol = TOL32 if dtype == torch.float32 else TOL16
+    if dtype == torch.bfloat16:      # compare against the oracle on the SAME bf16-rounded activations
+        x = x.bfloat16().float()
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    gy = torch.randn(yr.shape, generator=g)
+    if dtype == torch.bfloat16:
+        gy = gy.bfloat16().float()
+    yr.backward(gy)
+    xg = x.cuda().to(dtype).requires_grad_(True)
+    yg = mod(xg)
+    assert yg.dtype == dtype and tuple(yg.shape) == tuple(yr.shape)
+    assert yg.is_contiguous(memory_format=torch.channels_last_3d)
+    yg.backward(gy.cuda().to(dtype))
+    assert rel_err(yg.float(), yr) < tol, "forward"
+    assert rel_err(xg.grad.float(), xr.grad) < tol, "dgrad"
+    assert mod.weight.grad.dtype == torch.float32
+    assert rel_err(mod.weight.grad, ref.weight.grad) < tol, "wgrad"
+    if bias:
+        assert rel_err(mod.bias.grad, ref.bias.grad) < tol, "bias grad"
+
+
+def test_conv_stem_reads_fp32_and_heads_emit_fp32(B):
+    g = gen(5)
+    x = torch.randn(1, 1, 8, 8, 8, generator=g).cuda()
+    stem = B.nn.Conv3d(1, 16, 3, 1, 1).cuda()
+    stem.compute_dtype = torch.bfloat16
+    y = stem(x)                                   # fp32 in, bf16 out, no separate cast pass
+    assert y.dtype == torch.bfloat16
+    ref = F.conv3d(x.cpu(), stem.weight.detach().cpu(), stem.bias.detach().cpu(), 1, 1)
+    assert rel_err(y.float(), ref) < TOL16
+    head = B.nn.Conv3d(16, 2, 1).cuda()
+    head.compute_dtype, head.out_dtype = torch.bfloat16, torch.float32
+    z = head(y)
+    assert z.dtype == torch.float32
+    assert rel_err(z, F.conv3d(y.float().cpu(), head.weight.detach().cpu(), head.bias.detach().cpu())) < 1e-5
+
+
+@pytest.mark.parametrize("k,s,p", [(2, 2, 0), (4, 4, 0), (4, 2, 1), (3, 1, 1)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_conv_transpose3d(B, k, s, p, dtype):
+    g = gen(k * 10 + s)
+    ref = torch.nn.ConvTranspose3d(6, 5, k, s, p)
+    mod = B.nn.ConvTranspose3d(6, 5, k, s, p).cuda()
+    mod.load_state_dict(ref.state_dict())
+    mod.compute_dtype = dtype
+    x = torch.randn(2, 6, 5, 6, 7, generator=g)
+    if dtype == torch.bfloat16:
+        x = x.bfloat16().float()
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    gy = torch.randn(yr.shape, generator=g)
+    if dtype == torch.bfloat16:
+        gy = gy.bfloat16().float()
+    yr.backward(gy)
+    xg = x.cuda().to(dtype).requires_grad_(True)
+    yg = mod(xg)
+    yg.backward(gy.cuda().to(dtype))
+    tol = TOL32 if dtype == torch.float32 else TOL16
+    assert tuple(yg.shape) == tuple(yr.shape)
+    assert rel_err(yg.float(), yr) < tol and rel_err(xg.grad.float(), xr.grad) < tol
+    assert rel_err(mod.weight.grad, ref.weight.grad) < tol and rel_err(mod.bias.grad, ref.bias.grad) < tol
+
+
+def test_conv2d_patch_block(B):
+    g = gen(3)
+    ref = torch.nn.Conv2d(2, 16, 3)
+    mod = B.nn.Conv2d(2, 16, 3).cuda()
+    mod.load_state_dict(ref.state_dict())
+    x = torch.randn(8, 2, 16, 32, generator=g)
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    yr.sum().backward()
+    xg = x.cuda().requires_grad_(True)
+    yg = mod(xg)
+    yg.sum().backward()
+    assert tuple(yg.shape) == (8, 16, 14, 30)
+    assert rel_err(yg, yr) < TOL32 and rel_err(xg.grad, xr.grad) < TOL32 and rel_err(mod.weight.grad, ref.weight.grad) < TOL32
+
+
+def test_conv_errors_are_loud(B):
+    mod = B.nn.Conv3d(4, 4, 3).cuda()
+    with pytest.raises(RuntimeError):
+        mod(torch.randn(1, 4, 8, 8, 8))                      # CPU tensor: no CPU path
+    with pytest.raises(RuntimeError):
+        mod(torch.randn(1, 3, 8, 8, 8).cuda())               # channel mismatch
+    with pytest.raises(RuntimeError):
+        mod(torch.randn(1, 4, 2, 2, 2).cuda())               # output would be empty
+    with pytest.raises(RuntimeError):
+        B.nn.Conv3d(4, 4, 3, groups=2).cuda()(torch.randn(1, 4, 8, 8, 8).cuda())
+
+
+# ----------------------------------------------------------------------------- normalisation
+@pytest.mark.parametrize("C,shape", [(16, (2, 6, 8, 10)), (1, (2, 5, 6, 7)), (48, (1, 4, 4, 8)), (7, (3, 3, 4, 5)), (256, (2, 2, 2, 2))])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_batchnorm3d_train_eval(B, C, shape, dtype):
+    g = gen(C)
+    N, D, H, W = shape
+    x = torch.randn(N, C, D, H, W, generator=g) * 2 + 3
+    if dtype == torch.bfloat16:
+        x = x.bfloat16().float()
+    ref = torch.nn.BatchNorm3d(C)
+    with torch.no_grad():
+        ref.weight.copy_(torch.rand(C, generator=g) + 0.5)
+        ref.bias.copy_(torch.randn(C, generator=g))
+    mod = B.nn.BatchNorm3d(C).cuda()
+    mod.load_state_dict(ref.state_dict())
+    tol = TOL32 if dtype == torch.float32 else TOL16
+    for step in range(2):
+        xr = x.clone().requires_grad_(True)
+        yr = ref(xr)
+        gy = torch.randn(yr.shape, generator=g)
+        yr.backward(gy)
+        xg = x.cuda().to(dtype).requires_grad_(True)
+        yg = mod(xg)
+        yg.backward(gy.cuda().to(dtype))
+        assert rel_err(yg.float(), yr) < tol
+        assert rel_err(xg.grad.float(), xr.grad) < 5 * tol
+        assert rel_err(mod.weight.grad, ref.weight.grad) < 5 * tol and rel_err(mod.bias.grad, ref.bias.grad) < 5 * tol
+        ref.zero_grad(); mod.zero_grad()
+    # running statistics: momentum 0.1, unbiased variance, counter
+    assert rel_err(mod.running_mean, ref.running_mean) < tol and rel_err(mod.running_var, ref.running_var) < tol
+    assert int(mod.num_batches_tracked) == int(ref.num_batches_tracked) == 2
+    ref.eval(); mod.eval()
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr); yr.backward(torch.ones_like(yr))
+    xg = x.cuda().to(dtype).requires_grad_(True)
+    yg = mod(xg); yg.backward(torch.ones_like(yg))
+    assert rel_err(yg.float(), yr) < tol and rel_err(xg.grad.float(), xr.grad) < tol
+
+
+def test_batchnorm_large_mean_is_stable(B):
+    """mean >> std: the shifted accumulation must not lose the variance (fp32)."""
+    g = gen(0)
+    x = torch.randn(2, 8, 16, 16, 16, generator=g) * 0.01 + 100.0
+    ref = torch.nn.BatchNorm3d(8)
+    mod = B.nn.BatchNorm3d(8).cuda()
+    assert rel_err(mod(x.cuda()), ref(x)) < 1e-3
+
+
+@pytest.mark.parametrize("kind", ["in", "gn"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_instance_and_group_norm(B, kind, dtype):
+    g = gen(11)
+    C = 16
+    x = torch.randn(3, C, 5, 6, 8, generator=g) * 1.5 + 0.5
+    if dtype == torch.bfloat16:
+        x = x.bfloat16().float()
+    if kind == "in":
+        ref, mod = torch.nn.InstanceNorm3d(C), B.nn.InstanceNorm3d(C).cuda()
+    else:
+        ref, mod = torch.nn.GroupNorm(4, C), B.nn.GroupNorm(4, C).cuda()
+        with torch.no_grad():
+            ref.weight.copy_(torch.rand(C, generator=g) + 0.5); ref.bias.copy_(torch.randn(C, generator=g))
+        mod.load_state_dict(ref.state_dict())
+    assert len(mod.state_dict()) == len(ref.state_dict())
+    tol = TOL32 if dtype == torch.float32 else TOL16
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    gy = torch.randn(yr.shape, generator=g)
+    yr.backward(gy)
+    xg = x.cuda().to(dtype).requires_grad_(True)
+    yg = mod(xg)
+    yg.backward(gy.cuda().to(dtype))
+    assert rel_err(yg.float(), yr) < tol and rel_err(xg.grad.float(), xr.grad) < 5 * tol
+    if kind == "gn":
+        assert rel_err(mod.weight.grad, ref.weight.grad) < 5 * tol and rel_err(mod.bias.grad, ref.bias.grad) < 5 * tol
+
+
+def test_norm_fused_act_residual(B):
+    """y = relu(bn(x) + r): the fused kernel equals the three reference ops (unet3d.py:46-47)."""
+    from mri_epilepsy_diagnosis_b200 import _cabi, functional as BF
+    g = gen(2)
+    C = 16
+    x = torch.randn(2, C, 4, 6, 8, generator=g)
+    r = torch.randn(2, C, 4, 6, 8, generator=g)
+    w, b = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    xr, rr, wr, br = (t.clone().requires_grad_(True) for t in (x, r, w, b))
+    yr = F.relu(F.batch_norm(xr, None, None, wr, br, True, 0.1, 1e-5) + rr)
+    gy = torch.randn(yr.shape, generator=g)
+    yr.backward(gy)
+    xg, rg, wg, bg = (t.cuda().requires_grad_(True) for t in (x, r, w, b))
+    yg = BF.norm(xg, wg, bg, kind=_cabi.NORM_BATCH, act=_cabi.ACT_RELU, residual=rg)
+    yg.backward(gy.cuda())
+    for a, e in ((yg, yr), (xg.grad, xr.grad), (rg.grad, rr.grad), (wg.grad, wr.grad), (bg.grad, br.grad)):
+        assert rel_err(a, e) < TOL32
+
+
+# ----------------------------------------------------------------------------- activations
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_activations(B, dtype):
+    g = gen(4)
+    x = torch.randn(2, 6, 5, 7, 9, generator=g)
+    if dtype == torch.bfloat16:
+        x = x.bfloat16().float()
+    gy = torch.randn(x.shape, generator=g)
+    for ref, mod in ((torch.nn.ReLU(), B.nn.ReLU()), (torch.nn.LeakyReLU(), B.nn.LeakyReLU()), (torch.nn.PReLU(), B.nn.PReLU().cuda())):
+        xr = x.clone().requires_grad_(True)
+        yr = ref(xr); yr.backward(gy)
+        xg = x.cuda().to(dtype).requires_grad_(True)
+        yg = mod(xg); yg.backward(gy.cuda().to(dtype))
+        tol = 1e-6 if dtype == torch.float32 else TOL16
+        assert rel_err(yg.float(), yr) < tol and rel_err(xg.grad.float(), xr.grad) < tol
+        if isinstance(ref, torch.nn.PReLU):
+            assert rel_err(mod.weight.grad, ref.weight.grad) < (1e-5 if dtype == torch.float32 else TOL16)
+
+
+def test_relu_inplace_matches_reference_semantics(B):
+    x = torch.randn(2, 4, 3, 3, 3).cuda()
+    lin = (x * 2).requires_grad_(True)
+    h = lin * 1.0
+    y = B.nn.ReLU(inplace=True)(h)
+    assert y.data_ptr() == h.data_ptr()
+    y.sum().backward()
+    assert torch.equal(lin.grad, (lin > 0).float())
+    assert torch.isnan(B.nn.ReLU()(torch.tensor([float("nan"), -1.0, 2.0]).cuda()))[0]
+
+
+# ----------------------------------------------------------------------------- max pool
+def test_maxpool_kat3_bit_exact(B, golden):
+    g = golden("op_pins")
+    x = torch.randn(2, 4, 16, 16, 16, generator=gen(0))
+    y, idx = B.nn.MaxPool3d(2, 2, return_indices=True)(x.cuda())
+    yr, ir = F.max_pool3d(x, 2, 2, return_indices=True)
+    assert idx.dtype == torch.int64 and torch.equal(idx.cpu(), ir) and torch.equal(y.cpu(), yr)
+    assert int(idx.sum()) == 8382113 and sha16(idx.cpu().contiguous().numpy()) == "0329242df874dbc0"   # KAT-3
+    assert np.array_equal(idx.cpu().numpy(), g["pool_idx"])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_maxpool_ties_nan_odd_and_overlap(B, golden, dtype):
+    g = golden("op_pins")
+    ties = torch.zeros(1, 1, 4, 4, 4)
+    _, ti = B.nn.MaxPool3d(2, 2, return_indices=True)(ties.cuda().to(dtype))
+    assert np.array_equal(ti.cpu().numpy(), g["tie_idx"])                       # first element in raster order wins
+    x = torch.randn(1, 2, 5, 7, 9, generator=gen(1))
+    x[0, 0, 1, 1, 1] = float("nan"); x[0, 1, 2, 3, 5] = float("nan"); x[0, 1, 3, 3, 5] = float("nan")
+    xq = x.to(dtype)
+    yr, ir = F.max_pool3d(xq.float(), 2, 2, return_indices=True)                # floor mode: 5,7,9 -> 2,3,4
+    yg, ig = B.nn.MaxPool3d(2, 2, return_indices=True)(xq.cuda())
+    assert tuple(yg.shape) == (1, 2, 2, 3, 4) and torch.equal(ig.cpu(), ir)
+    assert torch.equal(torch.isnan(yg.cpu().float()), torch.isnan(yr)) and torch.equal(torch.nan_to_num(yg.cpu().float()), torch.nan_to_num(yr))
+    x2 = torch.randn(2, 3, 10, 9, 8, generator=gen(2)).to(dtype)
+    yr, ir = F.max_pool3d(x2.float(), 4, 2, return_indices=True)                # cnn_model.py:221 overlapping windows
+    yg, ig = B.nn.MaxPool3d(4, 2, return_indices=True)(x2.cuda())
+    assert torch.equal(ig.cpu(), ir) and torch.equal(yg.cpu().float(), yr)
+
+
+@pytest.mark.parametrize("k,s", [(2, 2), (4, 2), (3, 3)])
+def test_maxpool_backward(B, k, s):
+    x = torch.randn(2, 8, 9, 10, 11, generator=gen(k))
+    xr = x.clone().requires_grad_(True)
+    yr = F.max_pool3d(xr, k, s)
+    gy = torch.randn(yr.shape, generator=gen(9))
+    yr.backward(gy)
+    xg = x.cuda().requires_grad_(True)
+    yg = B.nn.MaxPool3d(k, s)(xg)
+    yg.backward(gy.cuda())
+    assert torch.equal(yg.cpu(), yr) and rel_err(xg.grad, xr.grad) < 1e-6
+
+
+def test_maxpool2d(B):
+    x = torch.randn(4, 8, 6, 22, generator=gen(6))
+    yr, ir = F.max_pool2d(x, 2, return_indices=True)
+    yg, ig = B.nn.MaxPool2d(2, return_indices=True)(x.cuda())
+    assert torch.equal(yg.cpu(), yr) and torch.equal(ig.cpu(), ir)
+
+
+# ----------------------------------------------------------------------------- upsample / concat
+@pytest.mark.parametrize("mode,ac,sf", [("trilinear", False, 2), ("trilinear", True, 2), ("nearest", None, 2), ("nearest", None, 4), ("trilinear", False, 4)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_upsample(B, mode, ac, sf, dtype):
+    g = gen(sf)
+    x = torch.randn(2, 8, 3, 5, 4, generator=g)
+    if dtype == torch.bfloat16:
+        x = x.bfloat16().float()
+    kw = dict(scale_factor=sf, mode=mode) if ac is None else dict(scale_factor=sf, mode=mode, align_corners=ac)
+    xr = x.clone().requires_grad_(True)
+    yr = torch.nn.Upsample(**kw)(xr)
+    gy = torch.randn(yr.shape, generator=g)
+    yr.backward(gy)
+    xg = x.cuda().to(dtype).requires_grad_(True)
+    yg = B.nn.Upsample(**kw)(xg)
+    yg.backward(gy.cuda().to(dtype))
+    tol = 1e-5 if dtype == torch.float32 else TOL16
+    assert rel_err(yg.float(), yr) < tol and rel_err(xg.grad.float(), xr.grad) < tol
+
+
+def test_upsample_pins_and_to_size(B, golden):
+    g = golden("op_pins")
+    line = torch.arange(4.0).view(1, 1, 1, 1, 4).expand(1, 1, 2, 2, 4).contiguous().cuda()
+    assert np.allclose(B.functional.interpolate(line, scale_factor=2, mode="trilinear", align_corners=False)[0, 0, 0, 0].cpu().numpy(), g["tri_false"])
+    assert np.allclose(B.functional.interpolate(line, scale_factor=2, mode="trilinear", align_corners=True)[0, 0, 0, 0].cpu().numpy(), g["tri_true"], atol=1e-6)
+    x = torch.randn(1, 4, 3, 4, 3, generator=gen(8))
+    yr = F.interpolate(x, (7, 9, 7))                                            # AE_model.py:119 nearest-to-size on odd shapes
+    assert torch.equal(B.functional.interpolate(x.cuda(), size=(7, 9, 7)).cpu(), yr)
+
+
+def test_upsample_concat_equals_cat(B):
+    g = gen(12)
+    skip = torch.randn(2, 16, 8, 8, 8, generator=g)
+    x = torch.randn(2, 32, 4, 4, 4, generator=g)
+    sr, xr = skip.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    yr = torch.cat((sr, F.interpolate(xr, scale_factor=2, mode="trilinear", align_corners=False)), 1)
+    gy = torch.randn(yr.shape, generator=g)
+    yr.backward(gy)
+    sg, xg = skip.cuda().requires_grad_(True), x.cuda().requires_grad_(True)
+    yg = B.functional.upsample_concat(sg, xg, 2, "trilinear", False)
+    yg.backward(gy.cuda())
+    assert rel_err(yg, yr) < 1e-5 and rel_err(sg.grad, sr.grad) < 1e-6 and rel_err(xg.grad, xr.grad) < 1e-5
+
+
+def test_layout_transpose(B):
+    x = torch.randn(2, 5, 3, 4, 6, generator=gen(1)).cuda()
+    y = B.functional.to_channels_last(x, torch.bfloat16)
+    assert y.is_contiguous(memory_format=torch.channels_last_3d) and torch.equal(y, x.to(torch.bfloat16))
+
+
+# ----------------------------------------------------------------------------- patches (bit-exact)
+@pytest.fixture(scope="module")
+def template():
+    from oracle import patches as OP
+    return OP.read_nifti1_f32(os.path.join(GOLDEN, "MNI152_T1_1mm_brain_gray.nii.gz")).astype(np.float64)
+
+
+def test_patches_kat4_bit_exact(B, golden, template):
+    from oracle import patches as OP
+    g = golden("patches_kat4")
+    img = np.random.default_rng(0).random((182, 218, 182))
+    plan = B.patches.patch_plan(template)
+    assert np.array_equal(plan.cpu().numpy().astype(np.int64)[:, :4], g["plan"].astype(np.int64)[:, :4])
+    out = B.patches.get_only_patches(img, template, 16, 32)
+    assert out.dtype == torch.float64 and tuple(out.shape) == (4752, 2, 16, 32)
+    arr = out.cpu().numpy()
+    assert sha16(arr) == str(g["sha"]) == "eefcd430a1f24abe"                    # KAT-4
+    assert np.array_equal(arr, OP.get_only_patches(img, template, 16, 32))
+
+
+def test_patches_labelled_bit_exact(B, golden, template):
+    g = golden("patches_labelled")
+    img = np.random.default_rng(0).random((182, 218, 182))
+    xx, yy, zz = np.meshgrid(np.arange(182), np.arange(218), np.arange(182), indexing="ij")
+    c, r = g["mask_center"], g["mask_radii"]
+    mask = ((xx - c[0]) / r[0]) ** 2 + ((yy - c[1]) / r[1]) ** 2 + ((zz - c[2]) / r[2]) ** 2 < 1
+    p, l = B.patches.get_all_patches_and_labels(img, template, mask, 16, 32)
+    assert tuple(p.shape) == tuple(g["shape"]) and sha16(p.cpu().numpy()) == str(g["sha"])
+    assert np.array_equal(l.cpu().numpy(), g["labels"])
+
+
+def test_patches_edge_cases(B):
+    from oracle import patches as OP
+    gm = np.zeros((182, 218, 182))
+    assert tuple(B.patches.get_only_patches(np.ones_like(gm), gm).shape) == (0, 2, 16, 32)
+    gm[0, 100, 5] = 1.0
+    with pytest.raises(AssertionError):
+        B.patches.patch_plan(gm)
+    gm[:] = 0; gm[40, 5, 7] = 0.5
+    with pytest.raises(ValueError):
+        B.patches.patch_plan(gm)
+    # random sparse template on a small ragged-free grid: plan identical to the oracle's
+    rng = np.random.default_rng(3)
+    gm = (rng.random((96, 64, 10)) > 0.97) * rng.random((96, 64, 10))
+    gm[0] = 0
+    mask = rng.random((96, 64, 10)) > 0.995
+    want = OP.patch_plan(gm, mask, 16, 32)
+    got = B.patches.patch_plan(gm, mask, 16, 32).cpu().numpy().astype(np.int64)
+    assert np.array_equal(got, want)
+    img = rng.random((96, 64, 10))
+    assert np.array_equal(B.patches.gather(img, torch.from_numpy(want.astype(np.int32)).cuda()).cpu().numpy(), OP.gather_patches(img, want))
