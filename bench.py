@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""Headline benchmark: 3-D U-Net training throughput (voxels/s) -- BASELINE.json configs[1].
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model unet3d|fepegar16|fepegar8]
+
+A step = one pass of the hot path over one batch of synthetic input, exactly the body of the reference's
+training loop (segmentation/routine.py:266-281): zero_grad -> model(x) -> softmax -> dice loss -> mean -> backward ->
+AdamW.step.  Workload at every N: `unet3d.Unet(c=1, n=16, norm='bn', num_classes=2)`, batch 4 x 128^3 per GPU, bf16
+activations (weak scaling: per-GPU batch fixed; gradients all-reduced over NCCL).
+
+One JSON line on stdout (rank 0):
+  value          voxels/s with the batch already resident in HBM (CUDA events, max over ranks)
+  e2e            the same step called with HOST (pinned) inputs: H2D copy of the batch and D2H read of the loss inside
+  roofline       tensor-pipe roofline of the dominant kernel (conv_umma_kernel): algorithmic conv FLOPs of its launches
+                 in the timed region / their CUDA-event durations, against MEASURED_PEAKS.json (sustained bf16)
+  cpu_baseline   the oracle (CPU restatement of the reference path, oracle/graphs.py) timed on this box's host cores
+  --impl reference  times that CPU path alone (the reference's own implementation of the path is its CPU PyTorch path)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "3D U-Net train voxels/s"
+FWD_BWD_FLOP_PER_VOXEL = 518186.0      # unet3d.Unet(c=1,n=16,num_classes=2): SURVEY section 8(a-1) / BASELINE.md section 3
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"bf16_tflops": float(p.get("bf16_tflops_sustained") or p["bf16_tflops"]), "hbm_gbs": float(p["hbm_gbs"]), "source": "measured"}
+    except Exception:
+        return {"bf16_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}     # B200_PROFILING.md fallback (sustained)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def summary(self, t0, t1):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for ts, line in self.rows:
+            if not (t0 <= ts <= t1 + 0.2):
+                continue
+            f = [c.strip() for c in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic_batch(n, size, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, 1, size, size, size, generator=g)
+    t = (torch.rand(n, 1, size, size, size, generator=g) > 0.5).float()
+    return x, t
+
+
+def dice_loss_mean(logits, targets, eps=1e-9):
+    """segmentation/routine.py:272-274 + :239-253 (device-side loss, stays PyTorch: SURVEY a-8)."""
+    p0 = torch.softmax(logits, dim=1)
+    p1, g0 = 1 - p0, targets
+    g1 = 1 - g0
+    tp = (p0 * g0).sum(dim=(2, 3, 4)); fp = (p0 * g1).sum(dim=(2, 3, 4)); fn = (p1 * g0).sum(dim=(2, 3, 4))
+    return (1 - 2 * tp / (2 * tp + fp + fn + eps)).mean()
+
+
+def build_model(pkg, name):
+    if name == "unet3d":
+        return pkg.zoo.Unet(c=1, n=16, dropout=0.5, norm="bn", num_classes=2), "unet3d.Unet(c=1,n=16,norm=bn,num_classes=2)"
+    if name == "fepegar16":
+        return pkg.zoo.FepegarUNet(out_channels_first_layer=16), "unet.UNet(first=16)"
+    if name == "fepegar8":
+        return pkg.zoo.FepegarUNet(out_channels_first_layer=8), "unet.UNet(first=8)"
+    raise SystemExit(f"unknown model {name}")
+
+
+def cpu_reference_step(model_name, size, steps, warmup, threads):
+    """The reference's CPU path for the step (oracle restatement), fp32, on `threads` host threads."""
+    from oracle import graphs, weights
+    torch.set_num_threads(threads)
+    if model_name == "unet3d":
+        sd = weights.unet3d_state(1, 16, 2, "bn", seed=0)
+        fwd = lambda s, x: graphs.unet3d(s, x, "bn", 0.5, True)
+    else:
+        sd = weights.fepegar_unet_state(16 if model_name == "fepegar16" else 8, seed=0, duplicate_keys=False)
+        fwd = lambda s, x: graphs.fepegar_unet(s, x, True)
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
+    opt = torch.optim.AdamW([v for v in sd.values() if v.requires_grad])
+    x, t = synthetic_batch(1, size, 0)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss = graphs.dice_loss_mean(fwd(sd, x), t)
+        loss.backward()
+        opt.step()
+        float(loss)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return x.numel(), times
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="unet3d")
+    ap.add_argument("--batch", type=int, default=4)
+    ap.add_argument("--size", type=int, default=128)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sync-bn", action="store_true")
+    ap.add_argument("--profile-json", default=None, help="write the per-layer conv timing table here")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+    workload = f"{args.model} train step (fwd+dice+bwd+AdamW), batch {args.batch} x {args.size}^3 per GPU, bf16"
+    base = {"metric": METRIC, "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "data": "synthetic (seeded randn volumes, random-init weights)"}
+
+    # ------------------------------------------------------------------ reference arm: the CPU path on host cores
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, args.steps)
+        nvox, times = cpu_reference_step(args.model, args.size, steps, min(args.warmup, 1), cores)
+        ms = 1e3 * sum(times) / len(times)
+        val = nvox / (ms / 1e3)
+        print(json.dumps({**base, "impl": "reference", "value": val, "ms_per_step": ms, "dtype": "f32",
+                          "config": {"workload": workload, "sample": f"1 x {args.size}^3 volume per step (the config's batch is {args.batch})", "timing": "time.perf_counter"},
+                          "cpu_baseline": {"value": val, "unit": "voxels/s", "cores": cores, "kind": "port",
+                                           "sample": f"oracle/graphs.py restatement, {steps} steps of 1 x {args.size}^3"},
+                          "e2e": {"value": val, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import __graft_entry__
+    pkg = __graft_entry__.build()
+    from mri_epilepsy_diagnosis_b200 import functional as BF
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    net, model_desc = build_model(pkg, args.model)
+    sync = (None, world) if (args.sync_bn and world > 1) else None
+    net = pkg.convert(net.to(dev).train(), dtype=torch.bfloat16, sync=sync)
+    opt = torch.optim.AdamW(net.parameters())
+    bucket = None
+    if world > 1:
+        pkg.dp.broadcast_parameters(net)
+        bucket = pkg.dp.attach(net, opt)
+    xh, th = synthetic_batch(args.batch, args.size, seed=rank)
+    xh, th = xh.pin_memory(), th.pin_memory()
+    xd, td = xh.to(dev), th.to(dev)
+    voxels = xh.numel()
+
+    def step(x, t):
+        opt.zero_grad()
+        loss = dice_loss_mean(net(x), t)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / n
+        if dist is not None:
+            tms = torch.tensor([ms], device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms)
+        return ms, t0, time.time()
+
+    for _ in range(max(3, args.warmup)):
+        step(xd, td)
+    sampler = ClockSampler(local) if rank == 0 else None
+    time.sleep(0.3)
+    launches0 = pkg.launch_count()
+    ms, t0, t1 = timed(lambda: step(xd, td), args.steps)
+    launches = pkg.launch_count() - launches0
+    clocks = sampler.summary(t0, t1) if sampler else None
+
+    # end to end: host (pinned) inputs in, host scalar out, every step
+    def e2e_step():
+        x = xh.to(dev, non_blocking=True)
+        t = th.to(dev, non_blocking=True)
+        return float(step(x, t))
+    e2e_step()
+    ms_e2e, _, _ = timed(e2e_step, args.steps)
+
+    # roofline leg: per-launch CUDA events around every conv kernel over another K steps
+    BF.PROFILE = []
+    torch.cuda.synchronize()
+    for _ in range(args.steps):
+        step(xd, td)
+    torch.cuda.synchronize()
+    rows, BF.PROFILE = BF.PROFILE, None
+    agg = {}
+    for which, algo, flops, shape, a, b in rows:
+        k = (which, algo, shape)
+        r = agg.setdefault(k, [0.0, 0.0, 0])
+        r[0] += flops; r[1] += a.elapsed_time(b) * 1e-3; r[2] += 1
+    umma_flops = sum(v[0] for k, v in agg.items() if k[1] == 1)
+    umma_s = sum(v[1] for k, v in agg.items() if k[1] == 1)
+    umma_n = sum(v[2] for k, v in agg.items() if k[1] == 1)
+    conv_s = sum(v[1] for v in agg.values())
+    pk = peaks()
+    achieved = umma_flops / umma_s / 1e12 if umma_s > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "conv_umma_kernel", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"] + " (sustained bf16)",
+                "launches_per_step": umma_n / max(1, args.steps), "ms_per_launch_avg": 1e3 * umma_s / max(1, umma_n),
+                "share_of_step": (umma_s / args.steps) / (ms / 1e3), "all_conv_share_of_step": (conv_s / args.steps) / (ms / 1e3),
+                "note": "algorithmic FLOPs = 2*N*Do*Ho*Wo*Co*Ci*taps per launch; events bracket each launch on the launching stream"}
+    if args.profile_json and rank == 0:
+        names = {0: "fwd", 1: "dgrad", 2: "wgrad"}
+        table = [{"pass": names[k[0]], "algo": "umma" if k[1] else "simt", "Ci": k[2][0], "Co": k[2][1], "out": list(k[2][2:5]), "kd": k[2][5],
+                  "calls": v[2], "ms_per_call": 1e3 * v[1] / v[2], "tflops": v[0] / v[1] / 1e12} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])]
+        with open(args.profile_json, "w") as f:
+            json.dump({"ms_per_step": ms, "rows": table}, f, indent=1)
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier(); dist.destroy_process_group()
+        return
+    out = {**base, "value": world * voxels / (ms / 1e3), "ms_per_step": ms, "dtype": "bf16",
+           "config": {"workload": workload, "model": model_desc, "global_batch": args.batch * world, "volume": [args.size] * 3,
+                      "parallelism": f"dp{world}" + ("+syncbn" if sync else ""),
+                      "l2": "inputs and every activation tensor (>= 268 MB each at 16ch x 128^3 x 4) exceed the 126 MB L2; no flush needed"},
+           "e2e": {"value": world * voxels / (ms_e2e / 1e3), "unit": "voxels/s", "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": xh.numel() * 4 + th.numel() * 4, "d2h_bytes_per_step": 4},
+           "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+           "model_tflops": FWD_BWD_FLOP_PER_VOXEL * voxels / (ms / 1e3) / 1e12 if args.model == "unet3d" else None}
+    if args.gpus == 1 and not args.no_cpu_baseline:
+        nvox, times = cpu_reference_step(args.model, args.size, 2, 1, cores)
+        v = nvox / (sum(times) / len(times))
+        out["cpu_baseline"] = {"value": v, "unit": "voxels/s", "cores": cores, "kind": "port",
+                               "sample": f"oracle/graphs.py (CPU restatement of the reference step), fp32, 2 timed steps of 1 x {args.size}^3 after 1 warm-up"}
+    print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

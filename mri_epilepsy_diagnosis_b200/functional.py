@@ -55,6 +55,30 @@ def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
+# Optional per-launch timing of the convolution kernels (bench.py's roofline leg): when PROFILE is a list, every conv
+# C-ABI call is bracketed by CUDA events on the launching stream and (pass, algo, flops, start, end) is appended.
+PROFILE = None
+
+
+class _Timed:
+    def __init__(self, cd, which):
+        self.on = PROFILE is not None
+        if self.on:
+            self.meta = (which, int(lib().b200_conv_algo(C.byref(cd), which)),
+                         2.0 * cd.N * cd.Do * cd.Ho * cd.Wo * cd.Co * cd.Ci * cd.kd * cd.kh * cd.kw,
+                         (cd.Ci, cd.Co, cd.Do, cd.Ho, cd.Wo, cd.kd))
+            self.t0, self.t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def __enter__(self):
+        if self.on:
+            self.t0.record()
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.t1.record()
+            PROFILE.append(self.meta + (self.t0, self.t1))
+
+
 # --------------------------------------------------------------------------- convolution
 class ConvConfig:
     """Static configuration of one Conv/ConvTranspose module + its packed-weight cache."""
@@ -122,7 +146,8 @@ class _ConvFn(Function):
                 b = b.float()
         nws = lib().b200_conv_workspace_bytes(C.byref(cd), cabi.PASS_FWD)
         ws = _workspace(nws, x.device)
-        check(lib().b200_conv_fwd(C.byref(cd), x.data_ptr(), wp.data_ptr(), ptr(b), y.data_ptr(), ws.data_ptr(), nws, stream()))
+        with _Timed(cd, cabi.PASS_FWD):
+            check(lib().b200_conv_fwd(C.byref(cd), x.data_ptr(), wp.data_ptr(), ptr(b), y.data_ptr(), ws.data_ptr(), nws, stream()))
         ctx.save_for_backward(x, weight)
         ctx.cfg, ctx.cd, ctx.has_bias, ctx.out_dtype = cfg, cd, bias is not None, out_dtype
         return y
@@ -140,14 +165,16 @@ class _ConvFn(Function):
             dx = _empty_cl(tuple(x.shape), x.dtype, x.device)
             nws = lib().b200_conv_workspace_bytes(C.byref(cd), cabi.PASS_DGRAD)
             ws = _workspace(nws, x.device)
-            check(lib().b200_conv_dgrad(C.byref(cd), dy.data_ptr(), wp.data_ptr(), dx.data_ptr(), ws.data_ptr(), nws, stream()))
+            with _Timed(cd, cabi.PASS_DGRAD):
+                check(lib().b200_conv_dgrad(C.byref(cd), dy.data_ptr(), wp.data_ptr(), dx.data_ptr(), ws.data_ptr(), nws, stream()))
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
             db = torch.empty(weight.shape[1] if cfg.transposed else weight.shape[0], dtype=torch.float32, device=x.device) \
                 if ctx.has_bias else None
             nws = lib().b200_conv_workspace_bytes(C.byref(cd), cabi.PASS_WGRAD)
             ws = _workspace(nws, x.device)
-            check(lib().b200_conv_wgrad(C.byref(cd), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ptr(db), ws.data_ptr(), nws, stream()))
+            with _Timed(cd, cabi.PASS_WGRAD):
+                check(lib().b200_conv_wgrad(C.byref(cd), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ptr(db), ws.data_ptr(), nws, stream()))
             if weight.dtype != torch.float32:
                 dw = dw.to(weight.dtype)
             if not ctx.needs_input_grad[1]:
