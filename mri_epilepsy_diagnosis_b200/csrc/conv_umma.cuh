@@ -91,6 +91,18 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same, with the two 64-bit shared-memory descriptors given as (lo, hi) halves: the hi halves (SBO, version) are loop
+// invariants and the lo halves advance by plain 32-bit adds, which keeps the single issuing thread's loop short
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
 // arrive on an mbarrier when every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -141,6 +153,7 @@ struct UmmaConvParams {
     int cg_pitch;           // bytes between channel groups inside a slab (128-byte multiple)
     int slab_bytes, nslabs;
     int wstage_bytes, nwstages;
+    int w_resident;         // 1: every (tap, kchunk) block is loaded once per CTA and stays in shared memory
     int nsets;              // TMEM accumulator sets (1 or 2)
     int tmem_cols;
     int tiles_y, tiles_x, zchunks;   // per range
@@ -171,6 +184,86 @@ __device__ __forceinline__ ItemCoord decode_item(const UmmaConvParams& p, int it
     c.y0 = ty * kTileH;
     c.x0 = tx * kTileW;
     return c;
+}
+
+// ------------------------------------------------------------------------------------------------ MMA issue loop
+// One thread issues every tcgen05.mma of the CTA, so its instruction count per MMA bounds the tensor pipe for small N.
+// KD is a template parameter so that the plane index q = pl + kz is static and the slab descriptors stay in registers.
+template <int KD>
+__device__ __forceinline__ void mma_issue_loop(const UmmaConvParams& p, UmmaBarriers* bars, uint8_t* slabs, uint8_t* wstages, uint32_t tmem_base) {
+    constexpr int NQ = kMaxP + KD - 1;
+    const uint32_t lbo_a16 = (uint32_t)p.cg_pitch >> 4, lbo_b16 = (uint32_t)p.OC;        // 16-byte units (OC*16 B >> 4)
+    const uint32_t a_hi = (((uint32_t)p.WW * 16) >> 4) | (1u << 14);                     // SBO | version 1 (bit 46)
+    const uint32_t b_hi = (128u >> 4) | (1u << 14);
+    const uint32_t a_lbo_field = lbo_a16 << 16, b_lbo_field = lbo_b16 << 16;
+    const uint32_t slabs16 = ptx::smem_u32(slabs) >> 4, slab16 = (uint32_t)p.slab_bytes >> 4;
+    const uint32_t w16 = ptx::smem_u32(wstages) >> 4, wstage16 = (uint32_t)p.wstage_bytes >> 4;
+    const int nks = p.KC / 16, khw = p.kh * p.kw;
+    const uint32_t a_kstep = 2 * lbo_a16, b_kstep = 2 * lbo_b16;
+    uint32_t ss = 0, sph = 0, ws = 0, wph = 0, group = 0;
+    if (p.w_resident) { ptx::mbar_wait(ptx::smem_u32(&bars->w_full[0]), 0); ptx::tc_fence_after(); }
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++group) {
+        const ItemCoord c = decode_item(p, item);
+        const uint32_t set = group % p.nsets, set_phase = (group / p.nsets) & 1;
+        ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[set]), set_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)(set * p.P * p.OC);
+        uint32_t started = 0;                                   // bit pl: accumulator pl already holds a partial sum
+        for (int kc = 0; kc < p.NKC; ++kc) {
+            uint32_t slab_lo[NQ], slab_bar[NQ], have = 0;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                slab_lo[q] = 0; slab_bar[q] = 0;
+                const int zi = c.z0 - p.pd + q;
+                if (q < c.pvalid + KD - 1 && zi >= 0 && zi < p.Dpi) {
+                    ptx::mbar_wait(ptx::smem_u32(&bars->slab_full[ss]), sph);
+                    slab_lo[q] = ((slabs16 + ss * slab16) & 0x3FFF) | a_lbo_field;
+                    slab_bar[q] = ptx::smem_u32(&bars->slab_empty[ss]);
+                    have |= 1u << q;
+                    if (++ss == (uint32_t)p.nslabs) { ss = 0; sph ^= 1; }
+                }
+            }
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int kz = 0; kz < KD; ++kz) {
+                uint32_t a_tap = 0;                             // (ky*WW + kx) in 16-byte units
+                int kx = 0;
+                for (int kyx = 0; kyx < khw; ++kyx) {
+                    uint32_t b_lo;
+                    if (p.w_resident) {
+                        b_lo = ((w16 + (uint32_t)((kz * khw + kyx) * p.NKC + kc) * wstage16) & 0x3FFF) | b_lbo_field;
+                    } else {
+                        ptx::mbar_wait(ptx::smem_u32(&bars->w_full[ws]), wph);
+                        ptx::tc_fence_after();
+                        b_lo = ((w16 + ws * wstage16) & 0x3FFF) | b_lbo_field;
+                    }
+#pragma unroll
+                    for (int pl = 0; pl < kMaxP; ++pl) {
+                        if (pl < c.pvalid && ((have >> (pl + kz)) & 1)) {
+                            uint32_t a_lo = slab_lo[pl + kz] + a_tap, bb = b_lo;
+                            const uint32_t d_tmem = d0 + (uint32_t)(pl * p.OC);
+                            uint32_t acc = (started >> pl) & 1;
+                            for (int ks = 0; ks < nks; ++ks) {
+                                ptx::umma_bf16_lohi(d_tmem, a_lo, a_hi, bb, b_hi, p.idesc, acc);
+                                a_lo += a_kstep; bb += b_kstep; acc = 1;
+                            }
+                            started |= 1u << pl;
+                        }
+                    }
+                    if (!p.w_resident) {
+                        ptx::umma_commit(ptx::smem_u32(&bars->w_empty[ws]));     // stage free once these MMAs retire
+                        if (++ws == (uint32_t)p.nwstages) { ws = 0; wph ^= 1; }
+                    }
+                    ++a_tap;
+                    if (++kx == p.kw) { kx = 0; a_tap += (uint32_t)(p.WW - p.kw); }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                if ((have >> q) & 1) ptx::umma_commit(slab_bar[q]);
+        }
+        ptx::umma_commit(ptx::smem_u32(&bars->acc_full[set]));                  // accumulators of this tile group are final
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -223,75 +316,35 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap in_map, const UmmaConvParam
             }
         }
     } else if (warp == 1) {
-        // ===================================================== weight producer: one (tap, kchunk) block per stage
+        // ===================================================== weight producer
         if (lane == 0) {
-            uint32_t it = 0;
-            for (int item = blockIdx.x; item < p.items; item += gridDim.x)
-                for (int kc = 0; kc < p.NKC; ++kc)
-                    for (int tap = 0; tap < ntaps; ++tap) {
-                        const uint32_t s = it % p.nwstages, ph = (it / p.nwstages) & 1;
-                        ptx::mbar_wait(ptx::smem_u32(&bars->w_empty[s]), ph ^ 1);
-                        const uint32_t full = ptx::smem_u32(&bars->w_full[s]);
-                        ptx::mbar_expect_tx(full, (uint32_t)p.wstage_bytes);
-                        ptx::bulk_load(ptx::smem_u32(wstages + (size_t)s * p.wstage_bytes),
-                                       reinterpret_cast<const uint8_t*>(p.w) + ((size_t)tap * p.NKC + kc) * p.wstage_bytes, (uint32_t)p.wstage_bytes, full);
-                        ++it;
-                    }
+            if (p.w_resident) {
+                // small layers: all taps stay resident -- one bulk copy per (tap, kchunk) block, one barrier, once per CTA
+                const uint32_t full = ptx::smem_u32(&bars->w_full[0]);
+                const int nblocks = ntaps * p.NKC;
+                ptx::mbar_expect_tx(full, (uint32_t)(nblocks * p.wstage_bytes));
+                for (int b = 0; b < nblocks; ++b)
+                    ptx::bulk_load(ptx::smem_u32(wstages + (size_t)b * p.wstage_bytes), reinterpret_cast<const uint8_t*>(p.w) + (size_t)b * p.wstage_bytes,
+                                   (uint32_t)p.wstage_bytes, full);
+            } else {
+                uint32_t s = 0, ph = 0;
+                for (int item = blockIdx.x; item < p.items; item += gridDim.x)
+                    for (int kc = 0; kc < p.NKC; ++kc)
+                        for (int tap = 0; tap < ntaps; ++tap) {
+                            ptx::mbar_wait(ptx::smem_u32(&bars->w_empty[s]), ph ^ 1);
+                            const uint32_t full = ptx::smem_u32(&bars->w_full[s]);
+                            ptx::mbar_expect_tx(full, (uint32_t)p.wstage_bytes);
+                            ptx::bulk_load(ptx::smem_u32(wstages + (size_t)s * p.wstage_bytes),
+                                           reinterpret_cast<const uint8_t*>(p.w) + ((size_t)tap * p.NKC + kc) * p.wstage_bytes, (uint32_t)p.wstage_bytes, full);
+                            if (++s == (uint32_t)p.nwstages) { s = 0; ph ^= 1; }
+                        }
+            }
         }
     } else if (warp == 2) {
         // ===================================================== MMA issuer (one thread)
         if (lane == 0) {
-            uint32_t slab_it = 0, w_it = 0, group = 0;
-            const uint32_t sbo_a = (uint32_t)p.WW * 16, lbo_a = (uint32_t)p.cg_pitch;
-            const uint32_t sbo_b = 128, lbo_b = (uint32_t)p.OC * 16;
-            for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++group) {
-                const ItemCoord c = decode_item(p, item);
-                const uint32_t set = group % p.nsets, set_phase = (group / p.nsets) & 1;
-                ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[set]), set_phase ^ 1);
-                ptx::tc_fence_after();
-                uint32_t started = 0;                       // bit p: accumulator p already holds a partial sum
-                for (int kc = 0; kc < p.NKC; ++kc) {
-                    // slabs of this (item, kchunk), in producer order
-                    uint32_t slab_addr[kMaxP + 2];
-                    uint32_t slab_stage[kMaxP + 2];
-                    uint32_t have = 0;
-                    for (int q = 0; q < c.pvalid + p.kd - 1; ++q) {
-                        const int zi = c.z0 - p.pd + q;
-                        if (zi < 0 || zi >= p.Dpi) continue;
-                        const uint32_t s = slab_it % p.nslabs, ph = (slab_it / p.nslabs) & 1;
-                        ptx::mbar_wait(ptx::smem_u32(&bars->slab_full[s]), ph);
-                        slab_addr[q] = ptx::smem_u32(slabs + (size_t)s * p.slab_bytes);
-                        slab_stage[q] = s;
-                        have |= 1u << q;
-                        ++slab_it;
-                    }
-                    ptx::tc_fence_after();
-                    for (int tap = 0; tap < ntaps; ++tap) {
-                        const int kz = tap / (p.kh * p.kw), kr = tap - kz * p.kh * p.kw, ky = kr / p.kw, kx = kr - ky * p.kw;
-                        const uint32_t ws = w_it % p.nwstages, wph = (w_it / p.nwstages) & 1;
-                        ptx::mbar_wait(ptx::smem_u32(&bars->w_full[ws]), wph);
-                        ptx::tc_fence_after();
-                        const uint32_t wbase = ptx::smem_u32(wstages + (size_t)ws * p.wstage_bytes);
-                        const uint32_t a_off = (uint32_t)(ky * p.WW + kx) * 16;
-                        for (int pl = 0; pl < c.pvalid; ++pl) {
-                            const int q = pl + kz;
-                            if (!((have >> q) & 1)) continue;          // plane outside the volume: zero contribution
-                            const uint32_t d_tmem = tmem_base + (uint32_t)((set * p.P + pl) * p.OC);
-                            for (int ks = 0; ks < p.KC / 16; ++ks) {
-                                const uint64_t a_desc = make_smem_desc(slab_addr[q] + a_off + (uint32_t)(2 * ks) * lbo_a, lbo_a, sbo_a);
-                                const uint64_t b_desc = make_smem_desc(wbase + (uint32_t)(2 * ks) * lbo_b, lbo_b, sbo_b);
-                                ptx::umma_bf16(d_tmem, a_desc, b_desc, p.idesc, (started >> pl) & 1);
-                                started |= 1u << pl;
-                            }
-                        }
-                        ptx::umma_commit(ptx::smem_u32(&bars->w_empty[ws]));      // weight stage free once these MMAs retire
-                        ++w_it;
-                    }
-                    for (int q = 0; q < c.pvalid + p.kd - 1; ++q)
-                        if ((have >> q) & 1) ptx::umma_commit(ptx::smem_u32(&bars->slab_empty[slab_stage[q]]));
-                }
-                ptx::umma_commit(ptx::smem_u32(&bars->acc_full[set]));          // accumulators of this tile group are final
-            }
+            if (p.kd == 3) mma_issue_loop<3>(p, bars, slabs, wstages, tmem_base);
+            else mma_issue_loop<1>(p, bars, slabs, wstages, tmem_base);
         }
     } else {
         // ===================================================== epilogue: TMEM -> registers -> (+bias) -> bf16 -> global
@@ -410,7 +463,9 @@ inline bool umma_geom(const b200_conv_desc* d, int pass, UmmaGeom* g) {
     return true;
 }
 
+inline bool umma_wgrad_geom(const b200_conv_desc* d);
 inline bool umma_conv_supported(const b200_conv_desc* d, int pass) {
+    if (pass == B200_PASS_WGRAD) return umma_wgrad_geom(d);
     UmmaGeom g;
     return umma_geom(d, pass, &g);
 }
@@ -419,7 +474,8 @@ inline size_t umma_packed_bytes(const b200_conv_desc* d, int pass) {
     (void)pass;
     return (size_t)d->kd * d->kh * d->kw * d->Ci * d->Co * sizeof(__nv_bfloat16);
 }
-inline size_t umma_workspace_bytes(const b200_conv_desc*, int) { return 0; }
+inline size_t umma_wgrad_workspace_bytes(const b200_conv_desc* d);
+inline size_t umma_workspace_bytes(const b200_conv_desc* d, int pass) { return pass == B200_PASS_WGRAD ? umma_wgrad_workspace_bytes(d) + 256 : 0; }
 
 inline int umma_pack_weights(const b200_conv_desc* d, int pass, const float* w, void* packed, void* stream) {
     UmmaGeom g;
@@ -459,13 +515,22 @@ inline int umma_plan(const UmmaGeom& g, int N, UmmaConvParams* p, size_t* smem_b
     // shared memory: slabs (at least one tile group's worth, two if they fit) + weight ring
     const size_t budget = 227 * 1024 - sizeof(UmmaBarriers) - 1024;
     const int need = P + g.kd - 1;
+    const size_t all_w = (size_t)g.kd * g.kh * g.kw * g.IC * g.OC * 2;
     int nslabs = need, nw = 2;
-    B200_REQUIRE((size_t)nslabs * p->slab_bytes + (size_t)nw * p->wstage_bytes <= budget, "umma: tile does not fit shared memory");
-    while (nw < kMaxWStages && nw < 4 && (size_t)nslabs * p->slab_bytes + (size_t)(nw + 1) * p->wstage_bytes <= budget) ++nw;
-    if ((size_t)2 * need * p->slab_bytes + (size_t)nw * p->wstage_bytes <= budget && 2 * need <= kMaxSlabs) nslabs = 2 * need;
-    while (nw < kMaxWStages && (size_t)nslabs * p->slab_bytes + (size_t)(nw + 1) * p->wstage_bytes <= budget) ++nw;
+    size_t wbytes;
+    if (all_w <= 96 * 1024 && (size_t)2 * need * p->slab_bytes + all_w <= budget && 2 * need <= kMaxSlabs) {
+        p->w_resident = 1;                       // small layers (<= 32x32x27, 64x16x27, ...): weights stay in shared memory
+        nslabs = 2 * need; nw = 1;
+        wbytes = all_w;
+    } else {
+        B200_REQUIRE((size_t)nslabs * p->slab_bytes + (size_t)nw * p->wstage_bytes <= budget, "umma: tile does not fit shared memory");
+        while (nw < kMaxWStages && nw < 4 && (size_t)nslabs * p->slab_bytes + (size_t)(nw + 1) * p->wstage_bytes <= budget) ++nw;
+        if ((size_t)2 * need * p->slab_bytes + (size_t)nw * p->wstage_bytes <= budget && 2 * need <= kMaxSlabs) nslabs = 2 * need;
+        while (nw < kMaxWStages && (size_t)nslabs * p->slab_bytes + (size_t)(nw + 1) * p->wstage_bytes <= budget) ++nw;
+        wbytes = (size_t)nw * p->wstage_bytes;
+    }
     p->nslabs = nslabs; p->nwstages = nw;
-    *smem_bytes = sizeof(UmmaBarriers) + (size_t)nslabs * p->slab_bytes + (size_t)nw * p->wstage_bytes;
+    *smem_bytes = sizeof(UmmaBarriers) + (size_t)nslabs * p->slab_bytes + wbytes;
     p->tiles_y = (g.Ho + kTileH - 1) / kTileH;
     p->tiles_x = (g.Wo + kTileW - 1) / kTileW;
     p->zchunks = (p->Dpo + P - 1) / P;
@@ -506,8 +571,359 @@ inline int umma_conv_run(const b200_conv_desc* d, int pass, const void* in, cons
     return 0;
 }
 
-inline int umma_wgrad_run(const b200_conv_desc*, const void*, const void*, float*, float*, void*, size_t, void*) {
-    return fail("umma wgrad is not selected by b200_conv_algo");
+// ================================================================================================ wgrad on tcgen05
+// dW[tap][co][ci] = sum over voxels v of dy[v][co] * x[v + tap - pad][ci]          (stride 1)
+//
+// GEMM per filter tap:  D[M = co (128 TMEM lanes)][N = ci] += A[co][K = 16 voxels] * B[16 voxels][ci]
+// Both operands are "MN-major": the SAME channel-group-major shared-memory layout [cg][voxel][8 ch] that the forward
+// kernel uses is, read the other way round, the canonical MN-major no-swizzle UMMA layout (8 channels contiguous, the
+// 8 voxels of one x-row 16 B apart = one core matrix, next x-row at LBO, next channel group at SBO).  One UMMA consumes
+// two x-rows (16 voxels); a tap is again only a different start address into the x halo slab.
+// A CTA owns a "unit" = (tap range, ci chunk <= 64, co chunk <= 128) whose accumulators (taps x ci columns <= 512) stay
+// in TMEM for the CTA's whole life while it marches over its share of the volume plane by plane; at the end the fp32
+// partial is written once and a second kernel reduces the partials in a fixed order (deterministic).
+constexpr int kWgThreads = 192;          // warp 0 = TMA producer, warp 1 = MMA issuer + TMEM, warps 2..5 = final epilogue
+constexpr int kWgMaxSlabs = 8, kWgMaxDy = 4;
+
+struct WgradParams {
+    int NB, Dpi, Dpo, Hi, Wi, Ho, Wo;
+    int Ci, Co;
+    int kd, kh, kw, pd, ph, pw;
+    int NC, MC;                 // ci / co chunk handled by one unit
+    int n_ci, n_co, n_tg;       // number of chunks / tap groups; units = n_tg * n_ci * n_co
+    int tpu;                    // taps per unit (last group may hold fewer)
+    int splits;                 // CTAs per unit
+    int HH, WW, slab_cg_pitch, slab_bytes, nslabs;
+    int dy_cg_pitch, dy_bytes, ndy;
+    int tmem_cols;
+    int tiles_y, tiles_x, zsegs, zs;   // z segments per range, planes per segment
+    int items;
+    uint32_t idesc;
+    float* partial;             // [splits][taps][Co][Ci]
+};
+
+struct alignas(128) WgradBarriers {
+    uint64_t slab_full[kWgMaxSlabs], slab_empty[kWgMaxSlabs];
+    uint64_t dy_full[kWgMaxDy], dy_empty[kWgMaxDy];
+    uint64_t done;
+    uint32_t tmem_base, started;
+};
+
+struct WgItem { int nb, z0, z1, y0, x0; };
+__device__ __forceinline__ WgItem wg_decode(const WgradParams& p, int item) {
+    WgItem c;
+    const int tx = item % p.tiles_x; item /= p.tiles_x;
+    const int ty = item % p.tiles_y; item /= p.tiles_y;
+    const int zg = item % p.zsegs;
+    c.nb = item / p.zsegs;
+    c.z0 = zg * p.zs;
+    c.z1 = min(p.Dpo, c.z0 + p.zs);
+    c.y0 = ty * kTileH; c.x0 = tx * kTileW;
+    return c;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap dy_map, const WgradParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    WgradBarriers* bars = reinterpret_cast<WgradBarriers*>(smem);
+    uint8_t* dyst = smem + sizeof(WgradBarriers);                       // dy stages first: M=128 descriptors of a narrow co chunk
+    uint8_t* slabs = dyst + (size_t)p.ndy * p.dy_bytes;                 // over-read into the slabs (rows >= Co are discarded)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // unit / split of this CTA
+    const int split = blockIdx.x % p.splits;
+    int unit = blockIdx.x / p.splits;
+    const int tg = unit % p.n_tg; unit /= p.n_tg;
+    const int cic = unit % p.n_ci;
+    const int coc = unit / p.n_ci;
+    const int ntaps = p.kd * p.kh * p.kw;
+    const int tap0 = tg * p.tpu, tap1 = min(ntaps, tap0 + p.tpu);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.nslabs; ++i) { ptx::mbar_init(ptx::smem_u32(&bars->slab_full[i]), 1); ptx::mbar_init(ptx::smem_u32(&bars->slab_empty[i]), 1); }
+        for (int i = 0; i < p.ndy; ++i) { ptx::mbar_init(ptx::smem_u32(&bars->dy_full[i]), 1); ptx::mbar_init(ptx::smem_u32(&bars->dy_empty[i]), 1); }
+        ptx::mbar_init(ptx::smem_u32(&bars->done), 1);
+        bars->started = 0;
+        ptx::fence_barrier_init();
+        ptx::prefetch_tmap(&x_map);
+        ptx::prefetch_tmap(&dy_map);
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer: x halo slabs (ring, one new plane per z) + dy tiles
+        if (lane == 0) {
+            uint32_t ss = 0, sph = 0, ds = 0, dph = 0;
+            const int ncg_x = p.NC / 8, ncg_y = p.MC / 8;
+            for (int item = split; item < p.items; item += p.splits) {
+                const WgItem c = wg_decode(p, item);
+                int next_plane = c.z0 - p.pd;                               // next input plane (relative to the range) to load
+                for (int z = c.z0; z < c.z1; ++z) {
+                    const int last_needed = z - p.pd + p.kd - 1;
+                    for (; next_plane <= last_needed; ++next_plane) {
+                        if (next_plane < 0 || next_plane >= p.Dpi) continue;
+                        ptx::mbar_wait(ptx::smem_u32(&bars->slab_empty[ss]), sph ^ 1);
+                        const uint32_t full = ptx::smem_u32(&bars->slab_full[ss]);
+                        ptx::mbar_expect_tx(full, (uint32_t)(ncg_x * p.HH * p.WW * 16));
+                        const uint32_t dst = ptx::smem_u32(slabs + (size_t)ss * p.slab_bytes);
+                        for (int cg = 0; cg < ncg_x; ++cg)
+                            ptx::tma_load_4d(dst + cg * p.slab_cg_pitch, &x_map, full, cic * p.NC + cg * 8, c.x0 - p.pw, c.y0 - p.ph, c.nb * p.Dpi + next_plane);
+                        if (++ss == (uint32_t)p.nslabs) { ss = 0; sph ^= 1; }
+                    }
+                    ptx::mbar_wait(ptx::smem_u32(&bars->dy_empty[ds]), dph ^ 1);
+                    const uint32_t full = ptx::smem_u32(&bars->dy_full[ds]);
+                    ptx::mbar_expect_tx(full, (uint32_t)(ncg_y * 128 * 16));
+                    const uint32_t dst = ptx::smem_u32(dyst + (size_t)ds * p.dy_bytes);
+                    for (int cg = 0; cg < ncg_y; ++cg)
+                        ptx::tma_load_4d(dst + cg * p.dy_cg_pitch, &dy_map, full, coc * p.MC + cg * 8, c.x0, c.y0, c.nb * p.Dpo + z);
+                    if (++ds == (uint32_t)p.ndy) { ds = 0; dph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t a_hi = ((uint32_t)p.dy_cg_pitch >> 4) | (1u << 14);          // SBO = next 8 output channels
+            const uint32_t b_hi = ((uint32_t)p.slab_cg_pitch >> 4) | (1u << 14);        // SBO = next 8 input channels
+            const uint32_t a_lbo = (128u >> 4) << 16;                                   // LBO = next x-row of the 16x8 dy tile
+            const uint32_t b_lbo = (((uint32_t)p.WW * 16) >> 4) << 16;                  // LBO = next x-row of the halo slab
+            const uint32_t dy16 = ptx::smem_u32(dyst) >> 4, dystage16 = (uint32_t)p.dy_bytes >> 4;
+            const uint32_t sl16 = ptx::smem_u32(slabs) >> 4, slab16 = (uint32_t)p.slab_bytes >> 4;
+            const int khw = p.kh * p.kw;
+            uint32_t ss = 0, sph = 0, ds = 0, dph = 0, started = 0;
+            for (int item = split; item < p.items; item += p.splits) {
+                const WgItem c = wg_decode(p, item);
+                // ring bookkeeping: slot[k] = shared-memory slab of input plane (z - pd + k), or -1 when outside the volume
+                int slot[3] = {-1, -1, -1};
+                uint32_t slot_bar[3] = {0, 0, 0};
+                int next_plane = c.z0 - p.pd;
+                for (int z = c.z0; z < c.z1; ++z) {
+                    if (z > c.z0) {                                        // slide the window: oldest plane was released last z
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) { slot[k] = slot[k + 1]; slot_bar[k] = slot_bar[k + 1]; }
+                    }
+                    const int last_needed = z - p.pd + p.kd - 1;
+                    for (; next_plane <= last_needed; ++next_plane) {
+                        const int k = next_plane - (z - p.pd);             // position inside the window
+                        int sidx = -1;
+                        uint32_t sbar = 0;
+                        if (next_plane >= 0 && next_plane < p.Dpi) {
+                            ptx::mbar_wait(ptx::smem_u32(&bars->slab_full[ss]), sph);
+                            sidx = (int)ss; sbar = ptx::smem_u32(&bars->slab_empty[ss]);
+                            if (++ss == (uint32_t)p.nslabs) { ss = 0; sph ^= 1; }
+                        }
+#pragma unroll
+                        for (int kk = 0; kk < 3; ++kk) if (kk == k) { slot[kk] = sidx; slot_bar[kk] = sbar; }
+                    }
+                    ptx::mbar_wait(ptx::smem_u32(&bars->dy_full[ds]), dph);
+                    ptx::tc_fence_after();
+                    const uint32_t a_base = ((dy16 + ds * dystage16) & 0x3FFF) | a_lbo;
+                    for (int tap = tap0; tap < tap1; ++tap) {
+                        const int kz = tap / khw, kr = tap - kz * khw, ky = kr / p.kw, kx = kr - ky * p.kw;
+                        int sidx = -1;
+#pragma unroll
+                        for (int kk = 0; kk < 3; ++kk) if (kk == kz) sidx = slot[kk];
+                        if (sidx < 0) continue;                            // plane outside the volume: zero contribution
+                        const uint32_t d_tmem = tmem_base + (uint32_t)((tap - tap0) * p.NC);
+                        uint32_t a_lo = a_base;
+                        uint32_t b_lo = (((sl16 + (uint32_t)sidx * slab16) + (uint32_t)(ky * p.WW + kx)) & 0x3FFF) | b_lbo;
+                        uint32_t acc = (started >> (tap - tap0)) & 1;
+#pragma unroll
+                        for (int r = 0; r < kTileH / 2; ++r) {              // two x-rows (16 voxels) per MMA
+                            ptx::umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, p.idesc, acc);
+                            a_lo += (2 * 128) >> 4;
+                            b_lo += (uint32_t)(2 * p.WW);
+                            acc = 1;
+                        }
+                        started |= 1u << (tap - tap0);
+                    }
+                    ptx::umma_commit(ptx::smem_u32(&bars->dy_empty[ds]));
+                    if (++ds == (uint32_t)p.ndy) { ds = 0; dph ^= 1; }
+                    // the oldest plane of the window is not needed by z+1 (for kd == 1 that is the only plane)
+                    if (slot[0] >= 0) ptx::umma_commit(slot_bar[0]);
+                    if (z + 1 == c.z1) {                                   // end of the column segment: release the rest
+#pragma unroll
+                        for (int k = 1; k < 3; ++k) if (k < p.kd && slot[k] >= 0) ptx::umma_commit(slot_bar[k]);
+                    }
+                }
+            }
+            bars->started = started;
+            __threadfence_block();
+            ptx::umma_commit(ptx::smem_u32(&bars->done));
+        }
+    } else {
+        // ===================================================== epilogue (once): TMEM -> fp32 partial[split][tap][co][ci]
+        const int lane_grp = warp & 3;
+        const int row = lane_grp * 32 + lane;                               // co inside the chunk
+        ptx::mbar_wait(ptx::smem_u32(&bars->done), 0);
+        ptx::tc_fence_after();
+        const uint32_t started = *reinterpret_cast<volatile uint32_t*>(&bars->started);
+        const int co = coc * p.MC + row;
+        const bool row_ok = row < p.MC && co < p.Co;
+        for (int tap = tap0; tap < tap1; ++tap) {
+            const bool has = (started >> (tap - tap0)) & 1;
+            float* dst = p.partial + (((size_t)split * ntaps + tap) * p.Co + co) * p.Ci + cic * p.NC;
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)((tap - tap0) * p.NC);
+            for (int c0 = 0; c0 < p.NC; c0 += 16) {
+                float v[16];
+                if (has) ptx::tmem_ld16(taddr + (uint32_t)c0, v);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                }
+                if (row_ok) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        *reinterpret_cast<float4*>(dst + c0 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
+            }
+        }
+        ptx::tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+}
+
+// dw[(co*Ci + ci)*taps + tap] = sum_s partial[s][tap][co][ci]
+__global__ void wgrad_umma_reduce_kernel(int splits, int taps, int Co, int Ci, const float* __restrict__ partial, float* __restrict__ dw) {
+    const int64_t total = (int64_t)taps * Co * Ci;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int s = 0; s < splits; ++s) acc += partial[(int64_t)s * total + e];
+        const int ci = (int)(e % Ci);
+        const int64_t r = e / Ci;
+        const int co = (int)(r % Co), tap = (int)(r / Co);
+        dw[((int64_t)co * Ci + ci) * taps + tap] = acc;
+    }
+}
+
+inline bool umma_wgrad_geom(const b200_conv_desc* d) {
+    if (!d->allow_umma || d->transposed) return false;
+    if (d->x_dtype != B200_BF16 || d->y_dtype != B200_BF16) return false;
+    if (d->sd != 1 || d->sh != 1 || d->sw != 1 || d->dd != 1 || d->dh != 1 || d->dw != 1) return false;
+    if (!((d->kd == 1 || d->kd == 3) && (d->kh == 1 || d->kh == 3) && (d->kw == 1 || d->kw == 3))) return false;
+    if (d->pd > d->kd - 1 || d->ph > d->kh - 1 || d->pw > d->kw - 1) return false;
+    if (d->Ci % 16 || d->Co % 16 || d->Ci > 512 || d->Co > 512) return false;
+    if ((int64_t)d->N * d->Do * d->Ho * d->Wo < 512) return false;
+    return true;
+}
+
+inline int wgrad_plan(const b200_conv_desc* d, WgradParams* p, size_t* smem_bytes, size_t* partial_bytes) {
+    memset(p, 0, sizeof *p);
+    p->Ci = d->Ci; p->Co = d->Co;
+    p->kd = d->kd; p->kh = d->kh; p->kw = d->kw; p->pd = d->pd; p->ph = d->ph; p->pw = d->pw;
+    p->Hi = d->Hi; p->Wi = d->Wi; p->Ho = d->Ho; p->Wo = d->Wo;
+    if (d->kd == 1) { p->NB = 1; p->Dpi = d->N * d->Di; p->Dpo = d->N * d->Do; }
+    else { p->NB = d->N; p->Dpi = d->Di; p->Dpo = d->Do; }
+    const int taps = d->kd * d->kh * d->kw;
+    p->NC = d->Ci <= 64 ? d->Ci : (d->Ci % 64 == 0 ? 64 : (d->Ci % 48 == 0 ? 48 : (d->Ci % 32 == 0 ? 32 : 16)));
+    p->MC = d->Co <= 128 ? d->Co : (d->Co % 128 == 0 ? 128 : (d->Co % 64 == 0 ? 64 : 16));
+    p->n_ci = d->Ci / p->NC; p->n_co = d->Co / p->MC;
+    p->tpu = 512 / p->NC;
+    if (p->tpu > taps) p->tpu = taps;
+    p->n_tg = (taps + p->tpu - 1) / p->tpu;
+    p->tpu = (taps + p->n_tg - 1) / p->n_tg;                     // balance the groups
+    int cols = p->tpu * p->NC, pow2 = 32;
+    while (pow2 < cols) pow2 <<= 1;
+    B200_REQUIRE(pow2 <= 512, "umma wgrad: accumulators do not fit TMEM");
+    p->tmem_cols = pow2;
+    p->HH = kTileH + d->kh - 1; p->WW = kTileW + d->kw - 1;
+    p->slab_cg_pitch = ((p->HH * p->WW * 16) + 127) & ~127;
+    p->slab_bytes = (p->NC / 8) * p->slab_cg_pitch;
+    p->dy_cg_pitch = 128 * 16;
+    p->dy_bytes = (p->MC / 8) * p->dy_cg_pitch;
+    const size_t budget = 227 * 1024 - sizeof(WgradBarriers) - 1024;
+    p->ndy = 3; p->nslabs = d->kd + 3;
+    while (p->nslabs > d->kd + 1 && (size_t)p->ndy * p->dy_bytes + (size_t)p->nslabs * p->slab_bytes > budget) --p->nslabs;
+    while (p->ndy > 2 && (size_t)p->ndy * p->dy_bytes + (size_t)p->nslabs * p->slab_bytes > budget) --p->ndy;
+    size_t total = (size_t)p->ndy * p->dy_bytes + (size_t)p->nslabs * p->slab_bytes;
+    B200_REQUIRE(total <= budget, "umma wgrad: tile does not fit shared memory");
+    // an M=128 descriptor on a narrow co chunk reads 16 channel groups: keep that over-read inside the allocation
+    const size_t overread_end = (size_t)(p->ndy - 1) * p->dy_bytes + (size_t)16 * p->dy_cg_pitch + 4096;
+    if (total < overread_end) total = overread_end;
+    *smem_bytes = sizeof(WgradBarriers) + total;
+    p->tiles_y = (d->Ho + kTileH - 1) / kTileH;
+    p->tiles_x = (d->Wo + kTileW - 1) / kTileW;
+    const int units = p->n_tg * p->n_ci * p->n_co;
+    int splits = kNumSMs / units;
+    if (splits < 1) splits = 1;
+    // column segments: enough items for every split, but long segments so that halo planes are reused along z
+    const int64_t columns = (int64_t)p->NB * p->tiles_y * p->tiles_x;
+    int zsegs = 1;
+    while (columns * zsegs < (int64_t)splits * 2 && zsegs < p->Dpo) zsegs *= 2;
+    p->zs = (p->Dpo + zsegs - 1) / zsegs;
+    p->zsegs = (p->Dpo + p->zs - 1) / p->zs;
+    const int64_t items = columns * p->zsegs;
+    if (splits > items) splits = (int)items;
+    p->splits = splits;
+    p->items = (int)items;
+    p->idesc = make_idesc_bf16(p->NC) | (1u << 15) | (1u << 16);            // A and B are MN-major
+    *partial_bytes = (size_t)splits * taps * d->Co * d->Ci * sizeof(float);
+    return 0;
+}
+
+inline size_t umma_wgrad_workspace_bytes(const b200_conv_desc* d) {
+    WgradParams p;
+    size_t smem = 0, part = 0;
+    if (wgrad_plan(d, &p, &smem, &part)) return 0;
+    int64_t chunks = ((int64_t)d->N * d->Do * d->Ho * d->Wo + 4095) / 4096;
+    if (chunks > 2 * kNumSMs) chunks = 2 * kNumSMs;
+    if (chunks < 1) chunks = 1;
+    return part + (size_t)chunks * d->Co * 4 + 512;
+}
+
+inline int make_act_map(CUtensorMap* map, const void* ptr, int C, int W, int H, int64_t planes, int box_w, int box_h) {
+    PFN_tmapEncodeTiled enc = tmap_encoder();
+    B200_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is unavailable in this driver");
+    const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+    const cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    const cuuint32_t box[4] = {8, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d", (int)r);
+    return 0;
+}
+
+inline int umma_wgrad_run(const b200_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias, void* workspace, size_t ws_bytes,
+                          void* stream) {
+    B200_REQUIRE(umma_wgrad_geom(d), "umma wgrad: unsupported descriptor");
+    B200_REQUIRE(aligned16(x) && aligned16(dy), "umma wgrad: pointers must be 16-byte aligned");
+    WgradParams p;
+    size_t smem_bytes = 0, partial_bytes = 0;
+    if (wgrad_plan(d, &p, &smem_bytes, &partial_bytes)) return 1;
+    B200_REQUIRE(ws_bytes >= umma_wgrad_workspace_bytes(d), "umma wgrad: workspace too small");
+    p.partial = (float*)workspace;
+    CUtensorMap x_map, dy_map;
+    if (make_act_map(&x_map, x, d->Ci, d->Wi, d->Hi, (int64_t)d->N * d->Di, p.WW, p.HH)) return 1;
+    if (make_act_map(&dy_map, dy, d->Co, d->Wo, d->Ho, (int64_t)d->N * d->Do, kTileW, kTileH)) return 1;
+    static std::once_flag attr_once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once, [] { attr_err = cudaFuncSetAttribute(conv_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+    B200_REQUIRE(attr_err == cudaSuccess, "umma wgrad: cannot raise the dynamic shared memory limit: %s", cudaGetErrorString(attr_err));
+    const int units = p.n_tg * p.n_ci * p.n_co;
+    B200_LAUNCH(conv_wgrad_umma_kernel, units * p.splits, kWgThreads, smem_bytes, stream, x_map, dy_map, p);
+    const int taps = d->kd * d->kh * d->kw;
+    const int64_t total = (int64_t)taps * d->Co * d->Ci;
+    B200_LAUNCH(wgrad_umma_reduce_kernel, stream_grid(total, 256), 256, 0, stream, p.splits, taps, d->Co, d->Ci, p.partial, dw);
+    if (dbias != nullptr) {
+        float* bpart = (float*)((char*)workspace + ((partial_bytes + 255) & ~(size_t)255));
+        const int64_t Vy = (int64_t)d->N * d->Do * d->Ho * d->Wo;
+        int64_t chunks = (Vy + 4095) / 4096;
+        if (chunks > 2 * kNumSMs) chunks = 2 * kNumSMs;
+        if (chunks < 1) chunks = 1;
+        const int64_t rows_per_chunk = (Vy + chunks - 1) / chunks;
+        const size_t smem = (size_t)(d->Co <= 256 ? (256 / d->Co) * d->Co : 1) * sizeof(float);
+        B200_LAUNCH(colsum_partial_kernel<__nv_bfloat16>, (int)chunks, 256, smem, stream, (const __nv_bfloat16*)dy, d->Co, Vy, rows_per_chunk, bpart);
+        B200_LAUNCH(colsum_final_kernel, (int)((d->Co + 127) / 128), 128, 0, stream, (int)chunks, d->Co, bpart, dbias);
+    }
+    return 0;
 }
 
 }  // namespace b200

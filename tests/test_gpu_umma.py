@@ -60,6 +60,7 @@ def test_umma_conv_fwd_dgrad(B, case):
     cd, _ = mod._cfg().desc(xg, mod.weight, torch.bfloat16)
     assert B._cabi.lib().b200_conv_algo(ctypes.byref(cd), B._cabi.PASS_FWD) == B._cabi.ALGO_UMMA, "case is meant to hit the tcgen05 path"
     assert B._cabi.lib().b200_conv_algo(ctypes.byref(cd), B._cabi.PASS_DGRAD) == B._cabi.ALGO_UMMA
+    assert B._cabi.lib().b200_conv_algo(ctypes.byref(cd), B._cabi.PASS_WGRAD) == B._cabi.ALGO_UMMA
     yg = mod(xg)
     yg.backward(gy.cuda().bfloat16())
     torch.cuda.synchronize()
@@ -97,3 +98,13 @@ def test_umma_large_volume_matches_simt(B):
     # linearity (size-independent property): conv(a*x) == a*conv(x) exactly for a power of two
     mod.allow_umma = True
     assert torch.equal(mod(x * 2), y * 2)
+    # wgrad: tcgen05 vs fp32-FMA kernels on identical bf16 operands, and run-to-run determinism
+    gy = torch.randn(y.shape, generator=g).cuda().bfloat16()
+    grads = []
+    for umma in (True, True, False):
+        mod.allow_umma = umma
+        mod.zero_grad()
+        mod(x).backward(gy)
+        grads.append(mod.weight.grad.clone())
+    assert torch.equal(grads[0], grads[1])
+    assert rel_err(grads[0], grads[2]) < 2e-3
