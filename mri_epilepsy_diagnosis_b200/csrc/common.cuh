@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <cstdarg>
 #include <cstdio>
 #include <string>
 

@@ -20,6 +20,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 #include "common.cuh"
@@ -57,6 +59,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (spin > (1u << 26)) __trap();
 }
 
+// one lane of a converged warp (the CUTLASS elect_one_sync idiom): keeps the surrounding control flow and all operands
+// warp-uniform, so descriptors live in uniform registers and UTCHMMA is issued without per-instruction R2UR/vote loops
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred));
+    return pred != 0;
+}
+
 // TMA: 4-D tiled tensor load, completes `bytes` on the mbarrier
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
     asm volatile(
@@ -68,6 +82,12 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// 16-byte asynchronous global->shared copy (LDGSTS); src_bytes = 0 zero-fills (padding / out-of-volume halo)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -136,8 +156,9 @@ __host__ __device__ inline uint32_t make_idesc_bf16(int n) {
 
 // ------------------------------------------------------------------------------------------------ kernel parameters
 constexpr int kTileH = 16, kTileW = 8;          // output tile (y, x); 16*8 = 128 = UMMA M
+constexpr int kStageThreads = 128;             // LDGSTS producer threads (4 warps)
 constexpr int kMaxP = 4;                        // output planes per tile group
-constexpr int kUmmaThreads = 224;
+constexpr int kUmmaThreads = 224 + kStageThreads;     // + 4 LDGSTS producer warps (7..10)
 constexpr int kMaxSlabs = 16, kMaxWStages = 8;
 
 struct UmmaConvParams {
@@ -159,6 +180,8 @@ struct UmmaConvParams {
     int tiles_y, tiles_x, zchunks;   // per range
     int items;
     uint32_t idesc;
+    int use_tma;                     // 1: halo slabs by TMA tensor loads, 0: by LDGSTS producer warps
+    const __nv_bfloat16* in;         // [NB*Dpi][Hi][Wi][IC]
     const __nv_bfloat16* w;          // [tap][kchunk][cg][oc][8]
     const float* bias;               // [OC] or null
     __nv_bfloat16* out;              // [NB*Dpo][Ho][Wo][OC]
@@ -186,11 +209,57 @@ __device__ __forceinline__ ItemCoord decode_item(const UmmaConvParams& p, int it
     return c;
 }
 
+// ------------------------------------------------------------------------------------------------ halo staging by LDGSTS
+// Measured on B200: TMA tensor loads with the 16-byte inner rows this layout needs cost ~10 cycles per row and capped
+// the kernel at ~9% of the tensor peak (profiles/r1_conv_table_tma.json).  128 producer threads issuing 16-byte
+// cp.async (one (voxel, channel-group) entry each, coalesced along the channels of a voxel, zero-filled outside the
+// volume) move the same slab ~30x faster; completion is published to the MMA thread through the same mbarriers after
+// a generic->async proxy fence.  The TMA variant stays available (B200_CONV_STAGING=tma) for comparison.
+__device__ __forceinline__ void ldgsts_tile(uint32_t dst, int cg_pitch, const __nv_bfloat16* plane, int C, int H, int W, int c0, int ncg,
+                                            int y0, int x0, int HH, int WW, int tid) {
+    const int n = ncg * HH * WW;
+    for (int e = tid; e < n; e += kStageThreads) {
+        const int v = e / ncg, cg = e - v * ncg;                 // channel group fastest: a voxel's channels are contiguous in HBM
+        const int hy = v / WW, hx = v - hy * WW;
+        const int y = y0 + hy, x = x0 + hx;
+        const bool ok = (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W;
+        const __nv_bfloat16* src = ok ? plane + ((int64_t)y * W + x) * C + c0 + cg * 8 : plane;
+        ptx::cp_async16(dst + (uint32_t)(cg * cg_pitch + v * 16), src, ok ? 16u : 0u);
+    }
+}
+
+// Software pipeline of one producer thread: the arrive for a stage is deferred until the next stage's copies have been
+// issued (so two stages are in flight), but never across a wait that could block on the consumer.
+struct StagePipe {
+    uint32_t pending = 0;
+    __device__ __forceinline__ void flush() {
+        if (pending) {
+            ptx::cp_async_wait<0>();
+            ptx::fence_proxy_async();
+            ptx::mbar_arrive(pending);
+            pending = 0;
+        }
+    }
+    __device__ __forceinline__ void acquire(uint32_t empty_bar, uint32_t parity) {
+        if (!ptx::mbar_try_wait(empty_bar, parity)) { flush(); ptx::mbar_wait(empty_bar, parity); }
+    }
+    __device__ __forceinline__ void publish(uint32_t full_bar) {
+        ptx::cp_async_commit();
+        if (pending) {
+            ptx::cp_async_wait<1>();
+            ptx::fence_proxy_async();
+            ptx::mbar_arrive(pending);
+        }
+        pending = full_bar;
+    }
+};
+
 // ------------------------------------------------------------------------------------------------ MMA issue loop
 // One thread issues every tcgen05.mma of the CTA, so its instruction count per MMA bounds the tensor pipe for small N.
 // KD is a template parameter so that the plane index q = pl + kz is static and the slab descriptors stay in registers.
 template <int KD>
 __device__ __forceinline__ void mma_issue_loop(const UmmaConvParams& p, UmmaBarriers* bars, uint8_t* slabs, uint8_t* wstages, uint32_t tmem_base) {
+    // Executed by ALL 32 lanes of the MMA warp with warp-uniform values; only the tcgen05 instructions are elected.
     constexpr int NQ = kMaxP + KD - 1;
     const uint32_t lbo_a16 = (uint32_t)p.cg_pitch >> 4, lbo_b16 = (uint32_t)p.OC;        // 16-byte units (OC*16 B >> 4)
     const uint32_t a_hi = (((uint32_t)p.WW * 16) >> 4) | (1u << 14);                     // SBO | version 1 (bit 46)
@@ -200,6 +269,7 @@ __device__ __forceinline__ void mma_issue_loop(const UmmaConvParams& p, UmmaBarr
     const uint32_t w16 = ptx::smem_u32(wstages) >> 4, wstage16 = (uint32_t)p.wstage_bytes >> 4;
     const int nks = p.KC / 16, khw = p.kh * p.kw;
     const uint32_t a_kstep = 2 * lbo_a16, b_kstep = 2 * lbo_b16;
+    const uint32_t idesc = p.idesc;
     uint32_t ss = 0, sph = 0, ws = 0, wph = 0, group = 0;
     if (p.w_resident) { ptx::mbar_wait(ptx::smem_u32(&bars->w_full[0]), 0); ptx::tc_fence_after(); }
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++group) {
@@ -237,32 +307,39 @@ __device__ __forceinline__ void mma_issue_loop(const UmmaConvParams& p, UmmaBarr
                         ptx::tc_fence_after();
                         b_lo = ((w16 + ws * wstage16) & 0x3FFF) | b_lbo_field;
                     }
+                    if (ptx::elect_one()) {
 #pragma unroll
-                    for (int pl = 0; pl < kMaxP; ++pl) {
-                        if (pl < c.pvalid && ((have >> (pl + kz)) & 1)) {
-                            uint32_t a_lo = slab_lo[pl + kz] + a_tap, bb = b_lo;
-                            const uint32_t d_tmem = d0 + (uint32_t)(pl * p.OC);
-                            uint32_t acc = (started >> pl) & 1;
-                            for (int ks = 0; ks < nks; ++ks) {
-                                ptx::umma_bf16_lohi(d_tmem, a_lo, a_hi, bb, b_hi, p.idesc, acc);
-                                a_lo += a_kstep; bb += b_kstep; acc = 1;
+                        for (int pl = 0; pl < kMaxP; ++pl) {
+                            if (pl < c.pvalid && ((have >> (pl + kz)) & 1)) {
+                                uint32_t a_lo = slab_lo[pl + kz] + a_tap, bb = b_lo;
+                                const uint32_t d_tmem = d0 + (uint32_t)(pl * p.OC);
+                                uint32_t acc = (started >> pl) & 1;
+                                for (int ks = 0; ks < nks; ++ks) {
+                                    ptx::umma_bf16_lohi(d_tmem, a_lo, a_hi, bb, b_hi, idesc, acc);
+                                    a_lo += a_kstep; bb += b_kstep; acc = 1;
+                                }
                             }
-                            started |= 1u << pl;
                         }
+                        if (!p.w_resident) ptx::umma_commit(ptx::smem_u32(&bars->w_empty[ws]));   // stage free once these MMAs retire
                     }
-                    if (!p.w_resident) {
-                        ptx::umma_commit(ptx::smem_u32(&bars->w_empty[ws]));     // stage free once these MMAs retire
-                        if (++ws == (uint32_t)p.nwstages) { ws = 0; wph ^= 1; }
-                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int pl = 0; pl < kMaxP; ++pl)
+                        if (pl < c.pvalid && ((have >> (pl + kz)) & 1)) started |= 1u << pl;
+                    if (!p.w_resident) { if (++ws == (uint32_t)p.nwstages) { ws = 0; wph ^= 1; } }
                     ++a_tap;
                     if (++kx == p.kw) { kx = 0; a_tap += (uint32_t)(p.WW - p.kw); }
                 }
             }
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int q = 0; q < NQ; ++q)
-                if ((have >> q) & 1) ptx::umma_commit(slab_bar[q]);
+                for (int q = 0; q < NQ; ++q)
+                    if ((have >> q) & 1) ptx::umma_commit(slab_bar[q]);
+            }
+            __syncwarp();
         }
-        ptx::umma_commit(ptx::smem_u32(&bars->acc_full[set]));                  // accumulators of this tile group are final
+        if (ptx::elect_one()) ptx::umma_commit(ptx::smem_u32(&bars->acc_full[set]));          // accumulators of this tile group are final
+        __syncwarp();
     }
 }
 
@@ -276,7 +353,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap in_map, const UmmaConvParam
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < p.nslabs; ++i) { ptx::mbar_init(ptx::smem_u32(&bars->slab_full[i]), 1); ptx::mbar_init(ptx::smem_u32(&bars->slab_empty[i]), 1); }
+        for (int i = 0; i < p.nslabs; ++i) {
+            ptx::mbar_init(ptx::smem_u32(&bars->slab_full[i]), p.use_tma ? 1 : kStageThreads);
+            ptx::mbar_init(ptx::smem_u32(&bars->slab_empty[i]), 1);
+        }
         for (int i = 0; i < p.nwstages; ++i) { ptx::mbar_init(ptx::smem_u32(&bars->w_full[i]), 1); ptx::mbar_init(ptx::smem_u32(&bars->w_empty[i]), 1); }
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(ptx::smem_u32(&bars->acc_full[i]), 1); ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[i]), 4); }
         ptx::fence_barrier_init();
@@ -294,8 +374,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap in_map, const UmmaConvParam
     const int ntaps = p.kd * p.kh * p.kw;
 
     if (warp == 0) {
-        // ===================================================== TMA producer: halo slabs
-        if (lane == 0) {
+        // ===================================================== TMA producer: halo slabs (B200_CONV_STAGING=tma only)
+        if (lane == 0 && p.use_tma) {
             uint32_t it = 0;
             for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
                 const ItemCoord c = decode_item(p, item);
@@ -341,10 +421,31 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap in_map, const UmmaConvParam
             }
         }
     } else if (warp == 2) {
-        // ===================================================== MMA issuer (one thread)
-        if (lane == 0) {
-            if (p.kd == 3) mma_issue_loop<3>(p, bars, slabs, wstages, tmem_base);
-            else mma_issue_loop<1>(p, bars, slabs, wstages, tmem_base);
+        // ===================================================== MMA issuer (whole warp converged, one elected lane issues)
+        if (p.kd == 3) mma_issue_loop<3>(p, bars, slabs, wstages, tmem_base);
+        else mma_issue_loop<1>(p, bars, slabs, wstages, tmem_base);
+    } else if (warp >= 7) {
+        // ===================================================== LDGSTS producers: halo slabs, 128 threads
+        if (!p.use_tma) {
+            const int tid = threadIdx.x - 7 * 32;
+            StagePipe pipe;
+            uint32_t ss = 0, sph = 0;
+            const int ncg = p.KC / 8;
+            for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+                const ItemCoord c = decode_item(p, item);
+                for (int kc = 0; kc < p.NKC; ++kc)
+                    for (int q = 0; q < c.pvalid + p.kd - 1; ++q) {
+                        const int zi = c.z0 - p.pd + q;
+                        if (zi < 0 || zi >= p.Dpi) continue;
+                        pipe.acquire(ptx::smem_u32(&bars->slab_empty[ss]), sph ^ 1);
+                        const __nv_bfloat16* plane = p.in + (int64_t)(c.nb * p.Dpi + zi) * p.Hi * p.Wi * p.IC;
+                        ldgsts_tile(ptx::smem_u32(slabs + (size_t)ss * p.slab_bytes), p.cg_pitch, plane, p.IC, p.Hi, p.Wi, kc * p.KC, ncg,
+                                    c.y0 - p.ph, c.x0 - p.pw, p.HH, p.WW, tid);
+                        pipe.publish(ptx::smem_u32(&bars->slab_full[ss]));
+                        if (++ss == (uint32_t)p.nslabs) { ss = 0; sph ^= 1; }
+                    }
+            }
+            pipe.flush();
         }
     } else {
         // ===================================================== epilogue: TMEM -> registers -> (+bias) -> bf16 -> global
@@ -432,6 +533,11 @@ inline PFN_tmapEncodeTiled tmap_encoder() {
     return fn;
 }
 
+inline bool staging_uses_tma() {
+    static const bool v = [] { const char* e = getenv("B200_CONV_STAGING"); return e != nullptr && strcmp(e, "tma") == 0; }();
+    return v;
+}
+
 inline int umma_kchunk(int IC) {
     for (int kc = 64; kc >= 16; kc -= 16)
         if (IC % kc == 0) return kc;
@@ -497,8 +603,10 @@ inline int umma_plan(const UmmaGeom& g, int N, UmmaConvParams* p, size_t* smem_b
     B200_REQUIRE(p->KC > 0, "umma: IC=%d is not a multiple of 16", g.IC);
     p->NKC = g.IC / p->KC;
     p->HH = kTileH + g.kh - 1; p->WW = kTileW + g.kw - 1;
-    p->cg_pitch = ((p->HH * p->WW * 16) + 127) & ~127;
-    p->slab_bytes = (p->KC / 8) * p->cg_pitch;
+    p->use_tma = staging_uses_tma() ? 1 : 0;
+    // TMA destinations must be 128-byte aligned; for LDGSTS an odd multiple of 16 B spreads the channel groups over the banks
+    p->cg_pitch = p->use_tma ? ((p->HH * p->WW * 16) + 127) & ~127 : p->HH * p->WW * 16 + 16;
+    p->slab_bytes = (((p->KC / 8) * p->cg_pitch) + 127) & ~127;
     p->wstage_bytes = p->KC * g.OC * 2;
     // accumulators: prefer two sets (epilogue/MMA overlap) of up to 4 planes
     int P = 256 / g.OC;
@@ -549,6 +657,7 @@ inline int umma_conv_run(const b200_conv_desc* d, int pass, const void* in, cons
     UmmaConvParams p;
     size_t smem_bytes = 0;
     if (umma_plan(g, d->N, &p, &smem_bytes)) return 1;
+    p.in = (const __nv_bfloat16*)in;
     p.w = (const __nv_bfloat16*)w_packed;
     p.bias = bias;
     p.out = (__nv_bfloat16*)out;
@@ -582,7 +691,7 @@ inline int umma_conv_run(const b200_conv_desc* d, int pass, const void* in, cons
 // A CTA owns a "unit" = (tap range, ci chunk <= 64, co chunk <= 128) whose accumulators (taps x ci columns <= 512) stay
 // in TMEM for the CTA's whole life while it marches over its share of the volume plane by plane; at the end the fp32
 // partial is written once and a second kernel reduces the partials in a fixed order (deterministic).
-constexpr int kWgThreads = 192;          // warp 0 = TMA producer, warp 1 = MMA issuer + TMEM, warps 2..5 = final epilogue
+constexpr int kWgThreads = 160;          // warps 0..3 = producers, then the final epilogue; warp 4 = MMA issuer + TMEM owner
 constexpr int kWgMaxSlabs = 8, kWgMaxDy = 4;
 
 struct WgradParams {
@@ -594,11 +703,14 @@ struct WgradParams {
     int tpu;                    // taps per unit (last group may hold fewer)
     int splits;                 // CTAs per unit
     int HH, WW, slab_cg_pitch, slab_bytes, nslabs;
-    int dy_cg_pitch, dy_bytes, ndy;
+    int dy_cg_pitch, dy_bytes, ndy, dy_row_pitch;
     int tmem_cols;
     int tiles_y, tiles_x, zsegs, zs;   // z segments per range, planes per segment
     int items;
     uint32_t idesc;
+    int use_tma;
+    const __nv_bfloat16* x;     // [NB*Dpi][Hi][Wi][Ci]
+    const __nv_bfloat16* dy;    // [NB*Dpo][Ho][Wo][Co]
     float* partial;             // [splits][taps][Co][Ci]
 };
 
@@ -639,15 +751,16 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_c
     const int tap0 = tg * p.tpu, tap1 = min(ntaps, tap0 + p.tpu);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < p.nslabs; ++i) { ptx::mbar_init(ptx::smem_u32(&bars->slab_full[i]), 1); ptx::mbar_init(ptx::smem_u32(&bars->slab_empty[i]), 1); }
-        for (int i = 0; i < p.ndy; ++i) { ptx::mbar_init(ptx::smem_u32(&bars->dy_full[i]), 1); ptx::mbar_init(ptx::smem_u32(&bars->dy_empty[i]), 1); }
+        const uint32_t nprod = p.use_tma ? 1 : kStageThreads;
+        for (int i = 0; i < p.nslabs; ++i) { ptx::mbar_init(ptx::smem_u32(&bars->slab_full[i]), nprod); ptx::mbar_init(ptx::smem_u32(&bars->slab_empty[i]), 1); }
+        for (int i = 0; i < p.ndy; ++i) { ptx::mbar_init(ptx::smem_u32(&bars->dy_full[i]), nprod); ptx::mbar_init(ptx::smem_u32(&bars->dy_empty[i]), 1); }
         ptx::mbar_init(ptx::smem_u32(&bars->done), 1);
         bars->started = 0;
         ptx::fence_barrier_init();
         ptx::prefetch_tmap(&x_map);
         ptx::prefetch_tmap(&dy_map);
     }
-    if (warp == 1) {
+    if (warp == 4) {
         ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);
         ptx::tmem_relinquish();
     }
@@ -656,8 +769,37 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_c
     ptx::tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
-    if (warp == 0) {
-        // ===================================================== TMA producer: x halo slabs (ring, one new plane per z) + dy tiles
+    if (warp < 4 && !p.use_tma) {
+        // ===================================================== LDGSTS producers (128 threads): x halo slabs (one new plane per z) + dy tiles
+        StagePipe pipe;
+        uint32_t ss = 0, sph = 0, ds = 0, dph = 0;
+        const int ncg_x = p.NC / 8, ncg_y = p.MC / 8;
+        for (int item = split; item < p.items; item += p.splits) {
+            const WgItem c = wg_decode(p, item);
+            int next_plane = c.z0 - p.pd;
+            for (int z = c.z0; z < c.z1; ++z) {
+                const int last_needed = z - p.pd + p.kd - 1;
+                for (; next_plane <= last_needed; ++next_plane) {
+                    if (next_plane < 0 || next_plane >= p.Dpi) continue;
+                    pipe.acquire(ptx::smem_u32(&bars->slab_empty[ss]), sph ^ 1);
+                    const __nv_bfloat16* plane = p.x + (int64_t)(c.nb * p.Dpi + next_plane) * p.Hi * p.Wi * p.Ci;
+                    ldgsts_tile(ptx::smem_u32(slabs + (size_t)ss * p.slab_bytes), p.slab_cg_pitch, plane, p.Ci, p.Hi, p.Wi, cic * p.NC, ncg_x,
+                                c.y0 - p.ph, c.x0 - p.pw, p.HH, p.WW, (int)threadIdx.x);
+                    pipe.publish(ptx::smem_u32(&bars->slab_full[ss]));
+                    if (++ss == (uint32_t)p.nslabs) { ss = 0; sph ^= 1; }
+                }
+                pipe.acquire(ptx::smem_u32(&bars->dy_empty[ds]), dph ^ 1);
+                const __nv_bfloat16* plane = p.dy + (int64_t)(c.nb * p.Dpo + z) * p.Ho * p.Wo * p.Co;
+                ldgsts_tile(ptx::smem_u32(dyst + (size_t)ds * p.dy_bytes), p.dy_cg_pitch, plane, p.Co, p.Ho, p.Wo, coc * p.MC, ncg_y, c.y0, c.x0,
+                            kTileH, kTileW, (int)threadIdx.x);
+                pipe.publish(ptx::smem_u32(&bars->dy_full[ds]));
+                if (++ds == (uint32_t)p.ndy) { ds = 0; dph ^= 1; }
+            }
+        }
+        pipe.flush();
+    }
+    if (warp == 0 && p.use_tma) {
+        // ===================================================== TMA producer (B200_CONV_STAGING=tma): same schedule, one thread
         if (lane == 0) {
             uint32_t ss = 0, sph = 0, ds = 0, dph = 0;
             const int ncg_x = p.NC / 8, ncg_y = p.MC / 8;
@@ -686,9 +828,10 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_c
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================================================== MMA issuer
-        if (lane == 0) {
+    }
+    if (warp == 4) {
+        // ===================================================== MMA issuer (whole warp converged, one elected lane issues)
+        {
             const uint32_t a_hi = ((uint32_t)p.dy_cg_pitch >> 4) | (1u << 14);          // SBO = next 8 output channels
             const uint32_t b_hi = ((uint32_t)p.slab_cg_pitch >> 4) | (1u << 14);        // SBO = next 8 input channels
             const uint32_t a_lbo = (128u >> 4) << 16;                                   // LBO = next x-row of the 16x8 dy tile
@@ -696,6 +839,7 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_c
             const uint32_t dy16 = ptx::smem_u32(dyst) >> 4, dystage16 = (uint32_t)p.dy_bytes >> 4;
             const uint32_t sl16 = ptx::smem_u32(slabs) >> 4, slab16 = (uint32_t)p.slab_bytes >> 4;
             const int khw = p.kh * p.kw;
+            const uint32_t idesc = p.idesc, a_rstep = (2 * (uint32_t)p.dy_row_pitch) >> 4, b_rstep = (uint32_t)(2 * p.WW);
             uint32_t ss = 0, sph = 0, ds = 0, dph = 0, started = 0;
             for (int item = split; item < p.items; item += p.splits) {
                 const WgItem c = wg_decode(p, item);
@@ -731,34 +875,44 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_c
                         for (int kk = 0; kk < 3; ++kk) if (kk == kz) sidx = slot[kk];
                         if (sidx < 0) continue;                            // plane outside the volume: zero contribution
                         const uint32_t d_tmem = tmem_base + (uint32_t)((tap - tap0) * p.NC);
-                        uint32_t a_lo = a_base;
-                        uint32_t b_lo = (((sl16 + (uint32_t)sidx * slab16) + (uint32_t)(ky * p.WW + kx)) & 0x3FFF) | b_lbo;
-                        uint32_t acc = (started >> (tap - tap0)) & 1;
+                        if (ptx::elect_one()) {
+                            uint32_t a_lo = a_base;
+                            uint32_t b_lo = (((sl16 + (uint32_t)sidx * slab16) + (uint32_t)(ky * p.WW + kx)) & 0x3FFF) | b_lbo;
+                            uint32_t acc = (started >> (tap - tap0)) & 1;
 #pragma unroll
-                        for (int r = 0; r < kTileH / 2; ++r) {              // two x-rows (16 voxels) per MMA
-                            ptx::umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, p.idesc, acc);
-                            a_lo += (2 * 128) >> 4;
-                            b_lo += (uint32_t)(2 * p.WW);
-                            acc = 1;
+                            for (int r = 0; r < kTileH / 2; ++r) {          // two x-rows (16 voxels) per MMA
+                                ptx::umma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, acc);
+                                a_lo += a_rstep;
+                                b_lo += b_rstep;
+                                acc = 1;
+                            }
                         }
+                        __syncwarp();
                         started |= 1u << (tap - tap0);
                     }
-                    ptx::umma_commit(ptx::smem_u32(&bars->dy_empty[ds]));
-                    if (++ds == (uint32_t)p.ndy) { ds = 0; dph ^= 1; }
-                    // the oldest plane of the window is not needed by z+1 (for kd == 1 that is the only plane)
-                    if (slot[0] >= 0) ptx::umma_commit(slot_bar[0]);
-                    if (z + 1 == c.z1) {                                   // end of the column segment: release the rest
+                    if (ptx::elect_one()) {
+                        ptx::umma_commit(ptx::smem_u32(&bars->dy_empty[ds]));
+                        // the oldest plane of the window is not needed by z+1 (for kd == 1 that is the only plane)
+                        if (slot[0] >= 0) ptx::umma_commit(slot_bar[0]);
+                        if (z + 1 == c.z1) {                               // end of the column segment: release the rest
 #pragma unroll
-                        for (int k = 1; k < 3; ++k) if (k < p.kd && slot[k] >= 0) ptx::umma_commit(slot_bar[k]);
+                            for (int k = 1; k < 3; ++k) if (k < p.kd && slot[k] >= 0) ptx::umma_commit(slot_bar[k]);
+                        }
                     }
+                    __syncwarp();
+                    if (++ds == (uint32_t)p.ndy) { ds = 0; dph ^= 1; }
                 }
             }
-            bars->started = started;
-            __threadfence_block();
-            ptx::umma_commit(ptx::smem_u32(&bars->done));
+            if (ptx::elect_one()) {
+                bars->started = started;
+                __threadfence_block();
+                ptx::umma_commit(ptx::smem_u32(&bars->done));
+            }
+            __syncwarp();
         }
     } else {
         // ===================================================== epilogue (once): TMEM -> fp32 partial[split][tap][co][ci]
+        __syncwarp();
         const int lane_grp = warp & 3;
         const int row = lane_grp * 32 + lane;                               // co inside the chunk
         ptx::mbar_wait(ptx::smem_u32(&bars->done), 0);
@@ -787,7 +941,7 @@ conv_wgrad_umma_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_c
         ptx::tc_fence_before();
     }
     __syncthreads();
-    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+    if (warp == 4) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
 }
 
 // dw[(co*Ci + ci)*taps + tap] = sum_s partial[s][tap][co][ci]
@@ -834,10 +988,12 @@ inline int wgrad_plan(const b200_conv_desc* d, WgradParams* p, size_t* smem_byte
     B200_REQUIRE(pow2 <= 512, "umma wgrad: accumulators do not fit TMEM");
     p->tmem_cols = pow2;
     p->HH = kTileH + d->kh - 1; p->WW = kTileW + d->kw - 1;
-    p->slab_cg_pitch = ((p->HH * p->WW * 16) + 127) & ~127;
-    p->slab_bytes = (p->NC / 8) * p->slab_cg_pitch;
-    p->dy_cg_pitch = 128 * 16;
-    p->dy_bytes = (p->MC / 8) * p->dy_cg_pitch;
+    p->use_tma = staging_uses_tma() ? 1 : 0;
+    p->slab_cg_pitch = p->use_tma ? ((p->HH * p->WW * 16) + 127) & ~127 : p->HH * p->WW * 16 + 16;
+    p->slab_bytes = (((p->NC / 8) * p->slab_cg_pitch) + 127) & ~127;
+    p->dy_row_pitch = kTileW * 16;
+    p->dy_cg_pitch = p->use_tma ? 128 * 16 : 128 * 16 + 16;
+    p->dy_bytes = (((p->MC / 8) * p->dy_cg_pitch) + 127) & ~127;
     const size_t budget = 227 * 1024 - sizeof(WgradBarriers) - 1024;
     p->ndy = 3; p->nslabs = d->kd + 3;
     while (p->nslabs > d->kd + 1 && (size_t)p->ndy * p->dy_bytes + (size_t)p->nslabs * p->slab_bytes > budget) --p->nslabs;
@@ -900,6 +1056,8 @@ inline int umma_wgrad_run(const b200_conv_desc* d, const void* x, const void* dy
     if (wgrad_plan(d, &p, &smem_bytes, &partial_bytes)) return 1;
     B200_REQUIRE(ws_bytes >= umma_wgrad_workspace_bytes(d), "umma wgrad: workspace too small");
     p.partial = (float*)workspace;
+    p.x = (const __nv_bfloat16*)x;
+    p.dy = (const __nv_bfloat16*)dy;
     CUtensorMap x_map, dy_map;
     if (make_act_map(&x_map, x, d->Ci, d->Wi, d->Hi, (int64_t)d->N * d->Di, p.WW, p.HH)) return 1;
     if (make_act_map(&dy_map, dy, d->Co, d->Wo, d->Ho, (int64_t)d->N * d->Do, kTileW, kTileH)) return 1;
