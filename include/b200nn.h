@@ -37,7 +37,7 @@ enum { B200_ACT_NONE = 0, B200_ACT_RELU = 1, B200_ACT_LEAKY = 2 };
 enum { B200_NORM_BATCH = 0, B200_NORM_INSTANCE = 1, B200_NORM_GROUP = 2 };
 enum { B200_UP_NEAREST = 0, B200_UP_TRILINEAR = 1, B200_UP_TRILINEAR_ALIGNED = 2 };
 enum { B200_PASS_FWD = 0, B200_PASS_DGRAD = 1, B200_PASS_WGRAD = 2 };
-enum { B200_ALGO_SIMT = 0, B200_ALGO_UMMA = 1 };
+enum { B200_ALGO_SIMT = 0, B200_ALGO_UMMA = 1, B200_ALGO_ROW = 2 };
 
 int b200_version(void);
 const char* b200_last_error(void);

@@ -15,7 +15,7 @@ ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 NORM_BATCH, NORM_INSTANCE, NORM_GROUP = 0, 1, 2
 UP_NEAREST, UP_TRILINEAR, UP_TRILINEAR_ALIGNED = 0, 1, 2
 PASS_FWD, PASS_DGRAD, PASS_WGRAD = 0, 1, 2
-ALGO_SIMT, ALGO_UMMA = 0, 1
+ALGO_SIMT, ALGO_UMMA, ALGO_ROW = 0, 1, 2
 
 i32, i64, f32, vp, sz = C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_size_t
 

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "conv_simt.cuh"
 #include "conv_umma.cuh"
+#include "conv_row.cuh"
 #include "elementwise.cuh"
 #include "norm.cuh"
 #include "patches.cuh"
@@ -21,6 +22,12 @@ uint64_t b200_launch_count(void) { return launch_counter().load(); }
 
 // ============================================================================ convolution
 namespace {
+
+// B200_CONV_V1=1 keeps the first-generation 16x8-tile tcgen05 kernels (A/B comparison in tools/ and tests)
+bool force_umma_v1() {
+    static const bool v = [] { const char* e = getenv("B200_CONV_V1"); return e != nullptr && e[0] == '1'; }();
+    return v;
+}
 
 struct ConvPlan {
     GatherGeom g;          // geometry of the gather for this pass
@@ -150,6 +157,7 @@ extern "C" {
 
 int b200_conv_algo(const b200_conv_desc* d, int pass) {
     if (d == nullptr || conv_validate(d) != 0) return B200_ALGO_SIMT;
+    if (pass == B200_PASS_WGRAD && row_wgrad_supported(d) && !force_umma_v1()) return B200_ALGO_ROW;
     return umma_conv_supported(d, pass) ? B200_ALGO_UMMA : B200_ALGO_SIMT;
 }
 
@@ -174,6 +182,7 @@ int b200_conv_pack_weights(const b200_conv_desc* d, int pass, const float* w, vo
 
 size_t b200_conv_workspace_bytes(const b200_conv_desc* d, int pass) {
     if (d == nullptr || conv_validate(d)) return 0;
+    if (b200_conv_algo(d, pass) == B200_ALGO_ROW) return pass == B200_PASS_WGRAD ? row_wgrad_workspace_bytes(d) : 0;
     if (b200_conv_algo(d, pass) == B200_ALGO_UMMA) return umma_workspace_bytes(d, pass);
     if (pass != B200_PASS_WGRAD) return 0;
     const ConvPlan p = conv_plan(d, pass);
@@ -205,6 +214,7 @@ int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const void* dy, floa
     if (conv_validate(d)) return 1;
     B200_REQUIRE(x && dy && dw, "conv_wgrad: null pointer");
     B200_REQUIRE(ws_bytes >= b200_conv_workspace_bytes(d, B200_PASS_WGRAD) && workspace != nullptr, "conv_wgrad: workspace too small");
+    if (b200_conv_algo(d, B200_PASS_WGRAD) == B200_ALGO_ROW) return row_wgrad_run(d, x, dy, dw, dbias, workspace, ws_bytes, stream);
     if (b200_conv_algo(d, B200_PASS_WGRAD) == B200_ALGO_UMMA) return umma_wgrad_run(d, x, dy, dw, dbias, workspace, ws_bytes, stream);
     const ConvPlan p = conv_plan(d, B200_PASS_WGRAD);
     const WgradSplit s = wgrad_split(d, p);

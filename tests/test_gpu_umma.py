@@ -60,7 +60,7 @@ def test_umma_conv_fwd_dgrad(B, case):
     cd, _ = mod._cfg().desc(xg, mod.weight, torch.bfloat16)
     assert B._cabi.lib().b200_conv_algo(ctypes.byref(cd), B._cabi.PASS_FWD) == B._cabi.ALGO_UMMA, "case is meant to hit the tcgen05 path"
     assert B._cabi.lib().b200_conv_algo(ctypes.byref(cd), B._cabi.PASS_DGRAD) == B._cabi.ALGO_UMMA
-    assert B._cabi.lib().b200_conv_algo(ctypes.byref(cd), B._cabi.PASS_WGRAD) == B._cabi.ALGO_UMMA
+    assert B._cabi.lib().b200_conv_algo(ctypes.byref(cd), B._cabi.PASS_WGRAD) in (B._cabi.ALGO_UMMA, B._cabi.ALGO_ROW)
     yg = mod(xg)
     yg.backward(gy.cuda().bfloat16())
     torch.cuda.synchronize()
