@@ -5,6 +5,7 @@
 #include "conv_simt.cuh"
 #include "conv_umma.cuh"
 #include "conv_row.cuh"
+#include "conv_rowf.cuh"
 #include "elementwise.cuh"
 #include "norm.cuh"
 #include "patches.cuh"
@@ -158,12 +159,13 @@ extern "C" {
 int b200_conv_algo(const b200_conv_desc* d, int pass) {
     if (d == nullptr || conv_validate(d) != 0) return B200_ALGO_SIMT;
     if (pass == B200_PASS_WGRAD && row_wgrad_supported(d) && !force_umma_v1()) return B200_ALGO_ROW;
+    if (pass != B200_PASS_WGRAD && !force_umma_v1() && row_fwd_supported(d, pass)) return B200_ALGO_ROW;
     return umma_conv_supported(d, pass) ? B200_ALGO_UMMA : B200_ALGO_SIMT;
 }
 
 size_t b200_conv_packed_bytes(const b200_conv_desc* d, int pass) {
     if (d == nullptr || pass == B200_PASS_WGRAD) return 0;
-    if (b200_conv_algo(d, pass) == B200_ALGO_UMMA) return umma_packed_bytes(d, pass);
+    if (b200_conv_algo(d, pass) != B200_ALGO_SIMT) return umma_packed_bytes(d, pass);
     const ConvPlan p = conv_plan(d, pass);
     return (size_t)p.taps * p.g.IC * p.g.OCp * sizeof(float);
 }
@@ -172,7 +174,7 @@ int b200_conv_pack_weights(const b200_conv_desc* d, int pass, const float* w, vo
     if (conv_validate(d)) return 1;
     B200_REQUIRE(pass == B200_PASS_FWD || pass == B200_PASS_DGRAD, "pack: pass must be FWD or DGRAD");
     B200_REQUIRE(w != nullptr && packed != nullptr, "pack: null pointer");
-    if (b200_conv_algo(d, pass) == B200_ALGO_UMMA) return umma_pack_weights(d, pass, w, packed, stream);
+    if (b200_conv_algo(d, pass) != B200_ALGO_SIMT) return umma_pack_weights(d, pass, w, packed, stream);
     const ConvPlan p = conv_plan(d, pass);
     const int64_t total = (int64_t)p.taps * p.g.IC * p.g.OCp;
     B200_LAUNCH(pack_weights_simt_kernel, stream_grid(total, 256), 256, 0, stream, d->Ci, d->Co, p.taps, p.param_is_ci_major, p.pass_swaps,
@@ -194,6 +196,7 @@ int b200_conv_fwd(const b200_conv_desc* d, const void* x, const void* w_packed, 
                   void* workspace, size_t ws_bytes, void* stream) {
     if (conv_validate(d)) return 1;
     B200_REQUIRE(x && w_packed && y, "conv_fwd: null pointer");
+    if (b200_conv_algo(d, B200_PASS_FWD) == B200_ALGO_ROW) return row_fwd_run(d, B200_PASS_FWD, x, w_packed, bias, y, nullptr, stream);
     if (b200_conv_algo(d, B200_PASS_FWD) == B200_ALGO_UMMA) return umma_conv_run(d, B200_PASS_FWD, x, w_packed, bias, y, workspace, ws_bytes, stream);
     const ConvPlan p = conv_plan(d, B200_PASS_FWD);
     return dispatch_gather(p, x, (const float*)w_packed, bias, y, stream);
@@ -203,6 +206,7 @@ int b200_conv_dgrad(const b200_conv_desc* d, const void* dy, const void* w_packe
                     void* workspace, size_t ws_bytes, void* stream) {
     if (conv_validate(d)) return 1;
     B200_REQUIRE(dy && w_packed_dgrad && dx, "conv_dgrad: null pointer");
+    if (b200_conv_algo(d, B200_PASS_DGRAD) == B200_ALGO_ROW) return row_fwd_run(d, B200_PASS_DGRAD, dy, w_packed_dgrad, nullptr, dx, nullptr, stream);
     if (b200_conv_algo(d, B200_PASS_DGRAD) == B200_ALGO_UMMA)
         return umma_conv_run(d, B200_PASS_DGRAD, dy, w_packed_dgrad, nullptr, dx, workspace, ws_bytes, stream);
     const ConvPlan p = conv_plan(d, B200_PASS_DGRAD);

@@ -1,0 +1,378 @@
+// "Row-slab" tcgen05 forward / dgrad convolution for sm_100a (second generation; conv_umma.cuh keeps the 16x8-tile kernel for
+// the shapes this one does not take).
+//
+// Shared-memory image of one input plane block: (YB + 2*ph) whole x-rows of the NDHWC tensor INCLUDING the x halo,
+//   [row][x = -pw .. W-1+pw][C channels],  C*2 = 32/64/128 bytes per voxel,
+// written by ONE TMA tensor load (box C x (W+2pw) x (YB+2ph) x 1, out-of-volume rows/columns zero-filled = the padding) in
+// the matching SWIZZLE_32B/64B/128B mode.  The image is a linear array of "slots" (slot = row*(W+2pw) + x + pw) and, read as a
+// K-major swizzled UMMA operand, ANY run of 128 consecutive slots is a valid A operand (probe: tools/desc_probe.cu T2).
+// An output tile is 128 consecutive OUTPUT slots; filter tap (kz,ky,kx) is the same run shifted by ky*(W+2pw) + kx slots in
+// the image of plane z+kz-pd: 27 descriptor start addresses, no im2col, every input byte staged once per plane block.
+// Slots that fall into the x halo produce garbage rows of D that are simply not stored.
+//   * planes stream through a ring along z (one new plane per output plane; 3 live for a 3x3x3 filter);
+//   * the packed weights of ALL taps stay resident in shared memory (this kernel takes the layers where they fit);
+//   * accumulators: T tiles x Cout fp32 columns of TMEM, two sets, so the epilogue of plane z overlaps the MMAs of z+1;
+//   * warp roles (192 threads): 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue (TMEM -> bf16 -> global,
+//     consecutive lanes = consecutive voxels = fully coalesced stores), optionally accumulating the per-channel sum / sum of
+//     squares of the outputs for the BatchNorm that follows (fp32, per-thread partials, one atomic flush per CTA).
+#pragma once
+#include "conv_row.cuh"
+
+namespace b200 {
+
+constexpr int kRfThreads = 192;
+constexpr int kRfRing = 4;
+constexpr int kRfMaxTiles = 16;
+
+struct RowFwdParams {
+    int N, D, H, W;              // output == input spatial size ("same" convolution, stride 1)
+    int IC, OC;
+    int kd, khw;                 // 1 or 3 each (kh == kw == khw); padding = k/2
+    int YB;                      // output rows per block
+    int pitchW;                  // W + 2*pw slots per image row
+    int tpr, rowstride;          // tile t starts at slot (t / tpr) * rowstride + (t % tpr) * 128
+    int T;                       // tiles per full block
+    int yblocks, zsegs, zs;
+    int items;
+    int plane_bytes, plane_tx;   // ring slot size (1024-byte multiple) / bytes one TMA box delivers
+    int w_bytes;                 // all packed weights
+    int tmem_cols;
+    uint32_t idesc;
+    const __nv_bfloat16* w;      // [tap][IC/8][OC][8]
+    const float* bias;           // [OC] or null
+    __nv_bfloat16* out;          // [N][D][H][W][OC]
+    float* stats;                // [2][OC] fp32 (sum, sum of squares), atomically accumulated; or null
+};
+
+struct alignas(128) RowFwdBarriers {
+    uint64_t pfull[kRfRing], pempty[kRfRing];
+    uint64_t wfull;
+    uint64_t afull[2], aempty[2];
+    uint32_t tmem_base;
+};
+
+struct RfItem { int n, y0, rows, z0, z1; };
+__device__ __forceinline__ RfItem rf_decode(const RowFwdParams& p, int item) {
+    RfItem c;
+    const int yb = item % p.yblocks; item /= p.yblocks;        // adjacent CTAs take adjacent row blocks: halo rows hit L2
+    const int zg = item % p.zsegs;
+    c.n = item / p.zsegs;
+    c.y0 = yb * p.YB;
+    c.rows = min(p.YB, p.H - c.y0);
+    c.z0 = zg * p.zs;
+    c.z1 = min(p.D, c.z0 + p.zs);
+    return c;
+}
+__device__ __forceinline__ int rf_tiles(const RowFwdParams& p, int rows) {
+    // tiles needed to cover output slots [0, (rows-1)*pitchW + W)
+    if (p.tpr < (1 << 20)) return rows * p.tpr;
+    return ((rows - 1) * p.pitchW + p.W + 127) >> 7;
+}
+
+template <int KD, int KHW, int NKS>
+__global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_constant__ CUtensorMap in_map, const RowFwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ RowFwdBarriers bars;
+    uint8_t* planes = smem;
+    uint8_t* wsm = smem + (size_t)kRfRing * p.plane_bytes;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int pd = KD / 2, ph = KHW / 2;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kRfRing; ++i) { ptx::mbar_init(ptx::smem_u32(&bars.pfull[i]), 1); ptx::mbar_init(ptx::smem_u32(&bars.pempty[i]), 1); }
+        ptx::mbar_init(ptx::smem_u32(&bars.wfull), 1);
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(ptx::smem_u32(&bars.afull[i]), 1); ptx::mbar_init(ptx::smem_u32(&bars.aempty[i]), 4); }
+        ptx::fence_barrier_init();
+        ptx::prefetch_tmap(&in_map);
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(ptx::smem_u32(&bars.tmem_base), (uint32_t)p.tmem_cols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = bars.tmem_base;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer: resident weights once, then the plane ring
+        if (lane == 0) {
+            const uint32_t wfull = ptx::smem_u32(&bars.wfull);
+            ptx::mbar_expect_tx(wfull, (uint32_t)p.w_bytes);
+            for (int off = 0; off < p.w_bytes; off += 32768) {
+                const int n = min(32768, p.w_bytes - off);
+                ptx::bulk_load(ptx::smem_u32(wsm + off), reinterpret_cast<const uint8_t*>(p.w) + off, (uint32_t)n, wfull);
+            }
+            uint32_t cnt = 0;
+            for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+                const RfItem c = rf_decode(p, item);
+                const int first = max(c.z0 - pd, 0), last = min(c.z1 - 1 + pd, p.D - 1);
+                for (int pl = first; pl <= last; ++pl, ++cnt) {
+                    const uint32_t s = cnt % kRfRing, phs = (cnt / kRfRing) & 1;
+                    ptx::mbar_wait(ptx::smem_u32(&bars.pempty[s]), phs ^ 1);
+                    const uint32_t full = ptx::smem_u32(&bars.pfull[s]);
+                    ptx::mbar_expect_tx(full, (uint32_t)p.plane_tx);
+                    ptx::tma_load_4d(ptx::smem_u32(planes + (size_t)s * p.plane_bytes), &in_map, full, 0, -ph, c.y0 - ph, c.n * p.D + pl);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer (whole warp converged, one elected lane issues)
+        const uint32_t vox16 = ((uint32_t)p.IC * 2) >> 4;                       // 16-byte units per voxel
+        const uint32_t a_hi = ((8 * (uint32_t)p.IC * 2) >> 4) | (1u << 14) | (row_layout_bits(p.IC * 2) << 29);   // SBO = 8 voxels
+        const uint32_t b_hi = (128u >> 4) | (1u << 14);                          // SBO = next 8 output channels
+        const uint32_t b_lbo = ((uint32_t)p.OC) << 16;                           // LBO = next 8 input channels = OC*16 B
+        const uint32_t pl16 = ptx::smem_u32(planes) >> 4, plane16 = (uint32_t)p.plane_bytes >> 4;
+        const uint32_t w16 = ptx::smem_u32(wsm) >> 4;
+        const uint32_t row16 = (uint32_t)p.pitchW * vox16;
+        constexpr int nks = NKS;
+        const uint32_t wtap16 = ((uint32_t)p.IC * p.OC * 2) >> 4, wks16 = (2 * (uint32_t)p.OC * 16) >> 4;
+        const uint32_t idesc = p.idesc;
+        ptx::mbar_wait(ptx::smem_u32(&bars.wfull), 0);
+        uint32_t cnt = 0, group = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+            const RfItem c = rf_decode(p, item);
+            const int first = max(c.z0 - pd, 0), last = min(c.z1 - 1 + pd, p.D - 1);
+            const int ntiles = rf_tiles(p, c.rows);
+            int ready = first - 1;                                               // highest plane known to be resident
+            for (int z = c.z0; z < c.z1; ++z, ++group) {
+                const int need = min(z + pd, p.D - 1);
+                for (; ready < need; ++ready) {
+                    const uint32_t i = cnt + (uint32_t)(ready + 1 - first);
+                    ptx::mbar_wait(ptx::smem_u32(&bars.pfull[i % kRfRing]), (i / kRfRing) & 1);
+                }
+                const uint32_t set = group & 1;
+                ptx::mbar_wait(ptx::smem_u32(&bars.aempty[set]), ((group >> 1) & 1) ^ 1);
+                ptx::tc_fence_after();
+                // ring slot of plane z+kz-pd is (i0 + kz) & 3 (kRfRing == 4; unsigned wrap-around keeps this right for z < pd)
+                const uint32_t i0 = cnt + (uint32_t)(z - pd - first);
+                uint32_t hasmask = 0;
+#pragma unroll
+                for (int kz = 0; kz < KD; ++kz) { const int pl = z + kz - pd; if (pl >= 0 && pl < p.D) hasmask |= 1u << kz; }
+                if (ptx::elect_one()) {
+                    // The single issuing thread is the bottleneck of the whole SM: keep its loop a few instructions per MMA
+                    // and small enough for the instruction cache (a fully unrolled 27-tap body stalled on instruction fetch).
+                    uint32_t off[KHW * KHW];
+#pragma unroll
+                    for (int j = 0; j < KHW * KHW; ++j) off[j] = (uint32_t)(j / KHW) * row16 + (uint32_t)(j % KHW) * vox16;
+                    const uint32_t a_flag = 1u << 16;
+                    for (int t = 0; t < ntiles; ++t) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)((set * p.T + t) * p.OC);
+                        const uint32_t tile16 = (uint32_t)((t / p.tpr) * p.rowstride + (t % p.tpr) * 128) * vox16;
+                        uint32_t acc = 0;
+                        uint32_t bb = w16 | b_lbo;
+#pragma unroll 1
+                        for (int kz = 0; kz < KD; ++kz) {
+                            if (!((hasmask >> kz) & 1)) { bb += (uint32_t)(KHW * KHW) * wtap16; continue; }
+                            const uint32_t a0 = (pl16 + ((i0 + (uint32_t)kz) & (kRfRing - 1)) * plane16 + tile16) | a_flag;
+                            if (nks == 1) {
+#pragma unroll
+                                for (int j = 0; j < KHW * KHW; ++j) {
+                                    ptx::umma_bf16_lohi(d_tmem, a0 + off[j], a_hi, bb, b_hi, idesc, acc);
+                                    bb += wtap16; acc = 1;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < KHW * KHW; ++j) {
+                                    uint32_t a = a0 + off[j], b2 = bb;
+#pragma unroll
+                                    for (int ks = 0; ks < nks; ++ks) {
+                                        ptx::umma_bf16_lohi(d_tmem, a, a_hi, b2, b_hi, idesc, acc);
+                                        a += 2; b2 += wks16; acc = 1;
+                                    }
+                                    bb += wtap16;
+                                }
+                            }
+                        }
+                    }
+                    ptx::umma_commit(ptx::smem_u32(&bars.afull[set]));
+                    // plane z-pd is not needed by z+1; at the end of the segment release everything that is left
+                    const int lo = z - pd, hi = (z + 1 == c.z1) ? last : lo;
+                    for (int pl = max(lo, first); pl <= hi; ++pl) {
+                        const uint32_t i = cnt + (uint32_t)(pl - first);
+                        ptx::umma_commit(ptx::smem_u32(&bars.pempty[i % kRfRing]));
+                    }
+                }
+                __syncwarp();
+            }
+            cnt += (uint32_t)(last - first + 1);
+        }
+    } else {
+        // ===================================================== epilogue: TMEM -> (+bias) -> bf16 -> global (+ BN statistics)
+        const int lane_grp = warp & 3;
+        const int m = lane_grp * 32 + lane;
+        uint32_t group = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+            const RfItem c = rf_decode(p, item);
+            const int ntiles = rf_tiles(p, c.rows);
+            for (int z = c.z0; z < c.z1; ++z, ++group) {
+                const uint32_t set = group & 1;
+                ptx::mbar_wait(ptx::smem_u32(&bars.afull[set]), (group >> 1) & 1);
+                ptx::tc_fence_after();
+                const int64_t plane_vox = ((int64_t)c.n * p.D + z) * p.H;
+                for (int t = 0; t < ntiles; ++t) {
+                    const int slot = (t / p.tpr) * p.rowstride + (t % p.tpr) * 128 + m;
+                    const int row = slot / p.pitchW, x = slot - row * p.pitchW;
+                    const bool valid = x < p.W && row < c.rows;
+                    __nv_bfloat16* dst = p.out + ((plane_vox + c.y0 + row) * p.W + x) * p.OC;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)((set * p.T + t) * p.OC);
+                    for (int c0 = 0; c0 < p.OC; c0 += 16) {
+                        float v[16];
+                        ptx::tmem_ld16(taddr + (uint32_t)c0, v);
+                        if (p.bias != nullptr) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + c0 + i);
+                        }
+                        if (valid) {
+                            uint4 lo, hi;
+                            __nv_bfloat162* l2 = reinterpret_cast<__nv_bfloat162*>(&lo);
+                            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&hi);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                l2[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                                h2[i] = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+                            }
+                            *reinterpret_cast<uint4*>(dst + c0) = lo;
+                            *reinterpret_cast<uint4*>(dst + c0 + 8) = hi;
+                        }
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars.aempty[set]));
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct RowFwdGeom { int IC, OC, D, H, W, kd, khw; };
+
+inline bool row_fwd_geom(const b200_conv_desc* d, int pass, RowFwdGeom* g) {
+    if (!d->allow_umma || d->transposed) return false;
+    if (pass != B200_PASS_FWD && pass != B200_PASS_DGRAD) return false;
+    if (d->x_dtype != B200_BF16 || d->y_dtype != B200_BF16) return false;
+    if (d->sd != 1 || d->sh != 1 || d->sw != 1 || d->dd != 1 || d->dh != 1 || d->dw != 1) return false;
+    if (!((d->kd == 1 || d->kd == 3) && (d->kh == 1 || d->kh == 3) && d->kw == d->kh)) return false;
+    if (d->pd != d->kd / 2 || d->ph != d->kh / 2 || d->pw != d->kw / 2) return false;       // "same": dgrad has the same geometry
+    g->IC = pass == B200_PASS_FWD ? d->Ci : d->Co;
+    g->OC = pass == B200_PASS_FWD ? d->Co : d->Ci;
+    g->D = d->Di; g->H = d->Hi; g->W = d->Wi; g->kd = d->kd; g->khw = d->kh;
+    if (!(g->IC == 16 || g->IC == 32 || g->IC == 64)) return false;                          // one swizzle atom per voxel
+    if (g->OC % 16 || g->OC > 256) return false;
+    if (g->W + 2 * (g->khw / 2) > 256 || g->W < 8) return false;                             // TMA box limit
+    if ((size_t)d->kd * d->kh * d->kw * g->IC * g->OC * 2 > 64 * 1024) return false;         // weights must stay resident
+    if ((int64_t)d->N * g->D * g->H * g->W < 4096) return false;                             // tiny problems: launch-bound either way
+    return true;
+}
+
+inline int row_fwd_plan(const RowFwdGeom& g, int N, RowFwdParams* p, size_t* smem_bytes) {
+    memset(p, 0, sizeof *p);
+    p->N = N; p->D = g.D; p->H = g.H; p->W = g.W; p->IC = g.IC; p->OC = g.OC; p->kd = g.kd; p->khw = g.khw;
+    const int ph = g.khw / 2, pd = g.kd / 2;
+    p->pitchW = g.W + 2 * ph;
+    const bool per_row = (g.W % 128) == 0;
+    p->tpr = per_row ? g.W / 128 : (1 << 30);
+    p->rowstride = per_row ? p->pitchW : 0;
+    p->w_bytes = g.kd * g.khw * g.khw * g.IC * g.OC * 2;
+    const size_t budget = 227 * 1024 - 2048 - (size_t)p->w_bytes;
+    int maxT = 256 / g.OC;
+    if (maxT > kRfMaxTiles) maxT = kRfMaxTiles;
+    // pick the row-block height: minimise (MMA tiles over the whole plane, counting the slots wasted in the x halo) x
+    // (rounds of the persistent grid), with a mild preference for tall blocks (fewer halo rows re-read)
+    int best = 0; double best_cost = 1e30; int best_zs = 1;
+    for (int YB = 1; YB <= 32 && YB <= g.H; ++YB) {
+        const int T = per_row ? YB * p->tpr : ((YB - 1) * p->pitchW + g.W + 127) / 128;
+        if (T > maxT) break;
+        const size_t pb = (((size_t)(YB + 2 * ph) * p->pitchW * g.IC * 2) + 1023) & ~(size_t)1023;
+        if ((size_t)kRfRing * pb > budget) break;
+        const int yblocks = (g.H + YB - 1) / YB;
+        const int rem = g.H - (yblocks - 1) * YB;
+        const int Trem = per_row ? rem * p->tpr : ((rem - 1) * p->pitchW + g.W + 127) / 128;
+        const double tiles_per_plane = (double)(yblocks - 1) * T + Trem;
+        for (int zs = g.D; zs >= 1; zs = (zs > 4 ? (zs + 1) / 2 : zs - 1)) {
+            if (g.kd == 1 && zs != 1) continue;
+            const int zsegs = (g.D + zs - 1) / zs;
+            const int64_t items = (int64_t)N * yblocks * zsegs;
+            const double rounds = (double)((items + kNumSMs - 1) / kNumSMs);
+            // per-item MMA work ~ zs * T; loads ~ (zs + 2pd) planes of (YB + 2ph) rows (weight 0.15: mostly hidden)
+            const double cost = rounds * (zs * (double)T + 0.15 * (zs + 2 * pd) * (double)(YB + 2 * ph) * p->pitchW / 128.0);
+            if (cost < best_cost) { best_cost = cost; best = YB; best_zs = zs; }
+            (void)tiles_per_plane;
+        }
+    }
+    B200_REQUIRE(best >= 1, "row fwd: a row block does not fit shared memory / TMEM");
+    p->YB = best;
+    p->T = per_row ? best * p->tpr : ((best - 1) * p->pitchW + g.W + 127) / 128;
+    p->plane_tx = (best + 2 * ph) * p->pitchW * g.IC * 2;
+    p->plane_bytes = (p->plane_tx + 1023) & ~1023;
+    p->yblocks = (g.H + best - 1) / best;
+    p->zs = best_zs;
+    p->zsegs = (g.D + p->zs - 1) / p->zs;
+    const int64_t items = (int64_t)N * p->yblocks * p->zsegs;
+    B200_REQUIRE(items < (1ll << 31), "row fwd: too many items");
+    p->items = (int)items;
+    int cols = 2 * p->T * g.OC, pow2 = 32;
+    while (pow2 < cols) pow2 <<= 1;
+    B200_REQUIRE(pow2 <= 512, "row fwd: accumulators do not fit TMEM");
+    p->tmem_cols = pow2;
+    p->idesc = make_idesc_bf16(g.OC);
+    // + 1 KB manual alignment; the last tile's taps over-read at most 2 rows + 2 voxels past the last plane slot: the
+    // resident weights follow the ring, so the over-read stays inside the allocation
+    *smem_bytes = (size_t)kRfRing * p->plane_bytes + (size_t)p->w_bytes + 1024;
+    return 0;
+}
+
+inline bool row_fwd_supported(const b200_conv_desc* d, int pass) {
+    RowFwdGeom g;
+    if (!row_fwd_geom(d, pass, &g)) return false;
+    RowFwdParams p; size_t smem;
+    const std::string saved = err_slot();
+    const bool ok = row_fwd_plan(g, d->N, &p, &smem) == 0;
+    err_slot() = saved;
+    return ok;
+}
+
+template <int KD, int KHW, int NKS>
+inline int row_fwd_launch(const CUtensorMap& map, const RowFwdParams& p, size_t smem_bytes, void* stream) {
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(row_fwd_kernel<KD, KHW, NKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024); });
+    B200_REQUIRE(attr_err == cudaSuccess, "row fwd: cannot raise the dynamic shared memory limit: %s", cudaGetErrorString(attr_err));
+    const int grid = p.items < kNumSMs ? p.items : kNumSMs;
+    B200_LAUNCH((row_fwd_kernel<KD, KHW, NKS>), grid, kRfThreads, smem_bytes, stream, map, p);
+    return 0;
+}
+
+// `stats` (optional): fp32 [2][OC], must be zeroed by the caller; receives sum / sum of squares of the fp32 outputs
+inline int row_fwd_run(const b200_conv_desc* d, int pass, const void* in, const void* w_packed, const float* bias, void* out, float* stats,
+                       void* stream) {
+    RowFwdGeom g;
+    B200_REQUIRE(row_fwd_geom(d, pass, &g), "row fwd: unsupported descriptor");
+    B200_REQUIRE(aligned16(in) && aligned16(out) && aligned16(w_packed), "row fwd: pointers must be 16-byte aligned");
+    RowFwdParams p;
+    size_t smem_bytes = 0;
+    if (row_fwd_plan(g, d->N, &p, &smem_bytes)) return 1;
+    p.w = (const __nv_bfloat16*)w_packed; p.bias = bias; p.out = (__nv_bfloat16*)out; p.stats = stats;
+    const int ph = g.khw / 2;
+    CUtensorMap map;
+    if (make_row_map(&map, in, g.IC, g.W, g.H, (int64_t)d->N * g.D, g.IC, p.pitchW, p.YB + 2 * ph)) return 1;
+#define B200_RF_CASE(KD_, KHW_)                                                                              \
+    if (g.kd == KD_ && g.khw == KHW_) {                                                                      \
+        if (g.IC == 16) return row_fwd_launch<KD_, KHW_, 1>(map, p, smem_bytes, stream);                     \
+        if (g.IC == 32) return row_fwd_launch<KD_, KHW_, 2>(map, p, smem_bytes, stream);                     \
+        return row_fwd_launch<KD_, KHW_, 4>(map, p, smem_bytes, stream);                                     \
+    }
+    B200_RF_CASE(3, 3)
+    B200_RF_CASE(1, 3)
+    B200_RF_CASE(3, 1)
+    B200_RF_CASE(1, 1)
+#undef B200_RF_CASE
+    return fail("row fwd: unreachable");
+}
+
+}  // namespace b200
