@@ -3,6 +3,7 @@
 
 #include "common.cuh"
 #include "conv_simt.cuh"
+#include "conv_small.cuh"
 #include "conv_umma.cuh"
 #include "conv_row.cuh"
 #include "conv_rowf.cuh"
@@ -187,6 +188,8 @@ size_t b200_conv_workspace_bytes(const b200_conv_desc* d, int pass) {
     if (b200_conv_algo(d, pass) == B200_ALGO_ROW) return pass == B200_PASS_WGRAD ? row_wgrad_workspace_bytes(d) : 0;
     if (b200_conv_algo(d, pass) == B200_ALGO_UMMA) return umma_workspace_bytes(d, pass);
     if (pass != B200_PASS_WGRAD) return 0;
+    if (stem3_supported(d)) return stem3_wgrad_ws_bytes(d) + 256;
+    if (head_supported(d)) return head_wgrad_ws_bytes(d) + 256;
     const ConvPlan p = conv_plan(d, pass);
     const WgradSplit s = wgrad_split(d, p);
     return s.partial_bytes + s.bias_bytes + 256;
@@ -198,6 +201,8 @@ int b200_conv_fwd(const b200_conv_desc* d, const void* x, const void* w_packed, 
     B200_REQUIRE(x && w_packed && y, "conv_fwd: null pointer");
     if (b200_conv_algo(d, B200_PASS_FWD) == B200_ALGO_ROW) return row_fwd_run(d, B200_PASS_FWD, x, w_packed, bias, y, nullptr, stream);
     if (b200_conv_algo(d, B200_PASS_FWD) == B200_ALGO_UMMA) return umma_conv_run(d, B200_PASS_FWD, x, w_packed, bias, y, workspace, ws_bytes, stream);
+    if (stem3_supported(d)) return stem3_fwd_run(d, x, (const float*)w_packed, bias, y, stream);
+    if (head_supported(d)) return head_fwd_run(d, x, (const float*)w_packed, bias, y, stream);
     const ConvPlan p = conv_plan(d, B200_PASS_FWD);
     return dispatch_gather(p, x, (const float*)w_packed, bias, y, stream);
 }
@@ -209,6 +214,7 @@ int b200_conv_dgrad(const b200_conv_desc* d, const void* dy, const void* w_packe
     if (b200_conv_algo(d, B200_PASS_DGRAD) == B200_ALGO_ROW) return row_fwd_run(d, B200_PASS_DGRAD, dy, w_packed_dgrad, nullptr, dx, nullptr, stream);
     if (b200_conv_algo(d, B200_PASS_DGRAD) == B200_ALGO_UMMA)
         return umma_conv_run(d, B200_PASS_DGRAD, dy, w_packed_dgrad, nullptr, dx, workspace, ws_bytes, stream);
+    if (head_supported(d)) return head_dgrad_run(d, dy, (const float*)w_packed_dgrad, dx, stream);
     const ConvPlan p = conv_plan(d, B200_PASS_DGRAD);
     return dispatch_gather(p, dy, (const float*)w_packed_dgrad, nullptr, dx, stream);
 }
@@ -220,6 +226,8 @@ int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const void* dy, floa
     B200_REQUIRE(ws_bytes >= b200_conv_workspace_bytes(d, B200_PASS_WGRAD) && workspace != nullptr, "conv_wgrad: workspace too small");
     if (b200_conv_algo(d, B200_PASS_WGRAD) == B200_ALGO_ROW) return row_wgrad_run(d, x, dy, dw, dbias, workspace, ws_bytes, stream);
     if (b200_conv_algo(d, B200_PASS_WGRAD) == B200_ALGO_UMMA) return umma_wgrad_run(d, x, dy, dw, dbias, workspace, ws_bytes, stream);
+    if (stem3_supported(d)) return stem3_wgrad_run(d, x, dy, dw, dbias, workspace, stream);
+    if (head_supported(d)) return head_wgrad_run(d, x, dy, dw, dbias, workspace, stream);
     const ConvPlan p = conv_plan(d, B200_PASS_WGRAD);
     const WgradSplit s = wgrad_split(d, p);
     float* partial = (float*)workspace;
@@ -233,7 +241,7 @@ int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const void* dy, floa
     else rc = launch_wgrad<float, __nv_bfloat16>(p, s, gathered, second, partial, stream);
     if (rc) return rc;
     const int64_t total = (int64_t)p.taps * p.g.IC * p.g.OC;
-    B200_LAUNCH(conv_wgrad_reduce_kernel, stream_grid(total, 256), 256, 0, stream, s.splits, p.taps, p.g.IC, p.g.OC, p.g.OCp, d->Ci, d->Co,
+    B200_LAUNCH(conv_wgrad_reduce_kernel, stream_grid(total * 32, 256), 256, 0, stream, s.splits, p.taps, p.g.IC, p.g.OC, p.g.OCp, d->Ci, d->Co,
                 p.param_is_ci_major, p.gathered_is_ci, partial, dw);
     if (dbias != nullptr) {
         float* bpart = (float*)((char*)workspace + ((s.partial_bytes + 255) & ~(size_t)255));
@@ -285,7 +293,7 @@ int b200_norm_stats(const b200_norm_desc* d, const void* x, float* mean, float* 
     B200_DISPATCH_T(d->dtype, T, {
         if (g.V == 1) B200_LAUNCH((norm_stats_partial_kernel<T, 1>), grid, 256, smem, stream, (const T*)x, d->C, g.R, g.rows_per_chunk, partial);
         else B200_LAUNCH((norm_stats_partial_kernel<T, Vec16<T>::N>), grid, 256, smem, stream, (const T*)x, d->C, g.R, g.rows_per_chunk, partial);
-        B200_LAUNCH(norm_stats_finalize_kernel<T>, (int)ceil_div(g.groups, 128), 128, 0, stream, (const T*)x, d->N, d->C, d->S, d->kind, d->G,
+        B200_LAUNCH(norm_stats_finalize_kernel<T>, (int)ceil_div(g.groups, 8), 256, 0, stream, (const T*)x, d->N, d->C, d->S, d->kind, d->G,
                     g.chunks, g.R, partial, d->eps, d->momentum, mean, rstd, running_mean, running_var);
     });
     return 0;
@@ -355,7 +363,7 @@ int b200_norm_bwd_reduce(const b200_norm_desc* d, const void* x, const void* y, 
         else B200_LAUNCH((norm_bwd_partial_kernel<T, Vec16<T>::N>), grid, 256, smem, stream, (const T*)x, (const T*)y, (const T*)dy, mean, rstd, d->C,
                          g.R, g.rows_per_chunk, d->kind, d->G, d->act, d->slope, w.partial);
     });
-    B200_LAUNCH(norm_bwd_sum_kernel, (int)ceil_div((int64_t)g.NB * d->C, 128), 128, 0, stream, g.NB, d->C, g.chunks, w.partial, sums);
+    B200_LAUNCH(norm_bwd_sum_kernel, (int)ceil_div((int64_t)g.NB * d->C, 8), 256, 0, stream, g.NB, d->C, g.chunks, w.partial, sums);
     return 0;
 }
 

@@ -303,20 +303,25 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(GatherGeom g, const TI*
     }
 }
 
-// dw(param layout) = sum over splits of partial[split][tap*IC+ic][oc] (fixed order -> deterministic)
+// dw(param layout) = sum over splits of partial[split][tap*IC+ic][oc]; one WARP per element, fixed order -> deterministic
 //   gathered_is_ci: 1 when the gathered tensor carries the parameter's Ci channels (conv: x), 0 when Co (convT: dy)
-__global__ void conv_wgrad_reduce_kernel(int splits, int taps, int IC, int OC, int OCp, int Ci, int Co, int param_is_ci_major,
-                                         int gathered_is_ci, const float* __restrict__ partial, float* __restrict__ dw) {
+__global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(int splits, int taps, int IC, int OC, int OCp, int Ci, int Co, int param_is_ci_major,
+                                                                int gathered_is_ci, const float* __restrict__ partial, float* __restrict__ dw) {
     const int64_t K = (int64_t)taps * IC, total = K * OC;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t e = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); e < total; e += (int64_t)gridDim.x * (blockDim.x >> 5)) {
         const int oc = (int)(e % OC);
         const int64_t k = e / OC;
         const int ic = (int)(k % IC), tap = (int)(k / IC);
         float acc = 0.f;
-        for (int s = 0; s < splits; ++s) acc += partial[((int64_t)s * K + k) * OCp + oc];
-        const int ci = gathered_is_ci ? ic : oc, co = gathered_is_ci ? oc : ic;
-        const int64_t dst = param_is_ci_major ? ((int64_t)ci * Co + co) * taps + tap : ((int64_t)co * Ci + ci) * taps + tap;
-        dw[dst] = acc;
+        for (int s = lane; s < splits; s += 32) acc += partial[((int64_t)s * K + k) * OCp + oc];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            const int ci = gathered_is_ci ? ic : oc, co = gathered_is_ci ? oc : ic;
+            const int64_t dst = param_is_ci_major ? ((int64_t)ci * Co + co) * taps + tap : ((int64_t)co * Ci + ci) * taps + tap;
+            dw[dst] = acc;
+        }
     }
 }
 

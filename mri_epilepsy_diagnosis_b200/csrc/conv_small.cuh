@@ -1,0 +1,403 @@
+// HBM-bound convolutions that are not GEMM-shaped enough for tcgen05: the Cin = 1 stems (3x3x3, pad 1) and the
+// 1x1x1 heads with a handful of output channels (segmentation logits).  Direct CUDA-core kernels, fp32 accumulation:
+//   stem fwd    thread = 2 output voxels x all CO channels; 27 coalesced input reads per voxel (L1-resident halo), weights
+//               broadcast from shared memory as float4, 32-byte bf16 stores            (algorithmic bytes: 4|2 + 2*CO per voxel)
+//   stem wgrad  lane = (output channel, row); each half-warp walks one x-row with a 3x3x3 sliding window in registers
+//               (9 new broadcast loads + 27 FMAs per voxel and lane), block partials, fixed-order final sum
+//   head fwd    Cin/8 lanes per voxel, one 16-byte load each, shuffle reduction         (2*Cin + 4*CO bytes per voxel)
+//   head dgrad  the same lane mapping, 16-byte stores
+//   head wgrad  per-lane CO x 8 accumulators over a grid-stride voxel loop, shuffle + shared-memory + fixed-order final sum
+// Weight operands use the SIMT packing of conv_simt.cuh (fp32 [tap*IC + ic][OCp]), so callers are unaffected.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+template <typename T> __device__ __forceinline__ float ldg_f(const T* p);
+template <> __device__ __forceinline__ float ldg_f<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ldg_f<__nv_bfloat16>(const __nv_bfloat16* p) {
+    return __bfloat162float(__ushort_as_bfloat16(__ldg(reinterpret_cast<const unsigned short*>(p))));
+}
+
+// ------------------------------------------------------------------------------------------------ stem forward
+// x [N][D][H][W] (one channel), w fp32 [27][CO], y bf16 [N][D][H][W][CO]
+template <typename TX, int CO>
+__global__ void __launch_bounds__(256) stem3_fwd_kernel(const TX* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                        __nv_bfloat16* __restrict__ y, int N, int D, int H, int W) {
+    __shared__ __align__(16) float ws[27 * CO];
+    for (int i = threadIdx.x; i < 27 * CO; i += 256) ws[i] = w[i];
+    __syncthreads();
+    const int64_t V = (int64_t)N * D * H * W;
+    for (int64_t v0 = (int64_t)blockIdx.x * 512 + threadIdx.x; v0 < V; v0 += (int64_t)gridDim.x * 512) {
+        float acc[2][CO];
+        int64_t vv[2] = {v0, v0 + 256};
+        int xx[2], yy[2], zz[2];
+        const TX* base[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            int64_t r = vv[u] < V ? vv[u] : V - 1;
+            xx[u] = (int)(r % W); r /= W;
+            yy[u] = (int)(r % H); r /= H;
+            zz[u] = (int)(r % D);
+            base[u] = x + (r / D) * (int64_t)D * H * W;
+#pragma unroll
+            for (int c = 0; c < CO; ++c) acc[u][c] = bias != nullptr ? __ldg(bias + c) : 0.f;
+        }
+#pragma unroll
+        for (int kz = 0; kz < 3; ++kz)
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    float in[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int z = zz[u] + kz - 1, yq = yy[u] + ky - 1, xq = xx[u] + kx - 1;
+                        const bool ok = (unsigned)z < (unsigned)D && (unsigned)yq < (unsigned)H && (unsigned)xq < (unsigned)W;
+                        in[u] = ok ? ldg_f<TX>(base[u] + ((int64_t)z * H + yq) * W + xq) : 0.f;
+                    }
+                    const float4* wt = reinterpret_cast<const float4*>(ws + ((kz * 3 + ky) * 3 + kx) * CO);
+#pragma unroll
+                    for (int q = 0; q < CO / 4; ++q) {
+                        const float4 f = wt[q];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            acc[u][4 * q + 0] = fmaf(in[u], f.x, acc[u][4 * q + 0]);
+                            acc[u][4 * q + 1] = fmaf(in[u], f.y, acc[u][4 * q + 1]);
+                            acc[u][4 * q + 2] = fmaf(in[u], f.z, acc[u][4 * q + 2]);
+                            acc[u][4 * q + 3] = fmaf(in[u], f.w, acc[u][4 * q + 3]);
+                        }
+                    }
+                }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (vv[u] >= V) continue;
+            __nv_bfloat16* dst = y + vv[u] * CO;
+#pragma unroll
+            for (int q = 0; q < CO / 8; ++q) {
+                uint4 pk;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(acc[u][8 * q + 2 * i], acc[u][8 * q + 2 * i + 1]);
+                *reinterpret_cast<uint4*>(dst + 8 * q) = pk;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ stem wgrad
+// partial[block][CO][28]: 27 taps + the bias gradient; dy bf16 [N][D][H][W][CO]
+template <typename TX, int CO>
+__global__ void __launch_bounds__(256) stem3_wgrad_kernel(const TX* __restrict__ x, const __nv_bfloat16* __restrict__ dy, float* __restrict__ partial,
+                                                          int N, int D, int H, int W) {
+    constexpr int RPW = 32 / CO;                 // rows walked concurrently by one warp
+    __shared__ float red[8][CO][28];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int co = lane % CO, sub = lane / CO;
+    float acc[28];
+#pragma unroll
+    for (int i = 0; i < 28; ++i) acc[i] = 0.f;
+    const int64_t rows = (int64_t)N * D * H;
+    const int64_t walkers = (int64_t)gridDim.x * 8 * RPW;
+    for (int64_t row = ((int64_t)blockIdx.x * 8 + warp) * RPW + sub; row < rows; row += walkers) {
+        const int yq = (int)(row % H);
+        const int zq = (int)((row / H) % D);
+        const int64_t n = row / ((int64_t)H * D);
+        const TX* rp[9];
+        bool rok[9];
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+            const int z = zq + r / 3 - 1, yy = yq + r % 3 - 1;
+            rok[r] = (unsigned)z < (unsigned)D && (unsigned)yy < (unsigned)H;
+            rp[r] = x + ((n * D + (rok[r] ? z : 0)) * H + (rok[r] ? yy : 0)) * (int64_t)W;
+        }
+        float win[9][3];
+#pragma unroll
+        for (int r = 0; r < 9; ++r) { win[r][0] = 0.f; win[r][1] = 0.f; win[r][2] = rok[r] ? ldg_f<TX>(rp[r]) : 0.f; }
+        const __nv_bfloat16* g = dy + row * (int64_t)W * CO + co;
+        for (int xq = 0; xq < W; ++xq) {
+#pragma unroll
+            for (int r = 0; r < 9; ++r) {
+                win[r][0] = win[r][1]; win[r][1] = win[r][2];
+                win[r][2] = (rok[r] && xq + 1 < W) ? ldg_f<TX>(rp[r] + xq + 1) : 0.f;
+            }
+            const float gv = ldg_f<__nv_bfloat16>(g + (int64_t)xq * CO);
+#pragma unroll
+            for (int r = 0; r < 9; ++r)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) acc[r * 3 + k] = fmaf(gv, win[r][k], acc[r * 3 + k]);
+            acc[27] += gv;
+        }
+    }
+    // lanes with the same co (different sub-rows) -> one value per warp, then across the 8 warps in a fixed order
+#pragma unroll
+    for (int i = 0; i < 28; ++i) {
+        float v = acc[i];
+#pragma unroll
+        for (int o = CO; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (sub == 0) red[warp][co][i] = v;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < CO * 28; e += 256) {
+        float s = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < 8; ++wq) s += (&red[wq][0][0])[e];
+        partial[(int64_t)blockIdx.x * CO * 28 + e] = s;
+    }
+}
+
+// dw[co*27 + tap] / dbias[co] = sum over blocks (one warp per element, fixed order)
+__global__ void __launch_bounds__(256) stem3_wgrad_reduce_kernel(const float* __restrict__ partial, int blocks, int CO, float* __restrict__ dw,
+                                                                 float* __restrict__ dbias) {
+    const int e = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (e >= CO * 28) return;
+    double s = 0.0;
+    for (int b = lane; b < blocks; b += 32) s += (double)partial[(int64_t)b * CO * 28 + e];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        const int co = e / 28, i = e % 28;
+        if (i < 27) dw[co * 27 + i] = (float)s;
+        else if (dbias != nullptr) dbias[co] = (float)s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ 1x1x1 heads (few outputs)
+// x bf16 [V][CI]; w fp32 [CI][OCp] (OCp = CO rounded up to 4); y [V][CO] (fp32 or bf16)
+template <typename TY, int CO>
+__global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                       TY* __restrict__ y, int64_t V, int CI) {
+    const int LPV = CI / 8, OCp = (CO + 3) & ~3;
+    const int lane = threadIdx.x & 31, j = lane % LPV;
+    float wr[CO][8], bv[CO];
+#pragma unroll
+    for (int c = 0; c < CO; ++c) {
+        bv[c] = bias != nullptr ? __ldg(bias + c) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) wr[c][k] = __ldg(w + (int64_t)(j * 8 + k) * OCp + c);
+    }
+    const int64_t total = V * LPV;               // one 16-byte chunk per thread and step
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i - lane < total; i += (int64_t)gridDim.x * 256) {
+        float xv[8];
+        const bool ok = i < total;
+        if (ok) Pack<__nv_bfloat16, 8>::load(x + i * 8, xv);
+        else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) xv[k] = 0.f;
+        }
+        float s[CO];
+#pragma unroll
+        for (int c = 0; c < CO; ++c) {
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a = fmaf(xv[k], wr[c][k], a);
+            for (int o = 1; o < LPV; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            s[c] = a + bv[c];
+        }
+        if (ok && j == 0) {
+            TY* dst = y + (i / LPV) * CO;
+#pragma unroll
+            for (int c = 0; c < CO; ++c) dst[c] = from_f<TY>(s[c]);
+        }
+    }
+}
+
+// dx[v][ci] = sum_co dy[v][co] * w[co][ci];  w fp32 [CO(ic)][OCp = CI]  (the SIMT dgrad packing)
+template <typename TY, int CO>
+__global__ void __launch_bounds__(256) head_dgrad_kernel(const TY* __restrict__ dy, const float* __restrict__ w, __nv_bfloat16* __restrict__ dx,
+                                                         int64_t V, int CI, int OCp) {
+    const int LPV = CI / 8;
+    const int j = (int)(((int64_t)blockIdx.x * 256 + threadIdx.x) % LPV);       // gridDim.x*256 is a multiple of LPV
+    float wr[CO][8];
+#pragma unroll
+    for (int c = 0; c < CO; ++c)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) wr[c][k] = __ldg(w + (int64_t)c * OCp + j * 8 + k);
+    const int64_t total = V * LPV;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int64_t v = i / LPV;
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = 0.f;
+#pragma unroll
+        for (int c = 0; c < CO; ++c) {
+            const float g = to_f<TY>(dy[v * CO + c]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = fmaf(g, wr[c][k], o[k]);
+        }
+        Pack<__nv_bfloat16, 8>::store(dx + i * 8, o);
+    }
+}
+
+// partial[block][CO][CI + 1]: dw[co][ci] and (last column) dbias[co]
+template <typename TY, int CO>
+__global__ void __launch_bounds__(256) head_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const TY* __restrict__ dy, float* __restrict__ partial,
+                                                         int64_t V, int CI) {
+    extern __shared__ float red[];               // [8 warps][CO][CI + 1]
+    const int LPV = CI / 8, stride_c = CI + 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = (int)(((int64_t)blockIdx.x * 256 + threadIdx.x) % LPV);
+    float acc[CO][8], accb[CO];
+#pragma unroll
+    for (int c = 0; c < CO; ++c) {
+        accb[c] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[c][k] = 0.f;
+    }
+    const int64_t total = V * LPV;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int64_t v = i / LPV;
+        float xv[8];
+        Pack<__nv_bfloat16, 8>::load(x + i * 8, xv);
+#pragma unroll
+        for (int c = 0; c < CO; ++c) {
+            const float g = to_f<TY>(dy[v * CO + c]);
+            accb[c] += g;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[c][k] = fmaf(g, xv[k], acc[c][k]);
+        }
+    }
+    // lanes j, j+LPV, ... hold the same channels
+#pragma unroll
+    for (int c = 0; c < CO; ++c) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float a = acc[c][k];
+            for (int o = LPV; o < 32; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane < LPV) red[(warp * CO + c) * stride_c + j * 8 + k] = a;
+        }
+        float b = accb[c];
+        for (int o = LPV; o < 32; o <<= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+        if (lane == 0) red[(warp * CO + c) * stride_c + CI] = b;       // every chunk lane saw every voxel once: take lane 0's
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < CO * stride_c; e += 256) {
+        float s = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < 8; ++wq) s += red[wq * CO * stride_c + e];
+        partial[(int64_t)blockIdx.x * CO * stride_c + e] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256) head_wgrad_reduce_kernel(const float* __restrict__ partial, int blocks, int CO, int CI, float* __restrict__ dw,
+                                                                float* __restrict__ dbias) {
+    const int e = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int stride_c = CI + 1;
+    if (e >= CO * stride_c) return;
+    double s = 0.0;
+    for (int b = lane; b < blocks; b += 32) s += (double)partial[(int64_t)b * CO * stride_c + e];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        const int co = e / stride_c, ci = e % stride_c;
+        if (ci < CI) dw[co * CI + ci] = (float)s;
+        else if (dbias != nullptr) dbias[co] = (float)s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+inline bool stem3_supported(const b200_conv_desc* d) {
+    return !d->transposed && d->Ci == 1 && (d->Co == 8 || d->Co == 16 || d->Co == 32) && d->kd == 3 && d->kh == 3 && d->kw == 3 && d->sd == 1 &&
+           d->sh == 1 && d->sw == 1 && d->pd == 1 && d->ph == 1 && d->pw == 1 && d->dd == 1 && d->dh == 1 && d->dw == 1 && d->y_dtype == B200_BF16;
+}
+inline bool head_supported(const b200_conv_desc* d) {
+    if (d->transposed || d->kd != 1 || d->kh != 1 || d->kw != 1 || d->sd != 1 || d->sh != 1 || d->sw != 1 || d->pd || d->ph || d->pw) return false;
+    if (d->x_dtype != B200_BF16 || d->Co < 1 || d->Co > 5) return false;
+    const int lpv = d->Ci / 8;
+    return d->Ci % 8 == 0 && lpv >= 1 && lpv <= 32 && (lpv & (lpv - 1)) == 0;
+}
+constexpr int kSmallBlocks = kNumSMs * 4;
+inline size_t stem3_wgrad_ws_bytes(const b200_conv_desc* d) { return (size_t)kSmallBlocks * d->Co * 28 * 4; }
+inline size_t head_wgrad_ws_bytes(const b200_conv_desc* d) { return (size_t)kSmallBlocks * d->Co * (d->Ci + 1) * 4; }
+
+#define B200_STEM_CO(CO_, ...)                                 \
+    do {                                                       \
+        if ((CO_) == 8) { constexpr int CO = 8; __VA_ARGS__; }  \
+        else if ((CO_) == 16) { constexpr int CO = 16; __VA_ARGS__; } \
+        else { constexpr int CO = 32; __VA_ARGS__; }            \
+    } while (0)
+#define B200_HEAD_CO(CO_, ...)                                 \
+    do {                                                       \
+        switch (CO_) {                                         \
+            case 1: { constexpr int CO = 1; __VA_ARGS__; } break; \
+            case 2: { constexpr int CO = 2; __VA_ARGS__; } break; \
+            case 3: { constexpr int CO = 3; __VA_ARGS__; } break; \
+            case 4: { constexpr int CO = 4; __VA_ARGS__; } break; \
+            default: { constexpr int CO = 5; __VA_ARGS__; } break; \
+        }                                                      \
+    } while (0)
+
+inline int stem3_fwd_run(const b200_conv_desc* d, const void* x, const float* w, const float* bias, void* y, void* stream) {
+    const int64_t V = (int64_t)d->N * d->Di * d->Hi * d->Wi;
+    const int grid = (int)(ceil_div(V, 512) < kNumSMs * 8 ? ceil_div(V, 512) : kNumSMs * 8);
+    B200_STEM_CO(d->Co, {
+        if (d->x_dtype == B200_F32)
+            B200_LAUNCH((stem3_fwd_kernel<float, CO>), grid, 256, 0, stream, (const float*)x, w, bias, (__nv_bfloat16*)y, d->N, d->Di, d->Hi, d->Wi);
+        else
+            B200_LAUNCH((stem3_fwd_kernel<__nv_bfloat16, CO>), grid, 256, 0, stream, (const __nv_bfloat16*)x, w, bias, (__nv_bfloat16*)y, d->N, d->Di,
+                        d->Hi, d->Wi);
+    });
+    return 0;
+}
+
+inline int stem3_wgrad_run(const b200_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias, void* workspace, void* stream) {
+    float* partial = (float*)workspace;
+    const int64_t rows = (int64_t)d->N * d->Di * d->Hi;
+    B200_STEM_CO(d->Co, {
+        const int64_t need = ceil_div(rows, 8 * (32 / CO));
+        const int grid = (int)(need < kSmallBlocks ? need : kSmallBlocks);
+        if (d->x_dtype == B200_F32)
+            B200_LAUNCH((stem3_wgrad_kernel<float, CO>), grid, 256, 0, stream, (const float*)x, (const __nv_bfloat16*)dy, partial, d->N, d->Di, d->Hi,
+                        d->Wi);
+        else
+            B200_LAUNCH((stem3_wgrad_kernel<__nv_bfloat16, CO>), grid, 256, 0, stream, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, partial, d->N,
+                        d->Di, d->Hi, d->Wi);
+        B200_LAUNCH(stem3_wgrad_reduce_kernel, (int)ceil_div(CO * 28, 8), 256, 0, stream, partial, grid, CO, dw, dbias);
+    });
+    return 0;
+}
+
+inline int head_grid(int64_t V, int lpv) {
+    int64_t need = ceil_div(V * lpv, 256 * 4);
+    if (need > kSmallBlocks) need = kSmallBlocks;
+    if (need < 1) need = 1;
+    return (int)need;                            // 256 threads per block is a multiple of every lpv (power of two <= 32)
+}
+
+inline int head_fwd_run(const b200_conv_desc* d, const void* x, const float* w, const float* bias, void* y, void* stream) {
+    const int64_t V = (int64_t)d->N * d->Di * d->Hi * d->Wi;
+    const int grid = head_grid(V, d->Ci / 8);
+    B200_HEAD_CO(d->Co, {
+        if (d->y_dtype == B200_F32) B200_LAUNCH((head_fwd_kernel<float, CO>), grid, 256, 0, stream, (const __nv_bfloat16*)x, w, bias, (float*)y, V, d->Ci);
+        else B200_LAUNCH((head_fwd_kernel<__nv_bfloat16, CO>), grid, 256, 0, stream, (const __nv_bfloat16*)x, w, bias, (__nv_bfloat16*)y, V, d->Ci);
+    });
+    return 0;
+}
+
+inline int head_dgrad_run(const b200_conv_desc* d, const void* dy, const float* w, void* dx, void* stream) {
+    const int64_t V = (int64_t)d->N * d->Di * d->Hi * d->Wi;
+    const int grid = head_grid(V, d->Ci / 8);
+    const int OCp = (d->Ci + 3) & ~3;
+    B200_HEAD_CO(d->Co, {
+        if (d->y_dtype == B200_F32) B200_LAUNCH((head_dgrad_kernel<float, CO>), grid, 256, 0, stream, (const float*)dy, w, (__nv_bfloat16*)dx, V, d->Ci, OCp);
+        else B200_LAUNCH((head_dgrad_kernel<__nv_bfloat16, CO>), grid, 256, 0, stream, (const __nv_bfloat16*)dy, w, (__nv_bfloat16*)dx, V, d->Ci, OCp);
+    });
+    return 0;
+}
+
+inline int head_wgrad_run(const b200_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias, void* workspace, void* stream) {
+    const int64_t V = (int64_t)d->N * d->Di * d->Hi * d->Wi;
+    const int grid = head_grid(V, d->Ci / 8);
+    float* partial = (float*)workspace;
+    const size_t smem = (size_t)8 * d->Co * (d->Ci + 1) * sizeof(float);
+    B200_HEAD_CO(d->Co, {
+        if (d->y_dtype == B200_F32)
+            B200_LAUNCH((head_wgrad_kernel<float, CO>), grid, 256, smem, stream, (const __nv_bfloat16*)x, (const float*)dy, partial, V, d->Ci);
+        else
+            B200_LAUNCH((head_wgrad_kernel<__nv_bfloat16, CO>), grid, 256, smem, stream, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, partial, V, d->Ci);
+        B200_LAUNCH(head_wgrad_reduce_kernel, (int)ceil_div(CO * (d->Ci + 1), 8), 256, 0, stream, partial, grid, CO, d->Ci, dw, dbias);
+    });
+    return 0;
+}
+
+}  // namespace b200

@@ -88,14 +88,21 @@ __global__ void __launch_bounds__(256) norm_stats_partial_kernel(const T* __rest
     }
 }
 
-// one thread per (mean, rstd) entry
+// fixed-order (deterministic) warp reduction in double
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// one WARP per (mean, rstd) entry: the lanes split the per-block partials, the combination order is fixed
 template <typename T>
-__global__ void norm_stats_finalize_kernel(const T* __restrict__ x, int N, int C, int64_t S, int kind, int G, int chunks, int64_t R,
-                                           const float* __restrict__ partial, float eps, float momentum,
-                                           float* __restrict__ mean, float* __restrict__ rstd,
-                                           float* __restrict__ running_mean, float* __restrict__ running_var) {
+__global__ void __launch_bounds__(256) norm_stats_finalize_kernel(const T* __restrict__ x, int N, int C, int64_t S, int kind, int G, int chunks, int64_t R,
+                                                                  const float* __restrict__ partial, float eps, float momentum,
+                                                                  float* __restrict__ mean, float* __restrict__ rstd,
+                                                                  float* __restrict__ running_mean, float* __restrict__ running_var) {
     const int groups = kind == B200_NORM_BATCH ? C : kind == B200_NORM_INSTANCE ? N * C : N * G;
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (g >= groups) return;
     int nb, c0, c1;
     if (kind == B200_NORM_BATCH) { nb = 0; c0 = g; c1 = g + 1; }
@@ -104,10 +111,11 @@ __global__ void norm_stats_finalize_kernel(const T* __restrict__ x, int N, int C
     double m_acc = 0.0, e2_acc = 0.0;
     for (int c = c0; c < c1; ++c) {
         double s = 0.0, q = 0.0;
-        for (int k = 0; k < chunks; ++k) {
+        for (int k = lane; k < chunks; k += 32) {
             s += (double)partial[(((int64_t)nb * chunks + k) * 2 + 0) * C + c];
             q += (double)partial[(((int64_t)nb * chunks + k) * 2 + 1) * C + c];
         }
+        s = warp_sum_d(s); q = warp_sum_d(q);
         const double K = (double)to_f<T>(x[(int64_t)nb * R * C + c]);
         const double ms = s / (double)R;
         const double mc = K + ms;
@@ -116,6 +124,7 @@ __global__ void norm_stats_finalize_kernel(const T* __restrict__ x, int N, int C
         m_acc += mc;
         e2_acc += vc + mc * mc;
     }
+    if (lane != 0) return;
     const int nc = c1 - c0;
     const double m = m_acc / nc;
     double var = e2_acc / nc - m * m;
@@ -221,18 +230,21 @@ __global__ void __launch_bounds__(256) norm_bwd_partial_kernel(const T* __restri
     }
 }
 
-// AB[(nb*C + c)*2 + {0,1}] = sum over chunks
-__global__ void norm_bwd_sum_kernel(int NB, int C, int chunks, const float* __restrict__ partial, float* __restrict__ AB) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// AB[(nb*C + c)*2 + {0,1}] = sum over chunks; one WARP per (nb, c)
+__global__ void __launch_bounds__(256) norm_bwd_sum_kernel(int NB, int C, int chunks, const float* __restrict__ partial, float* __restrict__ AB) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= NB * C) return;
     const int nb = i / C, c = i % C;
     double a = 0.0, b = 0.0;
-    for (int k = 0; k < chunks; ++k) {
+    for (int k = lane; k < chunks; k += 32) {
         a += (double)partial[(((int64_t)nb * chunks + k) * 2 + 0) * C + c];
         b += (double)partial[(((int64_t)nb * chunks + k) * 2 + 1) * C + c];
     }
-    AB[(int64_t)i * 2] = (float)a;
-    AB[(int64_t)i * 2 + 1] = (float)b;
+    a = warp_sum_d(a); b = warp_sum_d(b);
+    if (lane == 0) {
+        AB[(int64_t)i * 2] = (float)a;
+        AB[(int64_t)i * 2 + 1] = (float)b;
+    }
 }
 
 // coef[(nb*C + c)*3 + {0,1,2}] : dx = k1*dy' + k4*x + k5 ; also dgamma/dbeta (thread nb==0 sums over nb)

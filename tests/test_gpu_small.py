@@ -1,0 +1,86 @@
+"""Direct CUDA-core kernels for the HBM-bound convolutions (conv_small.cuh): Cin=1 3x3x3 stems and 1x1x1 heads with a few
+output channels, against the CPU oracle (torch fp32 conv on the same bf16-rounded operands).
+Tolerances: bf16 stored outputs rel <= 1e-2; fp32 outputs / fp32 parameter gradients rel <= 1e-4."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def B():
+    import mri_epilepsy_diagnosis_b200 as pkg
+    pkg._cabi.lib()
+    return pkg
+
+
+@pytest.mark.parametrize("co", [8, 16, 32])
+@pytest.mark.parametrize("xdtype", [torch.float32, torch.bfloat16], ids=["x_fp32", "x_bf16"])
+@pytest.mark.parametrize("size", [(5, 7, 9), (4, 16, 33), (3, 6, 128)], ids=["odd", "w33", "w128"])
+def test_stem_fwd_wgrad(B, co, xdtype, size):
+    g = torch.Generator().manual_seed(co + size[2])
+    ref = torch.nn.Conv3d(1, co, 3, 1, 1, bias=True)
+    mod = B.nn.Conv3d(1, co, 3, 1, 1, bias=True).cuda()
+    mod.load_state_dict(ref.state_dict())
+    mod.compute_dtype = torch.bfloat16
+    x = torch.randn(2, 1, *size, generator=g)
+    if xdtype == torch.bfloat16:
+        x = x.bfloat16().float()
+    yr = ref(x)
+    gy = torch.randn(yr.shape, generator=g).bfloat16().float()
+    yr.backward(gy)
+    y = mod(x.cuda().to(xdtype))
+    assert y.dtype == torch.bfloat16
+    y.backward(gy.cuda().bfloat16())
+    assert rel_err(y.float(), yr) < 1e-2, "forward"
+    assert rel_err(mod.weight.grad, ref.weight.grad) < 1e-4, "wgrad"       # fp32 accumulation of exact bf16/fp32 products
+    assert rel_err(mod.bias.grad, ref.bias.grad) < 1e-4, "bias grad"
+    mod.zero_grad()
+    mod(x.cuda().to(xdtype)).backward(gy.cuda().bfloat16())
+    first = mod.weight.grad.clone()
+    mod.zero_grad()
+    mod(x.cuda().to(xdtype)).backward(gy.cuda().bfloat16())
+    assert torch.equal(first, mod.weight.grad), "wgrad must be run-to-run deterministic"
+
+
+@pytest.mark.parametrize("ci", [8, 16, 32, 64, 128, 256])
+@pytest.mark.parametrize("co,out_dtype", [(2, torch.float32), (1, torch.float32), (4, torch.float32), (5, torch.bfloat16), (3, torch.bfloat16)])
+def test_head_fwd_dgrad_wgrad(B, ci, co, out_dtype):
+    g = torch.Generator().manual_seed(ci * 7 + co)
+    ref = torch.nn.Conv3d(ci, co, 1, bias=True)
+    mod = B.nn.Conv3d(ci, co, 1, bias=True).cuda()
+    mod.load_state_dict(ref.state_dict())
+    mod.compute_dtype, mod.out_dtype = torch.bfloat16, out_dtype
+    x = torch.randn(2, ci, 5, 9, 11, generator=g).bfloat16().float()
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    gy = torch.randn(yr.shape, generator=g)
+    if out_dtype == torch.bfloat16:
+        gy = gy.bfloat16().float()
+    yr.backward(gy)
+    xg = x.cuda().bfloat16().requires_grad_(True)
+    y = mod(xg)
+    assert y.dtype == out_dtype
+    y.backward(gy.cuda().to(out_dtype))
+    assert rel_err(y.float(), yr) < (1e-4 if out_dtype == torch.float32 else 1e-2), "forward"
+    assert rel_err(xg.grad.float(), xr.grad) < 1e-2, "dgrad (bf16 stored)"
+    assert rel_err(mod.weight.grad, ref.weight.grad) < 1e-4, "wgrad"
+    assert rel_err(mod.bias.grad, ref.bias.grad) < 1e-4, "bias grad"
+
+
+def test_head_argmax_bit_exact_on_ties(B):
+    """segmentation/routine.py:226 argmax(dim=1): equal logits must stay equal (first channel wins) -- identical rows of the
+    head weight give bit-identical fp32 logits from the fused dot product."""
+    mod = B.nn.Conv3d(32, 2, 1, bias=True).cuda()
+    with torch.no_grad():
+        mod.weight[1].copy_(mod.weight[0])
+        mod.bias[1].copy_(mod.bias[0])
+    mod.compute_dtype, mod.out_dtype = torch.bfloat16, torch.float32
+    x = torch.randn(1, 32, 4, 8, 16, generator=torch.Generator().manual_seed(0)).cuda().bfloat16()
+    y = mod(x)
+    assert torch.equal(y[:, 0], y[:, 1])
+    assert int(y.argmax(dim=1).sum()) == 0
