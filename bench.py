@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sync-bn", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="do not capture the step in a CUDA graph (launch-bound at this size)")
     ap.add_argument("--profile-json", default=None, help="write the per-layer conv timing table here")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -185,22 +186,25 @@ def main():
     net, model_desc = build_model(pkg, args.model)
     sync = (None, world) if (args.sync_bn and world > 1) else None
     net = pkg.convert(net.to(dev).train(), dtype=torch.bfloat16, sync=sync)
-    opt = torch.optim.AdamW(net.parameters())
-    bucket = None
-    if world > 1:
-        pkg.dp.broadcast_parameters(net)
-        bucket = pkg.dp.attach(net, opt)
+    opt = torch.optim.AdamW(net.parameters(), capturable=not args.eager)
     xh, th = synthetic_batch(args.batch, args.size, seed=rank)
     xh, th = xh.pin_memory(), th.pin_memory()
     xd, td = xh.to(dev), th.to(dev)
     voxels = xh.numel()
+    if world > 1:
+        pkg.dp.broadcast_parameters(net)
+    if args.eager:
+        bucket = pkg.dp.attach(net, opt) if world > 1 else None
 
-    def step(x, t):
-        opt.zero_grad()
-        loss = dice_loss_mean(net(x), t)
-        loss.backward()
-        opt.step()
-        return loss
+        def step(x, t):
+            opt.zero_grad()
+            loss = dice_loss_mean(net(x), t)
+            loss.backward()
+            opt.step()
+            return loss
+    else:
+        # the loop body of segmentation/routine.py:266-281 captured once in a CUDA graph and replayed (graphed.py)
+        step = pkg.graphed.GraphedTrainStep(net, dice_loss_mean, opt, xd, td)
 
     def barrier():
         if dist is not None:
@@ -223,28 +227,35 @@ def main():
             ms = float(tms)
         return ms, t0, time.time()
 
+    launches_a = pkg.launch_count()
+    if not args.eager:       # kernels of one step = kernels enqueued by one eager execution of the same body
+        step._body(eager=True)
+    launches_per_step = pkg.launch_count() - launches_a
     for _ in range(max(3, args.warmup)):
         step(xd, td)
     sampler = ClockSampler(local) if rank == 0 else None
     time.sleep(0.3)
     launches0 = pkg.launch_count()
     ms, t0, t1 = timed(lambda: step(xd, td), args.steps)
-    launches = pkg.launch_count() - launches0
+    launches = (pkg.launch_count() - launches0) if args.eager else launches_per_step * args.steps
     clocks = sampler.summary(t0, t1) if sampler else None
 
     # end to end: host (pinned) inputs in, host scalar out, every step
     def e2e_step():
+        if not args.eager:          # pinned host batch -> the graph's static input buffers -> replay -> host scalar
+            return float(step(xh, th))
         x = xh.to(dev, non_blocking=True)
         t = th.to(dev, non_blocking=True)
         return float(step(x, t))
     e2e_step()
     ms_e2e, _, _ = timed(e2e_step, args.steps)
 
-    # roofline leg: per-launch CUDA events around every conv kernel over another K steps
+    # roofline leg: per-launch CUDA events around every conv kernel over another K (eager) steps
+    eager_step = step if args.eager else (lambda x, t: step._body(eager=True))
     BF.PROFILE = []
     torch.cuda.synchronize()
     for _ in range(args.steps):
-        step(xd, td)
+        eager_step(xd, td)
     torch.cuda.synchronize()
     rows, BF.PROFILE = BF.PROFILE, None
     agg = {}
@@ -276,7 +287,7 @@ def main():
         return
     out = {**base, "value": world * voxels / (ms / 1e3), "ms_per_step": ms, "dtype": "bf16",
            "config": {"workload": workload, "model": model_desc, "global_batch": args.batch * world, "volume": [args.size] * 3,
-                      "parallelism": f"dp{world}" + ("+syncbn" if sync else ""),
+                      "parallelism": f"dp{world}" + ("+syncbn" if sync else ""), "launch": "eager" if args.eager else "cuda-graph replay of the step",
                       "l2": "inputs and every activation tensor (>= 268 MB each at 16ch x 128^3 x 4) exceed the 126 MB L2; no flush needed"},
            "e2e": {"value": world * voxels / (ms_e2e / 1e3), "unit": "voxels/s", "ms_per_step": ms_e2e,
                    "h2d_bytes_per_step": xh.numel() * 4 + th.numel() * 4, "d2h_bytes_per_step": 4},

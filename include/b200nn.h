@@ -73,6 +73,13 @@ size_t b200_conv_workspace_bytes(const b200_conv_desc* d, int pass);
 /* y = conv(x, w) + bias.  `bias` is fp32 [Co] or NULL. */
 int b200_conv_fwd(const b200_conv_desc* d, const void* x, const void* w_packed, const float* bias, void* y,
                   void* workspace, size_t ws_bytes, void* stream);
+/* Convolution + the statistics of the BatchNorm that follows (unet3d.py:42-46 conv->bn pairs), fused into the conv epilogue:
+ * `stat_partial` receives fp32 [chunks][2][Co] per-block (sum, sum of squares) of the fp32 outputs, chunks =
+ * b200_conv_stats_chunks(d) (0 = this descriptor has no fused-statistics kernel; use b200_norm_stats instead).
+ * Feed the partials to b200_norm_stats_from_partial. */
+int b200_conv_stats_chunks(const b200_conv_desc* d);
+int b200_conv_fwd_stats(const b200_conv_desc* d, const void* x, const void* w_packed, const float* bias, void* y,
+                        float* stat_partial, void* workspace, size_t ws_bytes, void* stream);
 /* dx = d(loss)/dx given dy (dtypes: dy has y_dtype, dx has x_dtype). */
 int b200_conv_dgrad(const b200_conv_desc* d, const void* dy, const void* w_packed_dgrad, void* dx,
                     void* workspace, size_t ws_bytes, void* stream);
@@ -105,6 +112,9 @@ typedef struct {
 size_t b200_norm_workspace_bytes(const b200_norm_desc* d);
 int b200_norm_stats(const b200_norm_desc* d, const void* x, float* mean, float* rstd,
                     float* running_mean, float* running_var, void* workspace, size_t ws_bytes, void* stream);
+/* BatchNorm batch statistics (and running update) from the partial sums written by b200_conv_fwd_stats */
+int b200_norm_stats_from_partial(const b200_norm_desc* d, const float* partial, int chunks, float* mean, float* rstd,
+                                 float* running_mean, float* running_var, void* stream);
 /* eval-mode BatchNorm: mean/rstd derived from the running statistics */
 int b200_norm_stats_from_running(const b200_norm_desc* d, const float* running_mean, const float* running_var,
                                  float* mean, float* rstd, void* stream);

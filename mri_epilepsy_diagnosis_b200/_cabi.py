@@ -52,10 +52,13 @@ _SIGS = {
     "b200_conv_pack_weights": (C.c_int, [P(ConvDesc), C.c_int, vp, vp, vp]),
     "b200_conv_workspace_bytes": (sz, [P(ConvDesc), C.c_int]),
     "b200_conv_fwd": (C.c_int, [P(ConvDesc), vp, vp, vp, vp, vp, sz, vp]),
+    "b200_conv_stats_chunks": (C.c_int, [P(ConvDesc)]),
+    "b200_conv_fwd_stats": (C.c_int, [P(ConvDesc), vp, vp, vp, vp, vp, vp, sz, vp]),
     "b200_conv_dgrad": (C.c_int, [P(ConvDesc), vp, vp, vp, vp, sz, vp]),
     "b200_conv_wgrad": (C.c_int, [P(ConvDesc), vp, vp, vp, vp, vp, sz, vp]),
     "b200_norm_workspace_bytes": (sz, [P(NormDesc)]),
     "b200_norm_stats": (C.c_int, [P(NormDesc), vp, vp, vp, vp, vp, vp, sz, vp]),
+    "b200_norm_stats_from_partial": (C.c_int, [P(NormDesc), vp, C.c_int, vp, vp, vp, vp, vp]),
     "b200_norm_stats_from_running": (C.c_int, [P(NormDesc), vp, vp, vp, vp, vp]),
     "b200_norm_apply": (C.c_int, [P(NormDesc), vp, vp, vp, vp, vp, vp, vp, vp]),
     "b200_norm_bwd": (C.c_int, [P(NormDesc), C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),

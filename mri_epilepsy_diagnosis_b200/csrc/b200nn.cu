@@ -207,6 +207,21 @@ int b200_conv_fwd(const b200_conv_desc* d, const void* x, const void* w_packed, 
     return dispatch_gather(p, x, (const float*)w_packed, bias, y, stream);
 }
 
+int b200_conv_stats_chunks(const b200_conv_desc* d) {
+    if (d == nullptr || conv_validate(d)) return 0;
+    if (b200_conv_algo(d, B200_PASS_FWD) != B200_ALGO_ROW) return 0;
+    return row_fwd_stats_chunks(d);
+}
+
+int b200_conv_fwd_stats(const b200_conv_desc* d, const void* x, const void* w_packed, const float* bias, void* y, float* stat_partial,
+                        void* workspace, size_t ws_bytes, void* stream) {
+    (void)workspace; (void)ws_bytes;
+    if (conv_validate(d)) return 1;
+    B200_REQUIRE(x && w_packed && y && stat_partial, "conv_fwd_stats: null pointer");
+    B200_REQUIRE(b200_conv_stats_chunks(d) > 0, "conv_fwd_stats: no fused-statistics kernel for this descriptor (check b200_conv_stats_chunks)");
+    return row_fwd_run(d, B200_PASS_FWD, x, w_packed, bias, y, stat_partial, stream);
+}
+
 int b200_conv_dgrad(const b200_conv_desc* d, const void* dy, const void* w_packed_dgrad, void* dx,
                     void* workspace, size_t ws_bytes, void* stream) {
     if (conv_validate(d)) return 1;
@@ -296,6 +311,16 @@ int b200_norm_stats(const b200_norm_desc* d, const void* x, float* mean, float* 
         B200_LAUNCH(norm_stats_finalize_kernel<T>, (int)ceil_div(g.groups, 8), 256, 0, stream, (const T*)x, d->N, d->C, d->S, d->kind, d->G,
                     g.chunks, g.R, partial, d->eps, d->momentum, mean, rstd, running_mean, running_var);
     });
+    return 0;
+}
+
+int b200_norm_stats_from_partial(const b200_norm_desc* d, const float* partial, int chunks, float* mean, float* rstd, float* running_mean,
+                                 float* running_var, void* stream) {
+    B200_REQUIRE(d && d->kind == B200_NORM_BATCH, "stats_from_partial: BatchNorm only");
+    B200_REQUIRE(partial && mean && rstd && chunks > 0, "stats_from_partial: null pointer");
+    const int64_t R = (int64_t)d->N * d->S;
+    B200_LAUNCH(norm_stats_finalize_kernel<float>, (int)ceil_div(d->C, 8), 256, 0, stream, (const float*)nullptr, d->N, d->C, d->S, d->kind, d->G, chunks, R,
+                partial, d->eps, d->momentum, mean, rstd, running_mean, running_var);
     return 0;
 }
 

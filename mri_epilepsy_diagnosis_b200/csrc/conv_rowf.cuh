@@ -23,6 +23,7 @@ namespace b200 {
 constexpr int kRfThreads = 192;
 constexpr int kRfRing = 4;
 constexpr int kRfMaxTiles = 16;
+constexpr int kRfMaxDynSmem = 227 * 1024 - 4096;      // 4 KB reserved for the kernel's static shared memory (barriers, statistics scratch)
 
 struct RowFwdParams {
     int N, D, H, W;              // output == input spatial size ("same" convolution, stride 1)
@@ -41,7 +42,7 @@ struct RowFwdParams {
     const __nv_bfloat16* w;      // [tap][IC/8][OC][8]
     const float* bias;           // [OC] or null
     __nv_bfloat16* out;          // [N][D][H][W][OC]
-    float* stats;                // [2][OC] fp32 (sum, sum of squares), atomically accumulated; or null
+    float* stats;                // [grid][2][OC] fp32 per-CTA (sum, sum of squares) of the outputs (OC <= 32); or null
 };
 
 struct alignas(128) RowFwdBarriers {
@@ -67,6 +68,19 @@ __device__ __forceinline__ int rf_tiles(const RowFwdParams& p, int rows) {
     // tiles needed to cover output slots [0, (rows-1)*pitchW + W)
     if (p.tpr < (1 << 20)) return rows * p.tpr;
     return ((rows - 1) * p.pitchW + p.W + 127) >> 7;
+}
+
+__device__ __forceinline__ void rf_store16(__nv_bfloat16* dst, const float (&v)[16]) {
+    uint4 lo, hi;
+    __nv_bfloat162* l2 = reinterpret_cast<__nv_bfloat162*>(&lo);
+    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&hi);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        l2[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        h2[i] = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+    }
+    *reinterpret_cast<uint4*>(dst) = lo;
+    *reinterpret_cast<uint4*>(dst + 8) = hi;
 }
 
 template <int KD, int KHW, int NKS>
@@ -202,6 +216,10 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
         // ===================================================== epilogue: TMEM -> (+bias) -> bf16 -> global (+ BN statistics)
         const int lane_grp = warp & 3;
         const int m = lane_grp * 32 + lane;
+        const bool want_stats = p.stats != nullptr;
+        float ssum[32], ssq[32];                                 // per-thread partial statistics (OC <= 32 when requested)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
         uint32_t group = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
             const RfItem c = rf_decode(p, item);
@@ -217,30 +235,59 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
                     const bool valid = x < p.W && row < c.rows;
                     __nv_bfloat16* dst = p.out + ((plane_vox + c.y0 + row) * p.W + x) * p.OC;
                     const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)((set * p.T + t) * p.OC);
-                    for (int c0 = 0; c0 < p.OC; c0 += 16) {
-                        float v[16];
-                        ptx::tmem_ld16(taddr + (uint32_t)c0, v);
-                        if (p.bias != nullptr) {
+                    if (p.OC <= 32) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + c0 + i);
-                        }
-                        if (valid) {
-                            uint4 lo, hi;
-                            __nv_bfloat162* l2 = reinterpret_cast<__nv_bfloat162*>(&lo);
-                            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&hi);
+                        for (int ch = 0; ch < 2; ++ch) {
+                            if (ch * 16 < p.OC) {
+                                float v[16];
+                                ptx::tmem_ld16(taddr + (uint32_t)(ch * 16), v);
+                                if (p.bias != nullptr) {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                l2[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-                                h2[i] = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+                                    for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + ch * 16 + i);
+                                }
+                                if (valid) {
+                                    rf_store16(dst + ch * 16, v);
+                                    if (want_stats) {
+#pragma unroll
+                                        for (int i = 0; i < 16; ++i) { ssum[ch * 16 + i] += v[i]; ssq[ch * 16 + i] = fmaf(v[i], v[i], ssq[ch * 16 + i]); }
+                                    }
+                                }
                             }
-                            *reinterpret_cast<uint4*>(dst + c0) = lo;
-                            *reinterpret_cast<uint4*>(dst + c0 + 8) = hi;
+                        }
+                    } else {
+                        for (int c0 = 0; c0 < p.OC; c0 += 16) {
+                            float v[16];
+                            ptx::tmem_ld16(taddr + (uint32_t)c0, v);
+                            if (p.bias != nullptr) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + c0 + i);
+                            }
+                            if (valid) rf_store16(dst + c0, v);
                         }
                     }
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars.aempty[set]));
+            }
+        }
+        if (want_stats) {
+            // per-CTA partial: lanes -> warp (shuffle), 4 warps -> CTA in a fixed order (deterministic); summed over CTAs by
+            // norm_stats_finalize_kernel in double
+            __shared__ float red[4][2][32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if (i < p.OC) {
+                    float a = ssum[i], b = ssq[i];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+                    if (lane == 0) { red[lane_grp][0][i] = a; red[lane_grp][1][i] = b; }
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (m < 2 * p.OC) {
+                const int which = m / p.OC, ch = m - which * p.OC;
+                p.stats[((size_t)blockIdx.x * 2 + which) * p.OC + ch] = (red[0][which][ch] + red[1][which][ch]) + (red[2][which][ch] + red[3][which][ch]);
             }
         }
     }
@@ -279,7 +326,7 @@ inline int row_fwd_plan(const RowFwdGeom& g, int N, RowFwdParams* p, size_t* sme
     p->tpr = per_row ? g.W / 128 : (1 << 30);
     p->rowstride = per_row ? p->pitchW : 0;
     p->w_bytes = g.kd * g.khw * g.khw * g.IC * g.OC * 2;
-    const size_t budget = 227 * 1024 - 2048 - (size_t)p->w_bytes;
+    const size_t budget = (size_t)kRfMaxDynSmem - 1024 - (size_t)p->w_bytes;
     int maxT = 256 / g.OC;
     if (maxT > kRfMaxTiles) maxT = kRfMaxTiles;
     // pick the row-block height: minimise (MMA tiles over the whole plane, counting the slots wasted in the x halo) x
@@ -341,19 +388,32 @@ template <int KD, int KHW, int NKS>
 inline int row_fwd_launch(const CUtensorMap& map, const RowFwdParams& p, size_t smem_bytes, void* stream) {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(row_fwd_kernel<KD, KHW, NKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024); });
+    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(row_fwd_kernel<KD, KHW, NKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRfMaxDynSmem); });
     B200_REQUIRE(attr_err == cudaSuccess, "row fwd: cannot raise the dynamic shared memory limit: %s", cudaGetErrorString(attr_err));
     const int grid = p.items < kNumSMs ? p.items : kNumSMs;
     B200_LAUNCH((row_fwd_kernel<KD, KHW, NKS>), grid, kRfThreads, smem_bytes, stream, map, p);
     return 0;
 }
 
-// `stats` (optional): fp32 [2][OC], must be zeroed by the caller; receives sum / sum of squares of the fp32 outputs
+// per-CTA statistics partials: chunks = CTAs of the launch; 0 when (desc, pass) cannot produce them
+inline int row_fwd_stats_chunks(const b200_conv_desc* d) {
+    RowFwdGeom g;
+    if (!row_fwd_geom(d, B200_PASS_FWD, &g) || g.OC > 32) return 0;
+    RowFwdParams p; size_t smem;
+    const std::string saved = err_slot();
+    const bool ok = row_fwd_plan(g, d->N, &p, &smem) == 0;
+    err_slot() = saved;
+    if (!ok) return 0;
+    return p.items < kNumSMs ? p.items : kNumSMs;
+}
+
+// `stats` (optional): fp32 [chunks][2][OC] per-CTA sum / sum of squares of the fp32 outputs (row_fwd_stats_chunks(d) > 0)
 inline int row_fwd_run(const b200_conv_desc* d, int pass, const void* in, const void* w_packed, const float* bias, void* out, float* stats,
                        void* stream) {
     RowFwdGeom g;
     B200_REQUIRE(row_fwd_geom(d, pass, &g), "row fwd: unsupported descriptor");
     B200_REQUIRE(aligned16(in) && aligned16(out) && aligned16(w_packed), "row fwd: pointers must be 16-byte aligned");
+    B200_REQUIRE(stats == nullptr || g.OC <= 32, "row fwd: fused statistics need Cout <= 32");
     RowFwdParams p;
     size_t smem_bytes = 0;
     if (row_fwd_plan(g, d->N, &p, &smem_bytes)) return 1;

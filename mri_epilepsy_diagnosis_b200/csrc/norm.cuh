@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) norm_stats_finalize_kernel(const T* __res
             q += (double)partial[(((int64_t)nb * chunks + k) * 2 + 1) * C + c];
         }
         s = warp_sum_d(s); q = warp_sum_d(q);
-        const double K = (double)to_f<T>(x[(int64_t)nb * R * C + c]);
+        const double K = x != nullptr ? (double)to_f<T>(x[(int64_t)nb * R * C + c]) : 0.0;     // null: unshifted partials (conv epilogue)
         const double ms = s / (double)R;
         const double mc = K + ms;
         double vc = q / (double)R - ms * ms;

@@ -133,7 +133,7 @@ class ConvConfig:
 
 class _ConvFn(Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, cfg, out_dtype):
+    def forward(ctx, x, weight, bias, cfg, out_dtype, want_stats):
         need_cuda(x, "conv")
         x = to_cl(x)
         cd, shape = cfg.desc(x, weight, out_dtype)
@@ -146,14 +146,26 @@ class _ConvFn(Function):
                 b = b.float()
         nws = lib().b200_conv_workspace_bytes(C.byref(cd), cabi.PASS_FWD)
         ws = _workspace(nws, x.device)
+        chunks = lib().b200_conv_stats_chunks(C.byref(cd)) if want_stats else 0
+        part = None
         with _Timed(cd, cabi.PASS_FWD):
-            check(lib().b200_conv_fwd(C.byref(cd), x.data_ptr(), wp.data_ptr(), ptr(b), y.data_ptr(), ws.data_ptr(), nws, stream()))
+            if chunks > 0:      # conv + the following BatchNorm's (sum, sum^2) partials in one kernel
+                part = torch.empty((chunks, 2, cd.Co), dtype=torch.float32, device=x.device)
+                check(lib().b200_conv_fwd_stats(C.byref(cd), x.data_ptr(), wp.data_ptr(), ptr(b), y.data_ptr(), part.data_ptr(), ws.data_ptr(), nws,
+                                                stream()))
+            else:
+                check(lib().b200_conv_fwd(C.byref(cd), x.data_ptr(), wp.data_ptr(), ptr(b), y.data_ptr(), ws.data_ptr(), nws, stream()))
         ctx.save_for_backward(x, weight)
         ctx.cfg, ctx.cd, ctx.has_bias, ctx.out_dtype = cfg, cd, bias is not None, out_dtype
-        return y
+        if not want_stats:
+            return y
+        if part is None:
+            part = torch.empty(0, dtype=torch.float32, device=x.device)       # "no fused statistics for this shape"
+        ctx.mark_non_differentiable(part)
+        return y, part
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, *unused):
         x, weight = ctx.saved_tensors
         cfg, cd = ctx.cfg, ctx.cd
         dy = to_cl(dy)
@@ -179,11 +191,16 @@ class _ConvFn(Function):
                 dw = dw.to(weight.dtype)
             if not ctx.needs_input_grad[1]:
                 dw = None
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
 
 
-def conv(x, weight, bias, cfg: ConvConfig, out_dtype=None):
-    return _ConvFn.apply(x, weight, bias, cfg, out_dtype or x.dtype)
+def conv(x, weight, bias, cfg: ConvConfig, out_dtype=None, want_stats=False):
+    """y = conv(x).  want_stats=True returns (y, partial): `partial` feeds `norm(..., stats_partial=partial)` (None when the
+    shape has no fused-statistics kernel)."""
+    if not want_stats:
+        return _ConvFn.apply(x, weight, bias, cfg, out_dtype or x.dtype, False)
+    y, part = _ConvFn.apply(x, weight, bias, cfg, out_dtype or x.dtype, True)
+    return y, (part if part.numel() else None)
 
 
 # --------------------------------------------------------------------------- normalisation
@@ -209,7 +226,8 @@ class _NormFn(Function):
     all-reduced across ranks (SyncBN), so N ranks x local batch == one device x global batch."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, kind, groups, use_batch_stats, momentum, eps, act, slope, sync):
+    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, kind, groups, use_batch_stats, momentum, eps, act, slope, sync,
+                stats_partial=None):
         need_cuda(x, "norm")
         x = to_cl(x)
         nd = _norm_desc(x, kind, groups, eps, momentum if momentum is not None else 0.0, act, slope)
@@ -235,6 +253,9 @@ class _NormFn(Function):
                     cnt = nd.N * nd.S * world
                     running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
                     running_var.mul_(1 - momentum).add_(var * (cnt / max(cnt - 1, 1)), alpha=momentum)
+            elif stats_partial is not None and kind == cabi.NORM_BATCH:
+                check(lib().b200_norm_stats_from_partial(C.byref(nd), stats_partial.data_ptr(), stats_partial.shape[0], mean.data_ptr(), rstd.data_ptr(),
+                                                         ptr(running_mean), ptr(running_var), stream()))
             else:
                 check(lib().b200_norm_stats(C.byref(nd), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ptr(running_mean), ptr(running_var),
                                             ws.data_ptr(), nws, stream()))
@@ -289,12 +310,31 @@ class _NormFn(Function):
             dgamma, dbeta = dgamma.to(gamma.dtype), dbeta.to(gamma.dtype)
         if not ctx.needs_input_grad[0]:
             dx = None
-        return (dx, dgamma if ctx.needs_input_grad[1] else None, dbeta if ctx.needs_input_grad[2] else None, dres) + (None,) * 10
+        return (dx, dgamma if ctx.needs_input_grad[1] else None, dbeta if ctx.needs_input_grad[2] else None, dres) + (None,) * 11
 
 
 def norm(x, gamma, beta, *, kind, groups=0, running_mean=None, running_var=None, use_batch_stats=True, momentum=0.1, eps=1e-5,
-         act=cabi.ACT_NONE, slope=0.01, residual=None, sync=None):
-    return _NormFn.apply(x, gamma, beta, residual, running_mean, running_var, kind, groups, use_batch_stats, momentum, eps, act, slope, sync)
+         act=cabi.ACT_NONE, slope=0.01, residual=None, sync=None, stats_partial=None):
+    return _NormFn.apply(x, gamma, beta, residual, running_mean, running_var, kind, groups, use_batch_stats, momentum, eps, act, slope, sync,
+                         stats_partial)
+
+
+def batchnorm_update_running(x, running_mean, running_var, momentum, eps, stats_partial=None):
+    """Only the side effect of a training-mode BatchNorm whose OUTPUT is discarded (unet3d.py:43-46: bn2 feeds a dead branch):
+    batch statistics -> running_mean / running_var.  No normalised tensor is written."""
+    need_cuda(x, "norm")
+    nd = _norm_desc(x, cabi.NORM_BATCH, 0, eps, momentum, cabi.ACT_NONE, 0.0)
+    mean = torch.empty(nd.C, dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    if stats_partial is not None:
+        check(lib().b200_norm_stats_from_partial(C.byref(nd), stats_partial.data_ptr(), stats_partial.shape[0], mean.data_ptr(), rstd.data_ptr(),
+                                                 ptr(running_mean), ptr(running_var), stream()))
+    else:
+        x = to_cl(x)
+        nws = lib().b200_norm_workspace_bytes(C.byref(nd))
+        ws = _workspace(nws, x.device)
+        check(lib().b200_norm_stats(C.byref(nd), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ptr(running_mean), ptr(running_var), ws.data_ptr(), nws,
+                                    stream()))
 
 
 # --------------------------------------------------------------------------- activations

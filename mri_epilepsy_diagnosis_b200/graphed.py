@@ -1,0 +1,93 @@
+"""Whole-step CUDA-graph capture for the reference's training-loop body (segmentation/routine.py:266-281:
+zero_grad -> model(x) -> loss -> backward -> optimizer.step).
+
+The 3-D U-Net step issues ~450 kernels of 10-700 us each; at batch 4 x 128^3 the host needs about as long to enqueue them
+through autograd as the B200 needs to run them, so the step is launch-bound.  Capturing the step once and replaying it
+removes the host from the loop.  Every library call only enqueues kernels on the current stream and takes caller-owned
+buffers, so the C ABI is capture-safe as it stands (tensor maps are built on the host and passed by value).
+
+Single GPU: the graph holds zero_grad + forward + loss + backward + optimizer.step (the optimizer must be constructed with
+`capturable=True`).  Data parallel: the graph holds zero_grad + forward + loss + backward; gradients accumulate directly into
+one flat fp32 buffer (each `p.grad` is a view of it), which is all-reduced over NCCL after the replay, followed by the
+optimizer step (eager or its own graph) -- one collective per step, no per-parameter copies.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+class GraphedTrainStep:
+    """step = GraphedTrainStep(model, loss_fn, optimizer, x_example, t_example); loss = step(x, t)
+
+    `x`/`t` may live on the host (pinned) or the device; they are copied into the static input buffers of the graph.
+    Returns the (static) loss tensor of the step; read it with `.item()` / `float()` when needed.
+    """
+
+    def __init__(self, model, loss_fn, optimizer, x_example, t_example, process_group=None, warmup=3):
+        self.model, self.loss_fn, self.opt = model, loss_fn, optimizer
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        dev = next(model.parameters()).device
+        self.x = torch.empty(x_example.shape, dtype=x_example.dtype, device=dev)
+        self.t = torch.empty(t_example.shape, dtype=t_example.dtype, device=dev)
+        self.x.copy_(x_example)
+        self.t.copy_(t_example)
+        # Probe step (eager): parameters that receive no gradient (unet3d's dead conv2/bn2 branch, unet3d.py:43-46; frozen
+        # fader sub-networks) must keep grad=None so that the optimizer skips them exactly like in the reference's loop.
+        optimizer.zero_grad(set_to_none=True)
+        self.loss_fn(model(self.x), self.t).backward()
+        self.params = [p for p in model.parameters() if p.requires_grad and p.grad is not None]
+        optimizer.zero_grad(set_to_none=True)
+        # gradients live in one flat buffer: zeroed by one memset inside the graph, all-reduced by one collective
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.capture_opt = self.world == 1
+        if self.capture_opt:
+            for g in optimizer.param_groups:
+                if "capturable" in g and not g["capturable"]:
+                    raise RuntimeError("GraphedTrainStep: construct the optimizer with capturable=True so optimizer.step() can be captured")
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._body(eager=True)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._body(eager=False)
+        self.opt_graph = None
+
+    def _fwd_bwd(self):
+        self.flat.zero_()
+        loss = self.loss_fn(self.model(self.x), self.t)
+        loss.backward()
+        return loss.detach()
+
+    def _reduce_and_step(self):
+        if self.world > 1:
+            dist.all_reduce(self.flat, group=self.pg)
+            self.flat.div_(self.world)
+        self.opt.step()
+
+    def _body(self, eager):
+        loss = self._fwd_bwd()
+        if eager or self.capture_opt:
+            if eager:
+                self._reduce_and_step()
+            else:
+                self.opt.step()
+        return loss
+
+    def __call__(self, x, t):
+        self.x.copy_(x, non_blocking=True)
+        self.t.copy_(t, non_blocking=True)
+        self.graph.replay()
+        if not self.capture_opt:
+            self._reduce_and_step()
+        return self.loss

@@ -62,7 +62,8 @@ class _ConvMixin(_B200Mixin):
             self.__dict__["_b200_cfg"] = cfg
         return cfg
 
-    def forward(self, x, output_size=None):
+    def forward(self, x, output_size=None, want_stats=False):
+        """want_stats=True (fused graphs only): returns (y, partial) -- see functional.conv."""
         if self.groups != 1:
             raise RuntimeError("b200nn convolutions support groups=1 (all the reference uses)")
         if self.padding_mode != "zeros" or isinstance(self.padding, str):
@@ -71,7 +72,7 @@ class _ConvMixin(_B200Mixin):
             raise RuntimeError("b200nn.ConvTranspose3d: output_padding/output_size are not supported")
         x = self._prep(x)
         out_dtype = self.out_dtype or (self.compute_dtype if self.compute_dtype is not None else x.dtype)
-        return BF.conv(x, self.weight, self.bias, self._cfg(), out_dtype)
+        return BF.conv(x, self.weight, self.bias, self._cfg(), out_dtype, want_stats)
 
 
 class Conv3d(_ConvMixin, tnn.Conv3d):
@@ -90,7 +91,10 @@ class _BatchNormMixin(_B200Mixin):
     fused_act = cabi.ACT_NONE     # set by fused graphs; plain drop-in use keeps NONE
     fused_slope = 0.01
 
-    def forward(self, x, residual=None):
+    def forward(self, x, residual=None, act=None, stats_partial=None, stats_only=False):
+        """Plain call = torch.nn.BatchNorm semantics.  Fused graphs (zoo) may pass `residual` / `act` (B200_ACT_*) to fold the
+        residual add and ReLU into the apply pass, `stats_partial` from a conv epilogue, and `stats_only=True` when the
+        normalised output is never used (only the running-statistics side effect is performed)."""
         x = self._prep(x)
         self._check_input_dim(x)
         # torch.nn.modules.batchnorm._BatchNorm.forward semantics
@@ -105,9 +109,16 @@ class _BatchNormMixin(_B200Mixin):
         use_batch = self.training or (self.running_mean is None and self.running_var is None)
         rm = self.running_mean if (not self.training or self.track_running_stats) else None
         rv = self.running_var if (not self.training or self.track_running_stats) else None
+        sync = self.sync if self.training else None
+        if stats_only:
+            if use_batch and rm is not None and sync is None:
+                BF.batchnorm_update_running(x, rm, rv, factor, self.eps, stats_partial)
+                return None
+            if not use_batch or rm is None:
+                return None             # eval mode / no running statistics: a discarded BatchNorm output has no side effect at all
         return BF.norm(x, self.weight, self.bias, kind=cabi.NORM_BATCH, running_mean=rm, running_var=rv, use_batch_stats=use_batch,
-                       momentum=factor, eps=self.eps, act=self.fused_act, slope=self.fused_slope, residual=residual,
-                       sync=self.sync if self.training else None)
+                       momentum=factor, eps=self.eps, act=self.fused_act if act is None else act, slope=self.fused_slope, residual=residual,
+                       sync=sync, stats_partial=stats_partial if sync is None else None)
 
 
 class BatchNorm3d(_BatchNormMixin, tnn.BatchNorm3d):
@@ -119,17 +130,23 @@ class BatchNorm2d(_BatchNormMixin, tnn.BatchNorm2d):
 
 
 class InstanceNorm3d(_B200Mixin, tnn.InstanceNorm3d):
-    def forward(self, x):
+    def forward(self, x, residual=None, act=None, stats_partial=None, stats_only=False):
+        if stats_only:
+            return None                 # no running statistics: a discarded output has no side effect
         x = self._prep(x)
         if self.track_running_stats:
             raise RuntimeError("b200nn.InstanceNorm3d: track_running_stats=True is not supported (the reference never sets it)")
-        return BF.norm(x, self.weight, self.bias, kind=cabi.NORM_INSTANCE, use_batch_stats=True, eps=self.eps)
+        return BF.norm(x, self.weight, self.bias, kind=cabi.NORM_INSTANCE, use_batch_stats=True, eps=self.eps,
+                       act=cabi.ACT_NONE if act is None else act, residual=residual)
 
 
 class GroupNorm(_B200Mixin, tnn.GroupNorm):
-    def forward(self, x):
+    def forward(self, x, residual=None, act=None, stats_partial=None, stats_only=False):
+        if stats_only:
+            return None
         x = self._prep(x)
-        return BF.norm(x, self.weight, self.bias, kind=cabi.NORM_GROUP, groups=self.num_groups, use_batch_stats=True, eps=self.eps)
+        return BF.norm(x, self.weight, self.bias, kind=cabi.NORM_GROUP, groups=self.num_groups, use_batch_stats=True, eps=self.eps,
+                       act=cabi.ACT_NONE if act is None else act, residual=residual)
 
 
 class ReLU(_B200Mixin, tnn.ReLU):

@@ -17,6 +17,7 @@ from __future__ import annotations
 import torch
 import torch.nn as tnn
 
+from . import _cabi as cabi
 from . import functional as BF
 from . import nn as bnn
 
@@ -37,6 +38,17 @@ def _c3(cin, cout, k):
     return bnn.Conv3d(cin, cout, k, 1, k // 2, bias=False)
 
 
+def _conv_norm(conv, norm, x, act=cabi.ACT_NONE, residual=None, stats_only=False):
+    """act(norm(conv(x)) [+ residual]) as two kernels + one finalize: the convolution's epilogue also accumulates the batch
+    statistics of its own output (BatchNorm, training), the apply pass folds the residual add and the activation."""
+    part = None
+    if isinstance(norm, bnn.BatchNorm3d) and norm.training and norm.sync is None:
+        y, part = conv(x, want_stats=True)
+    else:
+        y = conv(x)
+    return norm(y, residual=residual, act=act, stats_partial=part, stats_only=stats_only)
+
+
 class ConvD(tnn.Module):
     """Encoder stage (unet3d.py:20-47).  conv2/bn2 feed a branch whose result the reference discards
     (:43-46); it is still executed so BatchNorm running statistics and the RNG stream match."""
@@ -53,12 +65,14 @@ class ConvD(tnn.Module):
     def forward(self, x):
         if not self.first:
             x = self.maxpool(x)
-        x = self.bn1(self.conv1(x))
-        dead = self.relu(self.bn2(self.conv2(x)))
-        if self.dropout > 0:
-            dead = torch.nn.functional.dropout3d(dead, self.dropout)
-        del dead
-        return self.relu(x + self.bn3(self.conv3(x)))
+        x = _conv_norm(self.conv1, self.bn1, x)
+        # unet3d.py:43-45: y = relu(bn2(conv2(x))); y = dropout3d(y) is overwritten at :46.  Its only observable effects are
+        # bn2's running statistics (BatchNorm, training) and the RNG draw of dropout3d; exactly those are performed.
+        if isinstance(self.bn2, bnn.BatchNorm3d) and self.bn2.training:
+            _conv_norm(self.conv2, self.bn2, x, stats_only=True)
+        if self.dropout > 0:                       # F.dropout3d is always in training mode there: one Bernoulli draw per (n, c)
+            x.new_empty((x.shape[0], self.conv2.out_channels, 1, 1, 1)).bernoulli_(1 - self.dropout)
+        return _conv_norm(self.conv3, self.bn3, x, act=cabi.ACT_RELU, residual=x)
 
 
 class ConvU(tnn.Module):
@@ -75,11 +89,11 @@ class ConvU(tnn.Module):
 
     def forward(self, x, prev):
         if not self.first:
-            x = self.relu(self.bn1(self.conv1(x)))
+            x = _conv_norm(self.conv1, self.bn1, x, act=cabi.ACT_RELU)
         y = BF.interpolate(x, scale_factor=2, mode="trilinear", align_corners=False)
-        y = self.relu(self.bn2(self.conv2(y)))
+        y = _conv_norm(self.conv2, self.bn2, y, act=cabi.ACT_RELU)
         y = torch.cat([prev, y], 1)
-        return self.relu(self.bn3(self.conv3(y)))
+        return _conv_norm(self.conv3, self.bn3, y, act=cabi.ACT_RELU)
 
 
 class Unet(tnn.Module):
