@@ -503,6 +503,18 @@ int b200_maxpool_bwd(const b200_pool_desc* d, const void* dy, const uint8_t* cod
     if (pool_validate(d)) return 1;
     B200_REQUIRE(dy && code && dx, "maxpool_bwd: null pointer");
     const int64_t nin = (int64_t)d->N * d->Di * d->Hi * d->Wi;
+    const int64_t rows = (int64_t)d->N * d->Di * d->Hi;
+    if (d->kd == 2 && d->kh == 2 && d->kw == 2 && d->sd == 2 && d->sh == 2 && d->sw == 2 && rows < (1ll << 31) && (int64_t)d->Wi * d->C < (1ll << 30)) {
+        const int grid = (int)(rows < kNumSMs * 16 ? rows : kNumSMs * 16);
+        B200_DISPATCH_T(d->dtype, T, {
+            constexpr int VF = Vec16<T>::N;
+            if (d->C % VF == 0 && aligned16(dy) && aligned16(dx))
+                B200_LAUNCH((maxpool2_bwd_kernel<T, VF>), grid, 256, 0, stream, *d, (const T*)dy, code, (T*)dx);
+            else
+                B200_LAUNCH((maxpool2_bwd_kernel<T, 1>), grid, 256, 0, stream, *d, (const T*)dy, code, (T*)dx);
+        });
+        return 0;
+    }
     B200_DISPATCH_T(d->dtype, T, {
         constexpr int VF = Vec16<T>::N;
         if (d->C % VF == 0 && aligned16(dy) && aligned16(dx))
@@ -527,6 +539,18 @@ int b200_upsample_fwd(const b200_up_desc* d, const void* x, void* y, void* strea
     if (up_validate(d)) return 1;
     B200_REQUIRE(x && y, "upsample_fwd: null pointer");
     const int64_t nout = (int64_t)d->N * d->Do * d->Ho * d->Wo;
+    if (upsample_is_2x_trilinear(d)) {
+        const int64_t rows = (int64_t)d->N * d->Do * d->Ho;
+        const int grid = (int)(rows < kNumSMs * 16 ? rows : kNumSMs * 16);
+        B200_DISPATCH_T(d->dtype, T, {
+            constexpr int VF = Vec16<T>::N;
+            if (d->C % VF == 0 && d->Ctot % VF == 0 && d->c_off % VF == 0 && aligned16(x) && aligned16(y))
+                B200_LAUNCH((upsample2x_fwd_kernel<T, VF>), grid, 256, 0, stream, *d, (const T*)x, (T*)y);
+            else
+                B200_LAUNCH((upsample2x_fwd_kernel<T, 1>), grid, 256, 0, stream, *d, (const T*)x, (T*)y);
+        });
+        return 0;
+    }
     B200_DISPATCH_T(d->dtype, T, {
         constexpr int VF = Vec16<T>::N;
         if (d->C % VF == 0 && d->Ctot % VF == 0 && d->c_off % VF == 0 && aligned16(x) && aligned16(y))
@@ -540,6 +564,30 @@ int b200_upsample_bwd(const b200_up_desc* d, const void* dy, void* dx, void* str
     if (up_validate(d)) return 1;
     B200_REQUIRE(dy && dx, "upsample_bwd: null pointer");
     const int64_t nin = (int64_t)d->N * d->Di * d->Hi * d->Wi;
+    if (upsample_is_2x_trilinear(d)) {
+        const int64_t rows = (int64_t)d->N * d->Di * d->Hi;
+        const int grid = (int)(rows < kNumSMs * 16 ? rows : kNumSMs * 16);
+        B200_DISPATCH_T(d->dtype, T, {
+            constexpr int VF = Vec16<T>::N;
+            if (d->C % VF == 0 && d->Ctot % VF == 0 && d->c_off % VF == 0 && aligned16(dy) && aligned16(dx))
+                B200_LAUNCH((upsample2x_bwd_kernel<T, VF>), grid, 256, 0, stream, *d, (const T*)dy, (T*)dx);
+            else
+                B200_LAUNCH((upsample2x_bwd_kernel<T, 1>), grid, 256, 0, stream, *d, (const T*)dy, (T*)dx);
+        });
+        return 0;
+    }
+    if (upsample_is_2x_trilinear(d)) {
+        const int64_t rows = (int64_t)d->N * d->Di * d->Hi;
+        const int grid = (int)(rows < kNumSMs * 16 ? rows : kNumSMs * 16);
+        B200_DISPATCH_T(d->dtype, T, {
+            constexpr int VF = Vec16<T>::N;
+            if (d->C % VF == 0 && d->Ctot % VF == 0 && d->c_off % VF == 0 && aligned16(dy) && aligned16(dx))
+                B200_LAUNCH((upsample2x_bwd_kernel<T, VF>), grid, 256, 0, stream, *d, (const T*)dy, (T*)dx);
+            else
+                B200_LAUNCH((upsample2x_bwd_kernel<T, 1>), grid, 256, 0, stream, *d, (const T*)dy, (T*)dx);
+        });
+        return 0;
+    }
     B200_DISPATCH_T(d->dtype, T, {
         constexpr int VF = Vec16<T>::N;
         if (d->C % VF == 0 && d->Ctot % VF == 0 && d->c_off % VF == 0 && aligned16(dy) && aligned16(dx))

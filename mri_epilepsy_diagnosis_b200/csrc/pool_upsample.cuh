@@ -82,6 +82,38 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(b200_pool_desc d, cons
     }
 }
 
+// kernel = stride = 2 (every pool the benchmarked models use): each input voxel belongs to exactly one window
+template <typename T, int V>
+__global__ void __launch_bounds__(256) maxpool2_bwd_kernel(b200_pool_desc d, const T* __restrict__ dy, const uint8_t* __restrict__ code,
+                                                           T* __restrict__ dx) {
+    const int CV = d.C / V;
+    const int rows = d.N * d.Di * d.Hi, per_row = d.Wi * CV;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int yi = row % d.Hi, zi = (row / d.Hi) % d.Di, n = row / (d.Hi * d.Di);
+        const int zo = zi >> 1, yo = yi >> 1;
+        const bool row_in = zo < d.Do && yo < d.Ho;                   // floor mode: a trailing odd plane/row is in no window
+        const int64_t orow = (((int64_t)n * d.Do + zo) * d.Ho + yo) * d.Wo;
+        const int lzy = ((zi & 1) * 2 + (yi & 1)) * 2;
+        T* xr = dx + (int64_t)row * d.Wi * d.C;
+        for (int e = threadIdx.x; e < per_row; e += 256) {
+            const int xi = e / CV, cv = e - xi * CV;
+            const int xo = xi >> 1;
+            float acc[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] = 0.f;
+            if (row_in && xo < d.Wo) {
+                const int64_t o = ((orow + xo) * CV + cv) * V;
+                const int local = lzy + (xi & 1);
+                float g[V];
+                Pack<T, V>::load(dy + o, g);
+#pragma unroll
+                for (int k = 0; k < V; ++k) acc[k] = (code[o + k] == local) ? g[k] : 0.f;
+            }
+            Pack<T, V>::store(xr + e * V, acc);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ upsample
 // Source-index rules of ATen (UpSample.h): nearest: min(floor(dst*scale), in-1); linear align_corners=False:
 // max(scale*(dst+0.5)-0.5, 0); align_corners=True: dst*(in-1)/(out-1).
@@ -198,6 +230,122 @@ __global__ void __launch_bounds__(256) upsample_bwd_kernel(b200_up_desc d, const
             }
         Pack<T, V>::store(dx + i * V, acc);
     }
+}
+
+// ------------------------------------------------------------------------------------------------ x2 trilinear fast path
+// Exact factor 2, align_corners=False (unet3d.py:73,85; unet.UNet decoder): output 2i+a reads inputs (i-1+a, i+a) with weights
+// (0.25, 0.75) / (0.75, 0.25), indices clamped at the borders -- no floating-point index arithmetic, one block per output row,
+// 32-bit index math only.  Same arithmetic order as the generic kernel (weights are exact in binary).
+struct Lin2 { int i0, i1; float w0, w1; };
+__device__ __forceinline__ Lin2 lin2(int o, int in) {
+    Lin2 r;
+    const int i = o >> 1;
+    if (o & 1) { r.i0 = i; r.i1 = min(i + 1, in - 1); r.w0 = 0.75f; r.w1 = 0.25f; }
+    else if (i == 0) { r.i0 = 0; r.i1 = min(1, in - 1); r.w0 = 1.f; r.w1 = 0.f; }         // src clamped to 0
+    else { r.i0 = i - 1; r.i1 = i; r.w0 = 0.25f; r.w1 = 0.75f; }
+    return r;
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) upsample2x_fwd_kernel(b200_up_desc d, const T* __restrict__ x, T* __restrict__ y) {
+    const int CV = d.C / V;
+    const int rows = d.N * d.Do * d.Ho, per_row = d.Wo * CV;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int yo = row % d.Ho, zo = (row / d.Ho) % d.Do, n = row / (d.Ho * d.Do);
+        const Lin2 lz = lin2(zo, d.Di), ly = lin2(yo, d.Hi);
+        const T* xn = x + (int64_t)n * d.Di * d.Hi * d.Wi * d.C;
+        const T* r00 = xn + ((int64_t)lz.i0 * d.Hi + ly.i0) * d.Wi * d.C;
+        const T* r01 = xn + ((int64_t)lz.i0 * d.Hi + ly.i1) * d.Wi * d.C;
+        const T* r10 = xn + ((int64_t)lz.i1 * d.Hi + ly.i0) * d.Wi * d.C;
+        const T* r11 = xn + ((int64_t)lz.i1 * d.Hi + ly.i1) * d.Wi * d.C;
+        const float w00 = lz.w0 * ly.w0, w01 = lz.w0 * ly.w1, w10 = lz.w1 * ly.w0, w11 = lz.w1 * ly.w1;
+        T* yr = y + (int64_t)row * d.Wo * d.Ctot + d.c_off;
+        for (int e = threadIdx.x; e < per_row; e += 256) {
+            const int xo = e / CV, cv = e - xo * CV;
+            const Lin2 lx = lin2(xo, d.Wi);
+            const int o0 = lx.i0 * d.C + cv * V, o1 = lx.i1 * d.C + cv * V;
+            float acc[V], t[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] = 0.f;
+            // same (z, y, x) nesting and weight products as the generic kernel
+            Pack<T, V>::load(r00 + o0, t);
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] = fmaf(w00 * lx.w0, t[k], acc[k]);
+            Pack<T, V>::load(r00 + o1, t);
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] = fmaf(w00 * lx.w1, t[k], acc[k]);
+            Pack<T, V>::load(r01 + o0, t);
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] = fmaf(w01 * lx.w0, t[k], acc[k]);
+            Pack<T, V>::load(r01 + o1, t);
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] = fmaf(w01 * lx.w1, t[k], acc[k]);
+            Pack<T, V>::load(r10 + o0, t);
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] = fmaf(w10 * lx.w0, t[k], acc[k]);
+            Pack<T, V>::load(r10 + o1, t);
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] = fmaf(w10 * lx.w1, t[k], acc[k]);
+            Pack<T, V>::load(r11 + o0, t);
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] = fmaf(w11 * lx.w0, t[k], acc[k]);
+            Pack<T, V>::load(r11 + o1, t);
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] = fmaf(w11 * lx.w1, t[k], acc[k]);
+            Pack<T, V>::store(yr + (int64_t)xo * d.Ctot + cv * V, acc);
+        }
+    }
+}
+
+// adjoint: input index j receives from outputs 2j-1 (0.25), 2j (0.75), 2j+1 (0.75), 2j+2 (0.25); the clamped border outputs
+// (o = 0 and o = out-1) put their whole weight on the border input
+struct Touch2 { int n; int o[4]; float w[4]; };
+__device__ __forceinline__ Touch2 touch2(int j, int in) {
+    Touch2 t;
+    t.n = 0;
+    const int out = 2 * in;
+    if (2 * j - 1 >= 1) { t.o[t.n] = 2 * j - 1; t.w[t.n] = 0.25f; ++t.n; }          // odd output 2(j-1)+1, i1 = j
+    { t.o[t.n] = 2 * j; t.w[t.n] = j == 0 ? 1.f : 0.75f; ++t.n; }                     // even output 2j (clamped: all weight on 0)
+    { t.o[t.n] = 2 * j + 1; t.w[t.n] = (j == in - 1) ? 1.f : 0.75f; ++t.n; }          // odd output 2j+1 (i1 clamps to j at the end)
+    if (2 * j + 2 <= out - 2) { t.o[t.n] = 2 * j + 2; t.w[t.n] = 0.25f; ++t.n; }      // even output 2(j+1), i0 = j
+    return t;
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) upsample2x_bwd_kernel(b200_up_desc d, const T* __restrict__ dy, T* __restrict__ dx) {
+    const int CV = d.C / V;
+    const int rows = d.N * d.Di * d.Hi, per_row = d.Wi * CV;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int yi = row % d.Hi, zi = (row / d.Hi) % d.Di, n = row / (d.Hi * d.Di);
+        const Touch2 tz = touch2(zi, d.Di), ty = touch2(yi, d.Hi);
+        const T* gn = dy + (int64_t)n * d.Do * d.Ho * d.Wo * d.Ctot + d.c_off;
+        T* xr = dx + (int64_t)row * d.Wi * d.C;
+        for (int e = threadIdx.x; e < per_row; e += 256) {
+            const int xi = e / CV, cv = e - xi * CV;
+            const Touch2 tx = touch2(xi, d.Wi);
+            float acc[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] = 0.f;
+            for (int a = 0; a < tz.n; ++a)
+                for (int b = 0; b < ty.n; ++b) {
+                    const float wab = tz.w[a] * ty.w[b];
+                    const T* grow = gn + ((int64_t)tz.o[a] * d.Ho + ty.o[b]) * d.Wo * d.Ctot + cv * V;
+                    for (int c = 0; c < tx.n; ++c) {
+                        float g[V];
+                        Pack<T, V>::load(grow + (int64_t)tx.o[c] * d.Ctot, g);
+                        const float w = wab * tx.w[c];
+#pragma unroll
+                        for (int k = 0; k < V; ++k) acc[k] = fmaf(w, g[k], acc[k]);
+                    }
+                }
+            Pack<T, V>::store(xr + e * V, acc);
+        }
+    }
+}
+
+inline bool upsample_is_2x_trilinear(const b200_up_desc* d) {
+    return d->mode == B200_UP_TRILINEAR && d->Do == 2 * d->Di && d->Ho == 2 * d->Hi && d->Wo == 2 * d->Wi &&
+           (int64_t)d->N * d->Do * d->Ho < (1ll << 31) && (int64_t)d->Wo * d->C < (1ll << 30);
 }
 
 }  // namespace b200

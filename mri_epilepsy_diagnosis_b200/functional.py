@@ -527,6 +527,46 @@ def upsample_concat(skip, x, scale_factor=2, mode="trilinear", align_corners=Fal
     return _UpsampleFn.apply(x, _out_size(x, None, scale_factor), _MODES[(mode, align_corners)], skip)
 
 
+class _ConcatFn(Function):
+    """torch.cat([a, b], dim=1) on channels-last tensors as two channel-slice copies (unet3d.py:76)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        need_cuda(a, "concat")
+        a, b = to_cl(a), to_cl(b)
+        if b.dtype != a.dtype:
+            b = b.to(a.dtype)
+        if a.shape[0] != b.shape[0] or a.shape[2:] != b.shape[2:]:
+            raise RuntimeError(f"b200nn.concat: shapes {tuple(a.shape)} and {tuple(b.shape)} differ outside dim 1")
+        ca, cb = a.shape[1], b.shape[1]
+        y = _empty_cl((a.shape[0], ca + cb) + tuple(a.shape[2:]), a.dtype, a.device)
+        V = a.numel() // ca
+        dt = dtype_code(a.dtype)
+        check(lib().b200_copy_channels(dt, V, ca, a.data_ptr(), ca, 0, y.data_ptr(), ca + cb, 0, stream()))
+        check(lib().b200_copy_channels(dt, V, cb, b.data_ptr(), cb, 0, y.data_ptr(), ca + cb, ca, stream()))
+        ctx.ca, ctx.cb = ca, cb
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = to_cl(dy)
+        ca, cb = ctx.ca, ctx.cb
+        V = dy.numel() // (ca + cb)
+        dt = dtype_code(dy.dtype)
+        da = db = None
+        if ctx.needs_input_grad[0]:
+            da = _empty_cl((dy.shape[0], ca) + tuple(dy.shape[2:]), dy.dtype, dy.device)
+            check(lib().b200_copy_channels(dt, V, ca, dy.data_ptr(), ca + cb, 0, da.data_ptr(), ca, 0, stream()))
+        if ctx.needs_input_grad[1]:
+            db = _empty_cl((dy.shape[0], cb) + tuple(dy.shape[2:]), dy.dtype, dy.device)
+            check(lib().b200_copy_channels(dt, V, cb, dy.data_ptr(), ca + cb, ca, db.data_ptr(), cb, 0, stream()))
+        return da, db
+
+
+def concat(a, b):
+    return _ConcatFn.apply(a, b)
+
+
 # --------------------------------------------------------------------------- layout
 def to_channels_last(x, dtype=None):
     """(N,C,D,H,W) contiguous -> channels-last tensor of `dtype` through the library's transpose kernel."""

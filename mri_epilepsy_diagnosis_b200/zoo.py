@@ -90,9 +90,12 @@ class ConvU(tnn.Module):
     def forward(self, x, prev):
         if not self.first:
             x = _conv_norm(self.conv1, self.bn1, x, act=cabi.ACT_RELU)
-        y = BF.interpolate(x, scale_factor=2, mode="trilinear", align_corners=False)
-        y = _conv_norm(self.conv2, self.bn2, y, act=cabi.ACT_RELU)
-        y = torch.cat([prev, y], 1)
+        # unet3d.py:73-74 computes conv2(upsample(x)).  conv2 is 1x1x1 and trilinear interpolation is a per-channel convex
+        # combination of voxels, so the two commute exactly: upsample(conv2(x)) is the same function with the convolution done on
+        # 1/8 of the voxels and the interpolation on half of the channels (results differ by bf16 rounding only).
+        y = BF.interpolate(self.conv2(x), scale_factor=2, mode="trilinear", align_corners=False)
+        y = self.bn2(y, act=cabi.ACT_RELU)
+        y = BF.concat(prev, y)
         return _conv_norm(self.conv3, self.bn3, y, act=cabi.ACT_RELU)
 
 
