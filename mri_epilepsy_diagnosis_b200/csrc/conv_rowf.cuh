@@ -20,7 +20,8 @@
 
 namespace b200 {
 
-constexpr int kRfThreads = 192;
+constexpr int kRfThreads = 224;           // warp 6 = weight producer (streaming mode)
+constexpr int kRfMaxW = 8;                // weight ring depth (streaming mode)
 constexpr int kRfRing = 4;
 constexpr int kRfMaxTiles = 16;
 constexpr int kRfMaxDynSmem = 227 * 1024 - 4096;      // 4 KB reserved for the kernel's static shared memory (barriers, statistics scratch)
@@ -37,6 +38,9 @@ struct RowFwdParams {
     int items;
     int plane_bytes, plane_tx;   // ring slot size (1024-byte multiple) / bytes one TMA box delivers
     int w_bytes;                 // all packed weights
+    int stream_w;                // 0: every tap resident in shared memory; 1: taps stream through a ring of nw stages of wtap_bytes
+    int nw, wtap_bytes;
+    int ring;                    // plane ring depth (3 or 4)
     int tmem_cols;
     uint32_t idesc;
     const __nv_bfloat16* w;      // [tap][IC/8][OC][8]
@@ -47,7 +51,7 @@ struct RowFwdParams {
 
 struct alignas(128) RowFwdBarriers {
     uint64_t pfull[kRfRing], pempty[kRfRing];
-    uint64_t wfull;
+    uint64_t wfull[kRfMaxW], wempty[kRfMaxW];
     uint64_t afull[2], aempty[2];
     uint32_t tmem_base;
 };
@@ -89,13 +93,13 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ RowFwdBarriers bars;
     uint8_t* planes = smem;
-    uint8_t* wsm = smem + (size_t)kRfRing * p.plane_bytes;
+    uint8_t* wsm = smem + (size_t)p.ring * p.plane_bytes;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int pd = KD / 2, ph = KHW / 2;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kRfRing; ++i) { ptx::mbar_init(ptx::smem_u32(&bars.pfull[i]), 1); ptx::mbar_init(ptx::smem_u32(&bars.pempty[i]), 1); }
-        ptx::mbar_init(ptx::smem_u32(&bars.wfull), 1);
+        for (int i = 0; i < kRfMaxW; ++i) { ptx::mbar_init(ptx::smem_u32(&bars.wfull[i]), 1); ptx::mbar_init(ptx::smem_u32(&bars.wempty[i]), 1); }
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(ptx::smem_u32(&bars.afull[i]), 1); ptx::mbar_init(ptx::smem_u32(&bars.aempty[i]), 4); }
         ptx::fence_barrier_init();
         ptx::prefetch_tmap(&in_map);
@@ -112,18 +116,21 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
     if (warp == 0) {
         // ===================================================== TMA producer: resident weights once, then the plane ring
         if (lane == 0) {
-            const uint32_t wfull = ptx::smem_u32(&bars.wfull);
-            ptx::mbar_expect_tx(wfull, (uint32_t)p.w_bytes);
-            for (int off = 0; off < p.w_bytes; off += 32768) {
-                const int n = min(32768, p.w_bytes - off);
-                ptx::bulk_load(ptx::smem_u32(wsm + off), reinterpret_cast<const uint8_t*>(p.w) + off, (uint32_t)n, wfull);
+            if (!p.stream_w) {
+                const uint32_t wfull = ptx::smem_u32(&bars.wfull[0]);
+                ptx::mbar_expect_tx(wfull, (uint32_t)p.w_bytes);
+                for (int off = 0; off < p.w_bytes; off += 32768) {
+                    const int n = min(32768, p.w_bytes - off);
+                    ptx::bulk_load(ptx::smem_u32(wsm + off), reinterpret_cast<const uint8_t*>(p.w) + off, (uint32_t)n, wfull);
+                }
             }
+            const uint32_t ring = (uint32_t)p.ring;
             uint32_t cnt = 0;
             for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
                 const RfItem c = rf_decode(p, item);
                 const int first = max(c.z0 - pd, 0), last = min(c.z1 - 1 + pd, p.D - 1);
                 for (int pl = first; pl <= last; ++pl, ++cnt) {
-                    const uint32_t s = cnt % kRfRing, phs = (cnt / kRfRing) & 1;
+                    const uint32_t s = cnt % ring, phs = (cnt / ring) & 1;
                     ptx::mbar_wait(ptx::smem_u32(&bars.pempty[s]), phs ^ 1);
                     const uint32_t full = ptx::smem_u32(&bars.pfull[s]);
                     ptx::mbar_expect_tx(full, (uint32_t)p.plane_tx);
@@ -143,8 +150,9 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
         constexpr int nks = NKS;
         const uint32_t wtap16 = ((uint32_t)p.IC * p.OC * 2) >> 4, wks16 = (2 * (uint32_t)p.OC * 16) >> 4;
         const uint32_t idesc = p.idesc;
-        ptx::mbar_wait(ptx::smem_u32(&bars.wfull), 0);
         uint32_t cnt = 0, group = 0;
+        if (!p.stream_w) {
+        ptx::mbar_wait(ptx::smem_u32(&bars.wfull[0]), 0);
         for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
             const RfItem c = rf_decode(p, item);
             const int first = max(c.z0 - pd, 0), last = min(c.z1 - 1 + pd, p.D - 1);
@@ -211,6 +219,95 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
                 __syncwarp();
             }
             cnt += (uint32_t)(last - first + 1);
+        }
+        } else {
+        // ---------------------------------------------- streaming mode: tap-outer, tile-inner; one weight stage per tap
+        const uint32_t ring = (uint32_t)p.ring;
+        const uint32_t wstage16 = (uint32_t)p.wtap_bytes >> 4;
+        uint32_t ws = 0, wph = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+            const RfItem c = rf_decode(p, item);
+            const int first = max(c.z0 - pd, 0), last = min(c.z1 - 1 + pd, p.D - 1);
+            const int ntiles = rf_tiles(p, c.rows);
+            int ready = first - 1;
+            for (int z = c.z0; z < c.z1; ++z, ++group) {
+                const int need = min(z + pd, p.D - 1);
+                for (; ready < need; ++ready) {
+                    const uint32_t i = cnt + (uint32_t)(ready + 1 - first);
+                    ptx::mbar_wait(ptx::smem_u32(&bars.pfull[i % ring]), (i / ring) & 1);
+                }
+                const uint32_t set = group & 1;
+                ptx::mbar_wait(ptx::smem_u32(&bars.aempty[set]), ((group >> 1) & 1) ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_set = tmem_base + (uint32_t)(set * p.T * p.OC);
+                uint32_t acc = 0;
+                bool released = false;
+#pragma unroll 1
+                for (int kz = 0; kz < KD; ++kz) {
+                    const int pl = z + kz - pd;
+                    if (pl < 0 || pl >= p.D) continue;                                  // the weight producer skips the same taps
+                    const uint32_t a_pl = (pl16 + ((cnt + (uint32_t)(pl - first)) % ring) * plane16) | (1u << 16);
+#pragma unroll 1
+                    for (int j = 0; j < KHW * KHW; ++j) {
+                        ptx::mbar_wait(ptx::smem_u32(&bars.wfull[ws]), wph);
+                        ptx::tc_fence_after();
+                        if (ptx::elect_one()) {
+                            const uint32_t a_tap = a_pl + (uint32_t)(j / KHW) * row16 + (uint32_t)(j % KHW) * vox16;
+                            const uint32_t b0 = (w16 + ws * wstage16) | b_lbo;
+                            uint32_t d = d_set;
+                            for (int t = 0; t < ntiles; ++t) {
+                                uint32_t a = a_tap + (uint32_t)((t / p.tpr) * p.rowstride + (t % p.tpr) * 128) * vox16, b2 = b0;
+#pragma unroll
+                                for (int ks = 0; ks < nks; ++ks) {
+                                    ptx::umma_bf16_lohi(d, a, a_hi, b2, b_hi, idesc, ks == 0 ? acc : 1u);
+                                    a += 2; b2 += wks16;
+                                }
+                                d += (uint32_t)p.OC;
+                            }
+                            ptx::umma_commit(ptx::smem_u32(&bars.wempty[ws]));           // stage free once these MMAs retire
+                        }
+                        __syncwarp();
+                        acc = 1;
+                        if (++ws == (uint32_t)p.nw) { ws = 0; wph ^= 1; }
+                    }
+                    // the oldest plane of the window is only read by the kz = 0 pass: free it NOW so that the producer can refill
+                    // the slot during the remaining two thirds of this group (this is what makes a ring of 3 enough)
+                    if (KD == 3 && kz == 0 && z + 1 < c.z1 && pl >= first) {
+                        if (ptx::elect_one()) ptx::umma_commit(ptx::smem_u32(&bars.pempty[(cnt + (uint32_t)(pl - first)) % ring]));
+                        __syncwarp();
+                        released = true;
+                    }
+                }
+                if (ptx::elect_one()) {
+                    ptx::umma_commit(ptx::smem_u32(&bars.afull[set]));
+                    const int lo = released ? z - pd + 1 : z - pd, hi = (z + 1 == c.z1) ? last : z - pd;
+                    for (int pl = max(lo, first); pl <= hi; ++pl) ptx::umma_commit(ptx::smem_u32(&bars.pempty[(cnt + (uint32_t)(pl - first)) % ring]));
+                }
+                __syncwarp();
+            }
+            cnt += (uint32_t)(last - first + 1);
+        }
+        }
+    } else if (warp == 6) {
+        // ===================================================== weight producer (streaming mode): one tap per stage, in MMA order
+        if (lane == 0 && p.stream_w) {
+            uint32_t s = 0, ph = 0;
+            for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+                const RfItem c = rf_decode(p, item);
+                for (int z = c.z0; z < c.z1; ++z)
+                    for (int kz = 0; kz < KD; ++kz) {
+                        const int pl = z + kz - pd;
+                        if (pl < 0 || pl >= p.D) continue;
+                        for (int j = 0; j < KHW * KHW; ++j) {
+                            ptx::mbar_wait(ptx::smem_u32(&bars.wempty[s]), ph ^ 1);
+                            const uint32_t full = ptx::smem_u32(&bars.wfull[s]);
+                            ptx::mbar_expect_tx(full, (uint32_t)p.wtap_bytes);
+                            ptx::bulk_load(ptx::smem_u32(wsm + (size_t)s * p.wtap_bytes),
+                                           reinterpret_cast<const uint8_t*>(p.w) + (size_t)(kz * KHW * KHW + j) * p.wtap_bytes, (uint32_t)p.wtap_bytes, full);
+                            if (++s == (uint32_t)p.nw) { s = 0; ph ^= 1; }
+                        }
+                    }
+            }
         }
     } else {
         // ===================================================== epilogue: TMEM -> (+bias) -> bf16 -> global (+ BN statistics)
@@ -312,7 +409,6 @@ inline bool row_fwd_geom(const b200_conv_desc* d, int pass, RowFwdGeom* g) {
     if (!(g->IC == 16 || g->IC == 32 || g->IC == 64)) return false;                          // one swizzle atom per voxel
     if (g->OC % 16 || g->OC > 256) return false;
     if (g->W + 2 * (g->khw / 2) > 256 || g->W < 8) return false;                             // TMA box limit
-    if ((size_t)d->kd * d->kh * d->kw * g->IC * g->OC * 2 > 64 * 1024) return false;         // weights must stay resident
     if ((int64_t)d->N * g->D * g->H * g->W < 4096) return false;                             // tiny problems: launch-bound either way
     return true;
 }
@@ -326,32 +422,54 @@ inline int row_fwd_plan(const RowFwdGeom& g, int N, RowFwdParams* p, size_t* sme
     p->tpr = per_row ? g.W / 128 : (1 << 30);
     p->rowstride = per_row ? p->pitchW : 0;
     p->w_bytes = g.kd * g.khw * g.khw * g.IC * g.OC * 2;
-    const size_t budget = (size_t)kRfMaxDynSmem - 1024 - (size_t)p->w_bytes;
+    p->wtap_bytes = g.IC * g.OC * 2;
+    // weights: resident when every tap fits next to a 4-deep plane ring, otherwise streamed tap by tap through a ring (and
+    // the plane ring shrinks to 3: the kz = 0 plane is released after its pass, see the MMA loop)
+    p->stream_w = p->w_bytes > 64 * 1024 ? 1 : 0;
+    p->ring = p->stream_w ? 3 : kRfRing;
     int maxT = 256 / g.OC;
     if (maxT > kRfMaxTiles) maxT = kRfMaxTiles;
-    // pick the row-block height: minimise (MMA tiles over the whole plane, counting the slots wasted in the x halo) x
-    // (rounds of the persistent grid), with a mild preference for tall blocks (fewer halo rows re-read)
-    int best = 0; double best_cost = 1e30; int best_zs = 1;
-    for (int YB = 1; YB <= 32 && YB <= g.H; ++YB) {
-        const int T = per_row ? YB * p->tpr : ((YB - 1) * p->pitchW + g.W + 127) / 128;
-        if (T > maxT) break;
-        const size_t pb = (((size_t)(YB + 2 * ph) * p->pitchW * g.IC * 2) + 1023) & ~(size_t)1023;
-        if ((size_t)kRfRing * pb > budget) break;
-        const int yblocks = (g.H + YB - 1) / YB;
-        const int rem = g.H - (yblocks - 1) * YB;
-        const int Trem = per_row ? rem * p->tpr : ((rem - 1) * p->pitchW + g.W + 127) / 128;
-        const double tiles_per_plane = (double)(yblocks - 1) * T + Trem;
-        for (int zs = g.D; zs >= 1; zs = (zs > 4 ? (zs + 1) / 2 : zs - 1)) {
-            if (g.kd == 1 && zs != 1) continue;
-            const int zsegs = (g.D + zs - 1) / zs;
-            const int64_t items = (int64_t)N * yblocks * zsegs;
-            const double rounds = (double)((items + kNumSMs - 1) / kNumSMs);
-            // per-item MMA work ~ zs * T; loads ~ (zs + 2pd) planes of (YB + 2ph) rows (weight 0.15: mostly hidden)
-            const double cost = rounds * (zs * (double)T + 0.15 * (zs + 2 * pd) * (double)(YB + 2 * ph) * p->pitchW / 128.0);
-            if (cost < best_cost) { best_cost = cost; best = YB; best_zs = zs; }
-            (void)tiles_per_plane;
+    if (maxT < 1) maxT = 1;
+    // Search (weight stages, row-block height, z-segment length) with a small cost model of one persistent CTA:
+    //   MMA cycles per group  = tiles * taps * ksteps * cycles(N)         (probe: max(48, 32 + N/4, N/2) for 32..128-byte rows)
+    //   weight cycles / group = bytes of all taps / min(10, bytes in flight / 5000 cycles) B/clk/SM      (streaming mode)
+    //   item = zs groups + the z-halo planes it has to load first; total = rounds of the persistent grid * item
+    const int taps = g.kd * g.khw * g.khw, nks = g.IC / 16;
+    double mma_cyc = 32.0 + g.OC / 4.0;
+    if (mma_cyc < 48.0) mma_cyc = 48.0;
+    if (mma_cyc < g.OC / 2.0) mma_cyc = g.OC / 2.0;
+    int best = 0, best_zs = 1, best_nw = 1; double best_cost = 1e30;
+    const int nw_lo = p->stream_w ? 2 : 1, nw_hi = p->stream_w ? kRfMaxW : 1;
+    for (int nw = nw_lo; nw <= nw_hi; ++nw) {
+        const size_t wsm_bytes = p->stream_w ? (size_t)nw * p->wtap_bytes : (size_t)p->w_bytes;
+        if (wsm_bytes + 1024 >= (size_t)kRfMaxDynSmem) break;
+        const size_t budget = (size_t)kRfMaxDynSmem - 1024 - wsm_bytes;
+        for (int YB = 1; YB <= 32 && YB <= g.H; ++YB) {
+            const int T = per_row ? YB * p->tpr : ((YB - 1) * p->pitchW + g.W + 127) / 128;
+            if (T > maxT) break;
+            const size_t pb = (((size_t)(YB + 2 * ph) * p->pitchW * g.IC * 2) + 1023) & ~(size_t)1023;
+            const size_t reach = ((size_t)T * 128 + (size_t)(g.khw - 1) * (p->pitchW + 1)) * g.IC * 2;
+            const size_t tail = reach > pb ? reach - pb : 0;
+            if ((size_t)p->ring * pb + (tail > wsm_bytes ? tail - wsm_bytes : 0) > budget) continue;
+            const int yblocks = (g.H + YB - 1) / YB;
+            const double g_mma = (double)T * taps * nks * mma_cyc;
+            // measured (64->64 @ 64^3): a bulk copy of a tap takes ~5k cycles under load, so the ring depth bounds the rate
+            double w_bw = (double)nw * p->wtap_bytes / 5000.0;
+            if (w_bw > 10.0) w_bw = 10.0;
+            const double g_w = p->stream_w ? (double)p->w_bytes / w_bw : 0.0;
+            const double group = (g_mma > g_w ? g_mma : g_w) + 400.0;
+            const double plane_cyc = (double)pb / 20.0;
+            for (int zs = g.D; zs >= 1; zs = (zs > 4 ? (zs + 1) / 2 : zs - 1)) {
+                if (g.kd == 1 && zs != 1) continue;
+                const int zsegs = (g.D + zs - 1) / zs;
+                const int64_t items = (int64_t)N * yblocks * zsegs;
+                const double rounds = (double)((items + kNumSMs - 1) / kNumSMs);
+                const double cost = rounds * (zs * group + 2 * pd * plane_cyc + 1500.0);
+                if (cost < best_cost) { best_cost = cost; best = YB; best_zs = zs; best_nw = nw; }
+            }
         }
     }
+    p->nw = best_nw;
     B200_REQUIRE(best >= 1, "row fwd: a row block does not fit shared memory / TMEM");
     p->YB = best;
     p->T = per_row ? best * p->tpr : ((best - 1) * p->pitchW + g.W + 127) / 128;
@@ -368,9 +486,14 @@ inline int row_fwd_plan(const RowFwdGeom& g, int N, RowFwdParams* p, size_t* sme
     B200_REQUIRE(pow2 <= 512, "row fwd: accumulators do not fit TMEM");
     p->tmem_cols = pow2;
     p->idesc = make_idesc_bf16(g.OC);
-    // + 1 KB manual alignment; the last tile's taps over-read at most 2 rows + 2 voxels past the last plane slot: the
-    // resident weights follow the ring, so the over-read stays inside the allocation
-    *smem_bytes = (size_t)kRfRing * p->plane_bytes + (size_t)p->w_bytes + 1024;
+    // The MMAs of the last (partial) tile read slots past the end of a plane image: up to T*128 + (k-1)*(pitchW + 1) slots from
+    // the plane start.  Those rows of D are never stored, but the reads must stay inside the allocation: whatever follows the
+    // last ring slot (resident weights / weight ring) is padded up to that tail.  + 1 KB manual 1024-byte alignment.
+    const size_t wsm_bytes = p->stream_w ? (size_t)p->nw * p->wtap_bytes : (size_t)p->w_bytes;
+    const size_t reach = ((size_t)p->T * 128 + (size_t)(g.khw - 1) * (p->pitchW + 1)) * g.IC * 2;
+    const size_t tail = reach > (size_t)p->plane_bytes ? reach - p->plane_bytes : 0;
+    *smem_bytes = (size_t)p->ring * p->plane_bytes + (wsm_bytes > tail ? wsm_bytes : tail) + 1024;
+    B200_REQUIRE(*smem_bytes <= (size_t)kRfMaxDynSmem, "row fwd: plan exceeds shared memory");
     return 0;
 }
 
@@ -418,6 +541,10 @@ inline int row_fwd_run(const b200_conv_desc* d, int pass, const void* in, const 
     size_t smem_bytes = 0;
     if (row_fwd_plan(g, d->N, &p, &smem_bytes)) return 1;
     p.w = (const __nv_bfloat16*)w_packed; p.bias = bias; p.out = (__nv_bfloat16*)out; p.stats = stats;
+    static const bool debug = [] { const char* e = getenv("B200_ROWF_DEBUG"); return e != nullptr && e[0] == '1'; }();
+    if (debug)
+        fprintf(stderr, "[row_fwd] N=%d %dx%dx%d IC=%d OC=%d k=%d,%d: YB=%d T=%d zs=%d items=%d ring=%d stream=%d nw=%d plane=%dB smem=%zuB tmem=%d\n", d->N,
+                g.D, g.H, g.W, g.IC, g.OC, g.kd, g.khw, p.YB, p.T, p.zs, p.items, p.ring, p.stream_w, p.nw, p.plane_bytes, smem_bytes, p.tmem_cols);
     const int ph = g.khw / 2;
     CUtensorMap map;
     if (make_row_map(&map, in, g.IC, g.W, g.H, (int64_t)d->N * g.D, g.IC, p.pitchW, p.YB + 2 * ph)) return 1;

@@ -31,10 +31,19 @@ CASES = [
     ("c32_16_w224", 1, 32, 16, (4, 6, 224), 3, 1, True),
     ("c16_16_w254", 1, 16, 16, (3, 6, 254), 3, 1, False),
     ("pw32_16", 1, 32, 16, (8, 16, 32), 1, 0, False),
+    ("pw32_16_w64", 2, 32, 16, (6, 64, 64), 1, 0, False),        # tall row block, partial last tile reads past the plane image
     ("pw64_32_w128", 2, 64, 32, (3, 16, 128), 1, 0, True),
     ("pw64_64_w40", 1, 64, 64, (8, 13, 40), 1, 0, False),
     ("k133", 2, 16, 32, (7, 20, 16), (1, 3, 3), (0, 1, 1), True),
     ("k311", 1, 16, 16, (12, 12, 32), (3, 1, 1), (1, 0, 0), True),
+    # streamed weights (all 27 taps do not fit in shared memory), plane ring of 3 with early release
+    ("s64_64_w64", 1, 64, 64, (7, 15, 64), 3, 1, False),
+    ("s64_32_w64", 1, 64, 32, (8, 9, 64), 3, 1, True),
+    ("s32_64_w32", 2, 32, 64, (6, 20, 32), 3, 1, False),
+    ("s64_128_w16", 2, 64, 128, (9, 16, 16), 3, 1, True),
+    ("s16_256_w24", 1, 16, 256, (9, 20, 24), 3, 1, False),
+    ("s64_64_d1", 4, 64, 64, (1, 33, 32), 3, 1, False),
+    ("s64_64_d2", 2, 64, 64, (2, 27, 40), 3, 1, False),
     ("d1", 4, 32, 32, (1, 33, 64), 3, 1, False),                  # single plane: both z neighbours are padding
     ("d2", 2, 16, 16, (2, 17, 128), 3, 1, False),
 ]
@@ -59,7 +68,8 @@ def test_row_fwd_dgrad(B, case):
     cd, _ = mod._cfg().desc(xg, mod.weight, torch.bfloat16)
     lib = B._cabi.lib()
     assert lib.b200_conv_algo(ctypes.byref(cd), B._cabi.PASS_FWD) == B._cabi.ALGO_ROW, "case is meant to hit the row-slab forward kernel"
-    assert lib.b200_conv_algo(ctypes.byref(cd), B._cabi.PASS_DGRAD) == B._cabi.ALGO_ROW
+    # dgrad gathers Co channels: more than one swizzle atom per voxel (Co > 64) stays on the first-generation tile kernel
+    assert lib.b200_conv_algo(ctypes.byref(cd), B._cabi.PASS_DGRAD) == (B._cabi.ALGO_ROW if Co <= 64 else B._cabi.ALGO_UMMA)
     yg = mod(xg)
     yg.backward(gy.cuda().bfloat16())
     torch.cuda.synchronize()
