@@ -263,20 +263,46 @@ def main():
         k = (which, algo, shape)
         r = agg.setdefault(k, [0.0, 0.0, 0])
         r[0] += flops; r[1] += a.elapsed_time(b) * 1e-3; r[2] += 1
-    umma_flops = sum(v[0] for k, v in agg.items() if k[1] == 1)
-    umma_s = sum(v[1] for k, v in agg.items() if k[1] == 1)
-    umma_n = sum(v[2] for k, v in agg.items() if k[1] == 1)
+    # kernel behind every (pass, algo): the tcgen05 kernels are the dense contractions of the path
+    KERNEL = {(0, 2): "row_fwd_kernel", (1, 2): "row_fwd_kernel", (2, 2): "row_wgrad_kernel", (0, 1): "conv_umma_kernel", (1, 1): "conv_umma_kernel",
+              (2, 1): "conv_wgrad_umma_kernel"}
+    tc = {k: v for k, v in agg.items() if k[1] != 0}
+    tc_flops, tc_s = sum(v[0] for v in tc.values()), sum(v[1] for v in tc.values())
     conv_s = sum(v[1] for v in agg.values())
     pk = peaks()
-    achieved = umma_flops / umma_s / 1e12 if umma_s > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "conv_umma_kernel", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"] + " (sustained bf16)",
-                "launches_per_step": umma_n / max(1, args.steps), "ms_per_launch_avg": 1e3 * umma_s / max(1, umma_n),
-                "share_of_step": (umma_s / args.steps) / (ms / 1e3), "all_conv_share_of_step": (conv_s / args.steps) / (ms / 1e3),
-                "note": "algorithmic FLOPs = 2*N*Do*Ho*Wo*Co*Ci*taps per launch; events bracket each launch on the launching stream"}
+    # dominant launch signature = (kernel, layer shape) with the largest share of the step; fwd and dgrad of a "same" conv with
+    # Ci == Co are the same kernel on the same geometry
+    sig = {}
+    for (which, algo, shape), v in tc.items():
+        key = (KERNEL[(which, algo)], (min(shape[0], shape[1]), max(shape[0], shape[1])) + tuple(shape[2:])) if which != 2 else \
+              (KERNEL[(which, algo)], tuple(shape))
+        r = sig.setdefault(key, [0.0, 0.0, 0])
+        r[0] += v[0]; r[1] += v[1]; r[2] += v[2]
+    (dom_kernel, dom_shape), dom = max(sig.items(), key=lambda kv: kv[1][1]) if sig else (("none", ()), [0.0, 1e-9, 0])
+    achieved = dom[0] / dom[1] / 1e12
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(f"{dom_kernel}|" + "|".join(str(int(x)) for x in dom_shape) + f"|n{args.batch}")
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "kernel": dom_kernel,
+                "launch": (f"Conv3d {dom_shape[0]}<->{dom_shape[1]} k{dom_shape[5]} on {args.batch} x {dom_shape[2]}x{dom_shape[3]}x{dom_shape[4]} bf16"
+                           if dom_shape else ""),
+                "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
+                "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write, ncu --set full; profiles/traffic.json)",
+                "algorithmic_bytes": (2.0 * args.batch * dom_shape[2] * dom_shape[3] * dom_shape[4] * (dom_shape[0] + dom_shape[1]) if dom_shape else None),
+                "peak_source": pk["source"] + " (sustained bf16)",
+                "launches_per_step": dom[2] / max(1, args.steps), "ms_per_launch_avg": 1e3 * dom[1] / max(1, dom[2]),
+                "share_of_step": (dom[1] / args.steps) / (ms / 1e3),
+                "all_tcgen05_convs": {"achieved": tc_flops / tc_s / 1e12 if tc_s > 0 else 0.0, "frac": (tc_flops / tc_s / 1e12 / pk["bf16_tflops"]) if tc_s > 0 else 0.0,
+                                      "share_of_step": (tc_s / args.steps) / (ms / 1e3), "launches_per_step": sum(v[2] for v in tc.values()) / max(1, args.steps)},
+                "all_conv_share_of_step": (conv_s / args.steps) / (ms / 1e3),
+                "note": "achieved = algorithmic FLOPs (2*N*Do*Ho*Wo*Co*Ci*taps per launch) / CUDA-event duration of the dominant kernel's launches "
+                        "of that layer shape, events on the launching stream around each launch (eager replays of the same step)"}
     if args.profile_json and rank == 0:
         names = {0: "fwd", 1: "dgrad", 2: "wgrad"}
-        table = [{"pass": names[k[0]], "algo": "umma" if k[1] else "simt", "Ci": k[2][0], "Co": k[2][1], "out": list(k[2][2:5]), "kd": k[2][5],
+        table = [{"pass": names[k[0]], "algo": {0: "direct", 1: "umma", 2: "row"}[k[1]], "Ci": k[2][0], "Co": k[2][1], "out": list(k[2][2:5]), "kd": k[2][5],
                   "calls": v[2], "ms_per_call": 1e3 * v[1] / v[2], "tflops": v[0] / v[1] / 1e12} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])]
         with open(args.profile_json, "w") as f:
             json.dump({"ms_per_step": ms, "rows": table}, f, indent=1)

@@ -120,9 +120,11 @@ int b200_norm_stats_from_running(const b200_norm_desc* d, const float* running_m
                                  float* mean, float* rstd, void* stream);
 int b200_norm_apply(const b200_norm_desc* d, const void* x, const float* mean, const float* rstd,
                     const float* gamma, const float* beta, const void* residual, void* y, void* stream);
-/* training=1: batch statistics take part in the gradient; 0: eval-mode BN (mean/rstd are constants) */
+/* training=1: batch statistics take part in the gradient; 0: eval-mode BN (mean/rstd are constants).
+ * `y` (the saved OUTPUT) supplies the activation gate; it may be NULL when act != NONE and the forward had NO residual: the
+ * gate is then recomputed from x through the same affine form as the forward pass (needs `beta`), one tensor read less. */
 int b200_norm_bwd(const b200_norm_desc* d, int training, const void* x, const void* y, const void* dy,
-                  const float* mean, const float* rstd, const float* gamma,
+                  const float* mean, const float* rstd, const float* gamma, const float* beta,
                   void* dx, void* dresidual, float* dgamma, float* dbeta,
                   void* workspace, size_t ws_bytes, void* stream);
 
@@ -130,10 +132,10 @@ int b200_norm_bwd(const b200_norm_desc* d, int training, const void* x, const vo
  * sum dy'*xhat per (reduce-batch, channel); NB = 1 for BATCH, N otherwise) between the steps -- SyncBN.
  * `world` multiplies the BATCH element count (number of ranks whose sums were added). */
 int b200_norm_bwd_reduce(const b200_norm_desc* d, const void* x, const void* y, const void* dy,
-                         const float* mean, const float* rstd, float* sums,
+                         const float* mean, const float* rstd, const float* gamma, const float* beta, float* sums,
                          void* workspace, size_t ws_bytes, void* stream);
 int b200_norm_bwd_apply(const b200_norm_desc* d, int training, int world, const void* x, const void* y, const void* dy,
-                        const float* mean, const float* rstd, const float* gamma, const float* sums,
+                        const float* mean, const float* rstd, const float* gamma, const float* beta, const float* sums,
                         void* dx, void* dresidual, float* dgamma, float* dbeta,
                         void* workspace, size_t ws_bytes, void* stream);
 

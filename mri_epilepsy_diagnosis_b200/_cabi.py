@@ -61,9 +61,9 @@ _SIGS = {
     "b200_norm_stats_from_partial": (C.c_int, [P(NormDesc), vp, C.c_int, vp, vp, vp, vp, vp]),
     "b200_norm_stats_from_running": (C.c_int, [P(NormDesc), vp, vp, vp, vp, vp]),
     "b200_norm_apply": (C.c_int, [P(NormDesc), vp, vp, vp, vp, vp, vp, vp, vp]),
-    "b200_norm_bwd": (C.c_int, [P(NormDesc), C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
-    "b200_norm_bwd_reduce": (C.c_int, [P(NormDesc), vp, vp, vp, vp, vp, vp, vp, sz, vp]),
-    "b200_norm_bwd_apply": (C.c_int, [P(NormDesc), C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "b200_norm_bwd": (C.c_int, [P(NormDesc), C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "b200_norm_bwd_reduce": (C.c_int, [P(NormDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "b200_norm_bwd_apply": (C.c_int, [P(NormDesc), C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "b200_act_fwd": (C.c_int, [C.c_int, C.c_int, f32, i64, vp, vp, vp]),
     "b200_act_bwd": (C.c_int, [C.c_int, C.c_int, f32, i64, vp, vp, vp, vp]),
     "b200_prelu_fwd": (C.c_int, [C.c_int, i64, vp, vp, vp, vp]),

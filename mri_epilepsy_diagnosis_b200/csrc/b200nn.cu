@@ -292,7 +292,7 @@ size_t b200_norm_workspace_bytes(const b200_norm_desc* d) {
     norm_geom(d, true, &gv);
     const int chunks = g.chunks > gv.chunks ? g.chunks : gv.chunks;
     const size_t partial = (size_t)g.NB * chunks * 2 * d->C * 4;
-    const size_t ab = (size_t)g.NB * d->C * 2 * 4, coef = (size_t)g.NB * d->C * 3 * 4;
+    const size_t ab = (size_t)g.NB * d->C * 2 * 4, coef = (size_t)g.NB * d->C * 5 * 4;
     return partial + ab + coef + 768;
 }
 
@@ -373,28 +373,27 @@ static NormBwdWs norm_bwd_ws(const b200_norm_desc* d, const NormGeom& g, void* w
 }
 
 int b200_norm_bwd_reduce(const b200_norm_desc* d, const void* x, const void* y, const void* dy, const float* mean, const float* rstd,
-                         float* sums, void* workspace, size_t ws_bytes, void* stream) {
+                         const float* gamma, const float* beta, float* sums, void* workspace, size_t ws_bytes, void* stream) {
     NormGeom g;
     if (norm_validate(d, &g, {x, y, dy})) return 1;
     B200_REQUIRE(x && dy && mean && rstd && sums && workspace, "norm_bwd_reduce: null pointer");
-    B200_REQUIRE(d->act == B200_ACT_NONE || y != nullptr, "norm_bwd: fused activation needs the saved output y");
     B200_REQUIRE(ws_bytes >= b200_norm_workspace_bytes(d), "norm_bwd_reduce: workspace too small");
     const NormBwdWs w = norm_bwd_ws(d, g, workspace);
     dim3 grid(g.chunks, g.NB);
     const size_t smem = (size_t)2 * g.rpi * d->C * sizeof(float);
     B200_DISPATCH_T(d->dtype, T, {
-        if (g.V == 1) B200_LAUNCH((norm_bwd_partial_kernel<T, 1>), grid, 256, smem, stream, (const T*)x, (const T*)y, (const T*)dy, mean, rstd, d->C,
-                                  g.R, g.rows_per_chunk, d->kind, d->G, d->act, d->slope, w.partial);
-        else B200_LAUNCH((norm_bwd_partial_kernel<T, Vec16<T>::N>), grid, 256, smem, stream, (const T*)x, (const T*)y, (const T*)dy, mean, rstd, d->C,
-                         g.R, g.rows_per_chunk, d->kind, d->G, d->act, d->slope, w.partial);
+        if (g.V == 1) B200_LAUNCH((norm_bwd_partial_kernel<T, 1>), grid, 256, smem, stream, (const T*)x, (const T*)y, (const T*)dy, mean, rstd, gamma,
+                                  beta, d->C, g.R, g.rows_per_chunk, d->kind, d->G, d->act, d->slope, w.partial);
+        else B200_LAUNCH((norm_bwd_partial_kernel<T, Vec16<T>::N>), grid, 256, smem, stream, (const T*)x, (const T*)y, (const T*)dy, mean, rstd, gamma,
+                         beta, d->C, g.R, g.rows_per_chunk, d->kind, d->G, d->act, d->slope, w.partial);
     });
     B200_LAUNCH(norm_bwd_sum_kernel, (int)ceil_div((int64_t)g.NB * d->C, 8), 256, 0, stream, g.NB, d->C, g.chunks, w.partial, sums);
     return 0;
 }
 
 int b200_norm_bwd_apply(const b200_norm_desc* d, int training, int world, const void* x, const void* y, const void* dy, const float* mean,
-                        const float* rstd, const float* gamma, const float* sums, void* dx, void* dresidual, float* dgamma, float* dbeta,
-                        void* workspace, size_t ws_bytes, void* stream) {
+                        const float* rstd, const float* gamma, const float* beta, const float* sums, void* dx, void* dresidual, float* dgamma,
+                        float* dbeta, void* workspace, size_t ws_bytes, void* stream) {
     NormGeom g;
     if (norm_validate(d, &g, {x, y, dy, dx, dresidual})) return 1;
     B200_REQUIRE(x && dy && dx && mean && rstd && sums && workspace && world >= 1, "norm_bwd_apply: bad arguments");
@@ -403,7 +402,7 @@ int b200_norm_bwd_apply(const b200_norm_desc* d, int training, int world, const 
     dim3 agrid(apply_grid(g, d->S), d->N);
     const int per_sample = d->kind != B200_NORM_BATCH;
     B200_LAUNCH(norm_bwd_coef_kernel, (int)ceil_div((int64_t)g.NB * d->C, 128), 128, 0, stream, d->N, d->C, d->S, d->kind, d->G, training, world,
-                sums, mean, rstd, gamma, w.coef, dgamma, dbeta);
+                sums, mean, rstd, gamma, beta, w.coef, dgamma, dbeta);
     B200_DISPATCH_T(d->dtype, T, {
         if (g.V == 1) B200_LAUNCH((norm_bwd_apply_kernel<T, 1>), agrid, 256, 0, stream, (const T*)x, (const T*)y, (const T*)dy, w.coef, (T*)dx,
                                   (T*)dresidual, d->C, d->S, per_sample, d->act, d->slope);
@@ -414,13 +413,16 @@ int b200_norm_bwd_apply(const b200_norm_desc* d, int training, int world, const 
 }
 
 int b200_norm_bwd(const b200_norm_desc* d, int training, const void* x, const void* y, const void* dy, const float* mean, const float* rstd,
-                  const float* gamma, void* dx, void* dresidual, float* dgamma, float* dbeta, void* workspace, size_t ws_bytes, void* stream) {
+                  const float* gamma, const float* beta, void* dx, void* dresidual, float* dgamma, float* dbeta, void* workspace, size_t ws_bytes,
+                  void* stream) {
     NormGeom g;
     if (norm_validate(d, &g, {x, y, dy, dx, dresidual})) return 1;
     B200_REQUIRE(workspace != nullptr && ws_bytes >= b200_norm_workspace_bytes(d), "norm_bwd: workspace too small");
     const NormBwdWs w = norm_bwd_ws(d, g, workspace);
-    if (b200_norm_bwd_reduce(d, x, y, dy, mean, rstd, w.AB, workspace, ws_bytes, stream)) return 1;
-    return b200_norm_bwd_apply(d, training, 1, x, y, dy, mean, rstd, gamma, w.AB, dx, dresidual, dgamma, dbeta, workspace, ws_bytes, stream);
+    B200_REQUIRE(y != nullptr || d->act == B200_ACT_NONE || dresidual == nullptr,
+                 "norm_bwd: with a residual the activation gate needs the saved output y");
+    if (b200_norm_bwd_reduce(d, x, y, dy, mean, rstd, gamma, beta, w.AB, workspace, ws_bytes, stream)) return 1;
+    return b200_norm_bwd_apply(d, training, 1, x, y, dy, mean, rstd, gamma, beta, w.AB, dx, dresidual, dgamma, dbeta, workspace, ws_bytes, stream);
 }
 
 // ============================================================================ activations

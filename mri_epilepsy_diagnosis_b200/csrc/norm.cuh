@@ -144,6 +144,13 @@ __global__ void norm_from_running_kernel(int C, float eps, const float* __restri
     if (c < C) { mean[c] = rm[c]; rstd[c] = 1.0f / sqrtf(rv[c] + eps); }
 }
 
+// the affine form of the normalisation, y_pre = x * sc + sh: ONE definition, used by the forward apply pass and by the backward
+// passes that recompute the activation gate from x (bit-identical pre-activation values, hence identical gates)
+__device__ __forceinline__ void norm_scale_shift(float mean, float rstd, float ga, float be, float& sc, float& sh) {
+    sc = rstd * ga;
+    sh = be - mean * sc;
+}
+
 // y = act((x - mean) * rstd * gamma + beta [+ residual]); grid (gx, N); gx*256 is a multiple of CV so each thread owns fixed channels
 template <typename T, int V>
 __global__ void __launch_bounds__(256) norm_apply_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -159,11 +166,28 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const T* __restrict__ x
         const int c = cv * V + k;
         const int g = norm_group_index(kind, n, c, C, G);
         const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
-        sc[k] = rstd[g] * ga;
-        sh[k] = be - mean[g] * sc[k];
+        norm_scale_shift(mean[g], rstd[g], ga, be, sc[k], sh[k]);
     }
     const int64_t total = S * CV, stride = (int64_t)gridDim.x * 256, base = (int64_t)n * total;
-    for (int64_t i = i0; i < total; i += stride) {
+    int64_t i = i0;
+    for (; i + stride < total; i += 2 * stride) {            // two independent 16-byte streams per tensor in flight
+        float v[2][V], r[2][V];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            Pack<T, V>::load(x + (base + i + u * stride) * V, v[u]);
+            if (res != nullptr) Pack<T, V>::load(res + (base + i + u * stride) * V, r[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const float t = fmaf(v[u][k], sc[k], sh[k]);
+                v[u][k] = act_apply(res != nullptr ? t + r[u][k] : t, act, slope);
+            }
+            Pack<T, V>::store(y + (base + i + u * stride) * V, v[u]);
+        }
+    }
+    for (; i < total; i += stride) {
         float v[V];
         Pack<T, V>::load(x + (base + i) * V, v);
         if (res != nullptr) {
@@ -179,10 +203,13 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const T* __restrict__ x
     }
 }
 
-// partial[((nb*chunks+chunk)*2+{0,1})*C + c] = sum dy', sum dy' * xhat, with dy' = dy * act'(y)
+// partial[((nb*chunks+chunk)*2+{0,1})*C + c] = sum dy', sum dy' * xhat, with dy' = dy * act'(y).
+// The gate act'(.) comes from the saved output y when given; with y == nullptr (fused activation WITHOUT residual) it is
+// recomputed from x through the same affine form as the forward pass -- one tensor read less.  Two rows are in flight per thread.
 template <typename T, int V>
 __global__ void __launch_bounds__(256) norm_bwd_partial_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ dy,
                                                                const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                int C, int64_t R, int64_t rows_per_chunk, int kind, int G, int act, float slope,
                                                                float* __restrict__ partial) {
     extern __shared__ float sm[];
@@ -191,29 +218,52 @@ __global__ void __launch_bounds__(256) norm_bwd_partial_kernel(const T* __restri
     const bool active = rr < rpi;
     const int nb = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
     const int64_t off = (int64_t)nb * R * C;
-    float a[V], b[V], mu[V], rs[V];
+    const bool gate_y = act != B200_ACT_NONE && y != nullptr, gate_x = act != B200_ACT_NONE && y == nullptr;
+    float a[V], b[V], mu[V], rs[V], sc[V], sh[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) a[k] = b[k] = 0.f;
     if (active) {
 #pragma unroll
         for (int k = 0; k < V; ++k) {
-            const int g = norm_group_index(kind, nb, cv * V + k, C, G);
+            const int c = cv * V + k;
+            const int g = norm_group_index(kind, nb, c, C, G);
             mu[k] = mean[g]; rs[k] = rstd[g];
+            norm_scale_shift(mu[k], rs[k], gamma ? gamma[c] : 1.f, beta ? beta[c] : 0.f, sc[k], sh[k]);
         }
         const int64_t r_end = min(R, (int64_t)(chunk + 1) * rows_per_chunk);
-        for (int64_t r = (int64_t)chunk * rows_per_chunk + rr; r < r_end; r += rpi) {
-            float xv[V], gv[V];
+        int64_t r = (int64_t)chunk * rows_per_chunk + rr;
+        for (; r + rpi < r_end; r += 2 * rpi) {
+            float xv[2][V], gv[2][V], ov[2][V];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int64_t p = off + (r + u * rpi) * C + cv * V;
+                Pack<T, V>::load(x + p, xv[u]);
+                Pack<T, V>::load(dy + p, gv[u]);
+                if (gate_y) Pack<T, V>::load(y + p, ov[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    float g = gv[u][k];
+                    if (gate_y) g *= act_gate(ov[u][k], act, slope);
+                    else if (gate_x) g *= act_gate(fmaf(xv[u][k], sc[k], sh[k]), act, slope);
+                    a[k] += g; b[k] += g * (xv[u][k] - mu[k]) * rs[k];
+                }
+        }
+        for (; r < r_end; r += rpi) {
+            float xv[V], gv[V], ov[V];
             const int64_t p = off + r * C + cv * V;
             Pack<T, V>::load(x + p, xv);
             Pack<T, V>::load(dy + p, gv);
-            if (act != B200_ACT_NONE) {
-                float ov[V];
-                Pack<T, V>::load(y + p, ov);
+            if (gate_y) Pack<T, V>::load(y + p, ov);
 #pragma unroll
-                for (int k = 0; k < V; ++k) gv[k] *= act_gate(ov[k], act, slope);
+            for (int k = 0; k < V; ++k) {
+                float g = gv[k];
+                if (gate_y) g *= act_gate(ov[k], act, slope);
+                else if (gate_x) g *= act_gate(fmaf(xv[k], sc[k], sh[k]), act, slope);
+                a[k] += g; b[k] += g * (xv[k] - mu[k]) * rs[k];
             }
-#pragma unroll
-            for (int k = 0; k < V; ++k) { a[k] += gv[k]; b[k] += gv[k] * (xv[k] - mu[k]) * rs[k]; }
         }
 #pragma unroll
         for (int k = 0; k < V; ++k) {
@@ -247,10 +297,10 @@ __global__ void __launch_bounds__(256) norm_bwd_sum_kernel(int NB, int C, int ch
     }
 }
 
-// coef[(nb*C + c)*3 + {0,1,2}] : dx = k1*dy' + k4*x + k5 ; also dgamma/dbeta (thread nb==0 sums over nb)
+// coef[(nb*C + c)*5 + {0..4}] : dx = k1*dy' + k4*x + k5 ; (sc, sh) of the forward affine form; also dgamma/dbeta (thread nb==0 sums over nb)
 __global__ void norm_bwd_coef_kernel(int N, int C, int64_t S, int kind, int G, int training, int world, const float* __restrict__ AB,
                                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                     float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                     const float* __restrict__ beta, float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta) {
     const int NB = kind == B200_NORM_BATCH ? 1 : N;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NB * C) return;
@@ -278,7 +328,10 @@ __global__ void norm_bwd_coef_kernel(int N, int C, int64_t S, int kind, int G, i
             k5 = -ga * rs * P / M - k4 * mu;
         }
     }
-    coef[(int64_t)i * 3] = (float)k1; coef[(int64_t)i * 3 + 1] = (float)k4; coef[(int64_t)i * 3 + 2] = (float)k5;
+    coef[(int64_t)i * 5] = (float)k1; coef[(int64_t)i * 5 + 1] = (float)k4; coef[(int64_t)i * 5 + 2] = (float)k5;
+    float gsc, gsh;
+    norm_scale_shift(mean[g], rstd[g], gamma ? gamma[c] : 1.f, beta ? beta[c] : 0.f, gsc, gsh);
+    coef[(int64_t)i * 5 + 3] = gsc; coef[(int64_t)i * 5 + 4] = gsh;
     if (nb == 0 && (dgamma != nullptr || dbeta != nullptr)) {
         double dg = 0.0, db = 0.0;
         for (int b = 0; b < NB; ++b) { db += (double)AB[((int64_t)b * C + c) * 2]; dg += (double)AB[((int64_t)b * C + c) * 2 + 1]; }
@@ -287,6 +340,7 @@ __global__ void norm_bwd_coef_kernel(int N, int C, int64_t S, int kind, int G, i
     }
 }
 
+// gsc/gsh (optional, [NBg*C] each, per_sample-indexed like coef): affine form for recomputing the gate from x when y == nullptr
 template <typename T, int V>
 __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ dy,
                                                              const float* __restrict__ coef, T* __restrict__ dx, T* __restrict__ dres,
@@ -294,22 +348,50 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T* __restrict
     const int CV = C / V, n = blockIdx.y;
     const int64_t i0 = (int64_t)blockIdx.x * 256 + threadIdx.x;
     const int cv = (int)(i0 % CV);
-    float k1[V], k4[V], k5[V];
+    const bool gate_y = act != B200_ACT_NONE && y != nullptr, gate_x = act != B200_ACT_NONE && y == nullptr;
+    float k1[V], k4[V], k5[V], sc[V], sh[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) {
-        const int64_t e = ((int64_t)(per_sample ? n : 0) * C + cv * V + k) * 3;
-        k1[k] = coef[e]; k4[k] = coef[e + 1]; k5[k] = coef[e + 2];
+        const int64_t e = ((int64_t)(per_sample ? n : 0) * C + cv * V + k) * 5;
+        k1[k] = coef[e]; k4[k] = coef[e + 1]; k5[k] = coef[e + 2]; sc[k] = coef[e + 3]; sh[k] = coef[e + 4];
     }
     const int64_t total = S * CV, stride = (int64_t)gridDim.x * 256, base = (int64_t)n * total;
-    for (int64_t i = i0; i < total; i += stride) {
+    int64_t i = i0;
+    for (; i + stride < total; i += 2 * stride) {
+        float xv[2][V], gv[2][V], ov[2][V];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int64_t p = (base + i + u * stride) * V;
+            Pack<T, V>::load(x + p, xv[u]);
+            Pack<T, V>::load(dy + p, gv[u]);
+            if (gate_y) Pack<T, V>::load(y + p, ov[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int64_t p = (base + i + u * stride) * V;
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                if (gate_y) gv[u][k] *= act_gate(ov[u][k], act, slope);
+                else if (gate_x) gv[u][k] *= act_gate(fmaf(xv[u][k], sc[k], sh[k]), act, slope);
+            }
+            if (dres != nullptr) Pack<T, V>::store(dres + p, gv[u]);
+#pragma unroll
+            for (int k = 0; k < V; ++k) xv[u][k] = fmaf(k1[k], gv[u][k], fmaf(k4[k], xv[u][k], k5[k]));
+            Pack<T, V>::store(dx + p, xv[u]);
+        }
+    }
+    for (; i < total; i += stride) {
         float xv[V], gv[V];
         Pack<T, V>::load(x + (base + i) * V, xv);
         Pack<T, V>::load(dy + (base + i) * V, gv);
-        if (act != B200_ACT_NONE) {
+        if (gate_y) {
             float ov[V];
             Pack<T, V>::load(y + (base + i) * V, ov);
 #pragma unroll
             for (int k = 0; k < V; ++k) gv[k] *= act_gate(ov[k], act, slope);
+        } else if (gate_x) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) gv[k] *= act_gate(fmaf(xv[k], sc[k], sh[k]), act, slope);
         }
         if (dres != nullptr) Pack<T, V>::store(dres + (base + i) * V, gv);
 #pragma unroll

@@ -270,15 +270,17 @@ class _NormFn(Function):
             if res.dtype != x.dtype:
                 res = res.to(x.dtype)
         check(lib().b200_norm_apply(C.byref(nd), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ptr(g32), ptr(b32), ptr(res), y.data_ptr(), stream()))
-        ctx.save_for_backward(x, y if act != cabi.ACT_NONE else None, mean, rstd, gamma)
+        # the activation gate of the backward pass comes from y only when a residual was added; otherwise it is recomputed from x
+        ctx.save_for_backward(x, y if (act != cabi.ACT_NONE and residual is not None) else None, mean, rstd, gamma, beta)
         ctx.nd, ctx.training, ctx.world, ctx.sync = nd, bool(use_batch_stats), world, sync
         ctx.has_res, ctx.affine = residual is not None, gamma is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y, mean, rstd, gamma = ctx.saved_tensors
+        x, y, mean, rstd, gamma, beta = ctx.saved_tensors
         nd = ctx.nd
+        b32 = _f32(beta)
         dy = to_cl(dy)
         if dy.dtype != x.dtype:
             dy = dy.to(x.dtype)
@@ -294,18 +296,18 @@ class _NormFn(Function):
         if ctx.world > 1:
             import torch.distributed as dist
             sums = torch.empty(nd.C * 2, dtype=torch.float32, device=x.device)
-            check(lib().b200_norm_bwd_reduce(C.byref(nd), x.data_ptr(), ptr(y), dy.data_ptr(), mean.data_ptr(), rstd.data_ptr(), sums.data_ptr(),
-                                             ws.data_ptr(), nws, stream()))
+            check(lib().b200_norm_bwd_reduce(C.byref(nd), x.data_ptr(), ptr(y), dy.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ptr(g32), ptr(b32),
+                                             sums.data_ptr(), ws.data_ptr(), nws, stream()))
             local = sums.clone()
             dist.all_reduce(sums, group=ctx.sync[0])
             check(lib().b200_norm_bwd_apply(C.byref(nd), 1, ctx.world, x.data_ptr(), ptr(y), dy.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ptr(g32),
-                                            sums.data_ptr(), dx.data_ptr(), ptr(dres), ptr(dgamma), ptr(dbeta), ws.data_ptr(), nws, stream()))
+                                            ptr(b32), sums.data_ptr(), dx.data_ptr(), ptr(dres), ptr(dgamma), ptr(dbeta), ws.data_ptr(), nws, stream()))
             if ctx.affine:   # parameter grads stay LOCAL sums (the gradient all-reduce averages them like every other parameter)
                 lv = local.view(nd.C, 2)
                 dbeta, dgamma = lv[:, 0].contiguous(), lv[:, 1].contiguous()
         else:
             check(lib().b200_norm_bwd(C.byref(nd), int(ctx.training), x.data_ptr(), ptr(y), dy.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ptr(g32),
-                                      dx.data_ptr(), ptr(dres), ptr(dgamma), ptr(dbeta), ws.data_ptr(), nws, stream()))
+                                      ptr(b32), dx.data_ptr(), ptr(dres), ptr(dgamma), ptr(dbeta), ws.data_ptr(), nws, stream()))
         if ctx.affine and gamma.dtype != torch.float32:
             dgamma, dbeta = dgamma.to(gamma.dtype), dbeta.to(gamma.dtype)
         if not ctx.needs_input_grad[0]:
