@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sync-bn", action="store_true")
+    ap.add_argument("--torch-loss", action="store_true", help="compute the Dice loss with torch ops instead of the fused kernel")
     ap.add_argument("--eager", action="store_true", help="do not capture the step in a CUDA graph (launch-bound at this size)")
     ap.add_argument("--profile-json", default=None, help="write the per-layer conv timing table here")
     args = ap.parse_args()
@@ -193,18 +194,20 @@ def main():
     voxels = xh.numel()
     if world > 1:
         pkg.dp.broadcast_parameters(net)
+    # softmax -> get_dice_loss -> .mean() (segmentation/routine.py:272-274) as the library's fused loss kernel
+    loss_fn = dice_loss_mean if args.torch_loss else BF.softmax_dice_loss
     if args.eager:
         bucket = pkg.dp.attach(net, opt) if world > 1 else None
 
         def step(x, t):
             opt.zero_grad()
-            loss = dice_loss_mean(net(x), t)
+            loss = loss_fn(net(x), t)
             loss.backward()
             opt.step()
             return loss
     else:
         # the loop body of segmentation/routine.py:266-281 captured once in a CUDA graph and replayed (graphed.py)
-        step = pkg.graphed.GraphedTrainStep(net, dice_loss_mean, opt, xd, td)
+        step = pkg.graphed.GraphedTrainStep(net, loss_fn, opt, xd, td)
 
     def barrier():
         if dist is not None:

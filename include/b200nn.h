@@ -151,6 +151,24 @@ int b200_prelu_bwd(int dtype, int64_t n, const void* x, const float* a, const vo
 /* y = act(a + b) -- residual joins unet3d.py:47, cnn_model.py:37-38 */
 int b200_add_act_fwd(int dtype, int act, float slope, int64_t n, const void* a, const void* b, void* y, void* stream);
 
+/* ------------------------------------------------------------------ fused softmax + soft-Dice loss
+ * The loss of the segmentation loop (segmentation/routine.py:272-274 + get_dice_score/get_dice_loss :239-253):
+ *   p = softmax(logits, dim=1); per (n,c): tp = sum p*t, fp = sum p*(1-t), fn = sum (1-p)*t with t = targets (N,1,...) broadcast
+ *   over the channels (the reference scores both channels against the same mask); loss = mean(1 - 2tp/(2tp+fp+fn+eps)).
+ * logits: channels-last (N,S,C) fp32 or bf16, C <= 8; targets fp32 (N,S).  `sums` (fp32 [N][2C+1]: sum p_c, sum p_c*t, sum t)
+ * is written by fwd and read by bwd; `dloss` is the upstream gradient (a DEVICE scalar); dlogits has the logits' dtype. */
+typedef struct {
+    int32_t dtype;
+    int32_t N, C;
+    int64_t S;
+    float eps;
+} b200_dice_desc;
+size_t b200_softmax_dice_workspace_bytes(const b200_dice_desc* d);
+int b200_softmax_dice_fwd(const b200_dice_desc* d, const void* logits, const float* targets, float* sums, float* loss,
+                          void* workspace, size_t ws_bytes, void* stream);
+int b200_softmax_dice_bwd(const b200_dice_desc* d, const void* logits, const float* targets, const float* sums,
+                          const float* dloss, void* dlogits, void* stream);
+
 /* ------------------------------------------------------------------ max pooling
  * nn.MaxPool3d(k, s) no padding, floor mode: unet3d.py:25; AE_model.py:27; cnn_model.py:115-148,221,232;
  * nn.MaxPool2d(2) model_utils.py:29.  Ties -> first in (d,h,w) raster order; NaN wins.

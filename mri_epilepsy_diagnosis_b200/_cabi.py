@@ -38,6 +38,10 @@ class UpDesc(C.Structure):
     _fields_ = [(n, i32) for n in ("dtype", "mode", "N", "C", "Di", "Hi", "Wi", "Do", "Ho", "Wo", "Ctot", "c_off")]
 
 
+class DiceDesc(C.Structure):
+    _fields_ = [("dtype", i32), ("N", i32), ("C", i32), ("S", i64), ("eps", f32)]
+
+
 class PatchDesc(C.Structure):
     _fields_ = [(n, i32) for n in ("X", "Y", "Z", "h", "w", "with_mask", "upsample_passes")]
 
@@ -70,6 +74,9 @@ _SIGS = {
     "b200_prelu_workspace_bytes": (sz, [i64]),
     "b200_prelu_bwd": (C.c_int, [C.c_int, i64, vp, vp, vp, vp, vp, vp, sz, vp]),
     "b200_add_act_fwd": (C.c_int, [C.c_int, C.c_int, f32, i64, vp, vp, vp, vp]),
+    "b200_softmax_dice_workspace_bytes": (sz, [P(DiceDesc)]),
+    "b200_softmax_dice_fwd": (C.c_int, [P(DiceDesc), vp, vp, vp, vp, vp, sz, vp]),
+    "b200_softmax_dice_bwd": (C.c_int, [P(DiceDesc), vp, vp, vp, vp, vp, vp]),
     "b200_maxpool_fwd": (C.c_int, [P(PoolDesc), vp, vp, vp, vp, vp]),
     "b200_maxpool_bwd": (C.c_int, [P(PoolDesc), vp, vp, vp, vp]),
     "b200_upsample_fwd": (C.c_int, [P(UpDesc), vp, vp, vp]),

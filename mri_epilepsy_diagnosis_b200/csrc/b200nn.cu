@@ -8,6 +8,7 @@
 #include "conv_row.cuh"
 #include "conv_rowf.cuh"
 #include "elementwise.cuh"
+#include "loss.cuh"
 #include "norm.cuh"
 #include "patches.cuh"
 #include "pool_upsample.cuh"
@@ -423,6 +424,47 @@ int b200_norm_bwd(const b200_norm_desc* d, int training, const void* x, const vo
                  "norm_bwd: with a residual the activation gate needs the saved output y");
     if (b200_norm_bwd_reduce(d, x, y, dy, mean, rstd, gamma, beta, w.AB, workspace, ws_bytes, stream)) return 1;
     return b200_norm_bwd_apply(d, training, 1, x, y, dy, mean, rstd, gamma, beta, w.AB, dx, dresidual, dgamma, dbeta, workspace, ws_bytes, stream);
+}
+
+// ============================================================================ fused softmax + Dice loss
+static int dice_validate(const b200_dice_desc* d) {
+    B200_REQUIRE(d != nullptr, "null dice descriptor");
+    B200_REQUIRE(d->N > 0 && d->S > 0 && d->C >= 1 && d->C <= kDiceMaxC, "softmax_dice: 1 <= C <= %d classes and positive sizes required", kDiceMaxC);
+    B200_REQUIRE(d->dtype == B200_F32 || d->dtype == B200_BF16, "softmax_dice: bad dtype");
+    return 0;
+}
+size_t b200_softmax_dice_workspace_bytes(const b200_dice_desc* d) {
+    if (d == nullptr || d->N <= 0 || d->S <= 0) return 0;
+    return (size_t)d->N * dice_chunks(d->N, d->S) * (2 * d->C + 1) * sizeof(float) + 256;
+}
+int b200_softmax_dice_fwd(const b200_dice_desc* d, const void* logits, const float* targets, float* sums, float* loss, void* workspace,
+                          size_t ws_bytes, void* stream) {
+    if (dice_validate(d)) return 1;
+    B200_REQUIRE(logits && targets && sums && loss && workspace, "softmax_dice_fwd: null pointer");
+    B200_REQUIRE(ws_bytes >= b200_softmax_dice_workspace_bytes(d), "softmax_dice_fwd: workspace too small");
+    B200_REQUIRE(d->C != 2 || d->dtype != B200_F32 || (reinterpret_cast<uintptr_t>(logits) & 7) == 0, "softmax_dice_fwd: logits must be 8-byte aligned");
+    const int chunks = dice_chunks(d->N, d->S);
+    float* partial = (float*)workspace;
+    dim3 grid(chunks, d->N);
+    B200_DISPATCH_T(d->dtype, T, { B200_LAUNCH(dice_fwd_partial_kernel<T>, grid, 256, 0, stream, (const T*)logits, targets, d->C, d->S, partial); });
+    B200_LAUNCH(dice_fwd_final_kernel, 1, 256, 0, stream, partial, d->N, d->C, chunks, d->eps, sums, loss);
+    return 0;
+}
+int b200_softmax_dice_bwd(const b200_dice_desc* d, const void* logits, const float* targets, const float* sums, const float* dloss, void* dlogits,
+                          void* stream) {
+    if (dice_validate(d)) return 1;
+    B200_REQUIRE(logits && targets && sums && dloss && dlogits, "softmax_dice_bwd: null pointer");
+    B200_REQUIRE(d->C != 2 || d->dtype != B200_F32 || ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(dlogits)) & 7) == 0,
+                 "softmax_dice_bwd: logits/dlogits must be 8-byte aligned");
+    int gx = (int)ceil_div(d->S, 256 * 4);
+    const int cap = (kNumSMs * 16) / d->N > 0 ? (kNumSMs * 16) / d->N : 1;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, d->N);
+    B200_DISPATCH_T(d->dtype, T, {
+        B200_LAUNCH(dice_bwd_kernel<T>, grid, 256, 0, stream, (const T*)logits, targets, sums, dloss, d->N, d->C, d->S, d->eps, (T*)dlogits);
+    });
+    return 0;
 }
 
 // ============================================================================ activations

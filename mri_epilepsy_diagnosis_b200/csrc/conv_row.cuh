@@ -268,7 +268,8 @@ __global__ void row_wgrad_reduce_kernel(RowWgradParams p, float* __restrict__ dw
         const int unit = coc * p.n_ci + cic;
         const float* src = p.partial + ((size_t)unit * p.splits * ncols + (size_t)(kz * p.NN + a * p.cQ + col_)) * mrows + kx * p.cP + cil;
         float acc = 0.f;
-        for (int s = 0; s < p.splits; ++s) acc += src[(size_t)s * ncols * mrows];
+#pragma unroll 8
+        for (int s = 0; s < p.splits; ++s) acc += __ldg(src + (size_t)s * ncols * mrows);      // same order every run; 8 loads in flight
         dw[e] = acc;
     }
 }

@@ -949,7 +949,8 @@ __global__ void wgrad_umma_reduce_kernel(int splits, int taps, int Co, int Ci, c
     const int64_t total = (int64_t)taps * Co * Ci;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         float acc = 0.f;
-        for (int s = 0; s < splits; ++s) acc += partial[(int64_t)s * total + e];
+#pragma unroll 8
+        for (int s = 0; s < splits; ++s) acc += __ldg(partial + (int64_t)s * total + e);
         const int ci = (int)(e % Ci);
         const int64_t r = e / Ci;
         const int co = (int)(r % Co), tap = (int)(r / Co);

@@ -95,6 +95,23 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
+// This lane's share of the per-block partials p[(k*2 + {0,1})*C] (k = lane, lane+32, ...), loaded 8 at a time so that the loads
+// overlap (these finalize kernels are pure latency: one round trip to L2 per batch instead of one per element); fixed order.
+__device__ __forceinline__ void lane_partial_sums(const float* __restrict__ p, int chunks, int C, int lane, double& s0, double& s1) {
+    for (int k0 = lane; k0 < chunks; k0 += 32 * 8) {
+        float v0[8], v1[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = k0 + 32 * j;
+            const bool ok = k < chunks;
+            v0[j] = ok ? __ldg(p + ((int64_t)k * 2 + 0) * C) : 0.f;
+            v1[j] = ok ? __ldg(p + ((int64_t)k * 2 + 1) * C) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s0 += (double)v0[j]; s1 += (double)v1[j]; }
+    }
+}
+
 // one WARP per (mean, rstd) entry: the lanes split the per-block partials, the combination order is fixed
 template <typename T>
 __global__ void __launch_bounds__(256) norm_stats_finalize_kernel(const T* __restrict__ x, int N, int C, int64_t S, int kind, int G, int chunks, int64_t R,
@@ -111,10 +128,7 @@ __global__ void __launch_bounds__(256) norm_stats_finalize_kernel(const T* __res
     double m_acc = 0.0, e2_acc = 0.0;
     for (int c = c0; c < c1; ++c) {
         double s = 0.0, q = 0.0;
-        for (int k = lane; k < chunks; k += 32) {
-            s += (double)partial[(((int64_t)nb * chunks + k) * 2 + 0) * C + c];
-            q += (double)partial[(((int64_t)nb * chunks + k) * 2 + 1) * C + c];
-        }
+        lane_partial_sums(partial + (int64_t)nb * chunks * 2 * C + c, chunks, C, lane, s, q);
         s = warp_sum_d(s); q = warp_sum_d(q);
         const double K = x != nullptr ? (double)to_f<T>(x[(int64_t)nb * R * C + c]) : 0.0;     // null: unshifted partials (conv epilogue)
         const double ms = s / (double)R;
@@ -286,10 +300,7 @@ __global__ void __launch_bounds__(256) norm_bwd_sum_kernel(int NB, int C, int ch
     if (i >= NB * C) return;
     const int nb = i / C, c = i % C;
     double a = 0.0, b = 0.0;
-    for (int k = lane; k < chunks; k += 32) {
-        a += (double)partial[(((int64_t)nb * chunks + k) * 2 + 0) * C + c];
-        b += (double)partial[(((int64_t)nb * chunks + k) * 2 + 1) * C + c];
-    }
+    lane_partial_sums(partial + (int64_t)nb * chunks * 2 * C + c, chunks, C, lane, a, b);
     a = warp_sum_d(a); b = warp_sum_d(b);
     if (lane == 0) {
         AB[(int64_t)i * 2] = (float)a;

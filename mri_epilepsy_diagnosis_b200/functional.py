@@ -569,6 +569,46 @@ def concat(a, b):
     return _ConcatFn.apply(a, b)
 
 
+# --------------------------------------------------------------------------- fused softmax + Dice loss
+class _SoftmaxDiceFn(Function):
+    @staticmethod
+    def forward(ctx, logits, targets, eps):
+        need_cuda(logits, "softmax_dice_loss")
+        if logits.dim() not in (4, 5) or logits.shape[1] > 8:
+            raise RuntimeError(f"b200nn.softmax_dice_loss: logits of shape {tuple(logits.shape)} are not supported (4-D/5-D, <= 8 classes)")
+        if targets.shape[0] != logits.shape[0] or targets.shape[1] != 1 or tuple(targets.shape[2:]) != tuple(logits.shape[2:]):
+            raise RuntimeError(f"b200nn.softmax_dice_loss: targets {tuple(targets.shape)} must be (N,1,...) matching logits {tuple(logits.shape)}")
+        if logits.dtype not in (torch.float32, torch.bfloat16):
+            logits = logits.float()
+        lg = to_cl(logits)
+        tg = targets.detach().to(device=lg.device, dtype=torch.float32).contiguous()
+        N, Cc = lg.shape[0], lg.shape[1]
+        S = lg.numel() // (N * Cc)
+        dd = cabi.DiceDesc(dtype_code(lg.dtype), N, Cc, S, float(eps))
+        sums = torch.empty(N * (2 * Cc + 1), dtype=torch.float32, device=lg.device)
+        loss = torch.empty((), dtype=torch.float32, device=lg.device)
+        nws = lib().b200_softmax_dice_workspace_bytes(C.byref(dd))
+        ws = _workspace(nws, lg.device)
+        check(lib().b200_softmax_dice_fwd(C.byref(dd), lg.data_ptr(), tg.data_ptr(), sums.data_ptr(), loss.data_ptr(), ws.data_ptr(), nws, stream()))
+        ctx.save_for_backward(lg, tg, sums)
+        ctx.dd = dd
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        lg, tg, sums = ctx.saved_tensors
+        g = dloss.detach().to(torch.float32).contiguous()
+        dl = torch.empty_like(lg)
+        check(lib().b200_softmax_dice_bwd(C.byref(ctx.dd), lg.data_ptr(), tg.data_ptr(), sums.data_ptr(), g.data_ptr(), dl.data_ptr(), stream()))
+        return dl, None, None
+
+
+def softmax_dice_loss(logits, targets, eps=1e-9):
+    """mean over (n, c) of the soft-Dice loss of softmax(logits, dim=1) against `targets` (N,1,...) -- the composite of
+    segmentation/routine.py:272-274 (softmax -> get_dice_loss -> .mean()) in one pass over the logits (+ one for backward)."""
+    return _SoftmaxDiceFn.apply(logits, targets, eps)
+
+
 # --------------------------------------------------------------------------- layout
 def to_channels_last(x, dtype=None):
     """(N,C,D,H,W) contiguous -> channels-last tensor of `dtype` through the library's transpose kernel."""

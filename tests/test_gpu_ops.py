@@ -435,3 +435,29 @@ def test_patches_edge_cases(B):
     assert np.array_equal(got, want)
     img = rng.random((96, 64, 10))
     assert np.array_equal(B.patches.gather(img, torch.from_numpy(want.astype(np.int32)).cuda()).cpu().numpy(), OP.gather_patches(img, want))
+
+
+@pytest.mark.parametrize("C", [2, 5])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_softmax_dice_loss_matches_reference_loss(B, C, dtype):
+    """Fused softmax + Dice against the reference's composite (segmentation/routine.py:272-274, :239-253) restated in
+    oracle/graphs.dice_loss_mean: loss within 1e-6 (fp32 logits), gradient rel <= 1e-4 (fp32) / 1e-2 (bf16 stored gradient)."""
+    from oracle import graphs
+    g = gen(40 + C)
+    logits = (torch.randn(3, C, 6, 7, 9, generator=g) * 2).to(dtype).float()
+    t = (torch.rand(3, 1, 6, 7, 9, generator=g) > 0.6).float()
+    lr = logits.clone().requires_grad_(True)
+    ref = graphs.dice_loss_mean(lr, t)
+    ref.backward()
+    lg = logits.cuda().to(dtype).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+    out = B.functional.softmax_dice_loss(lg, t.cuda())
+    (out * 1.0).backward()
+    assert abs(float(out) - float(ref)) < 2e-6
+    assert rel_err(lg.grad.float(), lr.grad) < (1e-4 if dtype == torch.float32 else 1e-2)
+    # upstream gradient scaling and an all-background sample (T = 0: dice -> 0, loss term 1)
+    lg2 = logits.cuda().to(dtype).requires_grad_(True)
+    t0 = t.clone(); t0[1] = 0
+    lr2 = logits.clone().requires_grad_(True)
+    (graphs.dice_loss_mean(lr2, t0) * 3.0).backward()
+    (B.functional.softmax_dice_loss(lg2, t0.cuda()) * 3.0).backward()
+    assert rel_err(lg2.grad.float(), lr2.grad) < (1e-4 if dtype == torch.float32 else 1e-2)

@@ -33,7 +33,7 @@ x, t = x.to(dev), t.to(dev)
 
 def step():
     opt.zero_grad()
-    loss = bench.dice_loss_mean(net(x), t)
+    loss = pkg.functional.softmax_dice_loss(net(x), t)
     loss.backward()
     opt.step()
     return loss
