@@ -590,6 +590,8 @@ int b200_upsample_fwd(const b200_up_desc* d, const void* x, void* y, void* strea
             constexpr int VF = Vec16<T>::N;
             if (d->C % VF == 0 && d->Ctot % VF == 0 && d->c_off % VF == 0 && aligned16(x) && aligned16(y))
                 B200_LAUNCH((upsample2x_fwd_kernel<T, VF>), grid, 256, 0, stream, *d, (const T*)x, (T*)y);
+            else if (sizeof(T) == 4 && d->C % 2 == 0 && d->Ctot % 2 == 0 && d->c_off % 2 == 0 && aligned16(x) && aligned16(y))
+                B200_LAUNCH((upsample2x_fwd_kernel<float, 2>), grid, 256, 0, stream, *d, (const float*)x, (float*)y);      // 2-class fp32 logits
             else
                 B200_LAUNCH((upsample2x_fwd_kernel<T, 1>), grid, 256, 0, stream, *d, (const T*)x, (T*)y);
         });
@@ -615,6 +617,8 @@ int b200_upsample_bwd(const b200_up_desc* d, const void* dy, void* dx, void* str
             constexpr int VF = Vec16<T>::N;
             if (d->C % VF == 0 && d->Ctot % VF == 0 && d->c_off % VF == 0 && aligned16(dy) && aligned16(dx))
                 B200_LAUNCH((upsample2x_bwd_kernel<T, VF>), grid, 256, 0, stream, *d, (const T*)dy, (T*)dx);
+            else if (sizeof(T) == 4 && d->C % 2 == 0 && d->Ctot % 2 == 0 && d->c_off % 2 == 0 && aligned16(dy) && aligned16(dx))
+                B200_LAUNCH((upsample2x_bwd_kernel<float, 2>), grid, 256, 0, stream, *d, (const float*)dy, (float*)dx);
             else
                 B200_LAUNCH((upsample2x_bwd_kernel<T, 1>), grid, 256, 0, stream, *d, (const T*)dy, (T*)dx);
         });
@@ -627,6 +631,8 @@ int b200_upsample_bwd(const b200_up_desc* d, const void* dy, void* dx, void* str
             constexpr int VF = Vec16<T>::N;
             if (d->C % VF == 0 && d->Ctot % VF == 0 && d->c_off % VF == 0 && aligned16(dy) && aligned16(dx))
                 B200_LAUNCH((upsample2x_bwd_kernel<T, VF>), grid, 256, 0, stream, *d, (const T*)dy, (T*)dx);
+            else if (sizeof(T) == 4 && d->C % 2 == 0 && d->Ctot % 2 == 0 && d->c_off % 2 == 0 && aligned16(dy) && aligned16(dx))
+                B200_LAUNCH((upsample2x_bwd_kernel<float, 2>), grid, 256, 0, stream, *d, (const float*)dy, (float*)dx);
             else
                 B200_LAUNCH((upsample2x_bwd_kernel<T, 1>), grid, 256, 0, stream, *d, (const T*)dy, (T*)dx);
         });

@@ -71,6 +71,13 @@ template <> struct Pack<float, 4> {
         *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
     }
 };
+template <> struct Pack<float, 2> {
+    static __device__ __forceinline__ void load(const float* p, float (&o)[2]) {
+        float2 v = *reinterpret_cast<const float2*>(p);
+        o[0] = v.x; o[1] = v.y;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&o)[2]) { *reinterpret_cast<float2*>(p) = make_float2(o[0], o[1]); }
+};
 template <> struct Pack<float, 1> {
     static __device__ __forceinline__ void load(const float* p, float (&o)[1]) { o[0] = *p; }
     static __device__ __forceinline__ void store(float* p, const float (&o)[1]) { *p = o[0]; }
