@@ -285,15 +285,23 @@ static int norm_validate(const b200_norm_desc* d, NormGeom* g, std::initializer_
     return 0;
 }
 
+// largest chunk count over the geometries that exist for this descriptor (scalar: C <= 256 channels; vector: C/V <= 256)
+static int norm_max_chunks(const b200_norm_desc* d, int* NB) {
+    NormGeom gs, gv;
+    const bool ok_s = norm_geom(d, false, &gs), ok_v = norm_geom(d, true, &gv);
+    if (!ok_s && !ok_v) return 0;
+    *NB = ok_s ? gs.NB : gv.NB;
+    const int cs = ok_s ? gs.chunks : 0, cv = ok_v ? gv.chunks : 0;
+    return cs > cv ? cs : cv;
+}
+
 size_t b200_norm_workspace_bytes(const b200_norm_desc* d) {
-    NormGeom g;
-    if (d == nullptr || !norm_geom(d, false, &g)) return 0;
-    // chunks can only shrink when vectors are used; size for the scalar geometry (largest)
-    NormGeom gv;
-    norm_geom(d, true, &gv);
-    const int chunks = g.chunks > gv.chunks ? g.chunks : gv.chunks;
-    const size_t partial = (size_t)g.NB * chunks * 2 * d->C * 4;
-    const size_t ab = (size_t)g.NB * d->C * 2 * 4, coef = (size_t)g.NB * d->C * 5 * 4;
+    if (d == nullptr || d->C <= 0) return 0;
+    int NB = 1;
+    const int chunks = norm_max_chunks(d, &NB);
+    if (chunks == 0) return 0;
+    const size_t partial = (((size_t)NB * chunks * 2 * d->C + 63) & ~(size_t)63) * 4;
+    const size_t ab = (((size_t)NB * d->C * 2 + 63) & ~(size_t)63) * 4, coef = (size_t)NB * d->C * 5 * 4;
     return partial + ab + coef + 768;
 }
 
@@ -363,9 +371,8 @@ int b200_norm_apply(const b200_norm_desc* d, const void* x, const float* mean, c
 // workspace layout shared by the backward entry points
 struct NormBwdWs { float* partial; float* AB; float* coef; };
 static NormBwdWs norm_bwd_ws(const b200_norm_desc* d, const NormGeom& g, void* workspace) {
-    NormGeom gs;
-    norm_geom(d, false, &gs);
-    const int max_chunks = g.chunks > gs.chunks ? g.chunks : gs.chunks;
+    int NB = 1;
+    const int max_chunks = norm_max_chunks(d, &NB);
     NormBwdWs w;
     w.partial = (float*)workspace;
     w.AB = w.partial + (((size_t)g.NB * max_chunks * 2 * d->C + 63) & ~(size_t)63);

@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict
         float acc = 0.f;
         if (c < C && rr < rpi)
             for (int64_t r = (int64_t)blockIdx.x * rows_per_chunk + rr; r < r_end; r += rpi) acc += to_f<T>(x[r * C + c]);
-        if (c < C && rr < rpi) sm[rr * C + c] = acc;
+        if (C <= 256 && c < C && rr < rpi) sm[rr * C + c] = acc;      // wider tensors: one thread per channel, no shared staging
         __syncthreads();
         if (C <= 256) {
             if (t < C) { float s = 0.f; for (int j = 0; j < rpi; ++j) s += sm[j * C + t]; partial[(int64_t)blockIdx.x * C + t] = s; }

@@ -159,7 +159,7 @@ def test_conv_errors_are_loud(B):
 
 
 # ----------------------------------------------------------------------------- normalisation
-@pytest.mark.parametrize("C,shape", [(16, (2, 6, 8, 10)), (1, (2, 5, 6, 7)), (48, (1, 4, 4, 8)), (7, (3, 3, 4, 5)), (256, (2, 2, 2, 2))])
+@pytest.mark.parametrize("C,shape", [(16, (2, 6, 8, 10)), (1, (2, 5, 6, 7)), (48, (1, 4, 4, 8)), (7, (3, 3, 4, 5)), (256, (2, 2, 2, 2)), (512, (2, 2, 2, 2)), (1024, (1, 2, 2, 3))])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 def test_batchnorm3d_train_eval(B, C, shape, dtype):
     g = gen(C)
