@@ -262,11 +262,8 @@ int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const void* dy, floa
     if (dbias != nullptr) {
         float* bpart = (float*)((char*)workspace + ((s.partial_bytes + 255) & ~(size_t)255));
         const int64_t Vy = (int64_t)d->N * d->Do * d->Ho * d->Wo;
-        const size_t smem = (size_t)(d->Co <= 256 ? (256 / d->Co) * d->Co : 1) * sizeof(float);
-        if (d->y_dtype == B200_F32)
-            B200_LAUNCH(colsum_partial_kernel<float>, s.bias_chunks, 256, smem, stream, (const float*)dy, d->Co, Vy, s.bias_rows_per_chunk, bpart);
-        else
-            B200_LAUNCH(colsum_partial_kernel<__nv_bfloat16>, s.bias_chunks, 256, smem, stream, (const __nv_bfloat16*)dy, d->Co, Vy, s.bias_rows_per_chunk, bpart);
+        if (d->y_dtype == B200_F32) { if (colsum_launch<float>((const float*)dy, d->Co, Vy, s.bias_chunks, s.bias_rows_per_chunk, bpart, stream)) return 1; }
+        else if (colsum_launch<__nv_bfloat16>((const __nv_bfloat16*)dy, d->Co, Vy, s.bias_chunks, s.bias_rows_per_chunk, bpart, stream)) return 1;
         B200_LAUNCH(colsum_final_kernel, (int)ceil_div(d->Co, 128), 128, 0, stream, s.bias_chunks, d->Co, bpart, dbias);
     }
     return 0;

@@ -345,6 +345,61 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict
         __syncthreads();
     }
 }
+// vectorised variant for channel counts that are multiples of the 16-byte vector: block = (256 / CV) rows x CV channel vectors,
+// four rows in flight per thread, shared-memory reduction over the row groups; partial[chunk][C]
+template <typename T, int V>
+__global__ void __launch_bounds__(256) colsum_vec_partial_kernel(const T* __restrict__ x, int C, int64_t R, int64_t rows_per_chunk, float* __restrict__ partial) {
+    extern __shared__ float sm[];             // [rpi][C]
+    const int CV = C / V, rpi = 256 / CV;
+    const int t = threadIdx.x, cv = t % CV, rr = t / CV;
+    float s[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) s[k] = 0.f;
+    if (rr < rpi) {
+        const int64_t r_end = min(R, (int64_t)(blockIdx.x + 1) * rows_per_chunk);
+        int64_t r = (int64_t)blockIdx.x * rows_per_chunk + rr;
+        for (; r + 3 * rpi < r_end; r += 4 * rpi) {
+            float a[4][V];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) Pack<T, V>::load(x + (r + u * rpi) * C + cv * V, a[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int k = 0; k < V; ++k) s[k] += a[u][k];
+        }
+        for (; r < r_end; r += rpi) {
+            float a[V];
+            Pack<T, V>::load(x + r * C + cv * V, a);
+#pragma unroll
+            for (int k = 0; k < V; ++k) s[k] += a[k];
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) sm[rr * C + cv * V + k] = s[k];
+    }
+    __syncthreads();
+    for (int c = t; c < C; c += 256) {
+        float acc = 0.f;
+        for (int j = 0; j < rpi; ++j) acc += sm[j * C + c];
+        partial[(int64_t)blockIdx.x * C + c] = acc;
+    }
+}
+
+// dbias[c] = sum over rows of dy[r][c]: picks the vectorised kernel when it applies; bpart holds chunks*C floats
+template <typename T>
+inline int colsum_launch(const T* dy, int C, int64_t R, int chunks, int64_t rows_per_chunk, float* bpart, void* stream) {
+    constexpr int V = 16 / sizeof(T);
+    if (C % V == 0 && C / V <= 256 && aligned16(dy)) {
+        const size_t smem = (size_t)(256 / (C / V)) * C * sizeof(float);
+        if (smem <= 48 * 1024) {
+            B200_LAUNCH((colsum_vec_partial_kernel<T, V>), chunks, 256, smem, stream, dy, C, R, rows_per_chunk, bpart);
+            return 0;
+        }
+    }
+    const size_t smem = (size_t)(C <= 256 ? (256 / C) * C : 1) * sizeof(float);
+    B200_LAUNCH(colsum_partial_kernel<T>, chunks, 256, smem, stream, dy, C, R, rows_per_chunk, bpart);
+    return 0;
+}
+
 __global__ void colsum_final_kernel(int chunks, int C, const float* __restrict__ partial, float* __restrict__ out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;

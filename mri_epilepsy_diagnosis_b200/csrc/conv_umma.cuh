@@ -1078,8 +1078,7 @@ inline int umma_wgrad_run(const b200_conv_desc* d, const void* x, const void* dy
         if (chunks > 2 * kNumSMs) chunks = 2 * kNumSMs;
         if (chunks < 1) chunks = 1;
         const int64_t rows_per_chunk = (Vy + chunks - 1) / chunks;
-        const size_t smem = (size_t)(d->Co <= 256 ? (256 / d->Co) * d->Co : 1) * sizeof(float);
-        B200_LAUNCH(colsum_partial_kernel<__nv_bfloat16>, (int)chunks, 256, smem, stream, (const __nv_bfloat16*)dy, d->Co, Vy, rows_per_chunk, bpart);
+        if (colsum_launch<__nv_bfloat16>((const __nv_bfloat16*)dy, d->Co, Vy, (int)chunks, rows_per_chunk, bpart, stream)) return 1;
         B200_LAUNCH(colsum_final_kernel, (int)((d->Co + 127) / 128), 128, 0, stream, (int)chunks, d->Co, bpart, dbias);
     }
     return 0;

@@ -569,6 +569,34 @@ def concat(a, b):
     return _ConcatFn.apply(a, b)
 
 
+class _PadChannelsFn(Function):
+    """x (N,C,...) -> (N,C+pad,...) with zero channels appended (channels-last); backward slices the gradient."""
+
+    @staticmethod
+    def forward(ctx, x, pad):
+        need_cuda(x, "pad_channels")
+        x = to_cl(x)
+        c = x.shape[1]
+        y = _empty_cl((x.shape[0], c + pad) + tuple(x.shape[2:]), x.dtype, x.device).zero_()
+        V = x.numel() // c
+        check(lib().b200_copy_channels(dtype_code(x.dtype), V, c, x.data_ptr(), c, 0, y.data_ptr(), c + pad, 0, stream()))
+        ctx.c, ctx.pad = c, pad
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = to_cl(dy)
+        c, pad = ctx.c, ctx.pad
+        dx = _empty_cl((dy.shape[0], c) + tuple(dy.shape[2:]), dy.dtype, dy.device)
+        V = dy.numel() // (c + pad)
+        check(lib().b200_copy_channels(dtype_code(dy.dtype), V, c, dy.data_ptr(), c + pad, 0, dx.data_ptr(), c, 0, stream()))
+        return dx, None
+
+
+def pad_channels(x, pad):
+    return _PadChannelsFn.apply(x, pad)
+
+
 # --------------------------------------------------------------------------- fused softmax + Dice loss
 class _SoftmaxDiceFn(Function):
     @staticmethod

@@ -72,7 +72,25 @@ class _ConvMixin(_B200Mixin):
             raise RuntimeError("b200nn.ConvTranspose3d: output_padding/output_size are not supported")
         x = self._prep(x)
         out_dtype = self.out_dtype or (self.compute_dtype if self.compute_dtype is not None else x.dtype)
-        return BF.conv(x, self.weight, self.bias, self._cfg(), out_dtype, want_stats)
+        weight = self.weight
+        pad_c = self._tensor_core_channel_pad(x)
+        if pad_c:
+            # e.g. unet.UNet(first=8)'s 8 -> 16 convolution: 8 zero input channels (and zero weight columns) make the layer a
+            # 16-channel tcgen05 problem instead of a CUDA-core one; autograd slices both gradients back
+            x = BF.pad_channels(x, pad_c)
+            weight = torch.cat([weight, weight.new_zeros((weight.shape[0], pad_c) + tuple(weight.shape[2:]))], 1)
+        return BF.conv(x, weight, self.bias, self._cfg(), out_dtype, want_stats)
+
+    def _tensor_core_channel_pad(self, x):
+        ci = x.shape[1]
+        if not self.allow_umma or self._transposed_conv or x.dtype != torch.bfloat16 or ci < 8 or ci % 16 == 0 or ci % 8 != 0:
+            return 0
+        if self.out_channels % 16 != 0 or x.numel() // ci < 4096:
+            return 0
+        k, s, p, d = self.kernel_size, self.stride, self.padding, self.dilation
+        if any(v != 1 for v in s) or any(v != 1 for v in d) or any(kk not in (1, 3) for kk in k) or any(pp != kk // 2 for pp, kk in zip(p, k)):
+            return 0
+        return 16 - ci % 16
 
 
 class Conv3d(_ConvMixin, tnn.Conv3d):
