@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "conv_simt.cuh"
 #include "conv_small.cuh"
+#include "conv_axis.cuh"
 #include "conv_umma.cuh"
 #include "conv_row.cuh"
 #include "conv_rowf.cuh"
@@ -191,6 +192,7 @@ size_t b200_conv_workspace_bytes(const b200_conv_desc* d, int pass) {
     if (pass != B200_PASS_WGRAD) return 0;
     if (stem3_supported(d)) return stem3_wgrad_ws_bytes(d) + 256;
     if (head_supported(d)) return head_wgrad_ws_bytes(d) + 256;
+    if (axis_conv_supported(d, pass)) return axis_wgrad_ws_bytes(d) + 256;
     const ConvPlan p = conv_plan(d, pass);
     const WgradSplit s = wgrad_split(d, p);
     return s.partial_bytes + s.bias_bytes + 256;
@@ -204,6 +206,7 @@ int b200_conv_fwd(const b200_conv_desc* d, const void* x, const void* w_packed, 
     if (b200_conv_algo(d, B200_PASS_FWD) == B200_ALGO_UMMA) return umma_conv_run(d, B200_PASS_FWD, x, w_packed, bias, y, workspace, ws_bytes, stream);
     if (stem3_supported(d)) return stem3_fwd_run(d, x, (const float*)w_packed, bias, y, stream);
     if (head_supported(d)) return head_fwd_run(d, x, (const float*)w_packed, bias, y, stream);
+    if (axis_conv_supported(d, B200_PASS_FWD)) return axis_gather_run(d, B200_PASS_FWD, x, (const float*)w_packed, bias, y, stream);
     const ConvPlan p = conv_plan(d, B200_PASS_FWD);
     return dispatch_gather(p, x, (const float*)w_packed, bias, y, stream);
 }
@@ -231,6 +234,7 @@ int b200_conv_dgrad(const b200_conv_desc* d, const void* dy, const void* w_packe
     if (b200_conv_algo(d, B200_PASS_DGRAD) == B200_ALGO_UMMA)
         return umma_conv_run(d, B200_PASS_DGRAD, dy, w_packed_dgrad, nullptr, dx, workspace, ws_bytes, stream);
     if (head_supported(d)) return head_dgrad_run(d, dy, (const float*)w_packed_dgrad, dx, stream);
+    if (axis_conv_supported(d, B200_PASS_DGRAD)) return axis_gather_run(d, B200_PASS_DGRAD, dy, (const float*)w_packed_dgrad, nullptr, dx, stream);
     const ConvPlan p = conv_plan(d, B200_PASS_DGRAD);
     return dispatch_gather(p, dy, (const float*)w_packed_dgrad, nullptr, dx, stream);
 }
@@ -244,6 +248,7 @@ int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const void* dy, floa
     if (b200_conv_algo(d, B200_PASS_WGRAD) == B200_ALGO_UMMA) return umma_wgrad_run(d, x, dy, dw, dbias, workspace, ws_bytes, stream);
     if (stem3_supported(d)) return stem3_wgrad_run(d, x, dy, dw, dbias, workspace, stream);
     if (head_supported(d)) return head_wgrad_run(d, x, dy, dw, dbias, workspace, stream);
+    if (axis_conv_supported(d, B200_PASS_WGRAD)) return axis_wgrad_run(d, x, dy, dw, dbias, workspace, stream);
     const ConvPlan p = conv_plan(d, B200_PASS_WGRAD);
     const WgradSplit s = wgrad_split(d, p);
     float* partial = (float*)workspace;

@@ -84,3 +84,46 @@ def test_head_argmax_bit_exact_on_ties(B):
     y = mod(x)
     assert torch.equal(y[:, 0], y[:, 1])
     assert int(y.argmax(dim=1).sum()) == 0
+
+
+AXIS_CASES = [
+    # name, N, Ci, Co, (D,H,W), kernel, stride, padding
+    ("x_k6s2_1_8", 2, 1, 8, (24, 10, 12), (6, 1, 1), (2, 1, 1), (2, 0, 0)),        # fader encoder block 0 (AE_model.py:9-14)
+    ("y_k6s2_8_8", 2, 8, 8, (12, 20, 12), (1, 6, 1), (1, 2, 1), (0, 2, 0)),
+    ("z_k6s2_8_8", 2, 8, 8, (6, 10, 26), (1, 1, 6), (1, 1, 2), (0, 0, 2)),
+    ("x_k6s2_8_16", 1, 8, 16, (20, 9, 7), (6, 1, 1), (2, 1, 1), (2, 0, 0)),
+    ("x_k3_1_16", 2, 1, 16, (9, 8, 16), (3, 1, 1), 1, (1, 0, 0)),                  # autoencoder stem (train_AE.ipynb [cell 8])
+    ("y_k3_16_1", 1, 16, 1, (5, 12, 9), (1, 3, 1), 1, (0, 1, 0)),                  # reconstruction tail
+    ("z_k3_1_1", 2, 1, 1, (6, 7, 19), (1, 1, 3), 1, (0, 0, 1)),
+    ("x_k3p0_16_16", 1, 16, 16, (9, 5, 6), (3, 1, 1), 1, 0),
+]
+
+
+@pytest.mark.parametrize("case", AXIS_CASES, ids=[c[0] for c in AXIS_CASES])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_axis_conv_fwd_dgrad_wgrad(B, case, dtype):
+    """Separable 1-D convolutions with few channels (conv_axis.cuh) against torch fp32 on the same (rounded) operands."""
+    name, N, Ci, Co, size, k, s, p = case
+    g = torch.Generator().manual_seed(len(name) * 3 + Ci + Co)
+    ref = torch.nn.Conv3d(Ci, Co, k, s, p, bias=True)
+    mod = B.nn.Conv3d(Ci, Co, k, s, p, bias=True).cuda()
+    mod.load_state_dict(ref.state_dict())
+    mod.compute_dtype = dtype
+    x = torch.randn(N, Ci, *size, generator=g)
+    if dtype == torch.bfloat16:
+        x = x.bfloat16().float()
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    gy = torch.randn(yr.shape, generator=g)
+    if dtype == torch.bfloat16:
+        gy = gy.bfloat16().float()
+    yr.backward(gy)
+    xg = x.cuda().to(dtype).requires_grad_(True)
+    yg = mod(xg)
+    assert tuple(yg.shape) == tuple(yr.shape)
+    yg.backward(gy.cuda().to(yg.dtype))
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert rel_err(yg.float(), yr) < tol, "forward"
+    assert rel_err(xg.grad.float(), xr.grad) < tol, "dgrad"
+    assert rel_err(mod.weight.grad, ref.weight.grad) < (1e-4 if dtype == torch.float32 else 2e-3), "wgrad"
+    assert rel_err(mod.bias.grad, ref.bias.grad) < (1e-4 if dtype == torch.float32 else 2e-3), "bias grad"

@@ -27,10 +27,19 @@ dev = torch.device("cuda", 0)
 BF16 = torch.bfloat16
 
 
+PROFILE = os.environ.get("B200_PROFILE_ONE_STEP") == "1"      # under ncu --profile-from-start off: capture exactly one step
+
+
 def timeit(fn, iters=5, warmup=2):
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
+    if PROFILE:
+        torch.cuda.cudart().cudaProfilerStart()
+        fn()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return 1.0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
