@@ -273,36 +273,45 @@ def main():
     tc_flops, tc_s = sum(v[0] for v in tc.values()), sum(v[1] for v in tc.values())
     conv_s = sum(v[1] for v in agg.values())
     pk = peaks()
-    # dominant launch signature = (kernel, layer shape) with the largest share of the step; fwd and dgrad of a "same" conv with
-    # Ci == Co are the same kernel on the same geometry
-    sig = {}
+    # dominant kernel = the tcgen05 kernel with the largest share of the step; `achieved` = algorithmic FLOPs of ALL its launches /
+    # the sum of their durations (= FLOPs per launch / average launch duration).  Its heaviest layer shape is reported as detail
+    # (fwd and dgrad of a "same" convolution with Ci == Co are the same kernel on the same geometry).
+    per_kernel, sig = {}, {}
     for (which, algo, shape), v in tc.items():
-        key = (KERNEL[(which, algo)], (min(shape[0], shape[1]), max(shape[0], shape[1])) + tuple(shape[2:])) if which != 2 else \
-              (KERNEL[(which, algo)], tuple(shape))
+        kn = KERNEL[(which, algo)]
+        r = per_kernel.setdefault(kn, [0.0, 0.0, 0])
+        r[0] += v[0]; r[1] += v[1]; r[2] += v[2]
+        key = (kn, ((min(shape[0], shape[1]), max(shape[0], shape[1])) + tuple(shape[2:])) if which != 2 else tuple(shape))
         r = sig.setdefault(key, [0.0, 0.0, 0])
         r[0] += v[0]; r[1] += v[1]; r[2] += v[2]
-    (dom_kernel, dom_shape), dom = max(sig.items(), key=lambda kv: kv[1][1]) if sig else (("none", ()), [0.0, 1e-9, 0])
+    dom_kernel, dom = max(per_kernel.items(), key=lambda kv: kv[1][1]) if per_kernel else ("none", [0.0, 1e-9, 0])
+    top = max(((k, v) for k, v in sig.items() if k[0] == dom_kernel), key=lambda kv: kv[1][1], default=None)
     achieved = dom[0] / dom[1] / 1e12
-    traffic = None
+    traffic_tab = {}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(f"{dom_kernel}|" + "|".join(str(int(x)) for x in dom_shape) + f"|n{args.batch}")
+            traffic_tab = json.load(f)
     except Exception:
         pass
-    roofline = {"bound": "tensor", "kernel": dom_kernel,
-                "launch": (f"Conv3d {dom_shape[0]}<->{dom_shape[1]} k{dom_shape[5]} on {args.batch} x {dom_shape[2]}x{dom_shape[3]}x{dom_shape[4]} bf16"
-                           if dom_shape else ""),
-                "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
-                "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write, ncu --set full; profiles/traffic.json)",
-                "algorithmic_bytes": (2.0 * args.batch * dom_shape[2] * dom_shape[3] * dom_shape[4] * (dom_shape[0] + dom_shape[1]) if dom_shape else None),
+    top_launch = None
+    if top is not None:
+        (_, ts), tv = top
+        top_launch = {"layer": f"Conv3d {ts[0]}<->{ts[1]} k{ts[5]} on {args.batch} x {ts[2]}x{ts[3]}x{ts[4]} bf16", "launches_per_step": tv[2] / max(1, args.steps),
+                      "ms_per_launch": 1e3 * tv[1] / max(1, tv[2]), "achieved": tv[0] / tv[1] / 1e12, "frac": tv[0] / tv[1] / 1e12 / pk["bf16_tflops"],
+                      "algorithmic_bytes": 2.0 * args.batch * ts[2] * ts[3] * ts[4] * (ts[0] + ts[1]),
+                      "traffic": traffic_tab.get(f"{dom_kernel}|" + "|".join(str(int(x)) for x in ts) + f"|n{args.batch}")}
+    roofline = {"bound": "tensor", "kernel": dom_kernel, "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / pk["bf16_tflops"],
+                "traffic": traffic_tab.get(dom_kernel) if (args.model == "unet3d" and args.batch == 4 and args.size == 128) else None,
+                "traffic_unit": "bytes per launch, dram read + write averaged over the kernel's launches of one step (ncu; profiles/traffic.json)",
                 "peak_source": pk["source"] + " (sustained bf16)",
                 "launches_per_step": dom[2] / max(1, args.steps), "ms_per_launch_avg": 1e3 * dom[1] / max(1, dom[2]),
-                "share_of_step": (dom[1] / args.steps) / (ms / 1e3),
+                "share_of_step": (dom[1] / args.steps) / (ms / 1e3), "top_launch": top_launch,
                 "all_tcgen05_convs": {"achieved": tc_flops / tc_s / 1e12 if tc_s > 0 else 0.0, "frac": (tc_flops / tc_s / 1e12 / pk["bf16_tflops"]) if tc_s > 0 else 0.0,
                                       "share_of_step": (tc_s / args.steps) / (ms / 1e3), "launches_per_step": sum(v[2] for v in tc.values()) / max(1, args.steps)},
                 "all_conv_share_of_step": (conv_s / args.steps) / (ms / 1e3),
-                "note": "achieved = algorithmic FLOPs (2*N*Do*Ho*Wo*Co*Ci*taps per launch) / CUDA-event duration of the dominant kernel's launches "
-                        "of that layer shape, events on the launching stream around each launch (eager replays of the same step)"}
+                "note": "achieved = algorithmic FLOPs (2*N*Do*Ho*Wo*Co*Ci*taps per launch) of the dominant kernel's launches / their CUDA-event "
+                        "durations; events on the launching stream around each launch (eager replays of the same step)"}
     if args.profile_json and rank == 0:
         names = {0: "fwd", 1: "dgrad", 2: "wgrad"}
         table = [{"pass": names[k[0]], "algo": {0: "direct", 1: "umma", 2: "row"}[k[1]], "Ci": k[2][0], "Co": k[2][1], "out": list(k[2][2:5]), "kd": k[2][5],
