@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
         constexpr int nks = NKS;
         const uint32_t wtap16 = ((uint32_t)p.IC * p.OC * 2) >> 4, wks16 = (2 * (uint32_t)p.OC * 16) >> 4;
         const uint32_t idesc = p.idesc;
+        const bool leader = ptx::elect_one();                                   // one fixed lane issues every tcgen05 instruction of the CTA
         uint32_t cnt = 0, group = 0;
         if (!p.stream_w) {
         ptx::mbar_wait(ptx::smem_u32(&bars.wfull[0]), 0);
@@ -172,9 +173,11 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
                 uint32_t hasmask = 0;
 #pragma unroll
                 for (int kz = 0; kz < KD; ++kz) { const int pl = z + kz - pd; if (pl >= 0 && pl < p.D) hasmask |= 1u << kz; }
-                if (ptx::elect_one()) {
-                    // The single issuing thread is the bottleneck of the whole SM: keep its loop a few instructions per MMA
-                    // and small enough for the instruction cache (a fully unrolled 27-tap body stalled on instruction fetch).
+                {
+                    // The issue rate of this warp bounds the tensor pipe for N = 16/32 (39-40 cycles per MMA): all 32 lanes run
+                    // the loop with warp-uniform values -- descriptors live in uniform registers, no R2UR per MMA -- and only the
+                    // tcgen05 instructions are predicated on the elected lane.  The body stays small enough for the instruction
+                    // cache (a fully unrolled 27-tap body stalled on instruction fetch).
                     uint32_t off[KHW * KHW];
 #pragma unroll
                     for (int j = 0; j < KHW * KHW; ++j) off[j] = (uint32_t)(j / KHW) * row16 + (uint32_t)(j % KHW) * vox16;
@@ -188,32 +191,26 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
                         for (int kz = 0; kz < KD; ++kz) {
                             if (!((hasmask >> kz) & 1)) { bb += (uint32_t)(KHW * KHW) * wtap16; continue; }
                             const uint32_t a0 = (pl16 + ((i0 + (uint32_t)kz) & (kRfRing - 1)) * plane16 + tile16) | a_flag;
-                            if (nks == 1) {
 #pragma unroll
-                                for (int j = 0; j < KHW * KHW; ++j) {
-                                    ptx::umma_bf16_lohi(d_tmem, a0 + off[j], a_hi, bb, b_hi, idesc, acc);
-                                    bb += wtap16; acc = 1;
+                            for (int j = 0; j < KHW * KHW; ++j) {
+                                uint32_t a = a0 + off[j], b2 = bb;
+#pragma unroll
+                                for (int ks = 0; ks < nks; ++ks) {
+                                    if (leader) ptx::umma_bf16_lohi(d_tmem, a, a_hi, b2, b_hi, idesc, acc);
+                                    a += 2; b2 += wks16; acc = 1;
                                 }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < KHW * KHW; ++j) {
-                                    uint32_t a = a0 + off[j], b2 = bb;
-#pragma unroll
-                                    for (int ks = 0; ks < nks; ++ks) {
-                                        ptx::umma_bf16_lohi(d_tmem, a, a_hi, b2, b_hi, idesc, acc);
-                                        a += 2; b2 += wks16; acc = 1;
-                                    }
-                                    bb += wtap16;
-                                }
+                                bb += wtap16;
                             }
                         }
                     }
-                    ptx::umma_commit(ptx::smem_u32(&bars.afull[set]));
-                    // plane z-pd is not needed by z+1; at the end of the segment release everything that is left
-                    const int lo = z - pd, hi = (z + 1 == c.z1) ? last : lo;
-                    for (int pl = max(lo, first); pl <= hi; ++pl) {
-                        const uint32_t i = cnt + (uint32_t)(pl - first);
-                        ptx::umma_commit(ptx::smem_u32(&bars.pempty[i % kRfRing]));
+                    if (leader) {
+                        ptx::umma_commit(ptx::smem_u32(&bars.afull[set]));
+                        // plane z-pd is not needed by z+1; at the end of the segment release everything that is left
+                        const int lo = z - pd, hi = (z + 1 == c.z1) ? last : lo;
+                        for (int pl = max(lo, first); pl <= hi; ++pl) {
+                            const uint32_t i = cnt + (uint32_t)(pl - first);
+                            ptx::umma_commit(ptx::smem_u32(&bars.pempty[i % kRfRing]));
+                        }
                     }
                 }
                 __syncwarp();
@@ -251,7 +248,7 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
                     for (int j = 0; j < KHW * KHW; ++j) {
                         ptx::mbar_wait(ptx::smem_u32(&bars.wfull[ws]), wph);
                         ptx::tc_fence_after();
-                        if (ptx::elect_one()) {
+                        {
                             const uint32_t a_tap = a_pl + (uint32_t)(j / KHW) * row16 + (uint32_t)(j % KHW) * vox16;
                             const uint32_t b0 = (w16 + ws * wstage16) | b_lbo;
                             uint32_t d = d_set;
@@ -259,26 +256,24 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
                                 uint32_t a = a_tap + (uint32_t)((t / p.tpr) * p.rowstride + (t % p.tpr) * 128) * vox16, b2 = b0;
 #pragma unroll
                                 for (int ks = 0; ks < nks; ++ks) {
-                                    ptx::umma_bf16_lohi(d, a, a_hi, b2, b_hi, idesc, ks == 0 ? acc : 1u);
+                                    if (leader) ptx::umma_bf16_lohi(d, a, a_hi, b2, b_hi, idesc, ks == 0 ? acc : 1u);
                                     a += 2; b2 += wks16;
                                 }
                                 d += (uint32_t)p.OC;
                             }
-                            ptx::umma_commit(ptx::smem_u32(&bars.wempty[ws]));           // stage free once these MMAs retire
+                            if (leader) ptx::umma_commit(ptx::smem_u32(&bars.wempty[ws]));           // stage free once these MMAs retire
                         }
-                        __syncwarp();
                         acc = 1;
                         if (++ws == (uint32_t)p.nw) { ws = 0; wph ^= 1; }
                     }
                     // the oldest plane of the window is only read by the kz = 0 pass: free it NOW so that the producer can refill
                     // the slot during the remaining two thirds of this group (this is what makes a ring of 3 enough)
                     if (KD == 3 && kz == 0 && z + 1 < c.z1 && pl >= first) {
-                        if (ptx::elect_one()) ptx::umma_commit(ptx::smem_u32(&bars.pempty[(cnt + (uint32_t)(pl - first)) % ring]));
-                        __syncwarp();
+                        if (leader) ptx::umma_commit(ptx::smem_u32(&bars.pempty[(cnt + (uint32_t)(pl - first)) % ring]));
                         released = true;
                     }
                 }
-                if (ptx::elect_one()) {
+                if (leader) {
                     ptx::umma_commit(ptx::smem_u32(&bars.afull[set]));
                     const int lo = released ? z - pd + 1 : z - pd, hi = (z + 1 == c.z1) ? last : z - pd;
                     for (int pl = max(lo, first); pl <= hi; ++pl) ptx::umma_commit(ptx::smem_u32(&bars.pempty[(cnt + (uint32_t)(pl - first)) % ring]));

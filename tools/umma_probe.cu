@@ -39,9 +39,15 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeCfg c, long long* ou
         } else if (c.layout == 1) {
             a_hi = (128u >> 4) | (1u << 14); a_lo0 = ((a_base >> 4) & 0x3FFF) | ((2048u >> 4) << 16);
             b_hi = (128u >> 4) | (1u << 14); b_lo0 = ((b_base >> 4) & 0x3FFF) | (((uint32_t)c.n * 16 >> 4) << 16);
-        } else {
+        } else if (c.layout == 2) {
             a_hi = (1024u >> 4) | (1u << 14) | (2u << 29); a_lo0 = ((a_base >> 4) & 0x3FFF) | (1u << 16);
             b_hi = (1024u >> 4) | (1u << 14) | (2u << 29); b_lo0 = ((b_base >> 4) & 0x3FFF) | (1u << 16);
+        } else {
+            // 3: SWIZZLE_32B rows (32 B per voxel, SBO 256), 4: SWIZZLE_64B rows (SBO 512), 5: SWIZZLE_128B rows (SBO 1024) -- A as the
+            // row-slab kernels stage it; B = no-swizzle packed weights.  shift=1 moves the A start by whole 32-byte steps like the taps do
+            const uint32_t sbo = c.layout == 3 ? 256u : (c.layout == 4 ? 512u : 1024u), lbits = c.layout == 3 ? 6u : (c.layout == 4 ? 4u : 2u);
+            a_hi = (sbo >> 4) | (1u << 14) | (lbits << 29); a_lo0 = ((a_base >> 4) & 0x3FFF) | (1u << 16);
+            b_hi = (128u >> 4) | (1u << 14); b_lo0 = ((b_base >> 4) & 0x3FFF) | (((uint32_t)c.n * 16 >> 4) << 16);
         }
         const uint32_t idesc = make_idesc_bf16(c.n);
         __syncwarp();
@@ -51,7 +57,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeCfg c, long long* ou
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const uint32_t acc = (uint32_t)(j % NACCS);
-                    const uint32_t a_lo = a_lo0 + (SHIFT ? (uint32_t)((j % 9) / 3 * 10 + (j % 3)) : 0u);
+                    const uint32_t a_lo = a_lo0 + (SHIFT ? (c.layout >= 3 ? (uint32_t)((j % 9) / 3 * 260 + (j % 3) * 2) : (uint32_t)((j % 9) / 3 * 10 + (j % 3))) : 0u);
                     ptx::umma_bf16_lohi(tmem + acc * (uint32_t)c.n, a_lo, a_hi, b_lo0, b_hi, idesc, 1);
                 }
             }
@@ -73,13 +79,14 @@ int main() {
     cudaMalloc(&d_out, 148 * sizeof(long long));
     const int iters = 400;
     printf("%-8s %-5s %-6s %-6s %12s\n", "layout", "N", "naccs", "shift", "cyc/UMMA");
-    const char* names[3] = {"ns160", "ns128", "sw128"};
-    for (int layout = 0; layout < 3; ++layout)
+    const char* names[6] = {"ns160", "ns128", "sw128", "row32", "row64", "row128"};
+    for (int layout = 0; layout < 6; ++layout)
         for (int n : {16, 32, 64, 128, 256})
             for (int naccs : {1, 2, 4})
                 for (int shift : {0, 1}) {
                     if (naccs * n > 512) continue;
-                    if (layout != 0 && shift) continue;
+                    if (layout != 0 && layout < 3 && shift) continue;
+                    if (layout >= 3 && (n > 64 || naccs == 2)) continue;
                     ProbeCfg c{n, layout, naccs, shift, iters};
                     auto launch = [&](auto kern) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); kern<<<148, 128, 200 * 1024>>>(c, d_out); };
                     if (naccs == 1 && !shift) launch(probe_kernel<1, 0>);
