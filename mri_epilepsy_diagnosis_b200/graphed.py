@@ -91,3 +91,41 @@ class GraphedTrainStep:
         if not self.capture_opt:
             self._reduce_and_step()
         return self.loss
+
+    # ---- host-fed steps with the next batch's H2D copy overlapped with the current step (what a pin_memory DataLoader with
+    # non_blocking copies gives the reference loop): `prefetch(x, t)` starts the copy of a PINNED host batch into a staging
+    # buffer on a copy stream; `step_prefetched()` waits for it, moves it into the graph's static inputs (device-to-device)
+    # and replays.  Every step still performs exactly one H2D copy of its own inputs.
+    def prefetch(self, x_host, t_host):
+        if not hasattr(self, "_stage"):
+            self._stage = [(torch.empty_like(self.x), torch.empty_like(self.t)) for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(device=self.x.device)
+            self._ready = [None, None]
+            self._consumed = [None, None]
+            self._slot = 0
+            self._pending = []
+        s = self._slot
+        self._slot ^= 1
+        if self._consumed[s] is not None:                 # the step that read this staging slot must have copied it out
+            self._copy_stream.wait_event(self._consumed[s])
+        with torch.cuda.stream(self._copy_stream):
+            self._stage[s][0].copy_(x_host, non_blocking=True)
+            self._stage[s][1].copy_(t_host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._ready[s] = ev
+        self._pending.append(s)
+
+    def step_prefetched(self):
+        s = self._pending.pop(0)
+        cur = torch.cuda.current_stream(self.x.device)
+        cur.wait_event(self._ready[s])
+        self.x.copy_(self._stage[s][0], non_blocking=True)
+        self.t.copy_(self._stage[s][1], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self._consumed[s] = ev
+        self.graph.replay()
+        if not self.capture_opt:
+            self._reduce_and_step()
+        return self.loss
