@@ -80,6 +80,12 @@ int b200_conv_fwd(const b200_conv_desc* d, const void* x, const void* w_packed, 
 int b200_conv_stats_chunks(const b200_conv_desc* d);
 int b200_conv_fwd_stats(const b200_conv_desc* d, const void* x, const void* w_packed, const float* bias, void* y,
                         float* stat_partial, void* workspace, size_t ws_bytes, void* stream);
+/* Two convolutions of the SAME input evaluated as one with concatenated output channels (d->Co = Co_a + Co_b) when only the
+ * statistics of the first Co_a = first_stored_channel outputs are needed (unet3d.py:43-46: conv2 feeds a branch whose value is
+ * discarded, conv3 the live one): statistics cover all Co channels, `y_tail` receives channels [first_stored_channel, Co) as a
+ * dense (N, Co - first_stored_channel, ...) tensor.  first_stored_channel must be a multiple of 16, Co <= 64. */
+int b200_conv_fwd_stats_tail(const b200_conv_desc* d, const void* x, const void* w_packed, const float* bias, void* y_tail,
+                             int first_stored_channel, float* stat_partial, void* workspace, size_t ws_bytes, void* stream);
 /* dx = d(loss)/dx given dy (dtypes: dy has y_dtype, dx has x_dtype). */
 int b200_conv_dgrad(const b200_conv_desc* d, const void* dy, const void* w_packed_dgrad, void* dx,
                     void* workspace, size_t ws_bytes, void* stream);

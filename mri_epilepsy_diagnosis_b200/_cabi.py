@@ -58,6 +58,7 @@ _SIGS = {
     "b200_conv_fwd": (C.c_int, [P(ConvDesc), vp, vp, vp, vp, vp, sz, vp]),
     "b200_conv_stats_chunks": (C.c_int, [P(ConvDesc)]),
     "b200_conv_fwd_stats": (C.c_int, [P(ConvDesc), vp, vp, vp, vp, vp, vp, sz, vp]),
+    "b200_conv_fwd_stats_tail": (C.c_int, [P(ConvDesc), vp, vp, vp, vp, C.c_int, vp, vp, sz, vp]),
     "b200_conv_dgrad": (C.c_int, [P(ConvDesc), vp, vp, vp, vp, sz, vp]),
     "b200_conv_wgrad": (C.c_int, [P(ConvDesc), vp, vp, vp, vp, vp, sz, vp]),
     "b200_norm_workspace_bytes": (sz, [P(NormDesc)]),

@@ -226,6 +226,15 @@ int b200_conv_fwd_stats(const b200_conv_desc* d, const void* x, const void* w_pa
     return row_fwd_run(d, B200_PASS_FWD, x, w_packed, bias, y, stat_partial, stream);
 }
 
+int b200_conv_fwd_stats_tail(const b200_conv_desc* d, const void* x, const void* w_packed, const float* bias, void* y_tail, int first_stored_channel,
+                             float* stat_partial, void* workspace, size_t ws_bytes, void* stream) {
+    (void)workspace; (void)ws_bytes;
+    if (conv_validate(d)) return 1;
+    B200_REQUIRE(x && w_packed && y_tail && stat_partial, "conv_fwd_stats_tail: null pointer");
+    B200_REQUIRE(b200_conv_stats_chunks(d) > 0, "conv_fwd_stats_tail: no fused-statistics kernel for this descriptor (check b200_conv_stats_chunks)");
+    return row_fwd_run(d, B200_PASS_FWD, x, w_packed, bias, y_tail, stat_partial, stream, first_stored_channel);
+}
+
 int b200_conv_dgrad(const b200_conv_desc* d, const void* dy, const void* w_packed_dgrad, void* dx,
                     void* workspace, size_t ws_bytes, void* stream) {
     if (conv_validate(d)) return 1;

@@ -46,7 +46,8 @@ struct RowFwdParams {
     const __nv_bfloat16* w;      // [tap][IC/8][OC][8]
     const float* bias;           // [OC] or null
     __nv_bfloat16* out;          // [N][D][H][W][OC]
-    float* stats;                // [grid][2][OC] fp32 per-CTA (sum, sum of squares) of the outputs (OC <= 32); or null
+    float* stats;                // [grid][2][OC] fp32 per-CTA (sum, sum of squares) of the outputs (OC <= 64); or null
+    int store_c0;                // only channels [store_c0, OC) are stored (out has OC - store_c0 channels); statistics cover all
 };
 
 struct alignas(128) RowFwdBarriers {
@@ -309,9 +310,11 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
         const int lane_grp = warp & 3;
         const int m = lane_grp * 32 + lane;
         const bool want_stats = p.stats != nullptr;
-        float ssum[32], ssq[32];                                 // per-thread partial statistics (OC <= 32 when requested)
+        constexpr int kStatCh = 4;                               // statistics / fused stores: up to 4 x 16 output channels
+        float ssum[16 * kStatCh], ssq[16 * kStatCh];             // per-thread partial statistics
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
+        for (int i = 0; i < 16 * kStatCh; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
+        const int ocs = p.OC - p.store_c0;                       // stored channels per voxel
         uint32_t group = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
             const RfItem c = rf_decode(p, item);
@@ -325,11 +328,11 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
                     const int slot = (t / p.tpr) * p.rowstride + (t % p.tpr) * 128 + m;
                     const int row = slot / p.pitchW, x = slot - row * p.pitchW;
                     const bool valid = x < p.W && row < c.rows;
-                    __nv_bfloat16* dst = p.out + ((plane_vox + c.y0 + row) * p.W + x) * p.OC;
+                    __nv_bfloat16* dst = p.out + ((plane_vox + c.y0 + row) * p.W + x) * ocs - p.store_c0;
                     const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)((set * p.T + t) * p.OC);
-                    if (p.OC <= 32) {
+                    if (p.OC <= 16 * kStatCh) {
 #pragma unroll
-                        for (int ch = 0; ch < 2; ++ch) {
+                        for (int ch = 0; ch < kStatCh; ++ch) {
                             if (ch * 16 < p.OC) {
                                 float v[16];
                                 ptx::tmem_ld16(taddr + (uint32_t)(ch * 16), v);
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
                                     for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + ch * 16 + i);
                                 }
                                 if (valid) {
-                                    rf_store16(dst + ch * 16, v);
+                                    if (ch * 16 >= p.store_c0) rf_store16(dst + ch * 16, v);
                                     if (want_stats) {
 #pragma unroll
                                         for (int i = 0; i < 16; ++i) { ssum[ch * 16 + i] += v[i]; ssq[ch * 16 + i] = fmaf(v[i], v[i], ssq[ch * 16 + i]); }
@@ -354,7 +357,7 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + c0 + i);
                             }
-                            if (valid) rf_store16(dst + c0, v);
+                            if (valid && c0 >= p.store_c0) rf_store16(dst + c0, v);
                         }
                     }
                 }
@@ -366,9 +369,9 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
         if (want_stats) {
             // per-CTA partial: lanes -> warp (shuffle), 4 warps -> CTA in a fixed order (deterministic); summed over CTAs by
             // norm_stats_finalize_kernel in double
-            __shared__ float red[4][2][32];
+            __shared__ float red[4][2][16 * kStatCh];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < 16 * kStatCh; ++i) {
                 if (i < p.OC) {
                     float a = ssum[i], b = ssq[i];
 #pragma unroll
@@ -418,52 +421,58 @@ inline int row_fwd_plan(const RowFwdGeom& g, int N, RowFwdParams* p, size_t* sme
     p->rowstride = per_row ? p->pitchW : 0;
     p->w_bytes = g.kd * g.khw * g.khw * g.IC * g.OC * 2;
     p->wtap_bytes = g.IC * g.OC * 2;
-    // weights: resident when every tap fits next to a 4-deep plane ring, otherwise streamed tap by tap through a ring (and
-    // the plane ring shrinks to 3: the kz = 0 plane is released after its pass, see the MMA loop)
-    p->stream_w = p->w_bytes > 64 * 1024 ? 1 : 0;
-    p->ring = p->stream_w ? 3 : kRfRing;
+    // weights: RESIDENT (every tap in shared memory next to a 4-deep plane ring) or STREAMED tap by tap through a ring (the
+    // plane ring then shrinks to 3: the kz = 0 plane is released after its pass, see the MMA loop).  Both modes are costed.
     int maxT = 256 / g.OC;
     if (maxT > kRfMaxTiles) maxT = kRfMaxTiles;
     if (maxT < 1) maxT = 1;
-    // Search (weight stages, row-block height, z-segment length) with a small cost model of one persistent CTA:
-    //   MMA cycles per group  = tiles * taps * ksteps * cycles(N)         (probe: max(48, 32 + N/4, N/2) for 32..128-byte rows)
+    // Search (mode, weight stages, row-block height, z-segment length) with a small cost model of one persistent CTA:
+    //   MMA cycles per group  = tiles * taps * ksteps * cycles(N)         (probe: max(48, 32 + N/4, N/2) in situ)
     //   weight cycles / group = bytes of all taps / min(10, bytes in flight / 5000 cycles) B/clk/SM      (streaming mode)
     //   item = zs groups + the z-halo planes it has to load first; total = rounds of the persistent grid * item
     const int taps = g.kd * g.khw * g.khw, nks = g.IC / 16;
     double mma_cyc = 32.0 + g.OC / 4.0;
     if (mma_cyc < 48.0) mma_cyc = 48.0;
     if (mma_cyc < g.OC / 2.0) mma_cyc = g.OC / 2.0;
-    int best = 0, best_zs = 1, best_nw = 1; double best_cost = 1e30;
-    const int nw_lo = p->stream_w ? 2 : 1, nw_hi = p->stream_w ? kRfMaxW : 1;
-    for (int nw = nw_lo; nw <= nw_hi; ++nw) {
-        const size_t wsm_bytes = p->stream_w ? (size_t)nw * p->wtap_bytes : (size_t)p->w_bytes;
-        if (wsm_bytes + 1024 >= (size_t)kRfMaxDynSmem) break;
-        const size_t budget = (size_t)kRfMaxDynSmem - 1024 - wsm_bytes;
-        for (int YB = 1; YB <= 32 && YB <= g.H; ++YB) {
-            const int T = per_row ? YB * p->tpr : ((YB - 1) * p->pitchW + g.W + 127) / 128;
-            if (T > maxT) break;
-            const size_t pb = (((size_t)(YB + 2 * ph) * p->pitchW * g.IC * 2) + 1023) & ~(size_t)1023;
-            const size_t reach = ((size_t)T * 128 + (size_t)(g.khw - 1) * (p->pitchW + 1)) * g.IC * 2;
-            const size_t tail = reach > pb ? reach - pb : 0;
-            if ((size_t)p->ring * pb + (tail > wsm_bytes ? tail - wsm_bytes : 0) > budget) continue;
-            const int yblocks = (g.H + YB - 1) / YB;
-            const double g_mma = (double)T * taps * nks * mma_cyc;
-            // measured (64->64 @ 64^3): a bulk copy of a tap takes ~5k cycles under load, so the ring depth bounds the rate
-            double w_bw = (double)nw * p->wtap_bytes / 5000.0;
-            if (w_bw > 10.0) w_bw = 10.0;
-            const double g_w = p->stream_w ? (double)p->w_bytes / w_bw : 0.0;
-            const double group = (g_mma > g_w ? g_mma : g_w) + 400.0;
-            const double plane_cyc = (double)pb / 20.0;
-            for (int zs = g.D; zs >= 1; zs = (zs > 4 ? (zs + 1) / 2 : zs - 1)) {
-                if (g.kd == 1 && zs != 1) continue;
-                const int zsegs = (g.D + zs - 1) / zs;
-                const int64_t items = (int64_t)N * yblocks * zsegs;
-                const double rounds = (double)((items + kNumSMs - 1) / kNumSMs);
-                const double cost = rounds * (zs * group + 2 * pd * plane_cyc + 1500.0);
-                if (cost < best_cost) { best_cost = cost; best = YB; best_zs = zs; best_nw = nw; }
+    int best = 0, best_zs = 1, best_nw = 1, best_stream = 0; double best_cost = 1e30;
+    for (int stream_w = 0; stream_w <= 1; ++stream_w) {
+        const int ring = stream_w ? 3 : kRfRing;
+        const int nw_lo = stream_w ? 2 : 1, nw_hi = stream_w ? kRfMaxW : 1;
+        for (int nw = nw_lo; nw <= nw_hi; ++nw) {
+            const size_t wsm_bytes = stream_w ? (size_t)nw * p->wtap_bytes : (size_t)p->w_bytes;
+            if (wsm_bytes + 1024 >= (size_t)kRfMaxDynSmem) break;
+            const size_t budget = (size_t)kRfMaxDynSmem - 1024 - wsm_bytes;
+            for (int YB = 1; YB <= 32 && YB <= g.H; ++YB) {
+                const int T = per_row ? YB * p->tpr : ((YB - 1) * p->pitchW + g.W + 127) / 128;
+                if (T > maxT) break;
+                const size_t pb = (((size_t)(YB + 2 * ph) * p->pitchW * g.IC * 2) + 1023) & ~(size_t)1023;
+                const size_t reach = ((size_t)T * 128 + (size_t)(g.khw - 1) * (p->pitchW + 1)) * g.IC * 2;
+                const size_t tail = reach > pb ? reach - pb : 0;
+                if ((size_t)ring * pb + (tail > wsm_bytes ? tail - wsm_bytes : 0) > budget) continue;
+                const int yblocks = (g.H + YB - 1) / YB;
+                const double g_mma = (double)T * taps * nks * mma_cyc;
+                // measured (64->64 @ 64^3): a bulk copy of a tap takes ~5k cycles under load, so the ring depth bounds the rate
+                double w_bw = (double)nw * p->wtap_bytes / 5000.0;
+                if (w_bw > 10.0) w_bw = 10.0;
+                const double g_w = stream_w ? (double)p->w_bytes / w_bw : 0.0;
+                // streaming pays a full-barrier wait + commit per tap and cannot run ahead of the weight ring: measured ~1.5x the
+                // MMA time of the resident mode on the layers where both fit
+                const double group = stream_w ? 1.5 * (g_mma > g_w ? g_mma : g_w) + 150.0 * taps + 400.0 : g_mma + 400.0;
+                const double plane_cyc = (double)pb / 20.0;
+                for (int zs = g.D; zs >= 1; zs = (zs > 4 ? (zs + 1) / 2 : zs - 1)) {
+                    if (g.kd == 1 && zs != 1) continue;
+                    const int zsegs = (g.D + zs - 1) / zs;
+                    const int64_t items = (int64_t)N * yblocks * zsegs;
+                    const double rounds = (double)((items + kNumSMs - 1) / kNumSMs);
+                    // resident weights are loaded once per CTA (w_bytes / 10 B/clk)
+                    const double cost = rounds * (zs * group + 2 * pd * plane_cyc + 1500.0) + (stream_w ? 0.0 : (double)p->w_bytes / 10.0);
+                    if (cost < best_cost) { best_cost = cost; best = YB; best_zs = zs; best_nw = nw; best_stream = stream_w; }
+                }
             }
         }
     }
+    p->stream_w = best_stream;
+    p->ring = best_stream ? 3 : kRfRing;
     p->nw = best_nw;
     B200_REQUIRE(best >= 1, "row fwd: a row block does not fit shared memory / TMEM");
     p->YB = best;
@@ -516,7 +525,7 @@ inline int row_fwd_launch(const CUtensorMap& map, const RowFwdParams& p, size_t 
 // per-CTA statistics partials: chunks = CTAs of the launch; 0 when (desc, pass) cannot produce them
 inline int row_fwd_stats_chunks(const b200_conv_desc* d) {
     RowFwdGeom g;
-    if (!row_fwd_geom(d, B200_PASS_FWD, &g) || g.OC > 32) return 0;
+    if (!row_fwd_geom(d, B200_PASS_FWD, &g) || g.OC > 64) return 0;
     RowFwdParams p; size_t smem;
     const std::string saved = err_slot();
     const bool ok = row_fwd_plan(g, d->N, &p, &smem) == 0;
@@ -527,15 +536,16 @@ inline int row_fwd_stats_chunks(const b200_conv_desc* d) {
 
 // `stats` (optional): fp32 [chunks][2][OC] per-CTA sum / sum of squares of the fp32 outputs (row_fwd_stats_chunks(d) > 0)
 inline int row_fwd_run(const b200_conv_desc* d, int pass, const void* in, const void* w_packed, const float* bias, void* out, float* stats,
-                       void* stream) {
+                       void* stream, int store_c0 = 0) {
     RowFwdGeom g;
     B200_REQUIRE(row_fwd_geom(d, pass, &g), "row fwd: unsupported descriptor");
     B200_REQUIRE(aligned16(in) && aligned16(out) && aligned16(w_packed), "row fwd: pointers must be 16-byte aligned");
-    B200_REQUIRE(stats == nullptr || g.OC <= 32, "row fwd: fused statistics need Cout <= 32");
+    B200_REQUIRE(stats == nullptr || g.OC <= 64, "row fwd: fused statistics need Cout <= 64");
+    B200_REQUIRE(store_c0 >= 0 && store_c0 < g.OC && store_c0 % 16 == 0 && (store_c0 == 0 || g.OC <= 64), "row fwd: bad first stored channel %d", store_c0);
     RowFwdParams p;
     size_t smem_bytes = 0;
     if (row_fwd_plan(g, d->N, &p, &smem_bytes)) return 1;
-    p.w = (const __nv_bfloat16*)w_packed; p.bias = bias; p.out = (__nv_bfloat16*)out; p.stats = stats;
+    p.w = (const __nv_bfloat16*)w_packed; p.bias = bias; p.out = (__nv_bfloat16*)out; p.stats = stats; p.store_c0 = store_c0;
     static const bool debug = [] { const char* e = getenv("B200_ROWF_DEBUG"); return e != nullptr && e[0] == '1'; }();
     if (debug)
         fprintf(stderr, "[row_fwd] N=%d %dx%dx%d IC=%d OC=%d k=%d,%d: YB=%d T=%d zs=%d items=%d ring=%d stream=%d nw=%d plane=%dB smem=%zuB tmem=%d\n", d->N,

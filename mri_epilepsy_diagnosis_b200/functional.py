@@ -131,6 +131,32 @@ class ConvConfig:
         return buf
 
 
+def _conv_backward(cfg, cd, x, weight, dy, out_dtype, need_dx, need_dw, need_db, has_bias):
+    dy = to_cl(dy)
+    if dy.dtype != out_dtype:
+        dy = dy.to(out_dtype)
+    dx = dw = db = None
+    if need_dx:
+        wp = cfg.packed(cd, weight, cabi.PASS_DGRAD)
+        dx = _empty_cl(tuple(x.shape), x.dtype, x.device)
+        nws = lib().b200_conv_workspace_bytes(C.byref(cd), cabi.PASS_DGRAD)
+        ws = _workspace(nws, x.device)
+        with _Timed(cd, cabi.PASS_DGRAD):
+            check(lib().b200_conv_dgrad(C.byref(cd), dy.data_ptr(), wp.data_ptr(), dx.data_ptr(), ws.data_ptr(), nws, stream()))
+    if need_dw or need_db:
+        dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
+        db = torch.empty(weight.shape[1] if cfg.transposed else weight.shape[0], dtype=torch.float32, device=x.device) if has_bias else None
+        nws = lib().b200_conv_workspace_bytes(C.byref(cd), cabi.PASS_WGRAD)
+        ws = _workspace(nws, x.device)
+        with _Timed(cd, cabi.PASS_WGRAD):
+            check(lib().b200_conv_wgrad(C.byref(cd), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ptr(db), ws.data_ptr(), nws, stream()))
+        if weight.dtype != torch.float32:
+            dw = dw.to(weight.dtype)
+        if not need_dw:
+            dw = None
+    return dx, dw, db
+
+
 class _ConvFn(Function):
     @staticmethod
     def forward(ctx, x, weight, bias, cfg, out_dtype, want_stats):
@@ -167,31 +193,63 @@ class _ConvFn(Function):
     @staticmethod
     def backward(ctx, dy, *unused):
         x, weight = ctx.saved_tensors
-        cfg, cd = ctx.cfg, ctx.cd
-        dy = to_cl(dy)
-        if dy.dtype != ctx.out_dtype:
-            dy = dy.to(ctx.out_dtype)
-        dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            wp = cfg.packed(cd, weight, cabi.PASS_DGRAD)
-            dx = _empty_cl(tuple(x.shape), x.dtype, x.device)
-            nws = lib().b200_conv_workspace_bytes(C.byref(cd), cabi.PASS_DGRAD)
-            ws = _workspace(nws, x.device)
-            with _Timed(cd, cabi.PASS_DGRAD):
-                check(lib().b200_conv_dgrad(C.byref(cd), dy.data_ptr(), wp.data_ptr(), dx.data_ptr(), ws.data_ptr(), nws, stream()))
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
-            db = torch.empty(weight.shape[1] if cfg.transposed else weight.shape[0], dtype=torch.float32, device=x.device) \
-                if ctx.has_bias else None
-            nws = lib().b200_conv_workspace_bytes(C.byref(cd), cabi.PASS_WGRAD)
-            ws = _workspace(nws, x.device)
-            with _Timed(cd, cabi.PASS_WGRAD):
-                check(lib().b200_conv_wgrad(C.byref(cd), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ptr(db), ws.data_ptr(), nws, stream()))
-            if weight.dtype != torch.float32:
-                dw = dw.to(weight.dtype)
-            if not ctx.needs_input_grad[1]:
-                dw = None
+        dx, dw, db = _conv_backward(ctx.cfg, ctx.cd, x, weight, dy, ctx.out_dtype, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                    ctx.has_bias and ctx.needs_input_grad[2], ctx.has_bias)
         return dx, dw, db, None, None, None
+
+
+class _DualConvFn(Function):
+    """(statistics of conv(x, w_dead), conv(x, w_live) and its statistics) from ONE convolution with concatenated output channels
+    (b200_conv_fwd_stats_tail).  Only w_live takes part in autograd -- the dead branch of unet3d.py:43-46 has no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, w_dead, w_live, cfg, out_dtype):
+        need_cuda(x, "dual_conv")
+        x = to_cl(x)
+        cdead = w_dead.shape[0]
+        wcat = torch.cat([w_dead.detach(), w_live.detach()], 0)
+        cd, shape = cfg.desc(x, wcat, out_dtype)
+        chunks = lib().b200_conv_stats_chunks(C.byref(cd))
+        if chunks <= 0 or cdead % 16 != 0:
+            raise RuntimeError("b200nn.dual_conv: shape not supported (check dual_conv_supported)")
+        tag = (w_dead.data_ptr(), w_dead._version, w_live.data_ptr(), w_live._version, x.device)
+        hit = cfg._packed.get("dual")
+        if hit is not None and hit[0] == tag:
+            wp = hit[1]
+        else:
+            wp = torch.empty(max(lib().b200_conv_packed_bytes(C.byref(cd), cabi.PASS_FWD), 16), dtype=torch.uint8, device=x.device)
+            wf = wcat if wcat.dtype == torch.float32 else wcat.float()
+            check(lib().b200_conv_pack_weights(C.byref(cd), cabi.PASS_FWD, wf.contiguous().data_ptr(), wp.data_ptr(), stream()))
+            cfg._packed["dual"] = (tag, wp)
+        y = _empty_cl((shape[0], shape[1] - cdead) + tuple(shape[2:]), out_dtype, x.device)
+        part = torch.empty((chunks, 2, cd.Co), dtype=torch.float32, device=x.device)
+        ws = _workspace(0, x.device)
+        with _Timed(cd, cabi.PASS_FWD):
+            check(lib().b200_conv_fwd_stats_tail(C.byref(cd), x.data_ptr(), wp.data_ptr(), None, y.data_ptr(), cdead, part.data_ptr(), ws.data_ptr(), 0,
+                                                 stream()))
+        cd_live, _ = cfg.desc(x, w_live, out_dtype)
+        ctx.save_for_backward(x, w_live)
+        ctx.cfg, ctx.cd, ctx.has_bias, ctx.out_dtype = cfg, cd_live, False, out_dtype
+        ctx.mark_non_differentiable(part)
+        return y, part
+
+    @staticmethod
+    def backward(ctx, dy, *unused):
+        x, w_live = ctx.saved_tensors
+        dx, dw, _ = _conv_backward(ctx.cfg, ctx.cd, x, w_live, dy, ctx.out_dtype, ctx.needs_input_grad[0], ctx.needs_input_grad[2], False, False)
+        return dx, None, dw, None, None
+
+
+def dual_conv_supported(x, w_dead, w_live, cfg: ConvConfig, out_dtype):
+    if not x.is_cuda or w_dead.shape[1:] != w_live.shape[1:] or w_dead.shape[0] % 16 != 0:
+        return False
+    cd, _ = cfg.desc(x, torch.empty((w_dead.shape[0] + w_live.shape[0],) + tuple(w_live.shape[1:]), device="meta"), out_dtype)
+    return lib().b200_conv_stats_chunks(C.byref(cd)) > 0
+
+
+def dual_conv(x, w_dead, w_live, cfg: ConvConfig, out_dtype=None):
+    """returns (conv(x, w_live), partial statistics [chunks, 2, Cdead + Clive] of conv(x, cat(w_dead, w_live)))"""
+    return _DualConvFn.apply(x, w_dead, w_live, cfg, out_dtype or x.dtype)
 
 
 def conv(x, weight, bias, cfg: ConvConfig, out_dtype=None, want_stats=False):

@@ -68,10 +68,19 @@ class ConvD(tnn.Module):
         x = _conv_norm(self.conv1, self.bn1, x)
         # unet3d.py:43-45: y = relu(bn2(conv2(x))); y = dropout3d(y) is overwritten at :46.  Its only observable effects are
         # bn2's running statistics (BatchNorm, training) and the RNG draw of dropout3d; exactly those are performed.
-        if isinstance(self.bn2, bnn.BatchNorm3d) and self.bn2.training:
-            _conv_norm(self.conv2, self.bn2, x, stats_only=True)
+        bn_train = isinstance(self.bn2, bnn.BatchNorm3d) and self.bn2.training and self.bn2.sync is None
         if self.dropout > 0:                       # F.dropout3d is always in training mode there: one Bernoulli draw per (n, c)
             x.new_empty((x.shape[0], self.conv2.out_channels, 1, 1, 1)).bernoulli_(1 - self.dropout)
+        if bn_train and self.conv2.bias is None and self.conv3.bias is None and x.dtype == torch.bfloat16 and \
+                BF.dual_conv_supported(x, self.conv2.weight, self.conv3.weight, self.conv3._cfg(), x.dtype):
+            # conv2 and conv3 read the same x: ONE convolution with concatenated output channels gives both statistics; only
+            # conv3's half is written (b200_conv_fwd_stats_tail)
+            cdead = self.conv2.out_channels
+            y3, part = BF.dual_conv(x, self.conv2.weight, self.conv3.weight, self.conv3._cfg(), x.dtype)
+            self.bn2(y3, stats_partial=part[:, :, :cdead].contiguous(), stats_only=True)
+            return self.bn3(y3, residual=x, act=cabi.ACT_RELU, stats_partial=part[:, :, cdead:].contiguous())
+        if isinstance(self.bn2, bnn.BatchNorm3d) and self.bn2.training:
+            _conv_norm(self.conv2, self.bn2, x, stats_only=True)
         return _conv_norm(self.conv3, self.bn3, x, act=cabi.ACT_RELU, residual=x)
 
 
