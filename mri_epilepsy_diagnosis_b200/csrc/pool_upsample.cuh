@@ -246,10 +246,12 @@ __device__ __forceinline__ Lin2 lin2(int o, int in) {
     return r;
 }
 
+// One thread = the output pair (2i, 2i+1) of one row and one channel vector: the three input columns i-1, i, i+1 of the four
+// contributing (z, y) rows are loaded once (12 vector loads for 2 outputs instead of 16), the (z, y) weighted sums are shared.
 template <typename T, int V>
 __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(b200_up_desc d, const T* __restrict__ x, T* __restrict__ y) {
     const int CV = d.C / V;
-    const int rows = d.N * d.Do * d.Ho, per_row = d.Wo * CV;
+    const int rows = d.N * d.Do * d.Ho, per_row = d.Wi * CV;
     for (int row = blockIdx.x; row < rows; row += gridDim.x) {
         const int yo = row % d.Ho, zo = (row / d.Ho) % d.Do, n = row / (d.Ho * d.Do);
         const Lin2 lz = lin2(zo, d.Di), ly = lin2(yo, d.Hi);
@@ -261,53 +263,47 @@ __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(b200_up_desc d, con
         const float w00 = lz.w0 * ly.w0, w01 = lz.w0 * ly.w1, w10 = lz.w1 * ly.w0, w11 = lz.w1 * ly.w1;
         T* yr = y + (int64_t)row * d.Wo * d.Ctot + d.c_off;
         for (int e = threadIdx.x; e < per_row; e += 256) {
-            const int xo = e / CV, cv = e - xo * CV;
-            const Lin2 lx = lin2(xo, d.Wi);
-            const int o0 = lx.i0 * d.C + cv * V, o1 = lx.i1 * d.C + cv * V;
-            float acc[V], t[V];
+            const int xi = e / CV, cv = e - xi * CV;
+            const int xm = max(xi - 1, 0), xp = min(xi + 1, d.Wi - 1);
+            const int om = xm * d.C + cv * V, oc = xi * d.C + cv * V, op = xp * d.C + cv * V;
+            float a[4][3][V];
+            Pack<T, V>::load(r00 + om, a[0][0]); Pack<T, V>::load(r00 + oc, a[0][1]); Pack<T, V>::load(r00 + op, a[0][2]);
+            Pack<T, V>::load(r01 + om, a[1][0]); Pack<T, V>::load(r01 + oc, a[1][1]); Pack<T, V>::load(r01 + op, a[1][2]);
+            Pack<T, V>::load(r10 + om, a[2][0]); Pack<T, V>::load(r10 + oc, a[2][1]); Pack<T, V>::load(r10 + op, a[2][2]);
+            Pack<T, V>::load(r11 + om, a[3][0]); Pack<T, V>::load(r11 + oc, a[3][1]); Pack<T, V>::load(r11 + op, a[3][2]);
+            float c[3][V];                                  // (z, y)-interpolated columns i-1, i, i+1
 #pragma unroll
-            for (int k = 0; k < V; ++k) acc[k] = 0.f;
-            // same (z, y, x) nesting and weight products as the generic kernel
-            Pack<T, V>::load(r00 + o0, t);
+            for (int j = 0; j < 3; ++j)
 #pragma unroll
-            for (int k = 0; k < V; ++k) acc[k] = fmaf(w00 * lx.w0, t[k], acc[k]);
-            Pack<T, V>::load(r00 + o1, t);
+                for (int k = 0; k < V; ++k) c[j][k] = fmaf(w11, a[3][j][k], fmaf(w10, a[2][j][k], fmaf(w01, a[1][j][k], w00 * a[0][j][k])));
+            // even output 2i: 0.25*c[i-1] + 0.75*c[i] (i = 0: the clamped source is exactly column 0); odd output 2i+1:
+            // 0.75*c[i] + 0.25*c[i+1] (the clamped i+1 at the right border is column i itself)
+            float ev[V], od[V];
+            const float we = xi == 0 ? 0.f : 0.25f;
 #pragma unroll
-            for (int k = 0; k < V; ++k) acc[k] = fmaf(w00 * lx.w1, t[k], acc[k]);
-            Pack<T, V>::load(r01 + o0, t);
-#pragma unroll
-            for (int k = 0; k < V; ++k) acc[k] = fmaf(w01 * lx.w0, t[k], acc[k]);
-            Pack<T, V>::load(r01 + o1, t);
-#pragma unroll
-            for (int k = 0; k < V; ++k) acc[k] = fmaf(w01 * lx.w1, t[k], acc[k]);
-            Pack<T, V>::load(r10 + o0, t);
-#pragma unroll
-            for (int k = 0; k < V; ++k) acc[k] = fmaf(w10 * lx.w0, t[k], acc[k]);
-            Pack<T, V>::load(r10 + o1, t);
-#pragma unroll
-            for (int k = 0; k < V; ++k) acc[k] = fmaf(w10 * lx.w1, t[k], acc[k]);
-            Pack<T, V>::load(r11 + o0, t);
-#pragma unroll
-            for (int k = 0; k < V; ++k) acc[k] = fmaf(w11 * lx.w0, t[k], acc[k]);
-            Pack<T, V>::load(r11 + o1, t);
-#pragma unroll
-            for (int k = 0; k < V; ++k) acc[k] = fmaf(w11 * lx.w1, t[k], acc[k]);
-            Pack<T, V>::store(yr + (int64_t)xo * d.Ctot + cv * V, acc);
+            for (int k = 0; k < V; ++k) {
+                ev[k] = fmaf(we, c[0][k], (1.f - we) * c[1][k]);
+                od[k] = fmaf(0.25f, c[2][k], 0.75f * c[1][k]);
+            }
+            T* dst = yr + (int64_t)(2 * xi) * d.Ctot + cv * V;
+            Pack<T, V>::store(dst, ev);
+            Pack<T, V>::store(dst + d.Ctot, od);
         }
     }
 }
 
 // adjoint: input index j receives from outputs 2j-1 (0.25), 2j (0.75), 2j+1 (0.75), 2j+2 (0.25); the clamped border outputs
 // (o = 0 and o = out-1) put their whole weight on the border input
-struct Touch2 { int n; int o[4]; float w[4]; };
+// fixed four taps per dimension (weight 0 and a clamped, valid index for the taps that do not exist at the borders), so the
+// gather loops unroll completely and 16 loads are in flight per z-tap
+struct Touch2 { int o[4]; float w[4]; };
 __device__ __forceinline__ Touch2 touch2(int j, int in) {
     Touch2 t;
-    t.n = 0;
     const int out = 2 * in;
-    if (2 * j - 1 >= 1) { t.o[t.n] = 2 * j - 1; t.w[t.n] = 0.25f; ++t.n; }          // odd output 2(j-1)+1, i1 = j
-    { t.o[t.n] = 2 * j; t.w[t.n] = j == 0 ? 1.f : 0.75f; ++t.n; }                     // even output 2j (clamped: all weight on 0)
-    { t.o[t.n] = 2 * j + 1; t.w[t.n] = (j == in - 1) ? 1.f : 0.75f; ++t.n; }          // odd output 2j+1 (i1 clamps to j at the end)
-    if (2 * j + 2 <= out - 2) { t.o[t.n] = 2 * j + 2; t.w[t.n] = 0.25f; ++t.n; }      // even output 2(j+1), i0 = j
+    t.o[0] = max(2 * j - 1, 0);        t.w[0] = (2 * j - 1 >= 1) ? 0.25f : 0.f;          // odd output 2(j-1)+1, i1 = j
+    t.o[1] = 2 * j;                    t.w[1] = j == 0 ? 1.f : 0.75f;                     // even output 2j (clamped: all weight on 0)
+    t.o[2] = 2 * j + 1;                t.w[2] = (j == in - 1) ? 1.f : 0.75f;              // odd output 2j+1 (i1 clamps to j at the end)
+    t.o[3] = min(2 * j + 2, out - 1);  t.w[3] = (2 * j + 2 <= out - 2) ? 0.25f : 0.f;     // even output 2(j+1), i0 = j
     return t;
 }
 
@@ -326,18 +322,27 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(b200_up_desc d, con
             float acc[V];
 #pragma unroll
             for (int k = 0; k < V; ++k) acc[k] = 0.f;
-            for (int a = 0; a < tz.n; ++a)
-                for (int b = 0; b < ty.n; ++b) {
-                    const float wab = tz.w[a] * ty.w[b];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                if (tz.w[a] == 0.f) continue;                                   // warp-uniform (the whole block shares zi)
+                float g[4][4][V];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
                     const T* grow = gn + ((int64_t)tz.o[a] * d.Ho + ty.o[b]) * d.Wo * d.Ctot + cv * V;
-                    for (int c = 0; c < tx.n; ++c) {
-                        float g[V];
-                        Pack<T, V>::load(grow + (int64_t)tx.o[c] * d.Ctot, g);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) Pack<T, V>::load(grow + (int64_t)tx.o[c] * d.Ctot, g[b][c]);
+                }
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const float wab = tz.w[a] * ty.w[b];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
                         const float w = wab * tx.w[c];
 #pragma unroll
-                        for (int k = 0; k < V; ++k) acc[k] = fmaf(w, g[k], acc[k]);
+                        for (int k = 0; k < V; ++k) acc[k] = fmaf(w, g[b][c][k], acc[k]);
                     }
                 }
+            }
             Pack<T, V>::store(xr + e * V, acc);
         }
     }
