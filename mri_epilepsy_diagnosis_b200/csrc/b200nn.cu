@@ -440,6 +440,28 @@ int b200_norm_bwd(const b200_norm_desc* d, int training, const void* x, const vo
     const NormBwdWs w = norm_bwd_ws(d, g, workspace);
     B200_REQUIRE(y != nullptr || d->act == B200_ACT_NONE || dresidual == nullptr,
                  "norm_bwd: with a residual the activation gate needs the saved output y");
+    if (d->kind == B200_NORM_BATCH) {
+        // single device, BatchNorm: partial sums -> (sum over chunks + coefficients in one kernel) -> apply
+        B200_REQUIRE(x && dy && dx && mean && rstd, "norm_bwd: null pointer");
+        dim3 grid(g.chunks, g.NB);
+        const size_t smem = (size_t)2 * g.rpi * d->C * sizeof(float);
+        B200_DISPATCH_T(d->dtype, T, {
+            if (g.V == 1) B200_LAUNCH((norm_bwd_partial_kernel<T, 1>), grid, 256, smem, stream, (const T*)x, (const T*)y, (const T*)dy, mean, rstd, gamma,
+                                      beta, d->C, g.R, g.rows_per_chunk, d->kind, d->G, d->act, d->slope, w.partial);
+            else B200_LAUNCH((norm_bwd_partial_kernel<T, Vec16<T>::N>), grid, 256, smem, stream, (const T*)x, (const T*)y, (const T*)dy, mean, rstd, gamma,
+                             beta, d->C, g.R, g.rows_per_chunk, d->kind, d->G, d->act, d->slope, w.partial);
+        });
+        B200_LAUNCH(norm_bwd_sum_coef_bn_kernel, (int)ceil_div(d->C, 8), 256, 0, stream, d->N, d->C, d->S, g.chunks, training, w.partial, mean, rstd, gamma,
+                    beta, w.coef, dgamma, dbeta);
+        dim3 agrid(apply_grid(g, d->S), d->N);
+        B200_DISPATCH_T(d->dtype, T, {
+            if (g.V == 1) B200_LAUNCH((norm_bwd_apply_kernel<T, 1>), agrid, 256, 0, stream, (const T*)x, (const T*)y, (const T*)dy, w.coef, (T*)dx,
+                                      (T*)dresidual, d->C, d->S, 0, d->act, d->slope);
+            else B200_LAUNCH((norm_bwd_apply_kernel<T, Vec16<T>::N>), agrid, 256, 0, stream, (const T*)x, (const T*)y, (const T*)dy, w.coef, (T*)dx,
+                             (T*)dresidual, d->C, d->S, 0, d->act, d->slope);
+        });
+        return 0;
+    }
     if (b200_norm_bwd_reduce(d, x, y, dy, mean, rstd, gamma, beta, w.AB, workspace, ws_bytes, stream)) return 1;
     return b200_norm_bwd_apply(d, training, 1, x, y, dy, mean, rstd, gamma, beta, w.AB, dx, dresidual, dgamma, dbeta, workspace, ws_bytes, stream);
 }

@@ -308,6 +308,33 @@ __global__ void __launch_bounds__(256) norm_bwd_sum_kernel(int NB, int C, int ch
     }
 }
 
+// BatchNorm (one reduce-batch, no cross-channel terms): the sum over chunks and the coefficients in ONE kernel, one warp per channel
+__global__ void __launch_bounds__(256) norm_bwd_sum_coef_bn_kernel(int N, int C, int64_t S, int chunks, int training, const float* __restrict__ partial,
+                                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                   float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (c >= C) return;
+    double P = 0.0, Q = 0.0;
+    lane_partial_sums(partial + c, chunks, C, lane, P, Q);
+    P = warp_sum_d(P); Q = warp_sum_d(Q);
+    if (lane != 0) return;
+    P = (double)(float)P; Q = (double)(float)Q;              // the two-kernel path rounds the sums to fp32 (AB buffer): keep results identical
+    const double ga = gamma ? (double)gamma[c] : 1.0, rs = rstd[c], mu = mean[c];
+    double k1 = ga * rs, k4 = 0.0, k5 = 0.0;
+    if (training) {
+        const double M = (double)N * (double)S;
+        k4 = -ga * rs * rs * Q / M;
+        k5 = -ga * rs * P / M - k4 * mu;
+    }
+    coef[(int64_t)c * 5] = (float)k1; coef[(int64_t)c * 5 + 1] = (float)k4; coef[(int64_t)c * 5 + 2] = (float)k5;
+    float gsc, gsh;
+    norm_scale_shift(mean[c], rstd[c], gamma ? gamma[c] : 1.f, beta ? beta[c] : 0.f, gsc, gsh);
+    coef[(int64_t)c * 5 + 3] = gsc; coef[(int64_t)c * 5 + 4] = gsh;
+    if (dgamma) dgamma[c] = (float)Q;
+    if (dbeta) dbeta[c] = (float)P;
+}
+
 // coef[(nb*C + c)*5 + {0..4}] : dx = k1*dy' + k4*x + k5 ; (sc, sh) of the forward affine form; also dgamma/dbeta (thread nb==0 sums over nb)
 __global__ void norm_bwd_coef_kernel(int N, int C, int64_t S, int kind, int G, int training, int world, const float* __restrict__ AB,
                                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
