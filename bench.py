@@ -98,9 +98,9 @@ def dice_loss_mean(logits, targets, eps=1e-9):
     return (1 - 2 * tp / (2 * tp + fp + fn + eps)).mean()
 
 
-def build_model(pkg, name):
+def build_model(pkg, name, norm="bn"):
     if name == "unet3d":
-        return pkg.zoo.Unet(c=1, n=16, dropout=0.5, norm="bn", num_classes=2), "unet3d.Unet(c=1,n=16,norm=bn,num_classes=2)"
+        return pkg.zoo.Unet(c=1, n=16, dropout=0.5, norm=norm, num_classes=2), f"unet3d.Unet(c=1,n=16,norm={norm},num_classes=2)"
     if name == "fepegar16":
         return pkg.zoo.FepegarUNet(out_channels_first_layer=16), "unet.UNet(first=16)"
     if name == "fepegar8":
@@ -108,13 +108,13 @@ def build_model(pkg, name):
     raise SystemExit(f"unknown model {name}")
 
 
-def cpu_reference_step(model_name, size, steps, warmup, threads):
+def cpu_reference_step(model_name, size, steps, warmup, threads, norm="bn"):
     """The reference's CPU path for the step (oracle restatement), fp32, on `threads` host threads."""
     from oracle import graphs, weights
     torch.set_num_threads(threads)
     if model_name == "unet3d":
-        sd = weights.unet3d_state(1, 16, 2, "bn", seed=0)
-        fwd = lambda s, x: graphs.unet3d(s, x, "bn", 0.5, True)
+        sd = weights.unet3d_state(1, 16, 2, norm, seed=0)
+        fwd = lambda s, x: graphs.unet3d(s, x, norm, 0.5, True)
     else:
         sd = weights.fepegar_unet_state(16 if model_name == "fepegar16" else 8, seed=0, duplicate_keys=False)
         fwd = lambda s, x: graphs.fepegar_unet(s, x, True)
@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sync-bn", action="store_true")
+    ap.add_argument("--norm", default="bn", choices=["bn", "in", "gn"], help="unet3d normalisation (BASELINE config 2 names bn and in)")
     ap.add_argument("--torch-loss", action="store_true", help="compute the Dice loss with torch ops instead of the fused kernel")
     ap.add_argument("--eager", action="store_true", help="do not capture the step in a CUDA graph (launch-bound at this size)")
     ap.add_argument("--profile-json", default=None, help="write the per-layer conv timing table here")
@@ -162,7 +163,7 @@ def main():
         if rank != 0:
             return
         steps = max(1, args.steps)
-        nvox, times = cpu_reference_step(args.model, args.size, steps, min(args.warmup, 1), cores)
+        nvox, times = cpu_reference_step(args.model, args.size, steps, min(args.warmup, 1), cores, args.norm)
         ms = 1e3 * sum(times) / len(times)
         val = nvox / (ms / 1e3)
         print(json.dumps({**base, "impl": "reference", "value": val, "ms_per_step": ms, "dtype": "f32",
@@ -184,7 +185,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
-    net, model_desc = build_model(pkg, args.model)
+    net, model_desc = build_model(pkg, args.model, args.norm)
     sync = (None, world) if (args.sync_bn and world > 1) else None
     net = pkg.convert(net.to(dev).train(), dtype=torch.bfloat16, sync=sync)
     opt = torch.optim.AdamW(net.parameters(), capturable=not args.eager)
@@ -352,7 +353,7 @@ def main():
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
            "model_tflops": FWD_BWD_FLOP_PER_VOXEL * voxels / (ms / 1e3) / 1e12 if args.model == "unet3d" else None}
     if args.gpus == 1 and not args.no_cpu_baseline:
-        nvox, times = cpu_reference_step(args.model, args.size, 2, 1, cores)
+        nvox, times = cpu_reference_step(args.model, args.size, 2, 1, cores, args.norm)
         v = nvox / (sum(times) / len(times))
         out["cpu_baseline"] = {"value": v, "unit": "voxels/s", "cores": cores, "kind": "port",
                                "sample": f"oracle/graphs.py (CPU restatement of the reference step), fp32, 2 timed steps of 1 x {args.size}^3 after 1 warm-up"}
