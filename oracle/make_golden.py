@@ -209,6 +209,39 @@ def patch_cases():
          **{"grad:" + k: gr[k] for k in ("conv_blocks.0.conv.weight", "conv_blocks.4.conv.weight", "conv_blocks.2.bn.weight", "fc2.weight")})
 
 
+def detect_cases():
+    """FCD mask generation (detection/model_utils.py:118-228) run through the REFERENCE class with a deterministic stand-in
+    classifier (best_model.pth is not shipped): pins the patch map, the post-processing quirk and the painted mask."""
+    from oracle import detect
+    gm = patches.read_nifti1_f32(refload.path("detection/MNI152_T1_1mm_brain_gray.nii.gz")).astype(np.float64)
+    img = np.random.default_rng(1).random((182, 218, 182))
+    img[40:150, 60:150, 50:120] *= 1.35                     # a brighter block (both hemispheres) so that the labels are not spatially uniform
+    thr = 0.6
+
+    def model(patch_torch):                                   # what the reference's `model(patch_torch)` must look like
+        m = patch_torch[:, 0].double().mean(dim=(1, 2))
+        return torch.stack([thr - m, m - thr], dim=1)
+
+    Gen = refload.fcd_mask_generator_class(model)
+    gen = object.__new__(Gen)
+    gen.model, gen.h, gen.w, gen.gmpm = model, 16, 32, gm
+    t0 = time.time()
+    pm_ref = gen._get_predictions_per_batches(img)
+    post_ref = gen._postprocess(img, pm_ref.copy())
+    mask_ref = gen._masking(img, post_ref)
+    mask_unvoted_ref = gen._masking(img, pm_ref)              # the painting rule on a non-trivial map
+    print(f"  reference FCDMaskGenerator: {time.time() - t0:.1f}s, positives in map {int(pm_ref.sum())}, painted {int(mask_ref.sum())} / {int(mask_unvoted_ref.sum())}")
+    classify = lambda p: (torch.from_numpy(p[:, 0]).double().mean(dim=(1, 2)) > thr).numpy().astype(np.int64)
+    pm = detect.predictions_per_batches(img, gm, classify)
+    assert np.array_equal(pm, pm_ref), "oracle patch map != reference"
+    assert np.array_equal(detect.postprocess(pm), post_ref), "oracle postprocess != reference"
+    assert np.array_equal(detect.masking(img, gm, post_ref), mask_ref) and np.array_equal(detect.masking(img, gm, pm_ref), mask_unvoted_ref)
+    save("fcd_mask_kat5", patch_map=pm_ref.astype(np.int8), post=post_ref.astype(np.int8), mask_sum=np.array(mask_ref.sum()),
+         mask_sha=np.array(sha16(mask_ref.astype(np.int8))), mask_unvoted_sum=np.array(mask_unvoted_ref.sum()),
+         mask_unvoted_sha=np.array(sha16(mask_unvoted_ref.astype(np.int8))), thr=np.array(thr),
+         iou=np.array(gen.get_iou(mask_unvoted_ref, img > 1.0)))
+
+
 def op_pins():
     """SURVEY section 8 a-9 pins, produced by the same torch calls the reference modules make."""
     g = torch.Generator().manual_seed(0)
@@ -262,9 +295,9 @@ if __name__ == "__main__":
     assert refload.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["fixtures", "ops", "unet3d", "ae", "fader", "fepegar", "patches"]
+    which = sys.argv[1:] or ["fixtures", "ops", "unet3d", "ae", "fader", "fepegar", "patches", "detect"]
     table = dict(fixtures=copy_fixtures, ops=op_pins, unet3d=unet3d_cases, ae=ae_cases, fader=fader_cases,
-                 fepegar=fepegar_case, patches=patch_cases)
+                 fepegar=fepegar_case, patches=patch_cases, detect=detect_cases)
     for w in which:
         print(w)
         table[w]()

@@ -105,6 +105,24 @@ def patch_model_classes():
     return ns["PatchModel"], ns["ConvolutionBlock"]
 
 
+def fcd_mask_generator_class(model):
+    """`class FCDMaskGenerator` (detection/model_utils.py:118-228) out of the syntactically invalid file, exec'd with the
+    names it expects as globals (`model` -- :132 uses a GLOBAL, not self.model --, np, torch, scipy.signal.convolve).  The text
+    is used as it is except that `.cuda()` calls are dropped (no GPU in the build container); instances are created with
+    object.__new__ because __init__ reads best_model.pth and the template through nibabel (:120-127)."""
+    src = open(os.path.join(REF, "detection/model_utils.py")).read().splitlines()
+    start = next(i for i, l in enumerate(src) if l.startswith("class FCDMaskGenerator"))
+    end = next(i for i, l in enumerate(src) if "def save_nii_mask" in l)
+    code = "\n".join(src[start:end]).replace(".cuda()", "")
+    ast.parse(code)
+    import numpy as np
+    import torch
+    from scipy.signal import convolve
+    ns = {"torch": torch, "np": np, "convolve": convolve, "model": model, "nib": _Stub("nibabel"), "PatchModel": None}
+    exec(compile(code, "model_utils.py[118:228]", "exec"), ns)
+    return ns["FCDMaskGenerator"]
+
+
 def seg_routine_module():
     """segmentation/routine.py with its third-party imports stubbed."""
     _stub("IPython", "IPython.display", "matplotlib", "matplotlib.pyplot", "torchio", "torchio.transforms",

@@ -461,3 +461,59 @@ def test_softmax_dice_loss_matches_reference_loss(B, C, dtype):
     (graphs.dice_loss_mean(lr2, t0) * 3.0).backward()
     (B.functional.softmax_dice_loss(lg2, t0.cuda()) * 3.0).backward()
     assert rel_err(lg2.grad.float(), lr2.grad) < (1e-4 if dtype == torch.float32 else 1e-2)
+
+
+def test_fcd_mask_generator_kat5_bit_exact(B, golden, template):
+    """detection/model_utils.py:118-228 on the device (detect.FCDMaskGenerator) against the reference-generated KAT-5 vectors and
+    the oracle: patch map, post-processing and painted mask must be bit-exact (integer / index work)."""
+    from oracle import detect as OD
+    g = golden("fcd_mask_kat5")
+    img = np.random.default_rng(1).random((182, 218, 182))
+    img[40:150, 60:150, 50:120] *= 1.35
+    thr = float(g["thr"])
+
+    def model(p):                                                     # stand-in classifier (best_model.pth is not shipped)
+        m = p[:, 0].double().mean(dim=(1, 2))
+        return torch.stack([thr - m, m - thr], dim=1)
+
+    gen = B.detect.FCDMaskGenerator(model, template)
+    img_d = torch.as_tensor(img, device="cuda")
+    pm = gen._get_predictions_per_batches(img_d)
+    # fp32 patches vs the float64 reference mean: the stand-in's decision margin must not be razor thin for the comparison to be fair
+    assert np.array_equal(pm.cpu().numpy(), g["patch_map"].astype(np.int64))
+    post = gen._postprocess(img_d, pm.clone())
+    assert np.array_equal(post.cpu().numpy(), g["post"].astype(np.int64))
+    mask = gen._masking(img_d, post)
+    assert float(mask.sum()) == float(g["mask_sum"]) and sha16(mask.cpu().numpy().astype(np.int8)) == str(g["mask_sha"])
+    unvoted = gen._masking(img_d, pm)
+    assert sha16(unvoted.cpu().numpy().astype(np.int8)) == str(g["mask_unvoted_sha"])
+    assert np.array_equal(gen.get_mask(img).cpu().numpy(), OD.masking(img, template, g["post"].astype(np.int64)).astype(np.int64))
+    assert abs(gen.get_iou(unvoted, torch.as_tensor(img > 1.0, device="cuda")) - float(g["iou"])) < 1e-12
+    # the intended vote (fixed=True) differs from the reference's quirk and equals the boolean-mask restatement
+    fixed = gen._postprocess(img_d, pm.clone(), fixed=True).cpu().numpy()
+    m = g["patch_map"].astype(np.int64)
+    nb = np.zeros_like(m)                       # exact 4-neighbour count over (strip, slice) inside every slab, zero beyond the borders
+    nb[:, 1:, :] += m[:, :-1, :]; nb[:, :-1, :] += m[:, 1:, :]; nb[:, :, 1:] += m[:, :, :-1]; nb[:, :, :-1] += m[:, :, 1:]
+    want = m.copy(); want[nb == 4] = 1; want[nb == 0] = 0
+    assert np.array_equal(fixed, want)
+
+
+def test_fcd_mask_generator_with_patch_model(B, template):
+    """End to end with the real (converted) PatchModel on the GPU: batched inference must give the labels of patch-by-patch
+    inference through the oracle graph (model_utils.py:130-134) wherever the logit margin is not within bf16 noise."""
+    from oracle import graphs, weights, detect as OD, patches as OP
+    sd = weights.patch_model_state(seed=9)
+    net = B.zoo.PatchModel(); net.load_state_dict(sd, strict=True)
+    net = B.convert(net.cuda().eval(), dtype=torch.float32)
+    img = np.random.default_rng(2).random((182, 218, 182))
+    gen = B.detect.FCDMaskGenerator(net, template, batch=1024)
+    pm = gen._get_predictions_per_batches(torch.as_tensor(img, device="cuda")).cpu().numpy()
+    plan = OP.patch_plan(template, None, 16, 32)
+    patches = OP.gather_patches(img, plan)[:512]
+    with torch.no_grad():
+        logits = graphs.patch_model(sd, torch.from_numpy(patches).float())
+    ref = logits.argmax(1).numpy()
+    got = pm[OD.plan_slots(plan, 182, 32)[:512], plan[:512, 1] // 16, plan[:512, 0]]
+    sure = (logits[:, 0] - logits[:, 1]).abs().numpy() > 1e-3
+    assert np.array_equal(got[sure], ref[sure]) and sure.mean() > 0.9
+    assert tuple(gen.get_mask(img).shape) == (182, 218, 182)

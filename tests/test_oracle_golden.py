@@ -207,3 +207,31 @@ def test_op_pins(golden):
     assert np.array_equal(g["tie_idx"].reshape(-1), np.array([0, 2, 8, 10, 32, 34, 40, 42]))
     assert np.allclose(g["tri_false"], [0, .25, .75, 1.25, 1.75, 2.25, 2.75, 3])
     assert np.allclose(g["nearest_3to7"], [0, 0, 0, 1, 1, 2, 2])
+
+
+def _kat5_image():
+    img = np.random.default_rng(1).random((182, 218, 182))
+    img[40:150, 60:150, 50:120] *= 1.35
+    return img
+
+
+def test_fcd_mask_kat5(golden):
+    """oracle/detect.py against vectors produced by the REFERENCE FCDMaskGenerator (detection/model_utils.py:118-228; generated by
+    oracle/make_golden.py detect): patch map, the post-processing (int-array-as-index quirk included), the painted mask."""
+    from oracle import detect
+    g = golden("fcd_mask_kat5")
+    gm = patches.read_nifti1_f32(os.path.join(GOLDEN, "MNI152_T1_1mm_brain_gray.nii.gz")).astype(np.float64)
+    img = _kat5_image()
+    thr = float(g["thr"])
+    classify = lambda p: (torch.from_numpy(p[:, 0]).double().mean(dim=(1, 2)) > thr).numpy().astype(np.int64)
+    pm = detect.predictions_per_batches(img, gm, classify)
+    assert np.array_equal(pm, g["patch_map"].astype(np.int64)) and pm.shape == (4, 13, 182)
+    post = detect.postprocess(pm)
+    assert np.array_equal(post, g["post"].astype(np.int64))
+    assert not post[0].any() and not post[1].any() and np.array_equal(post[2:], pm[2:])      # the quirk: slabs 0/1 are overwritten
+    mask = detect.masking(img, gm, post)
+    assert float(mask.sum()) == float(g["mask_sum"]) and sha16(mask.astype(np.int8)) == str(g["mask_sha"])
+    unvoted = detect.masking(img, gm, pm)
+    assert float(unvoted.sum()) == float(g["mask_unvoted_sum"]) and sha16(unvoted.astype(np.int8)) == str(g["mask_unvoted_sha"])
+    assert not unvoted[:, 218 - 15:, :].any()                  # the first strip (j = 0) is never painted (`-0:-16:-1` is empty)
+    assert abs(detect.get_iou(unvoted, img > 1.0) - float(g["iou"])) < 1e-12
