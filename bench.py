@@ -98,9 +98,10 @@ def dice_loss_mean(logits, targets, eps=1e-9):
     return (1 - 2 * tp / (2 * tp + fp + fn + eps)).mean()
 
 
-def build_model(pkg, name, norm="bn"):
+def build_model(pkg, name, norm="bn", literal=False):
     if name == "unet3d":
-        return pkg.zoo.Unet(c=1, n=16, dropout=0.5, norm=norm, num_classes=2), f"unet3d.Unet(c=1,n=16,norm={norm},num_classes=2)"
+        return (pkg.zoo.Unet(c=1, n=16, dropout=0.5, norm=norm, num_classes=2, literal=literal),
+                f"unet3d.Unet(c=1,n=16,norm={norm},num_classes=2)" + (" [literal op sequence]" if literal else ""))
     if name == "fepegar16":
         return pkg.zoo.FepegarUNet(out_channels_first_layer=16), "unet.UNet(first=16)"
     if name == "fepegar8":
@@ -145,6 +146,10 @@ def main():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sync-bn", action="store_true")
+    ap.add_argument("--no-literal-leg", action="store_true", help="skip the extra timing of the literal operator sequence")
+    ap.add_argument("--literal-graph", action="store_true",
+                    help="unet3d only: execute unet3d.py's operator sequence one to one (dead branch materialised, conv2 after the "
+                         "upsample) instead of the equivalent rewritten graph")
     ap.add_argument("--norm", default="bn", choices=["bn", "in", "gn"], help="unet3d normalisation (BASELINE config 2 names bn and in)")
     ap.add_argument("--torch-loss", action="store_true", help="compute the Dice loss with torch ops instead of the fused kernel")
     ap.add_argument("--eager", action="store_true", help="do not capture the step in a CUDA graph (launch-bound at this size)")
@@ -185,7 +190,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
-    net, model_desc = build_model(pkg, args.model, args.norm)
+    net, model_desc = build_model(pkg, args.model, args.norm, args.literal_graph)
     sync = (None, world) if (args.sync_bn and world > 1) else None
     net = pkg.convert(net.to(dev).train(), dtype=torch.bfloat16, sync=sync)
     opt = torch.optim.AdamW(net.parameters(), capturable=not args.eager)
@@ -340,6 +345,23 @@ def main():
         with open(args.profile_json, "w") as f:
             json.dump({"ms_per_step": ms, "rows": table}, f, indent=1)
 
+    # transparency leg (single GPU, default workload): the same step with unet3d.py's operator sequence executed one to one
+    # (zoo.Unet(literal=True): dead branch materialised, conv2 on the upsampled tensor) -- see DESIGN.md section 4
+    literal = None
+    if world == 1 and args.model == "unet3d" and not args.literal_graph and not args.eager and not args.no_literal_leg:
+        del step
+        torch.cuda.empty_cache()
+        torch.manual_seed(0)
+        net2, _ = build_model(pkg, args.model, args.norm, True)
+        net2 = pkg.convert(net2.to(dev).train(), dtype=torch.bfloat16)
+        opt2 = torch.optim.AdamW(net2.parameters(), capturable=True)
+        step2 = pkg.graphed.GraphedTrainStep(net2, loss_fn, opt2, xd, td)
+        for _ in range(3):
+            step2(xd, td)
+        ms2, _, _ = timed(lambda: step2(xd, td), args.steps)
+        literal = {"ms_per_step": ms2, "value": voxels / (ms2 / 1e3), "unit": "voxels/s",
+                   "what": "same step, reference operator sequence executed one to one (no graph-level rewrites)"}
+        del step2, net2, opt2
     if rank != 0:
         if dist is not None:
             dist.barrier(); dist.destroy_process_group()
@@ -350,7 +372,7 @@ def main():
                       "l2": "inputs and every activation tensor (>= 268 MB each at 16ch x 128^3 x 4) exceed the 126 MB L2; no flush needed"},
            "e2e": {"value": world * voxels / (ms_e2e / 1e3), "unit": "voxels/s", "ms_per_step": ms_e2e,
                    "h2d_bytes_per_step": xh.numel() * 4 + th.numel() * 4, "d2h_bytes_per_step": 4},
-           "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+           "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "literal_graph": literal,
            "model_tflops": FWD_BWD_FLOP_PER_VOXEL * voxels / (ms / 1e3) / 1e12 if args.model == "unet3d" else None}
     if args.gpus == 1 and not args.no_cpu_baseline:
         nvox, times = cpu_reference_step(args.model, args.size, 2, 1, cores, args.norm)

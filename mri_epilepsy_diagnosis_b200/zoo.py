@@ -62,10 +62,18 @@ class ConvD(tnn.Module):
             setattr(self, f"conv{i}", _c3(cin, planes, 3))
             setattr(self, f"bn{i}", _norm3d(planes, norm))
 
+    literal = False       # True: execute unet3d.py:42-47 op by op (dead branch materialised), kernel-level fusions only
+
     def forward(self, x):
         if not self.first:
             x = self.maxpool(x)
         x = _conv_norm(self.conv1, self.bn1, x)
+        if self.literal:
+            y = _conv_norm(self.conv2, self.bn2, x, act=cabi.ACT_RELU)                       # :43
+            if self.dropout > 0:
+                y = torch.nn.functional.dropout3d(y, self.dropout)                           # :44-45
+            del y                                                                            # overwritten at :46
+            return _conv_norm(self.conv3, self.bn3, x, act=cabi.ACT_RELU, residual=x)        # :46-47
         # unet3d.py:43-45: y = relu(bn2(conv2(x))); y = dropout3d(y) is overwritten at :46.  Its only observable effects are
         # bn2's running statistics (BatchNorm, training) and the RNG draw of dropout3d; exactly those are performed.
         bn_train = isinstance(self.bn2, bnn.BatchNorm3d) and self.bn2.training and self.bn2.sync is None
@@ -96,9 +104,15 @@ class ConvU(tnn.Module):
         self.conv3, self.bn3 = _c3(planes, planes, 3), _norm3d(planes, norm)
         self.relu = bnn.ReLU(inplace=True)
 
+    literal = False       # True: conv2 runs on the upsampled tensor as written at unet3d.py:73-74
+
     def forward(self, x, prev):
         if not self.first:
             x = _conv_norm(self.conv1, self.bn1, x, act=cabi.ACT_RELU)
+        if self.literal:
+            y = BF.interpolate(x, scale_factor=2, mode="trilinear", align_corners=False)
+            y = _conv_norm(self.conv2, self.bn2, y, act=cabi.ACT_RELU)
+            return _conv_norm(self.conv3, self.bn3, BF.concat(prev, y), act=cabi.ACT_RELU)
         # unet3d.py:73-74 computes conv2(upsample(x)).  conv2 is 1x1x1 and trilinear interpolation is a per-channel convex
         # combination of voxels, so the two commute exactly: upsample(conv2(x)) is the same function with the convolution done on
         # 1/8 of the voxels and the interpolation on half of the channels (results differ by bf16 rounding only).
@@ -109,7 +123,12 @@ class ConvU(tnn.Module):
 
 
 class Unet(tnn.Module):
-    def __init__(self, c=4, n=16, dropout=0.5, norm="gn", num_classes=5):
+    """unet3d.py:82-126.  `literal=True` (not a reference argument) makes every stage execute the reference's operator sequence
+    one to one -- dead branch materialised, 1x1x1 conv on the upsampled tensor -- keeping only the kernel-level fusions
+    (statistics in the conv epilogue, activation / residual in the apply pass); the default graph computes the same function
+    with the rewrites described in DESIGN.md section 4."""
+
+    def __init__(self, c=4, n=16, dropout=0.5, norm="gn", num_classes=5, literal=False):
         super().__init__()
         self.upsample = bnn.Upsample(scale_factor=2, mode="trilinear", align_corners=False)   # intent of unet3d.py:85
         widths = [c, n, 2 * n, 4 * n, 8 * n, 16 * n]
@@ -118,6 +137,9 @@ class Unet(tnn.Module):
         self.convu4 = ConvU(16 * n, norm, True)
         self.convu3, self.convu2, self.convu1 = ConvU(8 * n, norm), ConvU(4 * n, norm), ConvU(2 * n, norm)
         self.seg3, self.seg2, self.seg1 = (bnn.Conv3d(w * n, num_classes, 1) for w in (8, 4, 2))
+        for m in self.modules():
+            if isinstance(m, (ConvD, ConvU)):
+                m.literal = bool(literal)
         for m in self.modules():                                                              # unet3d.py:103-108
             if isinstance(m, tnn.Conv3d):
                 tnn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")

@@ -304,3 +304,35 @@ def test_patch_context_swaps_torch_nn(B):
         m = nn.Conv3d(1, 4, 3)
         assert type(m).__module__.startswith("mri_epilepsy")
     assert type(nn.Conv3d(1, 4, 3)).__module__.startswith("torch")
+
+
+def test_unet3d_rewritten_graph_equals_literal_operator_sequence(B):
+    """zoo.Unet's default graph (dead branch reduced to its side effects, conv2 commuted with the upsample, dual conv) against
+    zoo.Unet(literal=True), which executes unet3d.py:42-47 / :71-77 op by op: same logits, loss gradients and BatchNorm running
+    statistics within the bf16 tolerance (both are checked against the reference's golden vectors elsewhere)."""
+    from oracle import weights
+    sd = weights.unet3d_state(1, 16, 2, "bn", seed=4)
+    nets = []
+    for literal in (False, True):
+        net = B.zoo.Unet(c=1, n=16, norm="bn", num_classes=2, literal=literal)
+        net.load_state_dict(sd, strict=True)
+        nets.append(B.convert(net.cuda().train(), dtype=torch.bfloat16))
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 1, 32, 32, 32, generator=g).cuda()
+    t = (torch.rand(2, 1, 32, 32, 32, generator=g) > 0.5).float().cuda()
+    outs = []
+    for net in nets:
+        torch.manual_seed(0)
+        y = net(x)
+        B.functional.softmax_dice_loss(y, t).backward()
+        outs.append(y.float())
+    assert rel_err(outs[0], outs[1]) < 2e-2
+    pa, pb = dict(nets[0].named_parameters()), dict(nets[1].named_parameters())
+    for k in ("convd1.conv3.weight", "convu1.conv2.weight", "convu1.conv3.weight", "seg1.weight"):
+        assert cosine(pa[k].grad, pb[k].grad) > 0.98, k
+    for k in ("convd1.conv2.weight", "convd3.bn2.weight"):
+        assert pa[k].grad is None and pb[k].grad is None                       # the dead branch has no gradient in either graph
+    ba, bb = dict(nets[0].named_buffers()), dict(nets[1].named_buffers())
+    for k in ("convd1.bn2.running_mean", "convd1.bn2.running_var", "convd2.bn2.running_var", "convu1.bn2.running_mean", "convu1.bn2.running_var"):
+        assert rel_err(ba[k], bb[k]) < 2e-2, k
+    assert int(ba["convd1.bn2.num_batches_tracked"]) == int(bb["convd1.bn2.num_batches_tracked"]) == 1
