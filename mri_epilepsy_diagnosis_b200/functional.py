@@ -131,11 +131,41 @@ class ConvConfig:
         return buf
 
 
+_SIDE_STREAMS = {}
+OVERLAP_WGRAD = True      # run wgrad on a side stream next to dgrad (they are independent); joined before backward() returns
+
+
+def _side_stream(device):
+    s = _SIDE_STREAMS.get(device)
+    if s is None:
+        s = _SIDE_STREAMS[device] = torch.cuda.Stream(device=device)
+    return s
+
+
 def _conv_backward(cfg, cd, x, weight, dy, out_dtype, need_dx, need_dw, need_db, has_bias):
     dy = to_cl(dy)
     if dy.dtype != out_dtype:
         dy = dy.to(out_dtype)
     dx = dw = db = None
+    do_w = need_dw or need_db
+    # dgrad and wgrad only share read-only inputs: with both requested, wgrad goes to a side stream so that the two kernels
+    # overlap when neither fills the GPU (the deep 8^3..32^3 levels); the main stream waits for it before returning, so autograd
+    # sees ordinary stream semantics.  Inside a CUDA-graph capture this becomes a fork/join in the graph.
+    cur = torch.cuda.current_stream(x.device)
+    side = _side_stream(x.device) if (OVERLAP_WGRAD and need_dx and do_w and PROFILE is None) else None
+    if do_w:
+        dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
+        db = torch.empty(weight.shape[1] if cfg.transposed else weight.shape[0], dtype=torch.float32, device=x.device) if has_bias else None
+        nws = lib().b200_conv_workspace_bytes(C.byref(cd), cabi.PASS_WGRAD)
+        ws_w = _workspace(nws, x.device)
+        if side is not None:
+            side.wait_stream(cur)
+            for t in (x, dy, dw, db, ws_w):
+                if t is not None:
+                    t.record_stream(side)
+        with _Timed(cd, cabi.PASS_WGRAD):
+            check(lib().b200_conv_wgrad(C.byref(cd), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ptr(db), ws_w.data_ptr(), nws,
+                                        side.cuda_stream if side is not None else stream()))
     if need_dx:
         wp = cfg.packed(cd, weight, cabi.PASS_DGRAD)
         dx = _empty_cl(tuple(x.shape), x.dtype, x.device)
@@ -143,13 +173,9 @@ def _conv_backward(cfg, cd, x, weight, dy, out_dtype, need_dx, need_dw, need_db,
         ws = _workspace(nws, x.device)
         with _Timed(cd, cabi.PASS_DGRAD):
             check(lib().b200_conv_dgrad(C.byref(cd), dy.data_ptr(), wp.data_ptr(), dx.data_ptr(), ws.data_ptr(), nws, stream()))
-    if need_dw or need_db:
-        dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
-        db = torch.empty(weight.shape[1] if cfg.transposed else weight.shape[0], dtype=torch.float32, device=x.device) if has_bias else None
-        nws = lib().b200_conv_workspace_bytes(C.byref(cd), cabi.PASS_WGRAD)
-        ws = _workspace(nws, x.device)
-        with _Timed(cd, cabi.PASS_WGRAD):
-            check(lib().b200_conv_wgrad(C.byref(cd), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ptr(db), ws.data_ptr(), nws, stream()))
+    if side is not None:
+        cur.wait_stream(side)
+    if do_w:
         if weight.dtype != torch.float32:
             dw = dw.to(weight.dtype)
         if not need_dw:
