@@ -628,8 +628,12 @@ int b200_upsample_fwd(const b200_up_desc* d, const void* x, void* y, void* strea
         const int grid = (int)(rows < kNumSMs * 16 ? rows : kNumSMs * 16);
         B200_DISPATCH_T(d->dtype, T, {
             constexpr int VF = Vec16<T>::N;
-            if (d->C % VF == 0 && d->Ctot % VF == 0 && d->c_off % VF == 0 && aligned16(x) && aligned16(y))
-                B200_LAUNCH((upsample2x_fwd_kernel<T, VF>), grid, 256, 0, stream, *d, (const T*)x, (T*)y);
+            if (d->C % VF == 0 && d->Ctot % VF == 0 && d->c_off % VF == 0 && aligned16(x) && aligned16(y)) {
+                constexpr int SEG = 16;
+                const int64_t items = (int64_t)d->N * d->Di * d->Hi * ((d->Wi + SEG - 1) / SEG) * (d->C / VF);
+                const int g2 = (int)(ceil_div(items, 128) < (int64_t)kNumSMs * 32 ? ceil_div(items, 128) : (int64_t)kNumSMs * 32);
+                B200_LAUNCH((upsample2x_fwd_slide_kernel<T, VF, SEG>), g2, 128, 0, stream, *d, (const T*)x, (T*)y);
+            }
             else if (sizeof(T) == 4 && d->C % 2 == 0 && d->Ctot % 2 == 0 && d->c_off % 2 == 0 && aligned16(x) && aligned16(y))
                 B200_LAUNCH((upsample2x_fwd_kernel<float, 2>), grid, 256, 0, stream, *d, (const float*)x, (float*)y);      // 2-class fp32 logits
             else
@@ -655,24 +659,13 @@ int b200_upsample_bwd(const b200_up_desc* d, const void* dy, void* dx, void* str
         const int grid = (int)(rows < kNumSMs * 16 ? rows : kNumSMs * 16);
         B200_DISPATCH_T(d->dtype, T, {
             constexpr int VF = Vec16<T>::N;
+            constexpr int SEG = 16;
+            const int64_t segrows = (int64_t)d->N * d->Di * d->Hi * ((d->Wi + SEG - 1) / SEG);
+            auto sgrid = [&](int cvn) { const int64_t b = ceil_div(segrows * cvn, 128); return (int)(b < (int64_t)kNumSMs * 32 ? b : (int64_t)kNumSMs * 32); };
             if (d->C % VF == 0 && d->Ctot % VF == 0 && d->c_off % VF == 0 && aligned16(dy) && aligned16(dx))
-                B200_LAUNCH((upsample2x_bwd_kernel<T, VF>), grid, 256, 0, stream, *d, (const T*)dy, (T*)dx);
+                B200_LAUNCH((upsample2x_bwd_slide_kernel<T, VF, SEG>), sgrid(d->C / VF), 128, 0, stream, *d, (const T*)dy, (T*)dx);
             else if (sizeof(T) == 4 && d->C % 2 == 0 && d->Ctot % 2 == 0 && d->c_off % 2 == 0 && aligned16(dy) && aligned16(dx))
-                B200_LAUNCH((upsample2x_bwd_kernel<float, 2>), grid, 256, 0, stream, *d, (const float*)dy, (float*)dx);
-            else
-                B200_LAUNCH((upsample2x_bwd_kernel<T, 1>), grid, 256, 0, stream, *d, (const T*)dy, (T*)dx);
-        });
-        return 0;
-    }
-    if (upsample_is_2x_trilinear(d)) {
-        const int64_t rows = (int64_t)d->N * d->Di * d->Hi;
-        const int grid = (int)(rows < kNumSMs * 16 ? rows : kNumSMs * 16);
-        B200_DISPATCH_T(d->dtype, T, {
-            constexpr int VF = Vec16<T>::N;
-            if (d->C % VF == 0 && d->Ctot % VF == 0 && d->c_off % VF == 0 && aligned16(dy) && aligned16(dx))
-                B200_LAUNCH((upsample2x_bwd_kernel<T, VF>), grid, 256, 0, stream, *d, (const T*)dy, (T*)dx);
-            else if (sizeof(T) == 4 && d->C % 2 == 0 && d->Ctot % 2 == 0 && d->c_off % 2 == 0 && aligned16(dy) && aligned16(dx))
-                B200_LAUNCH((upsample2x_bwd_kernel<float, 2>), grid, 256, 0, stream, *d, (const float*)dy, (float*)dx);
+                B200_LAUNCH((upsample2x_bwd_slide_kernel<float, 2, SEG>), sgrid(d->C / 2), 128, 0, stream, *d, (const float*)dy, (float*)dx);
             else
                 B200_LAUNCH((upsample2x_bwd_kernel<T, 1>), grid, 256, 0, stream, *d, (const T*)dy, (T*)dx);
         });

@@ -181,6 +181,11 @@ struct UmmaConvParams {
     int items;
     uint32_t idesc;
     int use_tma;                     // 1: halo slabs by TMA tensor loads, 0: by LDGSTS producer warps
+    // split-K for layers with fewer tile groups than SMs (8^3 / 16^3 levels): an item is (tile group, split) and a split owns
+    // NKC/skc channel chunks and, when skz > 1, one kz plane of the filter; fp32 partials go to `partial` and are reduced afterwards
+    int skc, skz, nsplit;
+    int64_t total_vox;
+    float* partial;                  // [nsplit][total_vox][OC] or null
     const __nv_bfloat16* in;         // [NB*Dpi][Hi][Wi][IC]
     const __nv_bfloat16* w;          // [tap][kchunk][cg][oc][8]
     const float* bias;               // [OC] or null
@@ -195,9 +200,16 @@ struct alignas(128) UmmaBarriers {
 };
 static_assert(sizeof(UmmaBarriers) % 128 == 0, "barrier block must keep the slabs 128-byte aligned");
 
-struct ItemCoord { int nb, z0, pvalid, y0, x0; };
+struct ItemCoord { int nb, z0, pvalid, y0, x0, sp, kc0, kc1, kz0, kz1; };
 __device__ __forceinline__ ItemCoord decode_item(const UmmaConvParams& p, int item) {
     ItemCoord c;
+    c.sp = 0; c.kc0 = 0; c.kc1 = p.NKC; c.kz0 = 0; c.kz1 = p.kd;
+    if (p.nsplit > 1) {
+        c.sp = item % p.nsplit; item /= p.nsplit;
+        const int per = p.NKC / p.skc, ikc = c.sp / p.skz;
+        c.kc0 = ikc * per; c.kc1 = c.kc0 + per;
+        if (p.skz > 1) { c.kz0 = c.sp % p.skz; c.kz1 = c.kz0 + 1; }
+    }
     const int tx = item % p.tiles_x; item /= p.tiles_x;
     const int ty = item % p.tiles_y; item /= p.tiles_y;
     const int zc = item % p.zchunks;
@@ -279,13 +291,13 @@ __device__ __forceinline__ void mma_issue_loop(const UmmaConvParams& p, UmmaBarr
         ptx::tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(set * p.P * p.OC);
         uint32_t started = 0;                                   // bit pl: accumulator pl already holds a partial sum
-        for (int kc = 0; kc < p.NKC; ++kc) {
+        for (int kc = c.kc0; kc < c.kc1; ++kc) {
             uint32_t slab_lo[NQ], slab_bar[NQ], have = 0;
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 slab_lo[q] = 0; slab_bar[q] = 0;
                 const int zi = c.z0 - p.pd + q;
-                if (q < c.pvalid + KD - 1 && zi >= 0 && zi < p.Dpi) {
+                if (q >= c.kz0 && q < c.pvalid + c.kz1 - 1 && zi >= 0 && zi < p.Dpi) {
                     ptx::mbar_wait(ptx::smem_u32(&bars->slab_full[ss]), sph);
                     slab_lo[q] = ((slabs16 + ss * slab16) & 0x3FFF) | a_lbo_field;
                     slab_bar[q] = ptx::smem_u32(&bars->slab_empty[ss]);
@@ -296,6 +308,7 @@ __device__ __forceinline__ void mma_issue_loop(const UmmaConvParams& p, UmmaBarr
             ptx::tc_fence_after();
 #pragma unroll
             for (int kz = 0; kz < KD; ++kz) {
+                if (kz < c.kz0 || kz >= c.kz1) continue;
                 uint32_t a_tap = 0;                             // (ky*WW + kx) in 16-byte units
                 int kx = 0;
                 for (int kyx = 0; kyx < khw; ++kyx) {
@@ -379,8 +392,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap in_map, const UmmaConvParam
             uint32_t it = 0;
             for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
                 const ItemCoord c = decode_item(p, item);
-                for (int kc = 0; kc < p.NKC; ++kc)
-                    for (int q = 0; q < c.pvalid + p.kd - 1; ++q) {
+                for (int kc = c.kc0; kc < c.kc1; ++kc)
+                    for (int q = c.kz0; q < c.pvalid + c.kz1 - 1; ++q) {
                         const int zi = c.z0 - p.pd + q;
                         if (zi < 0 || zi >= p.Dpi) continue;
                         const uint32_t s = it % p.nslabs, ph = (it / p.nslabs) & 1;
@@ -408,9 +421,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap in_map, const UmmaConvParam
                                    (uint32_t)p.wstage_bytes, full);
             } else {
                 uint32_t s = 0, ph = 0;
-                for (int item = blockIdx.x; item < p.items; item += gridDim.x)
-                    for (int kc = 0; kc < p.NKC; ++kc)
-                        for (int tap = 0; tap < ntaps; ++tap) {
+                const int khw = p.kh * p.kw;
+                for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+                    const ItemCoord c = decode_item(p, item);
+                    for (int kc = c.kc0; kc < c.kc1; ++kc)
+                        for (int tap = c.kz0 * khw; tap < c.kz1 * khw; ++tap) {
                             ptx::mbar_wait(ptx::smem_u32(&bars->w_empty[s]), ph ^ 1);
                             const uint32_t full = ptx::smem_u32(&bars->w_full[s]);
                             ptx::mbar_expect_tx(full, (uint32_t)p.wstage_bytes);
@@ -418,6 +433,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap in_map, const UmmaConvParam
                                            reinterpret_cast<const uint8_t*>(p.w) + ((size_t)tap * p.NKC + kc) * p.wstage_bytes, (uint32_t)p.wstage_bytes, full);
                             if (++s == (uint32_t)p.nwstages) { s = 0; ph ^= 1; }
                         }
+                }
             }
         }
     } else if (warp == 2) {
@@ -433,8 +449,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap in_map, const UmmaConvParam
             const int ncg = p.KC / 8;
             for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
                 const ItemCoord c = decode_item(p, item);
-                for (int kc = 0; kc < p.NKC; ++kc)
-                    for (int q = 0; q < c.pvalid + p.kd - 1; ++q) {
+                for (int kc = c.kc0; kc < c.kc1; ++kc)
+                    for (int q = c.kz0; q < c.pvalid + c.kz1 - 1; ++q) {
                         const int zi = c.z0 - p.pd + q;
                         if (zi < 0 || zi >= p.Dpi) continue;
                         pipe.acquire(ptx::smem_u32(&bars->slab_empty[ss]), sph ^ 1);
@@ -464,6 +480,26 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap in_map, const UmmaConvParam
                 const int64_t vox = (((int64_t)c.nb * p.Dpo + c.z0 + pl) * p.Ho + y) * p.Wo + x;
                 __nv_bfloat16* dst = p.out + vox * p.OC;
                 const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)((set * p.P + pl) * p.OC);
+                if (p.partial != nullptr) {
+                    // split-K: fp32 partial of this split; a split whose filter planes all fall outside the volume issued no MMA
+                    bool any = false;
+                    for (int kz = c.kz0; kz < c.kz1; ++kz) {
+                        const int zi = c.z0 + pl - p.pd + kz;
+                        any = any || (zi >= 0 && zi < p.Dpi);
+                    }
+                    float* dstp = p.partial + ((int64_t)c.sp * p.total_vox + vox) * p.OC;
+                    for (int c0 = 0; c0 < p.OC; c0 += 16) {
+                        float v[16];
+                        ptx::tmem_ld16(taddr + (uint32_t)c0, v);
+                        if (inside) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                *reinterpret_cast<float4*>(dstp + c0 + 4 * i) =
+                                    any ? make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                    continue;
+                }
                 for (int c0 = 0; c0 < p.OC; c0 += 16) {
                     float v[16];
                     ptx::tmem_ld16(taddr + (uint32_t)c0, v);
@@ -493,6 +529,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap in_map, const UmmaConvParam
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 2) ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// out[v][oc] = bf16(bias[oc] + sum over splits of partial[s][v][oc]), fixed order (deterministic); 8 channels per thread
+__global__ void umma_split_reduce_kernel(int nsplit, int64_t total, int OC, const float* __restrict__ partial, const float* __restrict__ bias,
+                                         __nv_bfloat16* __restrict__ out) {
+    const int64_t n8 = total / 8;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n8; e += (int64_t)gridDim.x * blockDim.x) {
+        float a[8];
+        const int oc = (int)((e * 8) % OC);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = bias != nullptr ? __ldg(bias + oc + i) : 0.f;
+        for (int s = 0; s < nsplit; ++s) {
+            const float4* src = reinterpret_cast<const float4*>(partial + (int64_t)s * total + e * 8);
+            const float4 u = __ldg(src), w = __ldg(src + 1);
+            a[0] += u.x; a[1] += u.y; a[2] += u.z; a[3] += u.w; a[4] += w.x; a[5] += w.y; a[6] += w.z; a[7] += w.w;
+        }
+        Pack<__nv_bfloat16, 8>::store(out + e * 8, a);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ weight packing
@@ -581,7 +635,10 @@ inline size_t umma_packed_bytes(const b200_conv_desc* d, int pass) {
     return (size_t)d->kd * d->kh * d->kw * d->Ci * d->Co * sizeof(__nv_bfloat16);
 }
 inline size_t umma_wgrad_workspace_bytes(const b200_conv_desc* d);
-inline size_t umma_workspace_bytes(const b200_conv_desc* d, int pass) { return pass == B200_PASS_WGRAD ? umma_wgrad_workspace_bytes(d) + 256 : 0; }
+inline size_t umma_split_workspace_bytes(const b200_conv_desc* d, int pass);
+inline size_t umma_workspace_bytes(const b200_conv_desc* d, int pass) {
+    return pass == B200_PASS_WGRAD ? umma_wgrad_workspace_bytes(d) + 256 : umma_split_workspace_bytes(d, pass);
+}
 
 inline int umma_pack_weights(const b200_conv_desc* d, int pass, const float* w, void* packed, void* stream) {
     UmmaGeom g;
@@ -646,11 +703,34 @@ inline int umma_plan(const UmmaGeom& g, int N, UmmaConvParams* p, size_t* smem_b
     B200_REQUIRE(items < (1ll << 31), "umma: too many tiles");
     p->items = (int)items;
     p->idesc = make_idesc_bf16(g.OC);
+    // split-K when the tile groups cannot fill the machine: pick the (channel-chunk, kz) split with the fewest rounds x work per item
+    p->skc = 1; p->skz = 1; p->nsplit = 1;
+    p->total_vox = (int64_t)N * g.Do * g.Ho * g.Wo;
+    static const bool allow_split = [] { const char* e = getenv("B200_UMMA_SPLIT"); return e == nullptr || strcmp(e, "0") != 0; }();
+    if (allow_split && items * 2 <= kNumSMs) {
+        double best = 1.0;
+        for (int skz = 1; skz <= g.kd; skz += g.kd > 1 ? g.kd - 1 : 1)
+            for (int skc = 1; skc <= p->NKC; ++skc) {
+                if (p->NKC % skc) continue;
+                const int ns = skc * skz;
+                const double cost = (double)ceil_div(items * ns, kNumSMs) / ns + 0.01 * ns;     // the partials are not free
+                if (cost < best - 1e-9) { best = cost; p->skc = skc; p->skz = skz; p->nsplit = ns; }
+            }
+        p->items = (int)(items * p->nsplit);
+    }
     return 0;
 }
 
-inline int umma_conv_run(const b200_conv_desc* d, int pass, const void* in, const void* w_packed, const float* bias, void* out, void*, size_t,
-                         void* stream) {
+inline size_t umma_split_workspace_bytes(const b200_conv_desc* d, int pass) {
+    UmmaGeom g;
+    UmmaConvParams p;
+    size_t smem = 0;
+    if (!umma_geom(d, pass, &g) || umma_plan(g, d->N, &p, &smem) || p.nsplit <= 1) return 0;
+    return (size_t)p.nsplit * p.total_vox * g.OC * sizeof(float) + 256;
+}
+
+inline int umma_conv_run(const b200_conv_desc* d, int pass, const void* in, const void* w_packed, const float* bias, void* out, void* workspace,
+                         size_t ws_bytes, void* stream) {
     UmmaGeom g;
     B200_REQUIRE(umma_geom(d, pass, &g), "umma conv: unsupported descriptor");
     B200_REQUIRE(aligned16(in) && aligned16(out) && aligned16(w_packed), "umma conv: pointers must be 16-byte aligned");
@@ -661,6 +741,12 @@ inline int umma_conv_run(const b200_conv_desc* d, int pass, const void* in, cons
     p.w = (const __nv_bfloat16*)w_packed;
     p.bias = bias;
     p.out = (__nv_bfloat16*)out;
+    if (p.nsplit > 1) {
+        B200_REQUIRE(workspace != nullptr && ws_bytes >= (size_t)p.nsplit * p.total_vox * g.OC * sizeof(float), "umma conv: split-K workspace too small");
+        p.partial = (float*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+        B200_REQUIRE((size_t)((char*)p.partial - (char*)workspace) + (size_t)p.nsplit * p.total_vox * g.OC * sizeof(float) <= ws_bytes,
+                     "umma conv: split-K workspace too small after alignment");
+    }
     PFN_tmapEncodeTiled enc = tmap_encoder();
     B200_REQUIRE(enc != nullptr, "umma conv: cuTensorMapEncodeTiled is unavailable in this driver");
     CUtensorMap map;
@@ -677,6 +763,10 @@ inline int umma_conv_run(const b200_conv_desc* d, int pass, const void* in, cons
     B200_REQUIRE(attr_err == cudaSuccess, "umma conv: cannot raise the dynamic shared memory limit: %s", cudaGetErrorString(attr_err));
     const int grid = p.items < kNumSMs ? p.items : kNumSMs;       // persistent: one CTA per SM
     B200_LAUNCH(conv_umma_kernel, grid, kUmmaThreads, smem_bytes, stream, map, p);
+    if (p.nsplit > 1) {
+        const int64_t total = p.total_vox * g.OC;
+        B200_LAUNCH(umma_split_reduce_kernel, stream_grid(total / 8, 256), 256, 0, stream, p.nsplit, total, g.OC, p.partial, bias, (__nv_bfloat16*)out);
+    }
     return 0;
 }
 

@@ -292,10 +292,99 @@ __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(b200_up_desc d, con
     }
 }
 
-// adjoint: input index j receives from outputs 2j-1 (0.25), 2j (0.75), 2j+1 (0.75), 2j+2 (0.25); the clamped border outputs
-// (o = 0 and o = out-1) put their whole weight on the border input
-// fixed four taps per dimension (weight 0 and a clamped, valid index for the taps that do not exist at the borders), so the
-// gather loops unroll completely and 16 loads are in flight per z-tap
+// Sliding-window variant for vector widths: one thread owns the input cell row (n, zi, yi), one x-segment and one channel vector and
+// produces the 2 x 2 output rows (2zi+a, 2yi+b) of that segment.  Per input column it loads the 9 neighbouring rows once, folds
+// them into the four (z, y)-interpolated values c[a][b], keeps c of the previous column in registers
+// and emits the outputs between consecutive columns: ~1/3 of the instructions of the pair kernel above (which remains the scalar path).
+template <typename T, int V, int SEG>
+__global__ void __launch_bounds__(128) upsample2x_fwd_slide_kernel(b200_up_desc d, const T* __restrict__ x, T* __restrict__ y) {
+    const int CV = d.C / V, nseg = (d.Wi + SEG - 1) / SEG;
+    const int64_t items = (int64_t)d.N * d.Di * d.Hi * nseg * CV;
+    for (int64_t it = (int64_t)blockIdx.x * 128 + threadIdx.x; it < items; it += (int64_t)gridDim.x * 128) {
+        int64_t r = it;
+        const int cv = (int)(r % CV); r /= CV;
+        const int seg = (int)(r % nseg); r /= nseg;
+        const int yi = (int)(r % d.Hi); r /= d.Hi;
+        const int zi = (int)(r % d.Di);
+        const int n = (int)(r / d.Di);
+        // weights of input planes/rows (i-1, i, i+1) for the even (a = 0) and odd (a = 1) output of index i, clamped borders folded in
+        float wz[2][3], wy[2][3];
+        wz[0][0] = zi > 0 ? 0.25f : 0.f; wz[0][1] = zi > 0 ? 0.75f : 1.f; wz[0][2] = 0.f;
+        wz[1][0] = 0.f; wz[1][1] = zi + 1 < d.Di ? 0.75f : 1.f; wz[1][2] = zi + 1 < d.Di ? 0.25f : 0.f;
+        wy[0][0] = yi > 0 ? 0.25f : 0.f; wy[0][1] = yi > 0 ? 0.75f : 1.f; wy[0][2] = 0.f;
+        wy[1][0] = 0.f; wy[1][1] = yi + 1 < d.Hi ? 0.75f : 1.f; wy[1][2] = yi + 1 < d.Hi ? 0.25f : 0.f;
+        const T* rows[3][3];
+#pragma unroll
+        for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                const int z = min(max(zi + dz - 1, 0), d.Di - 1), yy = min(max(yi + dy - 1, 0), d.Hi - 1);
+                rows[dz][dy] = x + ((((int64_t)n * d.Di + z) * d.Hi + yy) * d.Wi) * d.C + cv * V;
+            }
+        auto column = [&](int xi, float (&c)[2][2][V]) {
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+#pragma unroll
+                    for (int k = 0; k < V; ++k) c[a][b][k] = 0.f;
+#pragma unroll
+            for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    float v[V];
+                    Pack<T, V>::load(rows[dz][dy] + (int64_t)xi * d.C, v);
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        if ((a == 0 && dz == 2) || (a == 1 && dz == 0)) continue;          // structural zeros
+#pragma unroll
+                        for (int b = 0; b < 2; ++b) {
+                            if ((b == 0 && dy == 2) || (b == 1 && dy == 0)) continue;
+                            const float w = wz[a][dz] * wy[b][dy];
+#pragma unroll
+                            for (int k = 0; k < V; ++k) c[a][b][k] = fmaf(w, v[k], c[a][b][k]);
+                        }
+                    }
+                }
+        };
+        const int x0 = seg * SEG, x1 = min(x0 + SEG, d.Wi);
+        T* out0 = y + ((((int64_t)n * d.Do + 2 * zi) * d.Ho + 2 * yi) * d.Wo) * d.Ctot + d.c_off + cv * V;
+        const int64_t ystride = (int64_t)d.Wo * d.Ctot, zstride = (int64_t)d.Ho * d.Wo * d.Ctot;
+        // column xi yields the odd output 2xi-1 (with column xi-1) and the even output 2xi; only two column sets stay live
+        auto emit = [&](const float (&p)[2][2][V], const float (&c)[2][2][V], int xi) {
+            const float we = xi == 0 ? 0.f : 0.25f;
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    T* dst = out0 + a * zstride + b * ystride + (int64_t)(2 * xi) * d.Ctot;
+                    float o[V];
+                    if (xi > x0) {
+#pragma unroll
+                        for (int k = 0; k < V; ++k) o[k] = fmaf(0.25f, c[a][b][k], 0.75f * p[a][b][k]);
+                        Pack<T, V>::store(dst - d.Ctot, o);
+                    }
+                    if (xi < x1) {
+#pragma unroll
+                        for (int k = 0; k < V; ++k) o[k] = fmaf(we, p[a][b][k], (1.f - we) * c[a][b][k]);
+                        Pack<T, V>::store(dst, o);
+                    }
+                }
+        };
+        float ca[2][2][V], cb[2][2][V];
+        column(max(x0 - 1, 0), cb);
+        for (int xi = x0; xi <= x1; xi += 2) {
+            column(min(xi, d.Wi - 1), ca);
+            emit(cb, ca, xi);
+            if (xi + 1 <= x1) {
+                column(min(xi + 1, d.Wi - 1), cb);
+                emit(ca, cb, xi + 1);
+            }
+        }
+    }
+}
+
+// adjoint: input index j receives from outputs 2j-1 (0.25), 2j (0.75), 2j+1 (0.75), 2j+2 (0.25), with the clamped borders folded in
 struct Touch2 { int o[4]; float w[4]; };
 __device__ __forceinline__ Touch2 touch2(int j, int in) {
     Touch2 t;
@@ -305,6 +394,64 @@ __device__ __forceinline__ Touch2 touch2(int j, int in) {
     t.o[2] = 2 * j + 1;                t.w[2] = (j == in - 1) ? 1.f : 0.75f;              // odd output 2j+1 (i1 clamps to j at the end)
     t.o[3] = min(2 * j + 2, out - 1);  t.w[3] = (2 * j + 2 <= out - 2) ? 0.25f : 0.f;     // even output 2(j+1), i0 = j
     return t;
+}
+
+// Sliding-window adjoint: one thread owns the input cell row (n, zi, yi), one x-segment and one channel vector.  For every
+// output column ox it folds the 4 x 4 (z, y) rows that touch the cell into G[ox] (16 loads), and each input column xi combines
+// G[2xi-1 .. 2xi+2]; two of those four carry over from the previous column, so a column costs 32 loads instead of 64.
+template <typename T, int V, int SEG>
+__global__ void __launch_bounds__(128) upsample2x_bwd_slide_kernel(b200_up_desc d, const T* __restrict__ dy, T* __restrict__ dx) {
+    const int CV = d.C / V, nseg = (d.Wi + SEG - 1) / SEG;
+    const int64_t items = (int64_t)d.N * d.Di * d.Hi * nseg * CV;
+    for (int64_t it = (int64_t)blockIdx.x * 128 + threadIdx.x; it < items; it += (int64_t)gridDim.x * 128) {
+        int64_t r = it;
+        const int cv = (int)(r % CV); r /= CV;
+        const int seg = (int)(r % nseg); r /= nseg;
+        const int yi = (int)(r % d.Hi); r /= d.Hi;
+        const int zi = (int)(r % d.Di);
+        const int n = (int)(r / d.Di);
+        const Touch2 tz = touch2(zi, d.Di), ty = touch2(yi, d.Hi);
+        const T* gn = dy + (int64_t)n * d.Do * d.Ho * d.Wo * d.Ctot + d.c_off + cv * V;
+        const T* rows[4][4];
+        float wzy[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                rows[a][b] = gn + ((int64_t)tz.o[a] * d.Ho + ty.o[b]) * d.Wo * d.Ctot;
+                wzy[a][b] = tz.w[a] * ty.w[b];
+            }
+        auto gcol = [&](int ox, float (&g)[V]) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) g[k] = 0.f;
+            const int64_t off = (int64_t)ox * d.Ctot;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    float v[V];
+                    Pack<T, V>::load(rows[a][b] + off, v);
+#pragma unroll
+                    for (int k = 0; k < V; ++k) g[k] = fmaf(wzy[a][b], v[k], g[k]);
+                }
+        };
+        const int x0 = seg * SEG, x1 = min(x0 + SEG, d.Wi);
+        float ga[V], gb[V], gc[V], gd[V];
+        gcol(max(2 * x0 - 1, 0), ga);
+        gcol(2 * x0, gb);
+        T* xr = dx + ((((int64_t)n * d.Di + zi) * d.Hi + yi) * d.Wi) * d.C + cv * V;
+        for (int xi = x0; xi < x1; ++xi) {
+            gcol(2 * xi + 1, gc);
+            gcol(min(2 * xi + 2, d.Wo - 1), gd);
+            const Touch2 tx = touch2(xi, d.Wi);
+            float o[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k) o[k] = fmaf(tx.w[0], ga[k], fmaf(tx.w[1], gb[k], fmaf(tx.w[2], gc[k], tx.w[3] * gd[k])));
+            Pack<T, V>::store(xr + (int64_t)xi * d.C, o);
+#pragma unroll
+            for (int k = 0; k < V; ++k) { ga[k] = gc[k]; gb[k] = gd[k]; }
+        }
+    }
 }
 
 template <typename T, int V>

@@ -34,6 +34,12 @@ CASES = [
     ("c64_128", 2, 64, 128, (5, 8, 8), 3, 1, False),
     ("c256_128", 1, 256, 128, (4, 8, 16), 3, 1, False),
     ("c256_256", 1, 256, 256, (3, 16, 16), 3, 1, False),
+    # deep U-Net levels: fewer tile groups than SMs -> split-K over channel chunks and filter planes, fp32 partials + reduce
+    ("deep128_256", 2, 128, 256, (8, 8, 8), 3, 1, True),
+    ("deep256_256", 2, 256, 256, (8, 8, 8), 3, 1, False),
+    ("deep256_128", 1, 256, 128, (8, 8, 8), 3, 1, True),
+    ("deep128_128", 2, 128, 128, (16, 16, 16), 3, 1, False),
+    ("deep192_64", 1, 192, 64, (16, 16, 16), 3, 1, True),
     ("pw64_32", 1, 64, 32, (8, 16, 8), 1, 0, False),
     ("pw256_128", 1, 256, 128, (4, 16, 16), 1, 0, False),
     ("valid3", 1, 32, 64, (7, 14, 30), 3, 0, True),
