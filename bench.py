@@ -193,7 +193,7 @@ def main():
     net, model_desc = build_model(pkg, args.model, args.norm, args.literal_graph)
     sync = (None, world) if (args.sync_bn and world > 1) else None
     net = pkg.convert(net.to(dev).train(), dtype=torch.bfloat16, sync=sync)
-    opt = torch.optim.AdamW(net.parameters(), capturable=not args.eager)
+    opt = torch.optim.AdamW(net.parameters(), capturable=not args.eager, fused=True)
     xh, th = synthetic_batch(args.batch, args.size, seed=rank)
     xh, th = xh.pin_memory(), th.pin_memory()
     xd, td = xh.to(dev), th.to(dev)
@@ -354,7 +354,7 @@ def main():
         torch.manual_seed(0)
         net2, _ = build_model(pkg, args.model, args.norm, True)
         net2 = pkg.convert(net2.to(dev).train(), dtype=torch.bfloat16)
-        opt2 = torch.optim.AdamW(net2.parameters(), capturable=True)
+        opt2 = torch.optim.AdamW(net2.parameters(), capturable=True, fused=True)
         step2 = pkg.graphed.GraphedTrainStep(net2, loss_fn, opt2, xd, td)
         for _ in range(3):
             step2(xd, td)

@@ -662,10 +662,14 @@ int b200_upsample_bwd(const b200_up_desc* d, const void* dy, void* dx, void* str
             constexpr int SEG = 16;
             const int64_t segrows = (int64_t)d->N * d->Di * d->Hi * ((d->Wi + SEG - 1) / SEG);
             auto sgrid = [&](int cvn) { const int64_t b = ceil_div(segrows * cvn, 128); return (int)(b < (int64_t)kNumSMs * 32 ? b : (int64_t)kNumSMs * 32); };
-            if (d->C % VF == 0 && d->Ctot % VF == 0 && d->c_off % VF == 0 && aligned16(dy) && aligned16(dx))
+            // the sliding-window kernel has 1/16 of the threads of the per-cell kernel: it only wins on volumes that still fill the SMs
+            const bool vec = d->C % VF == 0 && d->Ctot % VF == 0 && d->c_off % VF == 0 && aligned16(dy) && aligned16(dx);
+            if (vec && segrows * (d->C / VF) >= 128 * 1024)
                 B200_LAUNCH((upsample2x_bwd_slide_kernel<T, VF, SEG>), sgrid(d->C / VF), 128, 0, stream, *d, (const T*)dy, (T*)dx);
+            else if (vec)
+                B200_LAUNCH((upsample2x_bwd_kernel<T, VF>), grid, 256, 0, stream, *d, (const T*)dy, (T*)dx);
             else if (sizeof(T) == 4 && d->C % 2 == 0 && d->Ctot % 2 == 0 && d->c_off % 2 == 0 && aligned16(dy) && aligned16(dx))
-                B200_LAUNCH((upsample2x_bwd_slide_kernel<float, 2, SEG>), sgrid(d->C / 2), 128, 0, stream, *d, (const float*)dy, (float*)dx);
+                B200_LAUNCH((upsample2x_bwd_kernel<float, 2>), grid, 256, 0, stream, *d, (const float*)dy, (float*)dx);
             else
                 B200_LAUNCH((upsample2x_bwd_kernel<T, 1>), grid, 256, 0, stream, *d, (const T*)dy, (T*)dx);
         });

@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(b200_up_desc d, con
 // them into the four (z, y)-interpolated values c[a][b], keeps c of the previous column in registers
 // and emits the outputs between consecutive columns: ~1/3 of the instructions of the pair kernel above (which remains the scalar path).
 template <typename T, int V, int SEG>
-__global__ void __launch_bounds__(128) upsample2x_fwd_slide_kernel(b200_up_desc d, const T* __restrict__ x, T* __restrict__ y) {
+__global__ void __launch_bounds__(128, 3) upsample2x_fwd_slide_kernel(b200_up_desc d, const T* __restrict__ x, T* __restrict__ y) {
     const int CV = d.C / V, nseg = (d.Wi + SEG - 1) / SEG;
     const int64_t items = (int64_t)d.N * d.Di * d.Hi * nseg * CV;
     for (int64_t it = (int64_t)blockIdx.x * 128 + threadIdx.x; it < items; it += (int64_t)gridDim.x * 128) {

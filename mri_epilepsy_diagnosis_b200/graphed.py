@@ -16,6 +16,8 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
+from . import nn as bnn
+
 
 class GraphedTrainStep:
     """step = GraphedTrainStep(model, loss_fn, optimizer, x_example, t_example); loss = step(x, t)
@@ -65,7 +67,8 @@ class GraphedTrainStep:
 
     def _fwd_bwd(self):
         self.flat.zero_()
-        loss = self.loss_fn(self.model(self.x), self.t)
+        with bnn.defer_batch_counters():
+            loss = self.loss_fn(self.model(self.x), self.t)
         loss.backward()
         return loss.detach()
 

@@ -105,6 +105,26 @@ class ConvTranspose3d(_ConvMixin, tnn.ConvTranspose3d):
     _transposed_conv = True
 
 
+# When a list, training-mode BatchNorm layers append their `num_batches_tracked` to it instead of launching one add each;
+# the owner (graphed.GraphedTrainStep) bumps them all with a single multi-tensor add after the forward pass.
+_deferred_counters = None
+
+
+class defer_batch_counters:
+    def __enter__(self):
+        global _deferred_counters
+        self._prev = _deferred_counters
+        _deferred_counters = self.counters = []
+        return self
+
+    def __exit__(self, *exc):
+        global _deferred_counters
+        _deferred_counters = self._prev
+        if self.counters and exc[0] is None:
+            torch._foreach_add_(self.counters, 1)
+        return False
+
+
 class _BatchNormMixin(_B200Mixin):
     fused_act = cabi.ACT_NONE     # set by fused graphs; plain drop-in use keeps NONE
     fused_slope = 0.01
@@ -121,7 +141,10 @@ class _BatchNormMixin(_B200Mixin):
         else:
             factor = self.momentum
         if self.training and self.track_running_stats and self.num_batches_tracked is not None:
-            self.num_batches_tracked.add_(1)
+            if _deferred_counters is not None and self.momentum is not None:
+                _deferred_counters.append(self.num_batches_tracked)      # bumped by one _foreach_add_ at the end of the step
+            else:
+                self.num_batches_tracked.add_(1)
             if self.momentum is None:
                 factor = 1.0 / float(self.num_batches_tracked)
         use_batch = self.training or (self.running_mean is None and self.running_var is None)
