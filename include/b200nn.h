@@ -187,6 +187,10 @@ typedef struct {
 } b200_pool_desc;
 int b200_maxpool_fwd(const b200_pool_desc* d, const void* x, void* y, uint8_t* code, int64_t* indices, void* stream);
 int b200_maxpool_bwd(const b200_pool_desc* d, const void* dy, const uint8_t* code, void* dx, void* stream);
+/* dx = maxpool_bwd(dy) + add, for a pooled tensor that has a second consumer (U-Net skip connection, unet3d.py:113-121 with
+ * torch.cat at :76): `add` is that consumer's gradient, channels-last with `add_ctot` channels per voxel (>= C; the pointer
+ * already addresses the first channel of the window).  Replaces autograd's accumulation kernel.  kernel = stride = 2 only. */
+int b200_maxpool_bwd_add(const b200_pool_desc* d, const void* dy, const uint8_t* code, const void* add, int add_ctot, void* dx, void* stream);
 
 /* ------------------------------------------------------------------ upsample (+ skip concat)
  * F.upsample/nn.Upsample trilinear align_corners=False (unet3d.py:73,85; unet.UNet), =True

@@ -80,6 +80,7 @@ _SIGS = {
     "b200_softmax_dice_bwd": (C.c_int, [P(DiceDesc), vp, vp, vp, vp, vp, vp]),
     "b200_maxpool_fwd": (C.c_int, [P(PoolDesc), vp, vp, vp, vp, vp]),
     "b200_maxpool_bwd": (C.c_int, [P(PoolDesc), vp, vp, vp, vp]),
+    "b200_maxpool_bwd_add": (C.c_int, [P(PoolDesc), vp, vp, vp, C.c_int, vp, vp]),
     "b200_upsample_fwd": (C.c_int, [P(UpDesc), vp, vp, vp]),
     "b200_upsample_bwd": (C.c_int, [P(UpDesc), vp, vp, vp]),
     "b200_copy_channels": (C.c_int, [C.c_int, i64, i32, vp, i32, i32, vp, i32, i32, vp]),

@@ -609,6 +609,24 @@ int b200_maxpool_bwd(const b200_pool_desc* d, const void* dy, const uint8_t* cod
     return 0;
 }
 
+int b200_maxpool_bwd_add(const b200_pool_desc* d, const void* dy, const uint8_t* code, const void* add, int add_ctot, void* dx, void* stream) {
+    if (pool_validate(d)) return 1;
+    B200_REQUIRE(dy && code && dx && add, "maxpool_bwd_add: null pointer");
+    const int64_t rows = (int64_t)d->N * d->Di * d->Hi;
+    B200_REQUIRE(d->kd == 2 && d->kh == 2 && d->kw == 2 && d->sd == 2 && d->sh == 2 && d->sw == 2 && rows < (1ll << 31) && (int64_t)d->Wi * d->C < (1ll << 30),
+                 "maxpool_bwd_add: only kernel = stride = 2");
+    B200_REQUIRE(add_ctot >= d->C, "maxpool_bwd_add: addend pitch %d is smaller than C=%d", add_ctot, d->C);
+    const int grid = (int)(rows < kNumSMs * 16 ? rows : kNumSMs * 16);
+    B200_DISPATCH_T(d->dtype, T, {
+        constexpr int VF = Vec16<T>::N;
+        if (d->C % VF == 0 && add_ctot % VF == 0 && aligned16(dy) && aligned16(dx) && aligned16(add))
+            B200_LAUNCH((maxpool2_bwd_kernel<T, VF>), grid, 256, 0, stream, *d, (const T*)dy, code, (T*)dx, (const T*)add, add_ctot);
+        else
+            B200_LAUNCH((maxpool2_bwd_kernel<T, 1>), grid, 256, 0, stream, *d, (const T*)dy, code, (T*)dx, (const T*)add, add_ctot);
+    });
+    return 0;
+}
+
 // ============================================================================ upsample / concat
 static int up_validate(const b200_up_desc* d) {
     B200_REQUIRE(d != nullptr, "null upsample descriptor");

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(b200_pool_desc d, cons
 // kernel = stride = 2 (every pool the benchmarked models use): each input voxel belongs to exactly one window
 template <typename T, int V>
 __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(b200_pool_desc d, const T* __restrict__ dy, const uint8_t* __restrict__ code,
-                                                           T* __restrict__ dx) {
+                                                           T* __restrict__ dx, const T* __restrict__ add = nullptr, int add_ctot = 0) {
     const int CV = d.C / V;
     const int rows = d.N * d.Di * d.Hi, per_row = d.Wi * CV;
     for (int row = blockIdx.x; row < rows; row += gridDim.x) {
@@ -108,6 +108,14 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(b200_pool_desc d, con
                 Pack<T, V>::load(dy + o, g);
 #pragma unroll
                 for (int k = 0; k < V; ++k) acc[k] = (code[o + k] == local) ? g[k] : 0.f;
+            }
+            if (add != nullptr) {
+                // second consumer of the pooled tensor (U-Net skip connection): its gradient, a channel window of a wider
+                // channels-last tensor (row pitch add_ctot), is summed here instead of by a separate add kernel
+                float a[V];
+                Pack<T, V>::load(add + ((int64_t)row * d.Wi + xi) * add_ctot + cv * V, a);
+#pragma unroll
+                for (int k = 0; k < V; ++k) acc[k] += a[k];
             }
             Pack<T, V>::store(xr + e * V, acc);
         }

@@ -540,6 +540,67 @@ def max_pool(x, kernel_size, stride=None, return_indices=False):
     return _MaxPoolFn.apply(x, kernel_size, stride, return_indices)
 
 
+def _channel_window(t):
+    """(pointer tensor, channels per voxel) when `t` (N,C,...) is dense channels-last or a channel slice of such a tensor."""
+    if t.dim() not in (4, 5) or t.stride(1) != 1:
+        return None
+    pitch = t.stride(-1)
+    want = pitch
+    for i in range(t.dim() - 1, 1, -1):                 # W, H, (D): each stride = product of the inner extents x pitch
+        if t.shape[i] != 1 and t.stride(i) != want:
+            return None
+        want *= t.shape[i]
+    if t.shape[0] != 1 and t.stride(0) != want:
+        return None
+    return pitch if pitch >= t.shape[1] else None
+
+
+class _PoolSkipFn(Function):
+    """x -> (max_pool(x, 2, 2), x): the encoder output of a U-Net level feeds both the next level (pooled) and the decoder's
+    concat (unet3d.py:113-121).  Backward sums the two gradients inside the max-pool backward kernel (b200_maxpool_bwd_add),
+    reading the skip gradient straight out of the concat gradient when it arrives as a channel-slice view."""
+
+    @staticmethod
+    def forward(ctx, x):
+        need_cuda(x, "max_pool")
+        x = to_cl(x)
+        pd, shape = _pool_desc(x, 2, 2)
+        if min(shape[2:]) <= 0:
+            raise RuntimeError(f"b200nn.pool_skip: input {tuple(x.shape)} is smaller than the window")
+        y = _empty_cl(shape, x.dtype, x.device)
+        code = torch.empty(y.numel(), dtype=torch.uint8, device=x.device)
+        check(lib().b200_maxpool_fwd(C.byref(pd), x.data_ptr(), y.data_ptr(), code.data_ptr(), None, stream()))
+        ctx.save_for_backward(code)
+        ctx.pd, ctx.in_shape, ctx.dtype = pd, tuple(x.shape), x.dtype
+        return y, x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dskip):
+        (code,) = ctx.saved_tensors
+        if dy is None:
+            return dskip
+        dy = to_cl(dy)
+        if dy.dtype != ctx.dtype:
+            dy = dy.to(ctx.dtype)
+        dx = _empty_cl(ctx.in_shape, ctx.dtype, dy.device)
+        if dskip is None:
+            check(lib().b200_maxpool_bwd(C.byref(ctx.pd), dy.data_ptr(), code.data_ptr(), dx.data_ptr(), stream()))
+            return dx
+        if dskip.dtype != ctx.dtype:
+            dskip = dskip.to(ctx.dtype)
+        pitch = _channel_window(dskip)
+        if pitch is None:
+            dskip = to_cl(dskip)
+            pitch = dskip.shape[1]
+        check(lib().b200_maxpool_bwd_add(C.byref(ctx.pd), dy.data_ptr(), code.data_ptr(), dskip.data_ptr(), pitch, dx.data_ptr(), stream()))
+        return dx
+
+
+def pool_skip(x):
+    """(max_pool(x, 2, 2), x) with the two gradients of x summed inside the pooling backward kernel."""
+    return _PoolSkipFn.apply(x)
+
+
 # --------------------------------------------------------------------------- upsample / concat
 _MODES = {("nearest", None): cabi.UP_NEAREST, ("nearest", False): cabi.UP_NEAREST,
           ("trilinear", None): cabi.UP_TRILINEAR, ("trilinear", False): cabi.UP_TRILINEAR, ("trilinear", True): cabi.UP_TRILINEAR_ALIGNED,
@@ -617,7 +678,7 @@ class _ConcatFn(Function):
     """torch.cat([a, b], dim=1) on channels-last tensors as two channel-slice copies (unet3d.py:76)."""
 
     @staticmethod
-    def forward(ctx, a, b):
+    def forward(ctx, a, b, lazy_a=False):
         need_cuda(a, "concat")
         a, b = to_cl(a), to_cl(b)
         if b.dtype != a.dtype:
@@ -630,7 +691,7 @@ class _ConcatFn(Function):
         dt = dtype_code(a.dtype)
         check(lib().b200_copy_channels(dt, V, ca, a.data_ptr(), ca, 0, y.data_ptr(), ca + cb, 0, stream()))
         check(lib().b200_copy_channels(dt, V, cb, b.data_ptr(), cb, 0, y.data_ptr(), ca + cb, ca, stream()))
-        ctx.ca, ctx.cb = ca, cb
+        ctx.ca, ctx.cb, ctx.lazy_a = ca, cb, lazy_a
         return y
 
     @staticmethod
@@ -640,17 +701,22 @@ class _ConcatFn(Function):
         V = dy.numel() // (ca + cb)
         dt = dtype_code(dy.dtype)
         da = db = None
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0] and ctx.lazy_a:
+            da = dy[:, :ca]                         # a view: the consumer (pool_skip) reads the channel window in place
+        elif ctx.needs_input_grad[0]:
             da = _empty_cl((dy.shape[0], ca) + tuple(dy.shape[2:]), dy.dtype, dy.device)
             check(lib().b200_copy_channels(dt, V, ca, dy.data_ptr(), ca + cb, 0, da.data_ptr(), ca, 0, stream()))
         if ctx.needs_input_grad[1]:
             db = _empty_cl((dy.shape[0], cb) + tuple(dy.shape[2:]), dy.dtype, dy.device)
             check(lib().b200_copy_channels(dt, V, cb, dy.data_ptr(), ca + cb, ca, db.data_ptr(), cb, 0, stream()))
-        return da, db
+        return da, db, None
 
 
-def concat(a, b):
-    return _ConcatFn.apply(a, b)
+def concat(a, b, lazy_grad_a=False):
+    """torch.cat((a, b), 1).  `lazy_grad_a=True` hands `a` its gradient as a channel-slice VIEW of the concat gradient instead
+    of a copy -- for producers whose backward reads a strided channel window (pool_skip); any other consumer still works, it
+    just makes the gradient contiguous itself."""
+    return _ConcatFn.apply(a, b, lazy_grad_a)
 
 
 class _PadChannelsFn(Function):

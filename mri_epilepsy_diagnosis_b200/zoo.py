@@ -64,8 +64,8 @@ class ConvD(tnn.Module):
 
     literal = False       # True: execute unet3d.py:42-47 op by op (dead branch materialised), kernel-level fusions only
 
-    def forward(self, x):
-        if not self.first:
+    def forward(self, x, pooled=False):
+        if not self.first and not pooled:
             x = self.maxpool(x)
         x = _conv_norm(self.conv1, self.bn1, x)
         if self.literal:
@@ -106,7 +106,7 @@ class ConvU(tnn.Module):
 
     literal = False       # True: conv2 runs on the upsampled tensor as written at unet3d.py:73-74
 
-    def forward(self, x, prev):
+    def forward(self, x, prev, lazy_prev_grad=False):
         if not self.first:
             x = _conv_norm(self.conv1, self.bn1, x, act=cabi.ACT_RELU)
         if self.literal:
@@ -118,7 +118,7 @@ class ConvU(tnn.Module):
         # 1/8 of the voxels and the interpolation on half of the channels (results differ by bf16 rounding only).
         y = BF.interpolate(self.conv2(x), scale_factor=2, mode="trilinear", align_corners=False)
         y = self.bn2(y, act=cabi.ACT_RELU)
-        y = BF.concat(prev, y)
+        y = BF.concat(prev, y, lazy_grad_a=lazy_prev_grad)
         return _conv_norm(self.conv3, self.bn3, y, act=cabi.ACT_RELU)
 
 
@@ -148,15 +148,28 @@ class Unet(tnn.Module):
                 tnn.init.constant_(m.bias, 0)
 
     def forward(self, x):
-        x1 = self.convd1(x)
-        x2 = self.convd2(x1)
-        x3 = self.convd3(x2)
-        x4 = self.convd4(x3)
-        x5 = self.convd5(x4)
-        y4 = self.convu4(x5, x4)
-        y3 = self.convu3(y4, x3)
-        y2 = self.convu2(y3, x2)
-        y1 = self.convu1(y2, x1)
+        if self.convd1.literal or not x.is_cuda:
+            x1 = self.convd1(x)
+            x2 = self.convd2(x1)
+            x3 = self.convd3(x2)
+            x4 = self.convd4(x3)
+            x5 = self.convd5(x4)
+            y4 = self.convu4(x5, x4)
+            y3 = self.convu3(y4, x3)
+            y2 = self.convu2(y3, x2)
+            y1 = self.convu1(y2, x1)
+        else:
+            # every encoder output has two consumers (the next level through the max-pool and the decoder's concat): pool_skip
+            # sums their gradients inside the pooling backward kernel, fed by the concat gradient's channel window in place
+            p1, x1 = BF.pool_skip(self.convd1(x))
+            p2, x2 = BF.pool_skip(self.convd2(p1, pooled=True))
+            p3, x3 = BF.pool_skip(self.convd3(p2, pooled=True))
+            p4, x4 = BF.pool_skip(self.convd4(p3, pooled=True))
+            x5 = self.convd5(p4, pooled=True)
+            y4 = self.convu4(x5, x4, lazy_prev_grad=True)
+            y3 = self.convu3(y4, x3, lazy_prev_grad=True)
+            y2 = self.convu2(y3, x2, lazy_prev_grad=True)
+            y1 = self.convu1(y2, x1, lazy_prev_grad=True)
         s3 = self.seg3(y3)
         s2 = self.seg2(y2) + self.upsample(s3)
         return self.seg1(y1) + self.upsample(s2)

@@ -354,6 +354,27 @@ def test_upsample(B, mode, ac, sf, dtype):
     assert rel_err(yg.float(), yr) < tol and rel_err(xg.grad.float(), xr.grad) < tol
 
 
+@pytest.mark.parametrize("dtype,shape", [(torch.float32, (1, 32, 64, 64, 64)), (torch.bfloat16, (2, 32, 64, 64, 64)), (torch.bfloat16, (1, 16, 20, 36, 70))],
+                         ids=["fp32", "bf16", "bf16_ragged"])
+def test_upsample_2x_large_volume(B, dtype, shape):
+    """Volumes large enough for the sliding-window x2 kernels (forward always for vector widths, backward from 128 Ki segment
+    threads); reference = ATen's trilinear kernels in fp32 on the same device (the CPU oracle would need minutes at this size)."""
+    g = gen(31)
+    x = torch.randn(shape, generator=g).to(dtype).float().cuda()
+    xr = x.clone().requires_grad_(True)
+    yr = F.interpolate(xr, scale_factor=2, mode="trilinear", align_corners=False)
+    gy = torch.randn(yr.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5)).to(dtype).float()
+    yr.backward(gy)
+    xg = x.to(dtype).requires_grad_(True)
+    yg = B.functional.interpolate(xg, scale_factor=2, mode="trilinear", align_corners=False)
+    yg.backward(gy.to(dtype))
+    tol = 1e-5 if dtype == torch.float32 else TOL16
+    assert rel_err(yg.float(), yr) < tol and rel_err(xg.grad.float(), xr.grad) < tol
+    # borders are where the clamped taps live: compare the six faces exactly as tightly
+    for sl in ((..., 0), (..., -1), (..., 0, slice(None)), (..., -1, slice(None)), (..., 0, slice(None), slice(None)), (..., -1, slice(None), slice(None))):
+        assert rel_err(xg.grad.float()[sl], xr.grad[sl]) < tol and rel_err(yg.float()[sl], yr[sl]) < tol
+
+
 def test_upsample_pins_and_to_size(B, golden):
     g = golden("op_pins")
     line = torch.arange(4.0).view(1, 1, 1, 1, 4).expand(1, 1, 2, 2, 4).contiguous().cuda()
@@ -376,6 +397,36 @@ def test_upsample_concat_equals_cat(B):
     yg = B.functional.upsample_concat(sg, xg, 2, "trilinear", False)
     yg.backward(gy.cuda())
     assert rel_err(yg, yr) < 1e-5 and rel_err(sg.grad, sr.grad) < 1e-6 and rel_err(xg.grad, xr.grad) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("lazy", [True, False], ids=["window", "dense"])
+def test_pool_skip_sums_both_gradients(B, dtype, lazy):
+    """pool_skip(x) = (max_pool(x, 2, 2), x) with the skip gradient read as a channel window of the concat gradient
+    (unet3d.py:113-121 + torch.cat at :76) and summed inside the pooling backward kernel."""
+    g = gen(44)
+    x = torch.randn(2, 16, 6, 8, 10, generator=g).to(dtype).float()
+    z = torch.randn(2, 8, 6, 8, 10, generator=g).to(dtype).float()
+    xr, zr = x.clone().requires_grad_(True), z.clone().requires_grad_(True)
+    pr = F.max_pool3d(xr, 2, 2)
+    cr = torch.cat((xr, zr), 1)
+    gp, gc = torch.randn(pr.shape, generator=g).to(dtype).float(), torch.randn(cr.shape, generator=g).to(dtype).float()
+    (pr * gp).sum().backward(retain_graph=True)
+    (cr * gc).sum().backward()
+    xg, zg = x.cuda().to(dtype).requires_grad_(True), z.cuda().to(dtype).requires_grad_(True)
+    pg, sg = B.functional.pool_skip(xg)
+    cg = B.functional.concat(sg, zg, lazy_grad_a=lazy)
+    assert torch.equal(pg.float().cpu(), pr.detach()) and torch.equal(cg.float().cpu(), cr.detach())
+    torch.autograd.backward([pg, cg], [gp.cuda().to(dtype), gc.cuda().to(dtype)])
+    tol = 1e-6 if dtype == torch.float32 else TOL16
+    assert rel_err(xg.grad.float(), xr.grad) < tol and rel_err(zg.grad.float(), zr.grad) < tol
+    # either output alone
+    xg2 = x.cuda().to(dtype).requires_grad_(True)
+    p2, s2 = B.functional.pool_skip(xg2)
+    p2.backward(gp.cuda().to(dtype))
+    xr.grad = None
+    F.max_pool3d(xr, 2, 2).backward(gp)
+    assert rel_err(xg2.grad.float(), xr.grad) < tol
 
 
 def test_layout_transpose(B):
