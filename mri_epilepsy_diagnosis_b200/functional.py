@@ -6,6 +6,8 @@ packed weights, saved statistics); the library only enqueues kernels on the curr
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch.autograd import Function
 
@@ -27,9 +29,31 @@ def to_cl(t):
     return t.contiguous(memory_format=_fmt(t))
 
 
+# B200_POISON=1 (debugging aid): every output and workspace handed to the library is pre-filled with NaN (0xFF for byte buffers),
+# so an element a kernel fails to write -- or a workspace entry read before it is written -- shows up in the tests.
+POISON = os.environ.get("B200_POISON", "0") == "1"
+
+
+def _poison(t):
+    if POISON and t.numel():
+        if t.is_floating_point():
+            t.fill_(float("nan"))
+        elif t.dtype == torch.uint8:
+            t.fill_(255)
+    return t
+
+
+def _tempty(*a, **k):
+    return _poison(torch.empty(*a, **k))
+
+
+def _tempty_like(*a, **k):
+    return _poison(torch.empty_like(*a, **k))
+
+
 def _empty_cl(shape, dtype, device):
     fmt = torch.channels_last_3d if len(shape) == 5 else torch.channels_last
-    return torch.empty(shape, dtype=dtype, device=device, memory_format=fmt)
+    return _tempty(shape, dtype=dtype, device=device, memory_format=fmt)
 
 
 def _dhw(t):
@@ -52,7 +76,7 @@ def _t3(v, dims, fill):
 
 
 def _workspace(nbytes, device):
-    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+    return _tempty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
 # Optional per-launch timing of the convolution kernels (bench.py's roofline leg): when PROFILE is a list, every conv
@@ -122,7 +146,7 @@ class ConvConfig:
         if hit is not None and hit[0] == tag:
             return hit[1]
         nbytes = lib().b200_conv_packed_bytes(C.byref(cd), which)
-        buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=weight.device)
+        buf = _tempty(max(nbytes, 16), dtype=torch.uint8, device=weight.device)
         w = weight.detach()
         if w.dtype != torch.float32 or not w.is_contiguous():
             w = w.float().contiguous()
@@ -154,8 +178,8 @@ def _conv_backward(cfg, cd, x, weight, dy, out_dtype, need_dx, need_dw, need_db,
     cur = torch.cuda.current_stream(x.device)
     side = _side_stream(x.device) if (OVERLAP_WGRAD and need_dx and do_w and PROFILE is None) else None
     if do_w:
-        dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
-        db = torch.empty(weight.shape[1] if cfg.transposed else weight.shape[0], dtype=torch.float32, device=x.device) if has_bias else None
+        dw = _tempty(weight.shape, dtype=torch.float32, device=x.device)
+        db = _tempty(weight.shape[1] if cfg.transposed else weight.shape[0], dtype=torch.float32, device=x.device) if has_bias else None
         nws = lib().b200_conv_workspace_bytes(C.byref(cd), cabi.PASS_WGRAD)
         ws_w = _workspace(nws, x.device)
         if side is not None:
@@ -202,7 +226,7 @@ class _ConvFn(Function):
         part = None
         with _Timed(cd, cabi.PASS_FWD):
             if chunks > 0:      # conv + the following BatchNorm's (sum, sum^2) partials in one kernel
-                part = torch.empty((chunks, 2, cd.Co), dtype=torch.float32, device=x.device)
+                part = _tempty((chunks, 2, cd.Co), dtype=torch.float32, device=x.device)
                 check(lib().b200_conv_fwd_stats(C.byref(cd), x.data_ptr(), wp.data_ptr(), ptr(b), y.data_ptr(), part.data_ptr(), ws.data_ptr(), nws,
                                                 stream()))
             else:
@@ -212,7 +236,7 @@ class _ConvFn(Function):
         if not want_stats:
             return y
         if part is None:
-            part = torch.empty(0, dtype=torch.float32, device=x.device)       # "no fused statistics for this shape"
+            part = _tempty(0, dtype=torch.float32, device=x.device)       # "no fused statistics for this shape"
         ctx.mark_non_differentiable(part)
         return y, part
 
@@ -243,12 +267,12 @@ class _DualConvFn(Function):
         if hit is not None and hit[0] == tag:
             wp = hit[1]
         else:
-            wp = torch.empty(max(lib().b200_conv_packed_bytes(C.byref(cd), cabi.PASS_FWD), 16), dtype=torch.uint8, device=x.device)
+            wp = _tempty(max(lib().b200_conv_packed_bytes(C.byref(cd), cabi.PASS_FWD), 16), dtype=torch.uint8, device=x.device)
             wf = wcat if wcat.dtype == torch.float32 else wcat.float()
             check(lib().b200_conv_pack_weights(C.byref(cd), cabi.PASS_FWD, wf.contiguous().data_ptr(), wp.data_ptr(), stream()))
             cfg._packed["dual"] = (tag, wp)
         y = _empty_cl((shape[0], shape[1] - cdead) + tuple(shape[2:]), out_dtype, x.device)
-        part = torch.empty((chunks, 2, cd.Co), dtype=torch.float32, device=x.device)
+        part = _tempty((chunks, 2, cd.Co), dtype=torch.float32, device=x.device)
         ws = _workspace(0, x.device)
         with _Timed(cd, cabi.PASS_FWD):
             check(lib().b200_conv_fwd_stats_tail(C.byref(cd), x.data_ptr(), wp.data_ptr(), None, y.data_ptr(), cdead, part.data_ptr(), ws.data_ptr(), 0,
@@ -269,7 +293,7 @@ class _DualConvFn(Function):
 def dual_conv_supported(x, w_dead, w_live, cfg: ConvConfig, out_dtype):
     if not x.is_cuda or w_dead.shape[1:] != w_live.shape[1:] or w_dead.shape[0] % 16 != 0:
         return False
-    cd, _ = cfg.desc(x, torch.empty((w_dead.shape[0] + w_live.shape[0],) + tuple(w_live.shape[1:]), device="meta"), out_dtype)
+    cd, _ = cfg.desc(x, _tempty((w_dead.shape[0] + w_live.shape[0],) + tuple(w_live.shape[1:]), device="meta"), out_dtype)
     return lib().b200_conv_stats_chunks(C.byref(cd)) > 0
 
 
@@ -316,8 +340,8 @@ class _NormFn(Function):
         x = to_cl(x)
         nd = _norm_desc(x, kind, groups, eps, momentum if momentum is not None else 0.0, act, slope)
         ngroups = {cabi.NORM_BATCH: nd.C, cabi.NORM_INSTANCE: nd.N * nd.C, cabi.NORM_GROUP: nd.N * max(groups, 1)}[kind]
-        mean = torch.empty(ngroups, dtype=torch.float32, device=x.device)
-        rstd = torch.empty_like(mean)
+        mean = _tempty(ngroups, dtype=torch.float32, device=x.device)
+        rstd = _tempty_like(mean)
         nws = lib().b200_norm_workspace_bytes(C.byref(nd))
         ws = _workspace(nws, x.device)
         world = 1
@@ -346,7 +370,7 @@ class _NormFn(Function):
         else:
             check(lib().b200_norm_stats_from_running(C.byref(nd), running_mean.data_ptr(), running_var.data_ptr(), mean.data_ptr(),
                                                      rstd.data_ptr(), stream()))
-        y = torch.empty_like(x)
+        y = _tempty_like(x)
         g32, b32 = _f32(gamma), _f32(beta)
         res = None
         if residual is not None:
@@ -368,18 +392,18 @@ class _NormFn(Function):
         dy = to_cl(dy)
         if dy.dtype != x.dtype:
             dy = dy.to(x.dtype)
-        dx = torch.empty_like(x)
-        dres = torch.empty_like(x) if ctx.has_res and ctx.needs_input_grad[3] else None
+        dx = _tempty_like(x)
+        dres = _tempty_like(x) if ctx.has_res and ctx.needs_input_grad[3] else None
         dgamma = dbeta = None
         if ctx.affine:
-            dgamma = torch.empty(nd.C, dtype=torch.float32, device=x.device)
-            dbeta = torch.empty(nd.C, dtype=torch.float32, device=x.device)
+            dgamma = _tempty(nd.C, dtype=torch.float32, device=x.device)
+            dbeta = _tempty(nd.C, dtype=torch.float32, device=x.device)
         g32 = _f32(gamma)
         nws = lib().b200_norm_workspace_bytes(C.byref(nd))
         ws = _workspace(nws, x.device)
         if ctx.world > 1:
             import torch.distributed as dist
-            sums = torch.empty(nd.C * 2, dtype=torch.float32, device=x.device)
+            sums = _tempty(nd.C * 2, dtype=torch.float32, device=x.device)
             check(lib().b200_norm_bwd_reduce(C.byref(nd), x.data_ptr(), ptr(y), dy.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ptr(g32), ptr(b32),
                                              sums.data_ptr(), ws.data_ptr(), nws, stream()))
             local = sums.clone()
@@ -410,8 +434,8 @@ def batchnorm_update_running(x, running_mean, running_var, momentum, eps, stats_
     batch statistics -> running_mean / running_var.  No normalised tensor is written."""
     need_cuda(x, "norm")
     nd = _norm_desc(x, cabi.NORM_BATCH, 0, eps, momentum, cabi.ACT_NONE, 0.0)
-    mean = torch.empty(nd.C, dtype=torch.float32, device=x.device)
-    rstd = torch.empty_like(mean)
+    mean = _tempty(nd.C, dtype=torch.float32, device=x.device)
+    rstd = _tempty_like(mean)
     if stats_partial is not None:
         check(lib().b200_norm_stats_from_partial(C.byref(nd), stats_partial.data_ptr(), stats_partial.shape[0], mean.data_ptr(), rstd.data_ptr(),
                                                  ptr(running_mean), ptr(running_var), stream()))
@@ -431,7 +455,7 @@ class _ActFn(Function):
         if not (x.is_contiguous() or (x.dim() in (4, 5) and x.is_contiguous(memory_format=_fmt(x)))):
             x = x.contiguous()
             inplace = False
-        y = x if inplace else torch.empty_like(x)
+        y = x if inplace else _tempty_like(x)
         check(lib().b200_act_fwd(dtype_code(x.dtype), act, float(slope), x.numel(), x.data_ptr(), y.data_ptr(), stream()))
         if inplace:
             ctx.mark_dirty(x)
@@ -446,7 +470,7 @@ class _ActFn(Function):
             dy = dy.contiguous(memory_format=_fmt(y)) if y.dim() in (4, 5) and not y.is_contiguous() else dy.contiguous()
         if dy.dtype != y.dtype:
             dy = dy.to(y.dtype)
-        dx = torch.empty_like(y)
+        dx = _tempty_like(y)
         check(lib().b200_act_bwd(dtype_code(y.dtype), ctx.act, ctx.slope, y.numel(), y.data_ptr(), dy.data_ptr(), dx.data_ptr(), stream()))
         return dx, None, None, None
 
@@ -467,7 +491,7 @@ class _PReLUFn(Function):
             raise RuntimeError("b200nn.PReLU supports num_parameters=1 (the reference's unet.UNet activation)")
         if not (x.is_contiguous() or (x.dim() in (4, 5) and x.is_contiguous(memory_format=_fmt(x)))):
             x = x.contiguous()
-        y = torch.empty_like(x)
+        y = _tempty_like(x)
         a32 = _f32(a)
         check(lib().b200_prelu_fwd(dtype_code(x.dtype), x.numel(), x.data_ptr(), a32.data_ptr(), y.data_ptr(), stream()))
         ctx.save_for_backward(x, a)
@@ -480,8 +504,8 @@ class _PReLUFn(Function):
             dy = dy.contiguous(memory_format=_fmt(x)) if x.dim() in (4, 5) and not x.is_contiguous() else dy.contiguous()
         if dy.dtype != x.dtype:
             dy = dy.to(x.dtype)
-        dx = torch.empty_like(x)
-        da = torch.empty(1, dtype=torch.float32, device=x.device)
+        dx = _tempty_like(x)
+        da = _tempty(1, dtype=torch.float32, device=x.device)
         nws = lib().b200_prelu_workspace_bytes(x.numel())
         ws = _workspace(nws, x.device)
         a32 = _f32(a)
@@ -515,7 +539,7 @@ class _MaxPoolFn(Function):
         if min(shape[2:]) <= 0:
             raise RuntimeError(f"b200nn.max_pool: input {tuple(x.shape)} is smaller than the window")
         y = _empty_cl(shape, x.dtype, x.device)
-        code = torch.empty(y.numel(), dtype=torch.uint8, device=x.device)
+        code = _tempty(y.numel(), dtype=torch.uint8, device=x.device)
         idx = _empty_cl(shape, torch.int64, x.device) if want_indices else None
         check(lib().b200_maxpool_fwd(C.byref(pd), x.data_ptr(), y.data_ptr(), code.data_ptr(), ptr(idx), stream()))
         ctx.save_for_backward(code)
@@ -568,7 +592,7 @@ class _PoolSkipFn(Function):
         if min(shape[2:]) <= 0:
             raise RuntimeError(f"b200nn.pool_skip: input {tuple(x.shape)} is smaller than the window")
         y = _empty_cl(shape, x.dtype, x.device)
-        code = torch.empty(y.numel(), dtype=torch.uint8, device=x.device)
+        code = _tempty(y.numel(), dtype=torch.uint8, device=x.device)
         check(lib().b200_maxpool_fwd(C.byref(pd), x.data_ptr(), y.data_ptr(), code.data_ptr(), None, stream()))
         ctx.save_for_backward(code)
         ctx.pd, ctx.in_shape, ctx.dtype = pd, tuple(x.shape), x.dtype
@@ -763,8 +787,8 @@ class _SoftmaxDiceFn(Function):
         N, Cc = lg.shape[0], lg.shape[1]
         S = lg.numel() // (N * Cc)
         dd = cabi.DiceDesc(dtype_code(lg.dtype), N, Cc, S, float(eps))
-        sums = torch.empty(N * (2 * Cc + 1), dtype=torch.float32, device=lg.device)
-        loss = torch.empty((), dtype=torch.float32, device=lg.device)
+        sums = _tempty(N * (2 * Cc + 1), dtype=torch.float32, device=lg.device)
+        loss = _tempty((), dtype=torch.float32, device=lg.device)
         nws = lib().b200_softmax_dice_workspace_bytes(C.byref(dd))
         ws = _workspace(nws, lg.device)
         check(lib().b200_softmax_dice_fwd(C.byref(dd), lg.data_ptr(), tg.data_ptr(), sums.data_ptr(), loss.data_ptr(), ws.data_ptr(), nws, stream()))
@@ -776,7 +800,7 @@ class _SoftmaxDiceFn(Function):
     def backward(ctx, dloss):
         lg, tg, sums = ctx.saved_tensors
         g = dloss.detach().to(torch.float32).contiguous()
-        dl = torch.empty_like(lg)
+        dl = _tempty_like(lg)
         check(lib().b200_softmax_dice_bwd(C.byref(ctx.dd), lg.data_ptr(), tg.data_ptr(), sums.data_ptr(), g.data_ptr(), dl.data_ptr(), stream()))
         return dl, None, None
 
