@@ -675,6 +675,7 @@ int b200_upsample_bwd(const b200_up_desc* d, const void* dy, void* dx, void* str
     if (upsample_is_2x_trilinear(d)) {
         const int64_t rows = (int64_t)d->N * d->Di * d->Hi;
         const int grid = (int)(rows < kNumSMs * 16 ? rows : kNumSMs * 16);
+        int rc = 0;
         B200_DISPATCH_T(d->dtype, T, {
             constexpr int VF = Vec16<T>::N;
             constexpr int SEG = 16;
@@ -682,6 +683,7 @@ int b200_upsample_bwd(const b200_up_desc* d, const void* dy, void* dx, void* str
             auto sgrid = [&](int cvn) { const int64_t b = ceil_div(segrows * cvn, 128); return (int)(b < (int64_t)kNumSMs * 32 ? b : (int64_t)kNumSMs * 32); };
             // the sliding-window kernel has 1/16 of the threads of the per-cell kernel: it only wins on volumes that still fill the SMs
             const bool vec = d->C % VF == 0 && d->Ctot % VF == 0 && d->c_off % VF == 0 && aligned16(dy) && aligned16(dx);
+            if (vec && sizeof(T) == 2 && d->C % 16 == 0 && up_bwd_tile_launch(d, dy, dx, stream, &rc)) return rc;
             if (vec && segrows * (d->C / VF) >= 128 * 1024)
                 B200_LAUNCH((upsample2x_bwd_slide_kernel<T, VF, SEG>), sgrid(d->C / VF), 128, 0, stream, *d, (const T*)dy, (T*)dx);
             else if (vec)

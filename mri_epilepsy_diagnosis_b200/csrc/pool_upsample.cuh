@@ -462,6 +462,82 @@ __global__ void __launch_bounds__(128) upsample2x_bwd_slide_kernel(b200_up_desc 
     }
 }
 
+// Tiled adjoint for bf16 (the decoder's upsamples): a 256-thread block owns TY x 16 input cells of one (n, zi) plane and CG
+// channel vectors.  Stage 1 folds the four output planes that touch zi into one z-reduced fp32 tile of (2TY+2) x 34 output
+// positions in shared memory (coalesced 16-byte loads, every dy element of the tile converted once); stage 2 gathers the 4 x 4
+// (y, x) taps of each cell from that tile.  ~30% fewer instructions than the sliding-window kernel and 4x its occupancy.
+template <int CG>
+struct UpBwdTile {
+    static constexpr int TX = 16, TY = 256 / (16 * CG), ROWS = 2 * TY + 2, COLS = 2 * TX + 2;
+    static constexpr int COL4 = CG * 2 + CG / 2;                     // float4 per column: [half][cv] + padding against bank conflicts
+    static constexpr int SMEM = ROWS * COLS * COL4 * 16;
+};
+template <int CG>
+__global__ void __launch_bounds__(256) upsample2x_bwd_tile_kernel(b200_up_desc d, const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx) {
+    using G = UpBwdTile<CG>;
+    extern __shared__ float4 up_sm[];
+    const int ntx = (d.Wi + G::TX - 1) / G::TX, nty = (d.Hi + G::TY - 1) / G::TY, ncg = d.C / (8 * CG);
+    int b = blockIdx.x;
+    const int xt = b % ntx; b /= ntx;
+    const int yt = b % nty; b /= nty;
+    const int cg = b % ncg; b /= ncg;
+    const int zi = b % d.Di, n = b / d.Di;
+    const int x0 = xt * G::TX, y0 = yt * G::TY;
+    const Touch2 tz = touch2(zi, d.Di);
+    const int64_t plane = (int64_t)d.Ho * d.Wo * d.Ctot;
+    const __nv_bfloat16* gn = dy + (int64_t)n * d.Do * plane + d.c_off + cg * CG * 8;
+    for (int it = threadIdx.x; it < G::ROWS * G::COLS * CG; it += 256) {
+        const int cv = it % CG, col = (it / CG) % G::COLS, row = it / (CG * G::COLS);
+        const int oy = min(max(2 * y0 - 1 + row, 0), d.Ho - 1), ox = min(max(2 * x0 - 1 + col, 0), d.Wo - 1);
+        const __nv_bfloat16* src = gn + ((int64_t)oy * d.Wo + ox) * d.Ctot + cv * 8;
+        float v[4][8], acc[8];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) Pack<__nv_bfloat16, 8>::load(src + tz.o[a] * plane, v[a]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(tz.w[0], v[0][k], fmaf(tz.w[1], v[1][k], fmaf(tz.w[2], v[2][k], tz.w[3] * v[3][k])));
+        float4* dst = up_sm + (row * G::COLS + col) * G::COL4 + cv;
+        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        dst[CG] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    __syncthreads();
+    const int cv = threadIdx.x % CG, xl = (threadIdx.x / CG) % G::TX, yl = threadIdx.x / (CG * G::TX);
+    const int yi = y0 + yl, xi = x0 + xl;
+    if (yi >= d.Hi || xi >= d.Wi) return;
+    const Touch2 ty = touch2(yi, d.Hi), tx = touch2(xi, d.Wi);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int bb = 0; bb < 4; ++bb)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float w = ty.w[bb] * tx.w[c];
+            const float4* src = up_sm + ((2 * yl + bb) * G::COLS + 2 * xl + c) * G::COL4 + cv;
+            const float4 lo = src[0], hi = src[CG];
+            acc[0] = fmaf(w, lo.x, acc[0]); acc[1] = fmaf(w, lo.y, acc[1]); acc[2] = fmaf(w, lo.z, acc[2]); acc[3] = fmaf(w, lo.w, acc[3]);
+            acc[4] = fmaf(w, hi.x, acc[4]); acc[5] = fmaf(w, hi.y, acc[5]); acc[6] = fmaf(w, hi.z, acc[6]); acc[7] = fmaf(w, hi.w, acc[7]);
+        }
+    Pack<__nv_bfloat16, 8>::store(dx + ((((int64_t)n * d.Di + zi) * d.Hi + yi) * d.Wi + xi) * d.C + (cg * CG + cv) * 8, acc);
+}
+
+// bf16 tiled adjoint (upsample2x_bwd_tile_kernel); false when the grid would not fit
+template <int CG>
+inline bool up_bwd_tile_launch_cg(const b200_up_desc* d, const void* dy, void* dx, void* stream, int* rc) {
+    using G = UpBwdTile<CG>;
+    const int64_t blocks = (int64_t)d->N * d->Di * ceil_div(d->Hi, G::TY) * ceil_div(d->Wi, G::TX) * (d->C / (8 * CG));
+    if (blocks >= (1ll << 31)) return false;
+    static cudaError_t attr = cudaFuncSetAttribute(upsample2x_bwd_tile_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+    if (attr != cudaSuccess) { *rc = fail("upsample_bwd: cannot raise the dynamic shared memory limit: %s", cudaGetErrorString(attr)); return true; }
+    *rc = [&]() -> int {
+        B200_LAUNCH((upsample2x_bwd_tile_kernel<CG>), (int)blocks, 256, G::SMEM, stream, *d, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx);
+        return 0;
+    }();
+    return true;
+}
+inline bool up_bwd_tile_launch(const b200_up_desc* d, const void* dy, void* dx, void* stream, int* rc) {
+    return d->C % 32 == 0 ? up_bwd_tile_launch_cg<4>(d, dy, dx, stream, rc) : up_bwd_tile_launch_cg<2>(d, dy, dx, stream, rc);
+}
+
 template <typename T, int V>
 __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(b200_up_desc d, const T* __restrict__ dy, T* __restrict__ dx) {
     const int CV = d.C / V;

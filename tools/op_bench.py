@@ -27,7 +27,7 @@ def cl(n, c, s, dtype=torch.bfloat16):
 
 ops = sys.argv[1:] or ["upsample", "norm", "pool", "stem", "head", "cat"]
 if "upsample" in ops:
-    for (c, s, dt) in ((32, 64, torch.bfloat16), (64, 32, torch.bfloat16), (2, 64, torch.float32)):
+    for (c, s, dt) in ((16, 64, torch.bfloat16), (32, 64, torch.bfloat16), (32, 32, torch.bfloat16), (64, 32, torch.bfloat16), (2, 64, torch.float32)):
         x = cl(4, c, s, dt).requires_grad_(True)
         y = BF.interpolate(x, scale_factor=2, mode="trilinear", align_corners=False)
         eb = x.element_size()
