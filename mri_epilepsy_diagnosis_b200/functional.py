@@ -137,11 +137,19 @@ class ConvConfig:
         shape = (N, Co) + (tuple(out) if dims == 5 else tuple(out[1:]))
         return cd, shape
 
-    def packed(self, cd, weight, which):
-        """Packed copy of `weight` for pass `which`; re-derived when the parameter changes (optimizer step / load_state_dict)."""
+    def packed(self, cd, weight, which, fresh):
+        """Packed copy of `weight` for pass `which`.
+
+        `fresh=True` (every call that takes part in autograd, forward and backward): always re-derived.  The parameter's
+        version counter cannot be trusted to announce an update -- fused optimizers (`AdamW(fused=True)`) and `p.data`
+        arithmetic change the values without bumping it -- and a stale packed copy would silently freeze the layer.
+        `fresh=False` (inference under no_grad): cached on (storage, version); any fresh call drops the cached copy, so the
+        first inference call after a training step re-packs."""
         algo = lib().b200_conv_algo(C.byref(cd), which)
         key = (which, algo, cd.x_dtype, cd.y_dtype, cd.Ci, cd.Co)
         tag = (weight.data_ptr(), weight._version, weight.device)
+        if fresh:
+            self._packed.clear()
         hit = self._packed.get(key)
         if hit is not None and hit[0] == tag:
             return hit[1]
@@ -151,7 +159,8 @@ class ConvConfig:
         if w.dtype != torch.float32 or not w.is_contiguous():
             w = w.float().contiguous()
         check(lib().b200_conv_pack_weights(C.byref(cd), which, w.data_ptr(), buf.data_ptr(), stream()))
-        self._packed[key] = (tag, buf)
+        if not fresh:
+            self._packed[key] = (tag, buf)
         return buf
 
 
@@ -191,7 +200,7 @@ def _conv_backward(cfg, cd, x, weight, dy, out_dtype, need_dx, need_dw, need_db,
             check(lib().b200_conv_wgrad(C.byref(cd), x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ptr(db), ws_w.data_ptr(), nws,
                                         side.cuda_stream if side is not None else stream()))
     if need_dx:
-        wp = cfg.packed(cd, weight, cabi.PASS_DGRAD)
+        wp = cfg.packed(cd, weight, cabi.PASS_DGRAD, fresh=True)
         dx = _empty_cl(tuple(x.shape), x.dtype, x.device)
         nws = lib().b200_conv_workspace_bytes(C.byref(cd), cabi.PASS_DGRAD)
         ws = _workspace(nws, x.device)
@@ -209,11 +218,11 @@ def _conv_backward(cfg, cd, x, weight, dy, out_dtype, need_dx, need_dw, need_db,
 
 class _ConvFn(Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, cfg, out_dtype, want_stats):
+    def forward(ctx, x, weight, bias, cfg, out_dtype, want_stats, tracked=True):
         need_cuda(x, "conv")
         x = to_cl(x)
         cd, shape = cfg.desc(x, weight, out_dtype)
-        wp = cfg.packed(cd, weight, cabi.PASS_FWD)
+        wp = cfg.packed(cd, weight, cabi.PASS_FWD, fresh=tracked)
         y = _empty_cl(shape, out_dtype, x.device)
         b = None
         if bias is not None:
@@ -245,7 +254,7 @@ class _ConvFn(Function):
         x, weight = ctx.saved_tensors
         dx, dw, db = _conv_backward(ctx.cfg, ctx.cd, x, weight, dy, ctx.out_dtype, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
                                     ctx.has_bias and ctx.needs_input_grad[2], ctx.has_bias)
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, None
 
 
 class _DualConvFn(Function):
@@ -262,15 +271,10 @@ class _DualConvFn(Function):
         chunks = lib().b200_conv_stats_chunks(C.byref(cd))
         if chunks <= 0 or cdead % 16 != 0:
             raise RuntimeError("b200nn.dual_conv: shape not supported (check dual_conv_supported)")
-        tag = (w_dead.data_ptr(), w_dead._version, w_live.data_ptr(), w_live._version, x.device)
-        hit = cfg._packed.get("dual")
-        if hit is not None and hit[0] == tag:
-            wp = hit[1]
-        else:
-            wp = _tempty(max(lib().b200_conv_packed_bytes(C.byref(cd), cabi.PASS_FWD), 16), dtype=torch.uint8, device=x.device)
-            wf = wcat if wcat.dtype == torch.float32 else wcat.float()
-            check(lib().b200_conv_pack_weights(C.byref(cd), cabi.PASS_FWD, wf.contiguous().data_ptr(), wp.data_ptr(), stream()))
-            cfg._packed["dual"] = (tag, wp)
+        # packed on every call (training-only path; see ConvConfig.packed on why the version counter is not trusted)
+        wp = _tempty(max(lib().b200_conv_packed_bytes(C.byref(cd), cabi.PASS_FWD), 16), dtype=torch.uint8, device=x.device)
+        wf = wcat if wcat.dtype == torch.float32 else wcat.float()
+        check(lib().b200_conv_pack_weights(C.byref(cd), cabi.PASS_FWD, wf.contiguous().data_ptr(), wp.data_ptr(), stream()))
         y = _empty_cl((shape[0], shape[1] - cdead) + tuple(shape[2:]), out_dtype, x.device)
         part = _tempty((chunks, 2, cd.Co), dtype=torch.float32, device=x.device)
         ws = _workspace(0, x.device)
@@ -302,12 +306,17 @@ def dual_conv(x, w_dead, w_live, cfg: ConvConfig, out_dtype=None):
     return _DualConvFn.apply(x, w_dead, w_live, cfg, out_dtype or x.dtype)
 
 
+def _tracked(*tensors):
+    """whether this call takes part in autograd (decided at apply time: inside Function.forward grad mode is always off)"""
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
 def conv(x, weight, bias, cfg: ConvConfig, out_dtype=None, want_stats=False):
     """y = conv(x).  want_stats=True returns (y, partial): `partial` feeds `norm(..., stats_partial=partial)` (None when the
     shape has no fused-statistics kernel)."""
     if not want_stats:
-        return _ConvFn.apply(x, weight, bias, cfg, out_dtype or x.dtype, False)
-    y, part = _ConvFn.apply(x, weight, bias, cfg, out_dtype or x.dtype, True)
+        return _ConvFn.apply(x, weight, bias, cfg, out_dtype or x.dtype, False, _tracked(x, weight, bias))
+    y, part = _ConvFn.apply(x, weight, bias, cfg, out_dtype or x.dtype, True, _tracked(x, weight, bias))
     return y, (part if part.numel() else None)
 
 

@@ -429,6 +429,43 @@ def test_pool_skip_sums_both_gradients(B, dtype, lazy):
     assert rel_err(xg2.grad.float(), xr.grad) < tol
 
 
+def test_packed_weights_follow_versionless_updates(B):
+    """The tcgen05 paths run on a re-laid-out bf16 copy of the weights.  Fused optimizers (AdamW(fused=True)) and `p.data`
+    arithmetic change a parameter WITHOUT bumping its version counter, so the copy must not be cached across autograd calls:
+    a stale copy would freeze the layer silently."""
+    g = gen(77)
+    mod = B.nn.Conv3d(16, 16, 3, 1, 1, bias=False).cuda()
+    mod.compute_dtype = torch.bfloat16
+    x = torch.randn(2, 16, 16, 16, 16, generator=g).cuda().bfloat16()
+
+    def ref():
+        return F.conv3d(x.float(), mod.weight.detach().bfloat16().float(), None, 1, 1)
+
+    assert rel_err(mod(x).float(), ref()) < 1e-2
+    v = mod.weight._version
+    mod.weight.data.mul_(-1.5)                                   # version-less update
+    assert mod.weight._version == v
+    assert rel_err(mod(x).float(), ref()) < 1e-2
+    opt = torch.optim.AdamW(mod.parameters(), lr=0.05, fused=True)
+    for _ in range(2):
+        opt.zero_grad()
+        mod(x).float().square().mean().backward()
+        opt.step()
+        with torch.no_grad():                                     # first inference call after a training step re-packs ...
+            n0 = B._cabi.lib().b200_launch_count()
+            y = mod(x)
+            n1 = B._cabi.lib().b200_launch_count()
+            mod(x)                                                # ... the second one hits the cache: one launch fewer
+            n2 = B._cabi.lib().b200_launch_count()
+            assert rel_err(y.float(), ref()) < 1e-2 and (n2 - n1) == (n1 - n0) - 1, (n0, n1, n2)
+    xg = x.clone().requires_grad_(True)                           # dgrad uses the transposed copy: same rule
+    mod.weight.data.mul_(2.0)
+    mod(xg).float().sum().backward()
+    xr = x.float().requires_grad_(True)
+    F.conv3d(xr, mod.weight.detach().bfloat16().float(), None, 1, 1).sum().backward()
+    assert rel_err(xg.grad.float(), xr.grad) < 1e-2
+
+
 def test_layout_transpose(B):
     x = torch.randn(2, 5, 3, 4, 6, generator=gen(1)).cuda()
     y = B.functional.to_channels_last(x, torch.bfloat16)
