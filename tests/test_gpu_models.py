@@ -336,3 +336,48 @@ def test_unet3d_rewritten_graph_equals_literal_operator_sequence(B):
     for k in ("convd1.bn2.running_mean", "convd1.bn2.running_var", "convd2.bn2.running_var", "convu1.bn2.running_mean", "convu1.bn2.running_var"):
         assert rel_err(ba[k], bb[k]) < 2e-2, k
     assert int(ba["convd1.bn2.num_batches_tracked"]) == int(bb["convd1.bn2.num_batches_tracked"]) == 1
+
+
+def test_graphed_train_step_learns_like_the_eager_loop(B):
+    """graphed.GraphedTrainStep (whole step captured once, fused AdamW inside the graph) against the plain eager loop of
+    segmentation/routine.py:266-281 with the default AdamW: same losses step by step, the weights really move (a packed
+    weight copy that missed an optimizer update would leave the loss flat), BatchNorm counters advance once per step."""
+    from oracle import weights
+    sd = weights.unet3d_state(1, 16, 2, "bn", seed=9)
+    g = torch.Generator().manual_seed(21)
+    xs = [torch.randn(2, 1, 32, 32, 32, generator=g).cuda() for _ in range(2)] * 3        # two batches, three passes: the loss must fall
+    ts = [(torch.rand(2, 1, 32, 32, 32, generator=g) > 0.6).float().cuda() for _ in range(2)] * 3
+    loss_fn = B.functional.softmax_dice_loss
+
+    def make():
+        net = B.zoo.Unet(c=1, n=16, dropout=0.0, norm="bn", num_classes=2)
+        net.load_state_dict(sd, strict=True)
+        return B.convert(net.cuda().train(), dtype=torch.bfloat16)
+
+    eager = make()
+    opt = torch.optim.AdamW(eager.parameters(), lr=2e-3)
+    want = []
+    for x, t in zip(xs, ts):
+        opt.zero_grad()
+        loss = loss_fn(eager(x), t)
+        loss.backward()
+        opt.step()
+        want.append(float(loss))
+    net = make()
+    step = B.graphed.GraphedTrainStep(net, loss_fn, torch.optim.AdamW(net.parameters(), lr=2e-3, capturable=True, fused=True), xs[0], ts[0], warmup=1)
+    # construction ran a probe and warm-up steps on (xs[0], ts[0]): restart both from the same state
+    net.load_state_dict(sd, strict=True)
+    for st in step.opt.state.values():                  # the graph holds these tensors by address: reset them in place
+        for v in st.values():
+            if torch.is_tensor(v):
+                v.zero_()
+    got = [float(step(x, t)) for x, t in zip(xs, ts)]
+    assert abs(got[0] - want[0]) < 5e-3
+    assert max(abs(a - b) for a, b in zip(got, want)) < 3e-2, (got, want)
+    assert want[4] < want[2] < want[0] - 0.003 and got[4] < got[2] < got[0] - 0.003, (got, want)      # both loops learn (batch 0 revisited)
+    pe, pg = dict(eager.named_parameters()), dict(net.named_parameters())
+    for k in ("convd1.conv1.weight", "convd3.conv3.weight", "convu2.conv3.weight", "seg1.weight"):
+        moved = rel_err(pg[k], sd[k].cuda())
+        assert moved > 1e-3, (k, moved)
+        assert rel_err(pg[k], pe[k]) < 0.5 * moved + 1e-3, (k, moved)
+    assert int(dict(net.named_buffers())["convd1.bn1.num_batches_tracked"]) == 6
