@@ -165,7 +165,8 @@ class ConvConfig:
 
 
 _SIDE_STREAMS = {}
-OVERLAP_WGRAD = True      # run wgrad on a side stream next to dgrad (they are independent); joined before backward() returns
+# run wgrad on a side stream next to dgrad (they are independent); joined before backward() returns.  B200_OVERLAP_WGRAD=0 disables.
+OVERLAP_WGRAD = os.environ.get("B200_OVERLAP_WGRAD", "1") != "0"
 
 
 def _side_stream(device):
@@ -183,9 +184,12 @@ def _conv_backward(cfg, cd, x, weight, dy, out_dtype, need_dx, need_dw, need_db,
     do_w = need_dw or need_db
     # dgrad and wgrad only share read-only inputs: with both requested, wgrad goes to a side stream so that the two kernels
     # overlap when neither fills the GPU (the deep 8^3..32^3 levels); the main stream waits for it before returning, so autograd
-    # sees ordinary stream semantics.  Inside a CUDA-graph capture this becomes a fork/join in the graph.
+    # sees ordinary stream semantics.
     cur = torch.cuda.current_stream(x.device)
-    side = _side_stream(x.device) if (OVERLAP_WGRAD and need_dx and do_w and PROFILE is None) else None
+    # Only while a CUDA graph is being captured (a fork/join in the graph): in eager mode the cross-stream lifetime tracking
+    # (record_stream) keeps the GB-sized activations from being reused by the caching allocator and the step gets slower
+    # (unet.UNet(first=16), 4 x 128^3: 28.6 ms without, 40-55 ms with).
+    side = _side_stream(x.device) if (OVERLAP_WGRAD and need_dx and do_w and PROFILE is None and torch.cuda.is_current_stream_capturing()) else None
     if do_w:
         dw = _tempty(weight.shape, dtype=torch.float32, device=x.device)
         db = _tempty(weight.shape[1] if cfg.transposed else weight.shape[0], dtype=torch.float32, device=x.device) if has_bias else None
