@@ -254,25 +254,46 @@ row_wgrad_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
 }
 
 // dw[(co*Ci + ci)*taps + tap] = sum_split partial[unit][split][kz*NN + a*cQ + co_l][kx*cP + ci_l],  ky = kh-1-a
-// (one thread per weight element, 8 loads in flight, fixed split order; a warp-per-element variant with the splits on the lanes
-// was 5x slower -- 148 scattered sectors per element instead of neighbouring threads sharing cache lines)
-__global__ void row_wgrad_reduce_kernel(RowWgradParams p, float* __restrict__ dw) {
+// Neighbouring threads take neighbouring weight elements (they share cache lines; a warp-per-element variant with the splits on
+// the lanes was 5x slower -- 148 scattered sectors per element).  The chain of `splits` dependent loads is what costs (20 us
+// for ANY layer size with one thread per element), so for layers with few elements SG thread groups of a block each take every
+// SG-th split and the groups are combined through shared memory in a fixed order (deterministic).
+template <int SG>
+__global__ void __launch_bounds__(256) row_wgrad_reduce_kernel(RowWgradParams p, float* __restrict__ dw) {
+    constexpr int EL = 256 / SG;
+    __shared__ float red[SG][EL];
+    const int el = threadIdx.x % EL, sg = threadIdx.x / EL;
     const int taps = p.kd * p.kh * p.kw;
     const int64_t total = (int64_t)p.Co * p.Ci * taps;
     const int mrows = p.kw * p.cP, ncols = p.kd * p.NN;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        const int tap = (int)(e % taps);
-        const int64_t r = e / taps;
-        const int ci = (int)(r % p.Ci), co = (int)(r / p.Ci);
-        const int kz = tap / (p.kh * p.kw), ky = (tap / p.kw) % p.kh, kx = tap % p.kw;
-        const int a = p.kh - 1 - ky;
-        const int cic = ci / p.cP, cil = ci % p.cP, coc = co / p.cQ, col_ = co % p.cQ;
-        const int unit = coc * p.n_ci + cic;
-        const float* src = p.partial + ((size_t)unit * p.splits * ncols + (size_t)(kz * p.NN + a * p.cQ + col_)) * mrows + kx * p.cP + cil;
+    for (int64_t base = (int64_t)blockIdx.x * EL; base < total; base += (int64_t)gridDim.x * EL) {
+        const int64_t e = base + el;
         float acc = 0.f;
+        if (e < total) {
+            const int tap = (int)(e % taps);
+            const int64_t r = e / taps;
+            const int ci = (int)(r % p.Ci), co = (int)(r / p.Ci);
+            const int kz = tap / (p.kh * p.kw), ky = (tap / p.kw) % p.kh, kx = tap % p.kw;
+            const int a = p.kh - 1 - ky;
+            const int cic = ci / p.cP, cil = ci % p.cP, coc = co / p.cQ, col_ = co % p.cQ;
+            const int unit = coc * p.n_ci + cic;
+            const float* src = p.partial + ((size_t)unit * p.splits * ncols + (size_t)(kz * p.NN + a * p.cQ + col_)) * mrows + kx * p.cP + cil;
 #pragma unroll 8
-        for (int s = 0; s < p.splits; ++s) acc += __ldg(src + (size_t)s * ncols * mrows);      // same order every run; 8 loads in flight
-        dw[e] = acc;
+            for (int s = sg; s < p.splits; s += SG) acc += __ldg(src + (size_t)s * ncols * mrows);      // same order every run; 8 loads in flight
+        }
+        if (SG == 1) {
+            if (e < total) dw[e] = acc;
+        } else {
+            red[sg][el] = acc;
+            __syncthreads();
+            if (sg == 0 && e < total) {
+                float t = red[0][el];
+#pragma unroll
+                for (int g = 1; g < SG; ++g) t += red[g][el];
+                dw[e] = t;
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -366,7 +387,8 @@ inline int row_wgrad_run(const b200_conv_desc* d, const void* x, const void* dy,
     const int units = p.n_ci * p.n_co;
     B200_LAUNCH(row_wgrad_kernel, units * p.splits, kRwThreads, smem_bytes, stream, x_map, dy_map, p);
     const int64_t total = (int64_t)d->kd * d->kh * d->kw * d->Co * d->Ci;
-    B200_LAUNCH(row_wgrad_reduce_kernel, stream_grid(total, 256), 256, 0, stream, p, dw);
+    if (total <= 128 * 1024) B200_LAUNCH(row_wgrad_reduce_kernel<8>, stream_grid(total, 32), 256, 0, stream, p, dw);
+    else B200_LAUNCH(row_wgrad_reduce_kernel<1>, stream_grid(total, 256), 256, 0, stream, p, dw);
     if (dbias != nullptr) {
         float* bpart = (float*)((char*)workspace + ((partial_bytes + 255) & ~(size_t)255));
         const int64_t Vy = (int64_t)d->N * d->Do * d->Ho * d->Wo;
