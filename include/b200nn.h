@@ -235,6 +235,26 @@ int b200_patch_plan(const b200_patch_desc* d, const double* gmpm, const uint8_t*
 int b200_patch_gather(const b200_patch_desc* d, const double* target, const int32_t* plan, int64_t rows,
                       int out_dtype_is_f32, void* out, void* stream);
 
+/* ---- intensity preprocessing -------------------------------------------------------------------
+ * Histogram standardisation of one volume = `normalize(tensor, landmarks, mask, cutoff, epsilon)` of
+ * classification/train_ENC_CLF.ipynb [cell 9] (the collate function of the classification loaders, cell 9 `default_collate`):
+ *   percentile_values = np.percentile(data[mask], percentiles)          exact order statistics, numpy 'linear' interpolation
+ *   piecewise-linear map of the percentiles listed in range_idx onto `landmarks`; np.digitize + slope * x + intercept in float64
+ * q: the percentiles as fractions in [0, 1] (ascending); landmarks: the trained mapping, one value per percentile;
+ * range_idx: which of them take part in the map (the notebook uses 11 of its 13).  x: n float32 values on the device, mask:
+ * optional n bytes (non-zero = selected for the percentiles; every element is mapped), out: n float32, percentiles_out: optional
+ * nq doubles on the device.  Finite inputs; n < 2^32. */
+typedef struct {
+    double q[16];
+    double landmarks[16];
+    int32_t range_idx[16];
+    int32_t nq, nrange;
+    double eps;
+} b200_histstd_desc;
+size_t b200_histstd_workspace_bytes(void);
+int b200_histstd_normalize(const b200_histstd_desc* d, const float* x, const uint8_t* mask, int64_t n, float* out,
+                           double* percentiles_out, void* workspace, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

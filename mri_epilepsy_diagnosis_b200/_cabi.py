@@ -42,6 +42,10 @@ class DiceDesc(C.Structure):
     _fields_ = [("dtype", i32), ("N", i32), ("C", i32), ("S", i64), ("eps", f32)]
 
 
+class HistStdDesc(C.Structure):
+    _fields_ = [("q", C.c_double * 16), ("landmarks", C.c_double * 16), ("range_idx", i32 * 16), ("nq", i32), ("nrange", i32), ("eps", C.c_double)]
+
+
 class PatchDesc(C.Structure):
     _fields_ = [(n, i32) for n in ("X", "Y", "Z", "h", "w", "with_mask", "upsample_passes")]
 
@@ -90,6 +94,8 @@ _SIGS = {
     "b200_patch_max_rows": (i64, [P(PatchDesc)]),
     "b200_patch_plan": (C.c_int, [P(PatchDesc), vp, vp, vp, vp, vp, vp, sz, vp]),
     "b200_patch_gather": (C.c_int, [P(PatchDesc), vp, vp, i64, C.c_int, vp, vp]),
+    "b200_histstd_workspace_bytes": (sz, []),
+    "b200_histstd_normalize": (C.c_int, [P(HistStdDesc), vp, vp, i64, vp, vp, vp, sz, vp]),
 }
 EXPORTS = tuple(_SIGS)
 

@@ -13,6 +13,7 @@
 #include "norm.cuh"
 #include "patches.cuh"
 #include "pool_upsample.cuh"
+#include "preprocess.cuh"
 
 using namespace b200;
 
@@ -792,6 +793,16 @@ int b200_patch_gather(const b200_patch_desc* d, const double* target, const int3
     if (out_is_f32) B200_LAUNCH(patch_gather_kernel<float>, stream_grid(total, 256), 256, 0, stream, g, target, plan, rows, (float*)out);
     else B200_LAUNCH(patch_gather_kernel<double>, stream_grid(total, 256), 256, 0, stream, g, target, plan, rows, (double*)out);
     return 0;
+}
+
+// ============================================================================ intensity preprocessing (f-1)
+size_t b200_histstd_workspace_bytes(void) { return histstd_workspace_bytes(); }
+
+int b200_histstd_normalize(const b200_histstd_desc* d, const float* x, const uint8_t* mask, int64_t n, float* out, double* percentiles_out,
+                           void* workspace, size_t ws_bytes, void* stream) {
+    B200_REQUIRE(d != nullptr, "hist_standardize: null descriptor");
+    B200_REQUIRE(out != nullptr || percentiles_out != nullptr, "hist_standardize: nothing to compute");
+    return histstd_run(x, mask, n, *d, out, percentiles_out, workspace, ws_bytes, stream);
 }
 
 }  // extern "C"

@@ -291,13 +291,46 @@ def copy_fixtures():
         print("  copied", rel)
 
 
+def histstd_cases():
+    """Histogram standardisation (classification/train_ENC_CLF.ipynb [cell 9] `normalize`) run through the NOTEBOOK's own
+    function with the shipped landmarks (classification/fcd_train_data_landmarks.npy): pins percentiles and mapped volumes."""
+    from oracle import preprocess
+    ref = refload.histstd_functions()
+    landmarks = np.load(refload.path("classification/fcd_train_data_landmarks.npy"))
+    assert landmarks.shape == (13,)
+    rng = np.random.default_rng(5)
+    vols = {}
+    brain = rng.gamma(2.0, 120.0, (24, 28, 20)).astype(np.float32)            # skewed intensities ...
+    brain[:6] = 0; brain[:, :5] = 0; brain[:, :, 15:] = 0                      # ... inside a zero background (55 % of the voxels)
+    vols["brain"] = brain
+    vols["dense"] = rng.normal(300.0, 80.0, (17, 19, 23)).astype(np.float32)   # odd sizes, negative values possible
+    vols["const"] = np.full((8, 8, 8), 3.5, np.float32)                        # every landmark equal: diff_perc < epsilon everywhere
+    vols["steps"] = np.repeat(np.arange(16, dtype=np.float32), 100).reshape(16, 10, 10) * 7.0      # heavy ties
+    out = {"landmarks": landmarks}
+    for name, v in vols.items():
+        want = ref["normalize"](torch.from_numpy(v), landmarks).numpy()
+        pv = np.percentile(v.reshape(-1), ref["_get_percentiles"](100 * np.array(ref["_standardize_cutoff"](ref["DEFAULT_CUTOFF"]))))
+        assert np.array_equal(preprocess.normalize(v, landmarks), want), f"oracle normalize != notebook ({name})"
+        assert np.array_equal(preprocess.percentile_values(v), pv)
+        out[f"{name}_x"], out[f"{name}_y"], out[f"{name}_pct"] = v, want, pv
+        print(f"  {name}: percentiles {pv[[0, 6, 12]]}, out range [{want.min():.3f}, {want.max():.3f}]")
+    m = vols["brain"] > 0                                                       # the `mask` argument (foreground only)
+    want = ref["normalize"](torch.from_numpy(vols["brain"]), landmarks, mask=m).numpy()
+    assert np.array_equal(preprocess.normalize(vols["brain"], landmarks, mask=m), want)
+    out["brain_masked_y"] = want
+    want = ref["normalize"](torch.from_numpy(vols["dense"]), landmarks, cutoff=(0.05, 0.95)).numpy()     # _standardize_cutoff clamps to (0.05, 0.95) -> 5 / 95
+    assert np.array_equal(preprocess.normalize(vols["dense"], landmarks, cutoff=(0.05, 0.95)), want)
+    out["dense_cut_y"] = want
+    save("histstd_cell9", **out)
+
+
 if __name__ == "__main__":
     assert refload.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["fixtures", "ops", "unet3d", "ae", "fader", "fepegar", "patches", "detect"]
+    which = sys.argv[1:] or ["fixtures", "ops", "unet3d", "ae", "fader", "fepegar", "patches", "detect", "histstd"]
     table = dict(fixtures=copy_fixtures, ops=op_pins, unet3d=unet3d_cases, ae=ae_cases, fader=fader_cases,
-                 fepegar=fepegar_case, patches=patch_cases, detect=detect_cases)
+                 fepegar=fepegar_case, patches=patch_cases, detect=detect_cases, histstd=histstd_cases)
     for w in which:
         print(w)
         table[w]()

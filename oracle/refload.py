@@ -123,6 +123,26 @@ def fcd_mask_generator_class(model):
     return ns["FCDMaskGenerator"]
 
 
+def histstd_functions():
+    """`normalize`, `_get_percentiles`, `_standardize_cutoff` of classification/train_ENC_CLF.ipynb [cell 9], exec'd as written
+    up to `def default_collate` with the names the notebook had imported; `np.bool` (removed in numpy 1.24, used at the
+    `mask is None` branch) is restored as an alias of `bool` on a numpy PROXY namespace, not on numpy itself."""
+    import json
+    import types
+    from typing import Tuple
+    import numpy as np
+    import torch
+    nb = json.load(open(os.path.join(REF, "classification/train_ENC_CLF.ipynb")))
+    src = "".join(nb["cells"][9]["source"])
+    assert "def normalize(" in src and "def default_collate" in src
+    code = src[:src.index("def default_collate")]
+    npx = types.SimpleNamespace(**{k: getattr(np, k) for k in dir(np) if not k.startswith("__")})
+    npx.bool = bool
+    ns = {"np": npx, "torch": torch, "Tuple": Tuple}
+    exec(compile(code, "train_ENC_CLF.ipynb[cell 9]", "exec"), ns)
+    return ns
+
+
 def seg_routine_module():
     """segmentation/routine.py with its third-party imports stubbed."""
     _stub("IPython", "IPython.display", "matplotlib", "matplotlib.pyplot", "torchio", "torchio.transforms",

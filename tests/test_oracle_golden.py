@@ -235,3 +235,24 @@ def test_fcd_mask_kat5(golden):
     assert float(unvoted.sum()) == float(g["mask_unvoted_sum"]) and sha16(unvoted.astype(np.int8)) == str(g["mask_unvoted_sha"])
     assert not unvoted[:, 218 - 15:, :].any()                  # the first strip (j = 0) is never painted (`-0:-16:-1` is empty)
     assert abs(detect.get_iou(unvoted, img > 1.0) - float(g["iou"])) < 1e-12
+
+
+def test_histstd_cell9(golden):
+    """oracle/preprocess.py against vectors produced by the NOTEBOOK's own `normalize` (classification/train_ENC_CLF.ipynb
+    [cell 9], generated by oracle/make_golden.py histstd) with the shipped 13 landmarks: bit-exact float32 volumes and float64
+    percentiles, incl. a zero background, heavy ties, a constant image (every diff_perc < epsilon), `mask=` and `cutoff=`."""
+    from oracle import preprocess
+    g = golden("histstd_cell9")
+    lm = g["landmarks"]
+    assert lm.shape == (13,) and lm.dtype == np.float64
+    for name in ("brain", "dense", "const", "steps"):
+        x = g[f"{name}_x"]
+        assert np.array_equal(preprocess.percentile_values(x), g[f"{name}_pct"]), name
+        assert np.array_equal(preprocess.normalize(x, lm), g[f"{name}_y"]), name
+    assert np.array_equal(preprocess.normalize(g["brain_x"], lm, mask=g["brain_x"] > 0), g["brain_masked_y"])
+    assert np.array_equal(preprocess.normalize(g["dense_x"], lm, cutoff=(0.05, 0.95)), g["dense_cut_y"])
+    assert np.all(np.diff(g["steps_y"].reshape(16, -1)[:, 0]) >= 0)             # the map is monotone
+    v = np.arange(5 * 6 * 7, dtype=np.float32).reshape(5, 6, 7)
+    assert np.array_equal(preprocess.reshape_image(v, (1, 2, 3), (3, 3, 3)), v[1:4, 2:5, 3:6].reshape(1, 3, 3, 3))
+    with pytest.raises(AssertionError):
+        preprocess.reshape_image(v, (3, 2, 3), (3, 3, 3))
