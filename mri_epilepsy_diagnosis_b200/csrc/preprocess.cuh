@@ -15,6 +15,7 @@ namespace b200 {
 constexpr int kSelMaxRanks = 32;          // 2 order statistics per percentile, <= 16 percentiles
 constexpr int kSelMaxQ = 16;
 constexpr int kSelBins0 = 4096, kSelBinsL = 1024;
+constexpr int kSelIlp = 8;                // independent loads per thread and iteration in the histogram passes
 
 using HsParams = b200_histstd_desc;       // host values, passed to the kernels by value (no H2D copies, capture-safe)
 static_assert(sizeof(((b200_histstd_desc*)nullptr)->q) / sizeof(double) == kSelMaxQ, "descriptor arrays are kSelMaxQ long");
@@ -57,12 +58,21 @@ __global__ void __launch_bounds__(512) sel_hist0_kernel(const float* __restrict_
     __shared__ uint32_t sh[kSelBins0];
     for (int i = threadIdx.x; i < kSelBins0; i += blockDim.x) sh[i] = 0;
     __syncthreads();
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t nround = (n + stride - 1) / stride * stride;          // whole warps stay converged for the warp votes
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
-        const bool take = i < n && (mask == nullptr || mask[i] != 0);
-        const uint32_t key = take ? sel_key(x[i]) : 0u;
-        sel_bump(sh, key >> 20, take);
+    // every thread runs the same number of iterations (the warp votes need whole warps); kSelIlp independent loads per
+    // iteration: one load per vote made the pass latency-bound (85 us for 28 MB)
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, step = stride * kSelIlp;
+    const int64_t nround = (n + step - 1) / step * step;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += step) {
+        float v[kSelIlp];
+        bool take[kSelIlp];
+#pragma unroll
+        for (int k = 0; k < kSelIlp; ++k) {
+            const int64_t idx = i + k * stride;
+            take[k] = idx < n && (mask == nullptr || mask[idx] != 0);
+            v[k] = take[k] ? x[idx] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < kSelIlp; ++k) sel_bump(sh, sel_key(v[k]) >> 20, take[k]);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < kSelBins0; i += blockDim.x)
@@ -78,21 +88,32 @@ __global__ void __launch_bounds__(512) sel_histL_kernel(const float* __restrict_
     if (threadIdx.x < kSelMaxRanks) uq[threadIdx.x] = threadIdx.x < nuniq ? st->uniq[threadIdx.x] : 0xFFFFFFFFu;
     for (int i = threadIdx.x; i < nuniq * kSelBinsL; i += blockDim.x) shl[i] = 0;
     __syncthreads();
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t nround = (n + stride - 1) / stride * stride;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
-        bool take = i < n && (mask == nullptr || mask[i] != 0);
-        uint32_t bin = 0;
-        if (take) {
-            const uint32_t key = sel_key(x[i]);
-            const uint32_t pfx = key >> prefix_shift;
-            int u = -1;
-            for (int k = 0; k < nuniq; ++k)
-                if (uq[k] == pfx) u = k;
-            take = u >= 0;
-            bin = (uint32_t)u * kSelBinsL + ((key >> digit_shift) & (kSelBinsL - 1));
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, step = stride * kSelIlp;
+    const int64_t nround = (n + step - 1) / step * step;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += step) {
+        float v[kSelIlp];
+        bool tk[kSelIlp];
+#pragma unroll
+        for (int k = 0; k < kSelIlp; ++k) {
+            const int64_t idx = i + k * stride;
+            tk[k] = idx < n && (mask == nullptr || mask[idx] != 0);
+            v[k] = tk[k] ? x[idx] : 0.f;
         }
-        sel_bump(shl, bin, take);
+#pragma unroll
+        for (int k = 0; k < kSelIlp; ++k) {
+            bool take = tk[k];
+            uint32_t bin = 0;
+            if (take) {
+                const uint32_t key = sel_key(v[k]);
+                const uint32_t pfx = key >> prefix_shift;
+                int u = -1;
+                for (int j = 0; j < nuniq; ++j)
+                    if (uq[j] == pfx) u = j;
+                take = u >= 0;
+                bin = (uint32_t)u * kSelBinsL + ((key >> digit_shift) & (kSelBinsL - 1));
+            }
+            sel_bump(shl, bin, take);
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < nuniq * kSelBinsL; i += blockDim.x)
@@ -166,8 +187,11 @@ __global__ void __launch_bounds__(1024) sel_scanL_kernel(const uint32_t* __restr
     const bool live = st->n > 0 && r < st->R;
     if (live) {
         const uint32_t* h = histL + (size_t)st->umap[r] * kSelBinsL + lane * 32;
-        uint32_t s = 0;
-        for (int k = 0; k < 32; ++k) s += h[k];
+        uint32_t s = 0, hv[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) hv[k] = h[k];                         // 32 loads in flight
+#pragma unroll
+        for (int k = 0; k < 32; ++k) s += hv[k];
         uint32_t inc = s;
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
@@ -178,9 +202,11 @@ __global__ void __launch_bounds__(1024) sel_scanL_kernel(const uint32_t* __restr
         if (mine) {
             uint32_t c = before;
             int d = 0;
-            for (; d < 31; ++d) {
-                if (resid < c + h[d]) break;
-                c += h[d];
+#pragma unroll
+            for (int k = 0; k < 31; ++k) {
+                const bool before_k = d == k && resid >= c + hv[k];       // still searching and the rank lies beyond digit k
+                c += before_k ? hv[k] : 0u;
+                d += before_k ? 1 : 0;
             }
             st->prefix[r] = (st->prefix[r] << 10) | (uint32_t)(lane * 32 + d);
             st->resid[r] = resid - c;

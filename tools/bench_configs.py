@@ -62,7 +62,7 @@ def unet_step(net, x, t, opt):
     return step
 
 
-cfgs = sys.argv[1:] or ["c1", "c3", "c4", "c5", "fp8", "fp16", "inf"]
+cfgs = sys.argv[1:] or ["c1", "c3", "c4", "c5", "fp8", "fp16", "inf", "pre"]
 torch.manual_seed(0)
 if "c1" in cfgs:
     net = pkg.convert(pkg.zoo.config1_autoencoder(depth=6, c_base=16).to(dev).train(), dtype=BF16)
@@ -149,3 +149,22 @@ if "c5" in cfgs:
     pf = patches.float()
     with torch.no_grad():
         report(f"c5 PatchModel inference, all {n} patches in one batch + argmax", timeit(lambda: pm(pf).argmax(dim=1)), n, "patch")
+
+if "pre" in cfgs:
+    # f-1: the collate-time histogram standardisation of classification/train_ENC_CLF.ipynb [cell 9] on one 192^3 volume
+    # (the loaders' size): device kernels vs the CPU restatement (numpy, the same code path the notebook runs per item)
+    sys.path.insert(0, ROOT)
+    from oracle import preprocess as O
+    lm = np.load(os.path.join(ROOT, "tests", "golden", "histstd_cell9.npz"))["landmarks"]
+    g = torch.Generator(device="cuda").manual_seed(0)
+    vol = torch.empty(192, 192, 192, device=dev).exponential_(0.01, generator=g)
+    vol[:40] = 0
+    ms = timeit(lambda: pkg.preprocess.normalize(vol, lm), iters=20, warmup=3)
+    nbytes = vol.numel() * 4 * 5
+    report("f-1 histogram standardisation, one 192^3 volume (3 select passes + map)", ms, vol.numel(), "voxel")
+    print(f"   ({nbytes / ms / 1e6:.0f} GB/s of the 5 x 4 B per voxel the passes move = {100 * nbytes / ms / 1e6 / 6544.7:.0f} % of the HBM peak)")
+    host = vol.cpu().numpy()
+    t0 = time.perf_counter()
+    O.normalize(host, lm)
+    cpu_ms = 1e3 * (time.perf_counter() - t0)
+    print(f"   (CPU restatement, numpy on the host: {cpu_ms:.0f} ms per volume = {cpu_ms / ms:.0f}x)")
