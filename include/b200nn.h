@@ -235,6 +235,13 @@ int b200_patch_plan(const b200_patch_desc* d, const double* gmpm, const uint8_t*
 int b200_patch_gather(const b200_patch_desc* d, const double* target, const int32_t* plan, int64_t rows,
                       int out_dtype_is_f32, void* out, void* stream);
 
+/* ---- validation overlap metrics (the counting part) ----------------------------------------------
+ * One pass over the predicted label volume and the ground truth (uint8, as validate_dsc_asd passes them,
+ * segmentation/routine.py:216-237) -> counts5 (device, 5 x uint64):
+ *   [0] gt.sum()  [1] pred.sum()  [2] (gt & pred).sum()      -- compute_dice_coefficient, segmentation/metrics.py:312-329
+ *   [3] #(pred > 0 and gt > 0)    [4] #(pred > 0 or gt > 0)  -- get_iou_score, segmentation/routine.py:198-204 */
+int b200_overlap_counts(const uint8_t* pred, const uint8_t* gt, int64_t n, uint64_t* counts5, void* stream);
+
 /* ---- intensity preprocessing -------------------------------------------------------------------
  * Histogram standardisation of one volume = `normalize(tensor, landmarks, mask, cutoff, epsilon)` of
  * classification/train_ENC_CLF.ipynb [cell 9] (the collate function of the classification loaders, cell 9 `default_collate`):

@@ -14,6 +14,7 @@
 #include "patches.cuh"
 #include "pool_upsample.cuh"
 #include "preprocess.cuh"
+#include "metrics.cuh"
 
 using namespace b200;
 
@@ -793,6 +794,11 @@ int b200_patch_gather(const b200_patch_desc* d, const double* target, const int3
     if (out_is_f32) B200_LAUNCH(patch_gather_kernel<float>, stream_grid(total, 256), 256, 0, stream, g, target, plan, rows, (float*)out);
     else B200_LAUNCH(patch_gather_kernel<double>, stream_grid(total, 256), 256, 0, stream, g, target, plan, rows, (double*)out);
     return 0;
+}
+
+// ============================================================================ validation overlap counts (f-2, counting part)
+int b200_overlap_counts(const uint8_t* pred, const uint8_t* gt, int64_t n, uint64_t* counts5, void* stream) {
+    return overlap_counts_run(pred, gt, n, counts5, stream);
 }
 
 // ============================================================================ intensity preprocessing (f-1)

@@ -324,13 +324,33 @@ def histstd_cases():
     save("histstd_cell9", **out)
 
 
+def metrics_cases():
+    """Dice / IoU of the validation loop through the REFERENCE's own functions (segmentation/metrics.py:312-329,
+    segmentation/routine.py:198-204) on uint8 label volumes, incl. empty masks and labels > 1."""
+    from oracle import metrics as M
+    ref_metrics = refload._load("_ref_metrics", "segmentation/metrics.py")
+    routine = refload.seg_routine_module()
+    rng = np.random.default_rng(8)
+    out = {}
+    cases = {"blobs": ((rng.random((24, 30, 22)) > 0.7).astype(np.uint8), (rng.random((24, 30, 22)) > 0.6).astype(np.uint8)),
+             "labels5": (rng.integers(0, 5, (17, 19, 13)).astype(np.uint8), rng.integers(0, 5, (17, 19, 13)).astype(np.uint8)),
+             "disjoint": (np.pad(np.ones((4, 4, 4), np.uint8), ((0, 8), (0, 8), (0, 8))), np.pad(np.ones((4, 4, 4), np.uint8), ((8, 0), (8, 0), (8, 0)))),
+             "pred_empty": (np.zeros((9, 9, 9), np.uint8), (rng.random((9, 9, 9)) > 0.5).astype(np.uint8))}
+    for name, (pred, gt) in cases.items():
+        dsc, iou = ref_metrics.compute_dice_coefficient(gt, pred), routine.get_iou_score(pred, gt)
+        assert M.compute_dice_coefficient(gt, pred) == dsc and M.get_iou_score(pred, gt) == iou and type(M.get_iou_score(pred, gt)) is type(iou)
+        out[f"{name}_pred"], out[f"{name}_gt"], out[f"{name}_dsc"], out[f"{name}_iou"] = pred, gt, np.array(dsc), np.array(iou)
+        print(f"  {name}: dice {dsc:.6f}  iou {iou:.6f} ({type(iou).__name__})")
+    save("overlap_metrics", **out)
+
+
 if __name__ == "__main__":
     assert refload.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["fixtures", "ops", "unet3d", "ae", "fader", "fepegar", "patches", "detect", "histstd"]
+    which = sys.argv[1:] or ["fixtures", "ops", "unet3d", "ae", "fader", "fepegar", "patches", "detect", "histstd", "metrics"]
     table = dict(fixtures=copy_fixtures, ops=op_pins, unet3d=unet3d_cases, ae=ae_cases, fader=fader_cases,
-                 fepegar=fepegar_case, patches=patch_cases, detect=detect_cases, histstd=histstd_cases)
+                 fepegar=fepegar_case, patches=patch_cases, detect=detect_cases, histstd=histstd_cases, metrics=metrics_cases)
     for w in which:
         print(w)
         table[w]()

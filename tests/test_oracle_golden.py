@@ -256,3 +256,17 @@ def test_histstd_cell9(golden):
     assert np.array_equal(preprocess.reshape_image(v, (1, 2, 3), (3, 3, 3)), v[1:4, 2:5, 3:6].reshape(1, 3, 3, 3))
     with pytest.raises(AssertionError):
         preprocess.reshape_image(v, (3, 2, 3), (3, 3, 3))
+
+
+def test_overlap_metrics(golden):
+    """oracle/metrics.py against the reference's own compute_dice_coefficient (segmentation/metrics.py:312-329) and get_iou_score
+    (segmentation/routine.py:198-204), vectors from oracle/make_golden.py metrics: bit-equal values AND result types."""
+    from oracle import metrics as M
+    g = golden("overlap_metrics")
+    for name in ("blobs", "labels5", "disjoint", "pred_empty"):
+        pred, gt = g[f"{name}_pred"], g[f"{name}_gt"]
+        assert M.compute_dice_coefficient(gt, pred) == float(g[f"{name}_dsc"]), name
+        iou = M.get_iou_score(pred, gt)
+        assert iou == g[f"{name}_iou"] and np.asarray(iou).dtype == g[f"{name}_iou"].dtype, name
+    z = np.zeros((4, 4, 4), np.uint8)
+    assert np.isnan(M.compute_dice_coefficient(z, z))                # metrics.py:325-326 (np.NaN there)

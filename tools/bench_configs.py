@@ -62,7 +62,7 @@ def unet_step(net, x, t, opt):
     return step
 
 
-cfgs = sys.argv[1:] or ["c1", "c3", "c4", "c5", "fp8", "fp16", "inf", "pre"]
+cfgs = sys.argv[1:] or ["c1", "c3", "c4", "c5", "fp8", "fp16", "inf", "pre", "val"]
 torch.manual_seed(0)
 if "c1" in cfgs:
     net = pkg.convert(pkg.zoo.config1_autoencoder(depth=6, c_base=16).to(dev).train(), dtype=BF16)
@@ -168,3 +168,21 @@ if "pre" in cfgs:
     O.normalize(host, lm)
     cpu_ms = 1e3 * (time.perf_counter() - t0)
     print(f"   (CPU restatement, numpy on the host: {cpu_ms:.0f} ms per volume = {cpu_ms / ms:.0f}x)")
+
+if "val" in cfgs:
+    # f-2 (counting part): Dice + IoU of one predicted label volume against the ground truth, 192x224x192 (config 3's volume)
+    sys.path.insert(0, ROOT)
+    from oracle import metrics as OM
+    g = torch.Generator(device="cuda").manual_seed(0)
+    pred = (torch.rand(192, 224, 192, device=dev, generator=g) > 0.8).to(torch.uint8)
+    gt = (torch.rand(192, 224, 192, device=dev, generator=g) > 0.7).to(torch.uint8)
+    out = torch.empty(5, dtype=torch.int64, device=dev)
+    lib = pkg._cabi.lib()
+    ms = timeit(lambda: lib.b200_overlap_counts(pred.data_ptr(), gt.data_ptr(), pred.numel(), out.data_ptr(), pkg._cabi.stream()), iters=50, warmup=5)
+    report("f-2 overlap counts (Dice + IoU), one 192x224x192 label pair", ms, pred.numel(), "voxel")
+    print(f"   ({2 * pred.numel() / ms / 1e6:.0f} GB/s of the 2 B per voxel read = {100 * 2 * pred.numel() / ms / 1e6 / 6544.7:.0f} % of the HBM peak; the pair is 16.5 MB, L2-resident)")
+    p, t = pred.cpu().numpy(), gt.cpu().numpy()
+    t0 = time.perf_counter()
+    OM.compute_dice_coefficient(t, p); OM.get_iou_score(p, t)
+    print(f"   (CPU restatement, numpy: {1e3 * (time.perf_counter() - t0):.1f} ms; host API incl. the 40-byte read-back: "
+          f"{timeit(lambda: pkg.metrics.calculate_overlap(gt, pred), iters=20, warmup=3):.3f} ms)")
