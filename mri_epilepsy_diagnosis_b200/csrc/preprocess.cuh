@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(512) sel_hist0_kernel(const float* __restrict_
 }
 
 // level 1: prefix = top 12 bits, digit = next 10; level 2: prefix = top 22 bits, digit = last 10
-__global__ void __launch_bounds__(512) sel_histL_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask, int64_t n,
+__global__ void __launch_bounds__(1024) sel_histL_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask, int64_t n,
                                                         const SelState* __restrict__ st, int prefix_shift, int digit_shift, uint32_t* __restrict__ histL) {
     extern __shared__ uint32_t shl[];                                   // [nuniq][1024]
     __shared__ uint32_t uq[kSelMaxRanks];
@@ -120,13 +120,16 @@ __global__ void __launch_bounds__(512) sel_histL_kernel(const float* __restrict_
         if (shl[i]) atomicAdd(histL + i, shl[i]);
 }
 
-__device__ __forceinline__ void sel_dedupe(SelState* st) {               // one thread
+// one thread; works on register/shared copies (a chain of ~350 dependent global loads cost 20 us per scan kernel)
+__device__ __forceinline__ void sel_dedupe(SelState* st, const uint32_t* prefix /* shared */, int R) {
+    uint32_t uq[kSelMaxRanks];
     int nu = 0;
-    for (int r = 0; r < st->R; ++r) {
+    for (int r = 0; r < R; ++r) {
+        const uint32_t p = prefix[r];
         int u = -1;
         for (int k = 0; k < nu; ++k)
-            if (st->uniq[k] == st->prefix[r]) u = k;
-        if (u < 0) { u = nu; st->uniq[nu++] = st->prefix[r]; }
+            if (uq[k] == p) u = k;
+        if (u < 0) { u = nu; uq[nu] = p; st->uniq[nu] = p; ++nu; }
         st->umap[r] = u;
     }
     st->nuniq = nu;
@@ -175,16 +178,19 @@ __global__ void __launch_bounds__(1024) sel_scan0_kernel(const uint32_t* __restr
         }
         st->prefix[t] = (uint32_t)lo;
         st->resid[t] = r - cum[lo];
+        part[t] = (uint32_t)lo;                                            // shared copy for the dedupe
     }
     __syncthreads();
-    if (t == 0 && n > 0) sel_dedupe(st);
+    if (t == 0 && n > 0) sel_dedupe(st, part, 2 * hp.nq);
     if (t == 0 && n == 0) st->nuniq = 0;
 }
 
 // one warp per rank: find the digit inside the rank's 1024-bin histogram
 __global__ void __launch_bounds__(1024) sel_scanL_kernel(const uint32_t* __restrict__ histL, SelState* __restrict__ st, int last) {
+    __shared__ uint32_t newp[kSelMaxRanks];
     const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool live = st->n > 0 && r < st->R;
+    const int R = st->R;
+    const bool live = st->n > 0 && r < R;
     if (live) {
         const uint32_t* h = histL + (size_t)st->umap[r] * kSelBinsL + lane * 32;
         uint32_t s = 0, hv[32];
@@ -208,13 +214,15 @@ __global__ void __launch_bounds__(1024) sel_scanL_kernel(const uint32_t* __restr
                 c += before_k ? hv[k] : 0u;
                 d += before_k ? 1 : 0;
             }
-            st->prefix[r] = (st->prefix[r] << 10) | (uint32_t)(lane * 32 + d);
+            const uint32_t np = (st->prefix[r] << 10) | (uint32_t)(lane * 32 + d);
+            st->prefix[r] = np;
+            newp[r] = np;
             st->resid[r] = resid - c;
-            if (last) st->val[r] = sel_unkey(st->prefix[r]);
+            if (last) st->val[r] = sel_unkey(np);
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0 && st->n > 0 && !last) sel_dedupe(st);
+    if (threadIdx.x == 0 && st->n > 0 && !last) sel_dedupe(st, newp, R);
 }
 
 // np.percentile's lerp (numpy/lib/_function_base_impl.py `_lerp`: the difference is taken in the array's float32, the rest in
@@ -271,12 +279,14 @@ inline int histstd_run(const float* x, const uint8_t* mask, int64_t n, const HsP
     static cudaError_t attr = cudaFuncSetAttribute(sel_histL_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelMaxRanks * kSelBinsL * 4);
     B200_REQUIRE(attr == cudaSuccess, "hist_standardize: cannot raise the dynamic shared memory limit: %s", cudaGetErrorString(attr));
     const int grid = stream_grid(n, 512, 2);
+    // the filtered passes keep 128 KB of histograms per block: one 1024-thread block per SM, and half as many flushes
+    const int gridL = stream_grid(n, 1024, 1);
     const size_t smemL = (size_t)kSelMaxRanks * kSelBinsL * 4;
     B200_LAUNCH(sel_hist0_kernel, grid, 512, 0, s, x, mask, n, ws->hist0);
     B200_LAUNCH(sel_scan0_kernel, 1, 1024, 0, s, ws->hist0, &ws->st, hp);
-    B200_LAUNCH(sel_histL_kernel, grid, 512, smemL, s, x, mask, n, &ws->st, 20, 10, ws->histL[0]);
+    B200_LAUNCH(sel_histL_kernel, gridL, 1024, smemL, s, x, mask, n, &ws->st, 20, 10, ws->histL[0]);
     B200_LAUNCH(sel_scanL_kernel, 1, 1024, 0, s, ws->histL[0], &ws->st, 0);
-    B200_LAUNCH(sel_histL_kernel, grid, 512, smemL, s, x, mask, n, &ws->st, 10, 0, ws->histL[1]);
+    B200_LAUNCH(sel_histL_kernel, gridL, 1024, smemL, s, x, mask, n, &ws->st, 10, 0, ws->histL[1]);
     B200_LAUNCH(sel_scanL_kernel, 1, 1024, 0, s, ws->histL[1], &ws->st, 1);
     B200_LAUNCH(hs_build_map_kernel, 1, 32, 0, s, &ws->st, hp);
     if (pct_out != nullptr) {
