@@ -247,7 +247,6 @@ def main():
     launches0 = pkg.launch_count()
     ms, t0, t1 = timed(lambda: step(xd, td), args.steps)
     launches = (pkg.launch_count() - launches0) if args.eager else launches_per_step * args.steps
-    clocks = sampler.summary(t0, t1) if sampler else None
 
     # end to end: host (pinned) inputs in, host scalar out, every step.  Graph mode: the H2D copy of step i+1's batch runs on a
     # copy stream while step i computes (graphed.prefetch / step_prefetched) -- K copies for K steps inside the timed region.
@@ -274,6 +273,8 @@ def main():
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1) / args.steps
+    # clocks: every nvidia-smi sample (100 ms period) that fell inside the two timed regions (device-resident and end-to-end)
+    clocks = sampler.summary(t0, time.time()) if sampler else None
     if dist is not None:
         tms = torch.tensor([ms_e2e], device=dev)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
