@@ -401,12 +401,13 @@ def test_upsample_concat_equals_cat(B):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 @pytest.mark.parametrize("lazy", [True, False], ids=["window", "dense"])
-def test_pool_skip_sums_both_gradients(B, dtype, lazy):
+@pytest.mark.parametrize("dims", [(6, 8, 10), (7, 9, 11)], ids=["even", "odd"])        # odd: trailing planes/rows/columns are in no window
+def test_pool_skip_sums_both_gradients(B, dtype, lazy, dims):
     """pool_skip(x) = (max_pool(x, 2, 2), x) with the skip gradient read as a channel window of the concat gradient
     (unet3d.py:113-121 + torch.cat at :76) and summed inside the pooling backward kernel."""
     g = gen(44)
-    x = torch.randn(2, 16, 6, 8, 10, generator=g).to(dtype).float()
-    z = torch.randn(2, 8, 6, 8, 10, generator=g).to(dtype).float()
+    x = torch.randn(2, 16, *dims, generator=g).to(dtype).float()
+    z = torch.randn(2, 8, *dims, generator=g).to(dtype).float()
     xr, zr = x.clone().requires_grad_(True), z.clone().requires_grad_(True)
     pr = F.max_pool3d(xr, 2, 2)
     cr = torch.cat((xr, zr), 1)
