@@ -368,7 +368,8 @@ def main():
             dist.barrier(); dist.destroy_process_group()
         return
     out = {**base, "value": world * voxels / (ms / 1e3), "ms_per_step": ms, "dtype": "bf16",
-           "config": {"workload": workload, "model": model_desc, "global_batch": args.batch * world, "volume": [args.size] * 3,
+           "config": {"workload": workload, "network": model_desc, "volumes_per_step": args.batch * world, "volume": [args.size] * 3,
+                      "optimizer": "torch.optim.AdamW(fused=True)" + ("" if args.eager or world > 1 else " inside the captured step"),
                       "parallelism": f"dp{world}" + ("+syncbn" if sync else ""), "launch": "eager" if args.eager else "cuda-graph replay of the step",
                       "l2": "inputs and every activation tensor (>= 268 MB each at 16ch x 128^3 x 4) exceed the 126 MB L2; no flush needed"},
            "e2e": {"value": world * voxels / (ms_e2e / 1e3), "unit": "voxels/s", "ms_per_step": ms_e2e,
