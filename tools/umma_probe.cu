@@ -81,12 +81,12 @@ int main() {
     printf("%-8s %-5s %-6s %-6s %12s\n", "layout", "N", "naccs", "shift", "cyc/UMMA");
     const char* names[6] = {"ns160", "ns128", "sw128", "row32", "row64", "row128"};
     for (int layout = 0; layout < 6; ++layout)
-        for (int n : {16, 32, 64, 128, 256})
+        for (int n : {16, 32, 48, 64, 96, 128, 144, 192, 256})
             for (int naccs : {1, 2, 4})
                 for (int shift : {0, 1}) {
                     if (naccs * n > 512) continue;
                     if (layout != 0 && layout < 3 && shift) continue;
-                    if (layout >= 3 && (n > 64 || naccs == 2)) continue;
+                    if (layout >= 3 && ((n > 64 && layout != 3) || naccs == 2)) continue;
                     ProbeCfg c{n, layout, naccs, shift, iters};
                     auto launch = [&](auto kern) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); kern<<<148, 128, 200 * 1024>>>(c, d_out); };
                     if (naccs == 1 && !shift) launch(probe_kernel<1, 0>);
