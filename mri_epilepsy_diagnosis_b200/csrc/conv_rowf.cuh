@@ -48,6 +48,12 @@ struct RowFwdParams {
     __nv_bfloat16* out;          // [N][D][H][W][OC]
     float* stats;                // [grid][2][OC] fp32 per-CTA (sum, sum of squares) of the outputs (OC <= 64); or null
     int store_c0;                // only channels [store_c0, OC) are stored (out has OC - store_c0 channels); statistics cover all
+    // kx-folded mode (small Cout, W == 128): ONE tcgen05.mma per (kz, ky) with the UNSHIFTED voxel rows as A and the three kx
+    // weight blocks side by side as B (N = 3*OC): TMEM holds P_kx[x] = x[x] . W[kx] in three column blocks per tile and the
+    // epilogue forms out[x] = P_0[x-1] + P_1[x] + P_2[x+1] (lane shuffles; warp-boundary lanes through shared memory).
+    // 9 instructions of max(32 + 3*OC/4, 3*OC/2) cycles per tile and plane instead of 27 of max(32 + OC/4, OC/2).
+    int fold;
+    int ncol;                    // TMEM columns per tile: OC, or 3*OC when folded
 };
 
 struct alignas(128) RowFwdBarriers {
@@ -88,7 +94,7 @@ __device__ __forceinline__ void rf_store16(__nv_bfloat16* dst, const float (&v)[
     *reinterpret_cast<uint4*>(dst + 8) = hi;
 }
 
-template <int KD, int KHW, int NKS>
+template <int KD, int KHW, int NKS, bool FOLD = false>
 __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_constant__ CUtensorMap in_map, const RowFwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -184,14 +190,28 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
                     for (int j = 0; j < KHW * KHW; ++j) off[j] = (uint32_t)(j / KHW) * row16 + (uint32_t)(j % KHW) * vox16;
                     const uint32_t a_flag = 1u << 16;
                     for (int t = 0; t < ntiles; ++t) {
-                        const uint32_t d_tmem = tmem_base + (uint32_t)((set * p.T + t) * p.OC);
+                        const uint32_t d_tmem = tmem_base + (uint32_t)((set * p.T + t) * p.ncol);
                         const uint32_t tile16 = (uint32_t)((t / p.tpr) * p.rowstride + (t % p.tpr) * 128) * vox16;
                         uint32_t acc = 0;
-                        uint32_t bb = w16 | b_lbo;
+                        uint32_t bb = w16 | (FOLD ? 3u * b_lbo : b_lbo);
 #pragma unroll 1
                         for (int kz = 0; kz < KD; ++kz) {
                             if (!((hasmask >> kz) & 1)) { bb += (uint32_t)(KHW * KHW) * wtap16; continue; }
                             const uint32_t a0 = (pl16 + ((i0 + (uint32_t)kz) & (kRfRing - 1)) * plane16 + tile16) | a_flag;
+                            if (FOLD) {
+                                // B block of (kz, ky): [ci group][kx][oc][8 ci] -> LBO = 3*OC*16 B, next 16 ci = 2 groups further
+#pragma unroll
+                                for (int ky = 0; ky < KHW; ++ky) {
+                                    uint32_t a = a0 + (uint32_t)ky * row16 + (uint32_t)(KHW / 2) * vox16, b2 = bb;
+#pragma unroll
+                                    for (int ks = 0; ks < nks; ++ks) {
+                                        if (leader) ptx::umma_bf16_lohi(d_tmem, a, a_hi, b2, b_hi, idesc, acc);
+                                        a += 2; b2 += 3u * wks16; acc = 1;
+                                    }
+                                    bb += (uint32_t)KHW * wtap16;
+                                }
+                                continue;
+                            }
 #pragma unroll
                             for (int j = 0; j < KHW * KHW; ++j) {
                                 uint32_t a = a0 + off[j], b2 = bb;
@@ -310,12 +330,12 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
         const int lane_grp = warp & 3;
         const int m = lane_grp * 32 + lane;
         const bool want_stats = p.stats != nullptr;
-        constexpr int kStatCh = 4;                               // statistics / fused stores: up to 4 x 16 output channels
+        constexpr int kStatCh = FOLD ? 2 : 4;                    // statistics / fused stores: up to 4 x 16 output channels (2 x 16 when folded)
         float ssum[16 * kStatCh], ssq[16 * kStatCh];             // per-thread partial statistics
 #pragma unroll
         for (int i = 0; i < 16 * kStatCh; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
         const int ocs = p.OC - p.store_c0;                       // stored channels per voxel
-        uint32_t group = 0;
+        uint32_t group = 0, xphase = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
             const RfItem c = rf_decode(p, item);
             const int ntiles = rf_tiles(p, c.rows);
@@ -329,8 +349,63 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
                     const int row = slot / p.pitchW, x = slot - row * p.pitchW;
                     const bool valid = x < p.W && row < c.rows;
                     __nv_bfloat16* dst = p.out + ((plane_vox + c.y0 + row) * p.W + x) * ocs - p.store_c0;
-                    const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)((set * p.T + t) * p.OC);
-                    if (p.OC <= 16 * kStatCh) {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)((set * p.T + t) * p.ncol);
+                    if (FOLD) {
+                        // out[x] = P_0[x-1] + P_1[x] + P_2[x+1]; the tile is one whole x-row (W == 128), so x-1 / x+1 outside the tile
+                        // are the zero halo.  Neighbour lanes by shuffle, the two warp-boundary lanes through shared memory.
+                        __shared__ __align__(16) float xch[2][4][2][16];
+#pragma unroll
+                        for (int ch = 0; ch < kStatCh; ++ch) {
+                            if (ch * 16 < p.OC) {
+                                float v[16], l[16], r[16];
+                                ptx::tmem_ld16(taddr + (uint32_t)(ch * 16), l);
+                                ptx::tmem_ld16(taddr + (uint32_t)(p.OC + ch * 16), v);
+                                ptx::tmem_ld16(taddr + (uint32_t)(2 * p.OC + ch * 16), r);
+                                float (&buf)[4][2][16] = xch[xphase & 1];
+                                if (lane == 31) {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) buf[lane_grp][0][i] = l[i];
+                                }
+                                if (lane == 0) {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) buf[lane_grp][1][i] = r[i];
+                                }
+                                asm volatile("bar.sync 1, 128;" ::: "memory");
+                                // EVERY lane loads both edge rows (broadcast reads) into registers and selects: per-value
+                                // `if (lane == 0)` branches cost ~100 cycles each in branch resolution (32 per tile: 3 200 cycles)
+                                float el[16], er[16];
+                                {
+                                    const float4* pl = reinterpret_cast<const float4*>(&buf[lane_grp > 0 ? lane_grp - 1 : 0][0][0]);
+                                    const float4* pr = reinterpret_cast<const float4*>(&buf[lane_grp < 3 ? lane_grp + 1 : 3][1][0]);
+                                    const float zl = lane_grp > 0 ? 1.f : 0.f, zr = lane_grp < 3 ? 1.f : 0.f;
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        const float4 a4 = pl[q], b4 = pr[q];
+                                        el[4 * q] = a4.x * zl; el[4 * q + 1] = a4.y * zl; el[4 * q + 2] = a4.z * zl; el[4 * q + 3] = a4.w * zl;
+                                        er[4 * q] = b4.x * zr; er[4 * q + 1] = b4.y * zr; er[4 * q + 2] = b4.z * zr; er[4 * q + 3] = b4.w * zr;
+                                    }
+                                }
+                                const bool first = lane == 0, last = lane == 31;
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) {
+                                    const float a = __shfl_up_sync(0xffffffffu, l[i], 1), b = __shfl_down_sync(0xffffffffu, r[i], 1);
+                                    v[i] += (first ? el[i] : a) + (last ? er[i] : b);
+                                }
+                                ++xphase;
+                                if (p.bias != nullptr) {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + ch * 16 + i);
+                                }
+                                if (valid) {
+                                    if (ch * 16 >= p.store_c0) rf_store16(dst + ch * 16, v);
+                                    if (want_stats) {
+#pragma unroll
+                                        for (int i = 0; i < 16; ++i) { ssum[ch * 16 + i] += v[i]; ssq[ch * 16 + i] = fmaf(v[i], v[i], ssq[ch * 16 + i]); }
+                                    }
+                                }
+                            }
+                        }
+                    } else if (p.OC <= 16 * kStatCh) {
 #pragma unroll
                         for (int ch = 0; ch < kStatCh; ++ch) {
                             if (ch * 16 < p.OC) {
@@ -411,7 +486,37 @@ inline bool row_fwd_geom(const b200_conv_desc* d, int pass, RowFwdGeom* g) {
     return true;
 }
 
+// kx-folded mode (see RowFwdParams::fold): one whole x-row per tile, small Cout, resident weights.  B200_ROWF_FOLD=0 disables.
+inline bool row_fwd_fold_geom(const RowFwdGeom& g) {
+    // Measured on B200, 4 x 128^3 forward: 32->32 0.684 -> 0.512 ms (907 TFLOP/s), 16->16 0.378 -> 0.338 ms, but 16->32
+    // 0.395 -> 0.500 ms (two 16-channel epilogue passes per tile against only nine K = 16 instructions): the epilogue, three TMEM
+    // loads + the shifted sum per 16 channels, is the new bound, so folding pays when there is enough K per epilogue pass.
+    // B200_ROWF_FOLD: 0 = never, 1 = that rule (default), 2 = whenever the geometry allows.
+    static const int mode = [] { const char* e = getenv("B200_ROWF_FOLD"); return e == nullptr ? 1 : atoi(e); }();
+    if (mode == 0 || g.khw != 3 || g.W != 128 || g.OC > 32) return false;
+    return mode >= 2 || g.IC >= 32 || g.OC == 16;
+}
+inline int row_fwd_plan_mode(const RowFwdGeom& g, int N, RowFwdParams* p, size_t* smem_bytes, bool fold);
+// the folded plan when the geometry allows it and it fits, the plain one otherwise
 inline int row_fwd_plan(const RowFwdGeom& g, int N, RowFwdParams* p, size_t* smem_bytes) {
+    if (row_fwd_fold_geom(g)) {
+        const std::string saved = err_slot();
+        if (row_fwd_plan_mode(g, N, p, smem_bytes, true) == 0) return 0;
+        err_slot() = saved;
+    }
+    return row_fwd_plan_mode(g, N, p, smem_bytes, false);
+}
+inline bool row_fwd_folds(const b200_conv_desc* d, int pass) {          // decides the packed-weight layout: must follow the plan
+    RowFwdGeom g;
+    if (!row_fwd_geom(d, pass, &g)) return false;
+    RowFwdParams p; size_t smem;
+    const std::string saved = err_slot();
+    const bool ok = row_fwd_plan(g, d->N, &p, &smem) == 0;
+    err_slot() = saved;
+    return ok && p.fold != 0;
+}
+
+inline int row_fwd_plan_mode(const RowFwdGeom& g, int N, RowFwdParams* p, size_t* smem_bytes, bool fold) {
     memset(p, 0, sizeof *p);
     p->N = N; p->D = g.D; p->H = g.H; p->W = g.W; p->IC = g.IC; p->OC = g.OC; p->kd = g.kd; p->khw = g.khw;
     const int ph = g.khw / 2, pd = g.kd / 2;
@@ -423,7 +528,9 @@ inline int row_fwd_plan(const RowFwdGeom& g, int N, RowFwdParams* p, size_t* sme
     p->wtap_bytes = g.IC * g.OC * 2;
     // weights: RESIDENT (every tap in shared memory next to a 4-deep plane ring) or STREAMED tap by tap through a ring (the
     // plane ring then shrinks to 3: the kz = 0 plane is released after its pass, see the MMA loop).  Both modes are costed.
-    int maxT = 256 / g.OC;
+    p->fold = fold ? 1 : 0;
+    p->ncol = p->fold ? 3 * g.OC : g.OC;
+    int maxT = 256 / p->ncol;
     if (maxT > kRfMaxTiles) maxT = kRfMaxTiles;
     if (maxT < 1) maxT = 1;
     // Search (mode, weight stages, row-block height, z-segment length) with a small cost model of one persistent CTA:
@@ -431,11 +538,11 @@ inline int row_fwd_plan(const RowFwdGeom& g, int N, RowFwdParams* p, size_t* sme
     //   weight cycles / group = bytes of all taps / min(10, bytes in flight / 5000 cycles) B/clk/SM      (streaming mode)
     //   item = zs groups + the z-halo planes it has to load first; total = rounds of the persistent grid * item
     const int taps = g.kd * g.khw * g.khw, nks = g.IC / 16;
-    double mma_cyc = 32.0 + g.OC / 4.0;
+    double mma_cyc = 32.0 + p->ncol / 4.0;
     if (mma_cyc < 48.0) mma_cyc = 48.0;
-    if (mma_cyc < g.OC / 2.0) mma_cyc = g.OC / 2.0;
+    if (mma_cyc < p->ncol / 2.0) mma_cyc = p->ncol / 2.0;
     int best = 0, best_zs = 1, best_nw = 1, best_stream = 0; double best_cost = 1e30;
-    for (int stream_w = 0; stream_w <= 1; ++stream_w) {
+    for (int stream_w = 0; stream_w <= (p->fold ? 0 : 1); ++stream_w) {
         const int ring = stream_w ? 3 : kRfRing;
         const int nw_lo = stream_w ? 2 : 1, nw_hi = stream_w ? kRfMaxW : 1;
         for (int nw = nw_lo; nw <= nw_hi; ++nw) {
@@ -450,7 +557,7 @@ inline int row_fwd_plan(const RowFwdGeom& g, int N, RowFwdParams* p, size_t* sme
                 const size_t tail = reach > pb ? reach - pb : 0;
                 if ((size_t)ring * pb + (tail > wsm_bytes ? tail - wsm_bytes : 0) > budget) continue;
                 const int yblocks = (g.H + YB - 1) / YB;
-                const double g_mma = (double)T * taps * nks * mma_cyc;
+                const double g_mma = (double)T * (p->fold ? taps / 3 : taps) * nks * mma_cyc;
                 // measured (64->64 @ 64^3): a bulk copy of a tap takes ~5k cycles under load, so the ring depth bounds the rate
                 double w_bw = (double)nw * p->wtap_bytes / 5000.0;
                 if (w_bw > 10.0) w_bw = 10.0;
@@ -485,11 +592,11 @@ inline int row_fwd_plan(const RowFwdGeom& g, int N, RowFwdParams* p, size_t* sme
     const int64_t items = (int64_t)N * p->yblocks * p->zsegs;
     B200_REQUIRE(items < (1ll << 31), "row fwd: too many items");
     p->items = (int)items;
-    int cols = 2 * p->T * g.OC, pow2 = 32;
+    int cols = 2 * p->T * p->ncol, pow2 = 32;
     while (pow2 < cols) pow2 <<= 1;
     B200_REQUIRE(pow2 <= 512, "row fwd: accumulators do not fit TMEM");
     p->tmem_cols = pow2;
-    p->idesc = make_idesc_bf16(g.OC);
+    p->idesc = make_idesc_bf16(p->ncol);
     // The MMAs of the last (partial) tile read slots past the end of a plane image: up to T*128 + (k-1)*(pitchW + 1) slots from
     // the plane start.  Those rows of D are never stored, but the reads must stay inside the allocation: whatever follows the
     // last ring slot (resident weights / weight ring) is padded up to that tail.  + 1 KB manual 1024-byte alignment.
@@ -511,14 +618,14 @@ inline bool row_fwd_supported(const b200_conv_desc* d, int pass) {
     return ok;
 }
 
-template <int KD, int KHW, int NKS>
+template <int KD, int KHW, int NKS, bool FOLD = false>
 inline int row_fwd_launch(const CUtensorMap& map, const RowFwdParams& p, size_t smem_bytes, void* stream) {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(row_fwd_kernel<KD, KHW, NKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRfMaxDynSmem); });
+    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(row_fwd_kernel<KD, KHW, NKS, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRfMaxDynSmem); });
     B200_REQUIRE(attr_err == cudaSuccess, "row fwd: cannot raise the dynamic shared memory limit: %s", cudaGetErrorString(attr_err));
     const int grid = p.items < kNumSMs ? p.items : kNumSMs;
-    B200_LAUNCH((row_fwd_kernel<KD, KHW, NKS>), grid, kRfThreads, smem_bytes, stream, map, p);
+    B200_LAUNCH((row_fwd_kernel<KD, KHW, NKS, FOLD>), grid, kRfThreads, smem_bytes, stream, map, p);
     return 0;
 }
 
@@ -548,11 +655,17 @@ inline int row_fwd_run(const b200_conv_desc* d, int pass, const void* in, const 
     p.w = (const __nv_bfloat16*)w_packed; p.bias = bias; p.out = (__nv_bfloat16*)out; p.stats = stats; p.store_c0 = store_c0;
     static const bool debug = [] { const char* e = getenv("B200_ROWF_DEBUG"); return e != nullptr && e[0] == '1'; }();
     if (debug)
-        fprintf(stderr, "[row_fwd] N=%d %dx%dx%d IC=%d OC=%d k=%d,%d: YB=%d T=%d zs=%d items=%d ring=%d stream=%d nw=%d plane=%dB smem=%zuB tmem=%d\n", d->N,
-                g.D, g.H, g.W, g.IC, g.OC, g.kd, g.khw, p.YB, p.T, p.zs, p.items, p.ring, p.stream_w, p.nw, p.plane_bytes, smem_bytes, p.tmem_cols);
+        fprintf(stderr, "[row_fwd] N=%d %dx%dx%d IC=%d OC=%d k=%d,%d: YB=%d T=%d zs=%d items=%d ring=%d stream=%d nw=%d plane=%dB smem=%zuB tmem=%d fold=%d\n", d->N,
+                g.D, g.H, g.W, g.IC, g.OC, g.kd, g.khw, p.YB, p.T, p.zs, p.items, p.ring, p.stream_w, p.nw, p.plane_bytes, smem_bytes, p.tmem_cols, p.fold);
     const int ph = g.khw / 2;
     CUtensorMap map;
     if (make_row_map(&map, in, g.IC, g.W, g.H, (int64_t)d->N * g.D, g.IC, p.pitchW, p.YB + 2 * ph)) return 1;
+    if (p.fold) {
+        if (g.kd == 3) return g.IC == 16 ? row_fwd_launch<3, 3, 1, true>(map, p, smem_bytes, stream)
+                            : g.IC == 32 ? row_fwd_launch<3, 3, 2, true>(map, p, smem_bytes, stream) : row_fwd_launch<3, 3, 4, true>(map, p, smem_bytes, stream);
+        return g.IC == 16 ? row_fwd_launch<1, 3, 1, true>(map, p, smem_bytes, stream)
+             : g.IC == 32 ? row_fwd_launch<1, 3, 2, true>(map, p, smem_bytes, stream) : row_fwd_launch<1, 3, 4, true>(map, p, smem_bytes, stream);
+    }
 #define B200_RF_CASE(KD_, KHW_)                                                                              \
     if (g.kd == KD_ && g.khw == KHW_) {                                                                      \
         if (g.IC == 16) return row_fwd_launch<KD_, KHW_, 1>(map, p, smem_bytes, stream);                     \

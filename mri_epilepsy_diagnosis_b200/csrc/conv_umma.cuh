@@ -553,7 +553,10 @@ __global__ void umma_split_reduce_kernel(int nsplit, int64_t total, int OC, cons
 // dst[tap'][kchunk][cg][oc][8] (bf16) from the fp32 PyTorch parameter (Co, Ci, taps).
 //   fwd  : ic = ci, oc = co, tap' = tap
 //   dgrad: ic = co, oc = ci, tap' = taps-1-tap (all three axes flipped)
-__global__ void pack_weights_umma_kernel(int Ci, int Co, int taps, int dgrad, int KC, const float* __restrict__ w, __nv_bfloat16* __restrict__ dst) {
+// fold = 1 (row_fwd_kernel's kx-folded mode, NKC == 1): dst[(kz,ky)][cg][kx][oc][8] -- the three kx blocks of a filter row
+// side by side, so one B operand of N = 3*OC covers them
+__global__ void pack_weights_umma_kernel(int Ci, int Co, int taps, int dgrad, int KC, const float* __restrict__ w, __nv_bfloat16* __restrict__ dst,
+                                         int fold) {
     const int IC = dgrad ? Co : Ci, OC = dgrad ? Ci : Co;
     const int NKC = IC / KC;
     const int64_t total = (int64_t)taps * IC * OC;
@@ -561,9 +564,17 @@ __global__ void pack_weights_umma_kernel(int Ci, int Co, int taps, int dgrad, in
         int64_t r = e;
         const int j = (int)(r % 8); r /= 8;
         const int oc = (int)(r % OC); r /= OC;
-        const int cg = (int)(r % (KC / 8)); r /= (KC / 8);
-        const int kc = (int)(r % NKC);
-        const int tp = (int)(r / NKC);
+        int cg, kc, tp;
+        if (fold) {
+            const int kx = (int)(r % 3); r /= 3;
+            cg = (int)(r % (KC / 8)); r /= (KC / 8);
+            kc = 0;
+            tp = (int)r * 3 + kx;
+        } else {
+            cg = (int)(r % (KC / 8)); r /= (KC / 8);
+            kc = (int)(r % NKC);
+            tp = (int)(r / NKC);
+        }
         const int ic = kc * KC + cg * 8 + j;
         const int tap = dgrad ? taps - 1 - tp : tp;
         const int ci = dgrad ? oc : ic, co = dgrad ? ic : oc;
@@ -624,6 +635,7 @@ inline bool umma_geom(const b200_conv_desc* d, int pass, UmmaGeom* g) {
 }
 
 inline bool umma_wgrad_geom(const b200_conv_desc* d);
+inline bool row_fwd_folds(const b200_conv_desc* d, int pass);          // conv_rowf.cuh: the row-slab kernel wants the kx-folded weight layout
 inline bool umma_conv_supported(const b200_conv_desc* d, int pass) {
     if (pass == B200_PASS_WGRAD) return umma_wgrad_geom(d);
     UmmaGeom g;
@@ -646,7 +658,7 @@ inline int umma_pack_weights(const b200_conv_desc* d, int pass, const float* w, 
     const int taps = d->kd * d->kh * d->kw;
     const int64_t total = (int64_t)taps * d->Ci * d->Co;
     B200_LAUNCH(pack_weights_umma_kernel, stream_grid(total, 256), 256, 0, stream, d->Ci, d->Co, taps, pass == B200_PASS_DGRAD ? 1 : 0,
-                umma_kchunk(g.IC), w, (__nv_bfloat16*)packed);
+                umma_kchunk(g.IC), w, (__nv_bfloat16*)packed, row_fwd_folds(d, pass) ? 1 : 0);
     return 0;
 }
 

@@ -46,6 +46,14 @@ CASES = [
     ("s64_64_d2", 2, 64, 64, (2, 27, 40), 3, 1, False),
     ("d1", 4, 32, 32, (1, 33, 64), 3, 1, False),                  # single plane: both z neighbours are padding
     ("d2", 2, 16, 16, (2, 17, 128), 3, 1, False),
+    # kx-folded mode (W == 128, Cout <= 32, see row_fwd_fold_geom): one MMA per (kz, ky) with N = 3*Cout, shifted sum in the epilogue
+    ("f32_32_w128", 2, 32, 32, (3, 9, 128), 3, 1, True),
+    ("f32_16_w128", 2, 32, 16, (3, 8, 128), 3, 1, False),
+    ("f64_16_w128", 1, 64, 16, (4, 9, 128), 3, 1, False),
+    ("f64_32_w128", 1, 64, 32, (4, 9, 128), 3, 1, True),
+    ("f133_w128", 2, 16, 16, (6, 10, 128), (1, 3, 3), (0, 1, 1), True),
+    ("f16_16_w128_tall", 1, 16, 16, (3, 37, 128), 3, 1, False),
+    ("f16_32_w128", 1, 16, 32, (4, 9, 128), 3, 1, True),          # NOT folded by the default rule (Cin = 16, Cout = 32)
 ]
 
 
@@ -115,3 +123,31 @@ def test_row_fwd_large_volume_properties(B):
     # against the fp32-FMA kernels on identical operands: only output rounding separates them
     mod.allow_umma = False
     assert rel_err(y.float(), mod(x).float()) < 6e-3
+
+
+@pytest.mark.parametrize("W,Ci", [(128, 16), (128, 32), (64, 16)], ids=["folded_16", "folded_32", "plain_w64"])
+def test_fused_statistics_and_dual_conv(B, W, Ci):
+    """conv + BatchNorm partial sums in the epilogue (b200_conv_fwd_stats) and the dead/live pair of unet3d.py:43-46 in one launch
+    (b200_conv_fwd_stats_tail), in the kx-folded mode (W = 128) and the plain one: statistics against the stored outputs."""
+    F_ = B.functional
+    g = torch.Generator().manual_seed(W + Ci)
+    x = torch.randn(2, Ci, 5, 12, W, generator=g).cuda().bfloat16()
+    conv = B.nn.Conv3d(Ci, 16, 3, 1, 1, bias=False).cuda()
+    conv.compute_dtype = torch.bfloat16
+    y, part = F_.conv(x, conv.weight, None, conv._cfg(), torch.bfloat16, want_stats=True)
+    assert part is not None
+    y_plain = conv(x)
+    assert torch.equal(y, y_plain)
+    s = part.double().sum(0)                                                   # sums of the fp32 accumulators, before the bf16 rounding of y
+    yd = y.double().permute(1, 0, 2, 3, 4).reshape(16, -1)
+    assert rel_err(s[0], yd.sum(1)) < 2e-3 and rel_err(s[1], (yd * yd).sum(1)) < 2e-3
+    dead = B.nn.Conv3d(Ci, 16, 3, 1, 1, bias=False).cuda()
+    assert F_.dual_conv_supported(x, dead.weight, conv.weight, conv._cfg(), torch.bfloat16)
+    y3, part2 = F_.dual_conv(x, dead.weight, conv.weight, conv._cfg(), torch.bfloat16)
+    # the live half is the plain convolution: bit-equal when both launches use the same mode, else equal up to the summation order
+    assert torch.equal(y3, y_plain) if W != 128 else rel_err(y3.float(), y_plain.float()) < 2e-3
+    dead.compute_dtype = torch.bfloat16
+    yd2 = dead(x).double().permute(1, 0, 2, 3, 4).reshape(16, -1)
+    s2 = part2.double().sum(0)
+    assert rel_err(s2[0, :16], yd2.sum(1)) < 2e-3 and rel_err(s2[1, :16], (yd2 * yd2).sum(1)) < 2e-3
+    assert rel_err(s2[0, 16:], yd.sum(1)) < 2e-3 and rel_err(s2[1, 16:], (yd * yd).sum(1)) < 2e-3
