@@ -9,7 +9,8 @@ __graft_entry__.build()
 import mri_epilepsy_diagnosis_b200 as B
 
 CASES = [(1, 128, 64, (4, 16, 8)), (2, 64, 128, (5, 8, 8)), (1, 256, 128, (4, 8, 16)), (1, 256, 256, (3, 16, 16)), (2, 128, 256, (8, 8, 8)),
-         (2, 128, 128, (16, 16, 16)), (1, 96, 32, (5, 16, 16)), (2, 16, 16, (10, 12, 16)), (1, 64, 64, (6, 17, 9)), (2, 32, 32, (9, 20, 11))]
+         (2, 128, 128, (16, 16, 16)), (1, 96, 32, (5, 16, 16)), (2, 16, 16, (10, 12, 16)), (1, 64, 64, (6, 17, 9)), (2, 32, 32, (9, 20, 11)),
+         (1, 32, 32, (4, 9, 128)), (2, 16, 16, (6, 10, 128)), (1, 16, 32, (4, 9, 128))]          # W = 128: the kx-folded mode of row_fwd_kernel
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 50
 bad = 0
 for (N, Ci, Co, size) in CASES:
