@@ -142,3 +142,7 @@ def stream():
 def need_cuda(t, what):
     if not t.is_cuda:
         raise RuntimeError(f"b200nn.{what}: expected a CUDA tensor (there is no CPU path), got device {t.device}")
+    if t.device.index != torch.cuda.current_device():
+        # kernels are enqueued on the CURRENT device's stream; a tensor of another device would be touched from the wrong context
+        raise RuntimeError(f"b200nn.{what}: tensor lives on {t.device} but the current device is cuda:{torch.cuda.current_device()}; "
+                           f"call torch.cuda.set_device({t.device.index}) (one process per GPU) or wrap the call in torch.cuda.device(...)")

@@ -7,8 +7,13 @@ One process per GPU.  The loops take `model` and `optimizer` as arguments
     when the last expected gradient of the step has landed the bucket is all-reduced (NCCL over NVLink on
     GPUs, gloo in the CPU tests) on a side stream, overlapping the rest of backward;
   * an optimizer step-pre-hook waits for the collective, divides by the world size and hands the averaged
-    gradients back, zero-filling parameters that received no gradient this step (unet3d's dead conv2/bn2
-    branch, unet3d.py:43-46; frozen fader sub-networks, train_ENC_CLF.ipynb [cell 16]);
+    gradients back.  Parameters that received no gradient on ANY rank this step (unet3d's dead conv2/bn2
+    branch, unet3d.py:43-46; frozen fader sub-networks, train_ENC_CLF.ipynb [cell 16]) keep grad=None, so the
+    optimizer skips them exactly as on one GPU (no weight decay, no Adam state); the ranks agree on that set
+    with one small MAX all-reduce of a seen-mask.  A parameter seen on some ranks only contributes zeros from
+    the others;
+  * a second backward before optimizer.step() (gradient accumulation) marks the bucket dirty: its collective
+    is re-issued from the accumulated p.grad values at step time instead of racing the one in flight;
   * BatchNorm statistics are all-reduced when the model was converted with `sync=` (nn.convert).
 
 `optimizer.step()` at routine.py:278 therefore runs unmodified.
@@ -39,9 +44,10 @@ class GradientBucket:
                 cur, size = [], 0
         if cur:
             self._close(cur, dev)
-        self.pending = [0] * len(self.flat)
         self.seen = [set() for _ in self.flat]
+        self.dirty = [False] * len(self.flat)
         self.works = [None] * len(self.flat)
+        self.index = {p: i for i, p in enumerate(self.params)}
         self.comm_stream = torch.cuda.Stream() if dev.type == "cuda" else None
         self.handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
         self.handles.append(optimizer.register_step_pre_hook(self._before_step))
@@ -58,6 +64,11 @@ class GradientBucket:
 
     def _on_grad(self, p):
         b, off, n = self.slots[p]
+        if p in self.seen[b]:
+            # gradient accumulation: p.grad now holds the SUM of several backward passes while the bucket (and possibly a
+            # collective in flight) holds the first one -- re-reduce this bucket from p.grad at step time
+            self.dirty[b] = True
+            return
         self.flat[b][off:off + n].copy_(p.grad.reshape(-1))
         self.seen[b].add(p)
         # fire once every member that CAN still get a gradient has one; members without grads are resolved at step time
@@ -74,9 +85,30 @@ class GradientBucket:
         else:
             self.works[b] = dist.all_reduce(self.flat[b], group=self.pg, async_op=True)
 
+    def _seen_anywhere(self):
+        """per-parameter flag: some rank produced a gradient this step (one small MAX all-reduce)"""
+        mask = torch.zeros(len(self.params), dtype=torch.int32, device=self.flat[0].device)
+        idx = [self.index[p] for s in self.seen for p in s]
+        if idx:
+            mask[torch.tensor(idx, device=mask.device)] = 1
+        if self.world > 1:
+            dist.all_reduce(mask, op=dist.ReduceOp.MAX, group=self.pg)
+        return mask.cpu().tolist()
+
     def _before_step(self, optimizer, args, kwargs):
+        anywhere = self._seen_anywhere()
         for b, buf in enumerate(self.flat):
-            # parameters that received no gradient this step contribute zeros (and get a zero grad back)
+            if self.dirty[b]:
+                if self.works[b] is not None:           # drain the collective issued after the first backward
+                    self.works[b].wait()
+                    if self.comm_stream is not None:
+                        torch.cuda.current_stream().wait_stream(self.comm_stream)
+                    self.works[b] = None
+                for p in self.seen[b]:
+                    _, off, n = self.slots[p]
+                    buf[off:off + n].copy_(p.grad.reshape(-1))
+                self.dirty[b] = False
+            # parameters without a local gradient this step contribute zeros
             for p in self.members[b]:
                 if p not in self.seen[b]:
                     _, off, n = self.slots[p]
@@ -91,9 +123,10 @@ class GradientBucket:
             for p in self.members[b]:
                 _, off, n = self.slots[p]
                 g = buf[off:off + n].view_as(p)
+                if not anywhere[self.index[p]]:
+                    continue                            # no gradient on any rank: grad stays None, the optimizer skips it
                 if p.grad is None:
-                    if p in self.seen[b] or self.world > 1:
-                        p.grad = g.clone()
+                    p.grad = g.clone()
                 else:
                     p.grad.copy_(g)
             self.seen[b].clear()

@@ -146,7 +146,9 @@ class ConvConfig:
         `fresh=False` (inference under no_grad): cached on (storage, version); any fresh call drops the cached copy, so the
         first inference call after a training step re-packs."""
         algo = lib().b200_conv_algo(C.byref(cd), which)
-        key = (which, algo, cd.x_dtype, cd.y_dtype, cd.Ci, cd.Co)
+        # the packed layout depends on the GEOMETRY too (the kx-folded row kernel packs the three kx blocks side by side and is
+        # chosen per input shape), so the whole descriptor is the key: one module called at W=128 and then at W=64 packs twice
+        key = (which, algo) + tuple(getattr(cd, f) for f, _ in ConvDesc._fields_)
         tag = (weight.data_ptr(), weight._version, weight.device)
         if fresh:
             self._packed.clear()
@@ -669,6 +671,10 @@ class _UpsampleFn(Function):
         o = (1,) + tuple(out_size) if dims == 4 else tuple(out_size)
         Cx = x.shape[1]
         c_off = 0 if skip is None else skip.shape[1]
+        if skip is not None and (skip.shape[0] != x.shape[0] or tuple(skip.shape[2:]) != tuple(out_size)):
+            # torch.cat raises here too (unet3d.py:76); the copy below would otherwise read the skip with the wrong strides
+            raise RuntimeError(f"b200nn.upsample_concat: skip {tuple(skip.shape)} does not match the upsampled tensor "
+                               f"{(x.shape[0], Cx) + tuple(out_size)} outside dim 1")
         ctot = Cx + c_off
         y = _empty_cl((x.shape[0], ctot) + tuple(out_size), x.dtype, x.device)
         ud = UpDesc(dtype_code(x.dtype), mode, x.shape[0], Cx, Di, Hi, Wi, o[0], o[1], o[2], ctot, c_off)

@@ -24,6 +24,13 @@ class GraphedTrainStep:
 
     `x`/`t` may live on the host (pinned) or the device; they are copied into the static input buffers of the graph.
     Returns the (static) loss tensor of the step; read it with `.item()` / `float()` when needed.
+
+    Construction runs a probe step and `warmup` eager steps on `x_example` (CUDA-graph capture needs warmed-up allocations
+    and lazily created optimizer state).  Those steps are UNDONE before the capture: parameters, buffers (BatchNorm running
+    statistics, `num_batches_tracked`), optimizer state and the CPU/CUDA RNG streams are restored in place, so that N calls
+    perform exactly the N optimizer steps of the reference loop.  Optimizer state that did not exist before construction is
+    zeroed rather than deleted (the captured `optimizer.step()` needs the tensors): identical to a fresh Adam/AdamW/SGD(momentum,
+    dampening=0) state; an optimizer whose fresh state is not all zeros must be stepped once by the caller before construction.
     """
 
     def __init__(self, model, loss_fn, optimizer, x_example, t_example, process_group=None, warmup=3):
@@ -35,6 +42,7 @@ class GraphedTrainStep:
         self.t = torch.empty(t_example.shape, dtype=t_example.dtype, device=dev)
         self.x.copy_(x_example)
         self.t.copy_(t_example)
+        snap = self._snapshot(dev)
         # Probe step (eager): parameters that receive no gradient (unet3d's dead conv2/bn2 branch, unet3d.py:43-46; frozen
         # fader sub-networks) must keep grad=None so that the optimizer skips them exactly like in the reference's loop.
         optimizer.zero_grad(set_to_none=True)
@@ -60,10 +68,35 @@ class GraphedTrainStep:
                 self._body(eager=True)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        self._restore(snap, dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = self._body(eager=False)
         self.opt_graph = None
+
+    def _snapshot(self, dev):
+        state = {}
+        for p, st in self.opt.state.items():
+            state[p] = {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+        return {"tensors": [(t, t.detach().clone()) for t in list(self.model.parameters()) + list(self.model.buffers())],
+                "opt": state, "cpu_rng": torch.get_rng_state(), "cuda_rng": torch.cuda.get_rng_state(dev)}
+
+    def _restore(self, snap, dev):
+        with torch.no_grad():
+            for t, saved in snap["tensors"]:
+                t.copy_(saved)
+            for p, st in self.opt.state.items():
+                before = snap["opt"].get(p)
+                for k, v in st.items():
+                    if not torch.is_tensor(v):
+                        if before is not None and k in before:
+                            st[k] = before[k]
+                    elif before is not None and torch.is_tensor(before.get(k)):
+                        v.copy_(before[k])
+                    else:
+                        v.zero_()
+        torch.set_rng_state(snap["cpu_rng"])
+        torch.cuda.set_rng_state(snap["cuda_rng"], dev)
 
     def _fwd_bwd(self):
         self.flat.zero_()

@@ -149,7 +149,13 @@ def _dp_worker(rank, world, port, q):
         opt.zero_grad()
         torch.nn.functional.mse_loss(net(X[mine]), Y[mine]).backward()
         opt.step()
-    q.put((rank, [p.detach().tolist() for p in net.parameters()], [p.grad is None or float(p.grad.abs().sum()) == 0 for p in dead.parameters()]))
+    # gradient accumulation: two backward passes before one step (the second must not race the first pass's collective)
+    opt.zero_grad()
+    for half in (mine[:2], mine[2:]):
+        torch.nn.functional.mse_loss(net(X[half]), Y[half]).backward()
+    opt.step()
+    # parameters without a gradient on any rank keep grad=None: the optimizer skips them as on one GPU
+    q.put((rank, [p.detach().tolist() for p in net.parameters()], [p.grad is None for p in dead.parameters()]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -173,6 +179,10 @@ def test_data_parallel_bucket_matches_single_process_gloo():
         opt.zero_grad()
         torch.nn.functional.mse_loss(net(X), Y).backward()
         opt.step()
+    opt.zero_grad()
+    for half in ([0, 1, 4, 5], [2, 3, 6, 7]):           # first / second halves of both ranks' shards
+        torch.nn.functional.mse_loss(net(X[half]), Y[half]).backward()
+    opt.step()
     for r in res:
         for a, b in zip(r[1], net.parameters()):
             assert torch.allclose(torch.tensor(a), b.detach(), atol=1e-6)

@@ -365,12 +365,14 @@ def test_graphed_train_step_learns_like_the_eager_loop(B):
         want.append(float(loss))
     net = make()
     step = B.graphed.GraphedTrainStep(net, loss_fn, torch.optim.AdamW(net.parameters(), lr=2e-3, capturable=True, fused=True), xs[0], ts[0], warmup=1)
-    # construction ran a probe and warm-up steps on (xs[0], ts[0]): restart both from the same state
-    net.load_state_dict(sd, strict=True)
-    for st in step.opt.state.values():                  # the graph holds these tensors by address: reset them in place
+    # construction ran a probe and warm-up steps on (xs[0], ts[0]) and must have undone them: weights, BatchNorm buffers and
+    # optimizer state are those of a loop that has not stepped yet
+    for k, v in net.state_dict().items():
+        assert torch.equal(v.cpu(), sd[k]), k
+    for st in step.opt.state.values():
         for v in st.values():
             if torch.is_tensor(v):
-                v.zero_()
+                assert float(v.abs().sum()) == 0.0
     got = [float(step(x, t)) for x, t in zip(xs, ts)]
     assert abs(got[0] - want[0]) < 5e-3
     assert max(abs(a - b) for a, b in zip(got, want)) < 3e-2, (got, want)

@@ -606,3 +606,32 @@ def test_fcd_mask_generator_with_patch_model(B, template):
     sure = (logits[:, 0] - logits[:, 1]).abs().numpy() > 1e-3
     assert np.array_equal(got[sure], ref[sure]) and sure.mean() > 0.9
     assert tuple(gen.get_mask(img).shape) == (182, 218, 182)
+
+
+def test_inference_pack_cache_follows_geometry(B):
+    """One Conv3d module called under no_grad at W=128 (kx-folded packed layout) and then at W=64 / W=192 (unfolded layout), and
+    back: the packed-weight cache is keyed on the whole descriptor, so no call may reuse the other geometry's buffer."""
+    g = gen(77)
+    ref = torch.nn.Conv3d(16, 16, 3, 1, 1, bias=False)
+    with torch.no_grad():
+        ref.weight.copy_(torch.randn(ref.weight.shape, generator=g) * 0.07)
+    mod = B.nn.Conv3d(16, 16, 3, 1, 1, bias=False).cuda()
+    mod.load_state_dict(ref.state_dict())
+    mod.compute_dtype = torch.bfloat16
+    for W in (128, 64, 128, 192, 64):
+        x = torch.randn(1, 16, 4, 8, W, generator=g).bfloat16().float()
+        with torch.no_grad():
+            want = ref(x)
+            got = mod(x.cuda().bfloat16())
+        assert rel_err(got, want) < TOL16, W
+    assert len(mod._cfg()._packed) == 3          # one cached copy per geometry
+
+
+def test_upsample_concat_rejects_mismatched_skip(B):
+    """torch.cat raises when the skip and the upsampled tensor differ outside dim 1 (e.g. 193 -> pool 96 -> up 192); so must we."""
+    x = torch.randn(1, 4, 4, 4, 4).cuda()
+    ok = B.functional.upsample_concat(torch.randn(1, 3, 8, 8, 8).cuda(), x)
+    assert tuple(ok.shape) == (1, 7, 8, 8, 8)
+    for bad in ((1, 3, 9, 8, 8), (1, 3, 8, 8, 7), (2, 3, 8, 8, 8)):
+        with pytest.raises(RuntimeError):
+            B.functional.upsample_concat(torch.randn(*bad).cuda(), x)
