@@ -83,9 +83,11 @@ class ClockSampler:
 
 
 def synthetic_batch(n, size, seed):
+    """size: edge of a cubic volume or (D, H, W)"""
+    dhw = (size,) * 3 if isinstance(size, int) else tuple(size)
     g = torch.Generator().manual_seed(seed)
-    x = torch.randn(n, 1, size, size, size, generator=g)
-    t = (torch.rand(n, 1, size, size, size, generator=g) > 0.5).float()
+    x = torch.randn(n, 1, *dhw, generator=g)
+    t = (torch.rand(n, 1, *dhw, generator=g) > 0.5).float()
     return x, t
 
 
@@ -109,20 +111,28 @@ def build_model(pkg, name, norm="bn", literal=False):
     raise SystemExit(f"unknown model {name}")
 
 
-def cpu_reference_step(model_name, size, steps, warmup, threads, norm="bn"):
-    """The reference's CPU path for the step (oracle restatement), fp32, on `threads` host threads."""
+def _oracle_state(model_name, norm):
     from oracle import graphs, weights
-    torch.set_num_threads(threads)
     if model_name == "unet3d":
         sd = weights.unet3d_state(1, 16, 2, norm, seed=0)
         fwd = lambda s, x: graphs.unet3d(s, x, norm, 0.5, True)
     else:
         sd = weights.fepegar_unet_state(16 if model_name == "fepegar16" else 8, seed=0, duplicate_keys=False)
         fwd = lambda s, x: graphs.fepegar_unet(s, x, True)
+    return sd, fwd
+
+
+def cpu_reference_step(model_name, size, steps, warmup, threads, norm="bn", batch=1, budget_s=None):
+    """The reference's CPU path for the step (oracle restatement), fp32, on `threads` host threads.  With `budget_s` the
+    number of timed steps is cut so that the run ends in about that many seconds; returns (voxels per step, times of the timed steps,
+    warm-up steps actually run)."""
+    from oracle import graphs
+    torch.set_num_threads(threads)
+    sd, fwd = _oracle_state(model_name, norm)
     sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
     opt = torch.optim.AdamW([v for v in sd.values() if v.requires_grad])
-    x, t = synthetic_batch(1, size, 0)
-    times = []
+    x, t = synthetic_batch(batch, size, 0)
+    times, began = [], time.perf_counter()
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         opt.zero_grad()
@@ -130,9 +140,90 @@ def cpu_reference_step(model_name, size, steps, warmup, threads, norm="bn"):
         loss.backward()
         opt.step()
         float(loss)
+        dt = time.perf_counter() - t0
         if i >= warmup:
-            times.append(time.perf_counter() - t0)
-    return x.numel(), times
+            times.append(dt)
+            if budget_s is not None and time.perf_counter() - began + dt > budget_s:
+                break
+    return x.numel(), times, warmup
+
+
+def torch_gpu_baseline(model_name, batch, size, steps, warmup, norm, dev):
+    """Stock PyTorch on the SAME B200 for the same step -- what the unmodified reference modules execute on a GPU: ATen/cuDNN
+    convolutions, eager BatchNorm/ReLU/cat/interpolate, autograd, torch.optim.AdamW.  The graph is the oracle's functional
+    restatement of unet3d.py (torch.nn.functional calls, identical operator sequence incl. the dead branch), moved to CUDA.
+    Variants: fp32 (PyTorch defaults, i.e. TF32 convolutions allowed) and bf16 autocast, NCDHW and channels_last_3d, eager and
+    whole-step CUDA graph; cudnn.benchmark on.  Nothing of this repo's library runs here."""
+    from oracle import graphs
+    torch.backends.cudnn.benchmark = True
+    x, t = synthetic_batch(batch, size, 0)
+    voxels = x.numel()
+    out = {}
+
+    def variant(name, autocast, channels_last, graphed):
+        sd0, fwd = _oracle_state(model_name, norm)
+        sd = {}
+        for k, v in sd0.items():
+            v = v.to(dev)
+            if channels_last and v.dim() == 5:
+                v = v.contiguous(memory_format=torch.channels_last_3d)
+            sd[k] = v.requires_grad_(True) if v.is_floating_point() and "running" not in k else v
+        opt = torch.optim.AdamW([v for v in sd.values() if v.requires_grad], capturable=graphed)
+        xd, td = x.to(dev), t.to(dev)
+        if channels_last:
+            xd = xd.contiguous(memory_format=torch.channels_last_3d)
+
+        def body():
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                logits = fwd(sd, xd)
+            loss = graphs.dice_loss_mean(logits.float(), td)
+            loss.backward()
+            opt.step()
+            return loss
+        run = None
+        if graphed:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    opt.zero_grad(set_to_none=True)
+                    body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            opt.zero_grad(set_to_none=True)
+            with torch.cuda.graph(graph):
+                body()
+            run = graph.replay
+        else:
+            def run():
+                opt.zero_grad(set_to_none=True)
+                body()
+        for _ in range(max(3, warmup)):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[name] = {"ms_per_step": ms, "value": voxels / (ms / 1e3), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+
+    for name, ac, cl, gr in (("bf16_autocast_channels_last_3d_graph", True, True, True), ("bf16_autocast_channels_last_3d_eager", True, True, False),
+                             ("bf16_autocast_ncdhw_graph", True, False, True), ("fp32_tf32_ncdhw_graph", False, False, True)):
+        try:
+            torch.cuda.reset_peak_memory_stats()
+            variant(name, ac, cl, gr)
+        except Exception as e:      # a variant PyTorch cannot run (e.g. capture failure) is reported, not hidden
+            out[name] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+    ok = {k: v for k, v in out.items() if "value" in v}
+    best = max(ok.items(), key=lambda kv: kv[1]["value"]) if ok else (None, {})
+    return {"what": "stock torch " + torch.__version__ + " / cuDNN " + str(torch.backends.cudnn.version()) + " on this GPU, same step, same batch",
+            "best_variant": best[0], "value": best[1].get("value"), "ms_per_step": best[1].get("ms_per_step"), "unit": "voxels/s", "variants": out}
 
 
 def main():
@@ -140,10 +231,14 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_gpu"])
     ap.add_argument("--model", default="unet3d")
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--size", type=int, default=128)
+    ap.add_argument("--volume", default=None, help="D,H,W of a non-cubic volume (overrides --size), e.g. 192,224,192")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3],
+                    help="BASELINE.json config: 2 = batch 4 x 128^3 (default), 3 = one 192x224x192 volume per GPU (data parallel)")
+    ap.add_argument("--no-torch-baseline", action="store_true", help="skip the stock-PyTorch-on-this-GPU leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sync-bn", action="store_true")
     ap.add_argument("--no-literal-leg", action="store_true", help="skip the extra timing of the literal operator sequence")
@@ -159,7 +254,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     cores = os.cpu_count() or 1
-    workload = f"{args.model} train step (fwd+dice+bwd+AdamW), batch {args.batch} x {args.size}^3 per GPU, bf16"
+    if args.config == 3 and args.volume is None:
+        args.volume, args.batch = "192,224,192", 1
+    vol = tuple(int(v) for v in args.volume.split(",")) if args.volume else (args.size,) * 3
+    vol_s = f"{vol[0]}^3" if vol[0] == vol[1] == vol[2] else "x".join(str(v) for v in vol)
+    workload = f"{args.model} train step (fwd+dice+bwd+AdamW), batch {args.batch} x {vol_s} per GPU, bf16"
     base = {"metric": METRIC, "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "data": "synthetic (seeded randn volumes, random-init weights)"}
 
@@ -167,15 +266,27 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, args.steps)
-        nvox, times = cpu_reference_step(args.model, args.size, steps, min(args.warmup, 1), cores, args.norm)
+        # the config's own batch (e.g. 4 x 128^3: about 5-6 s per step on 16 cores); the number of timed steps is cut to a
+        # ~150 s budget and the line reports the steps / warm-up ACTUALLY run
+        nvox, times, wu = cpu_reference_step(args.model, vol, max(1, args.steps), min(args.warmup, 1), cores, args.norm, batch=args.batch, budget_s=150.0)
         ms = 1e3 * sum(times) / len(times)
         val = nvox / (ms / 1e3)
-        print(json.dumps({**base, "impl": "reference", "value": val, "ms_per_step": ms, "dtype": "f32",
-                          "config": {"workload": workload, "sample": f"1 x {args.size}^3 volume per step (the config's batch is {args.batch})", "timing": "time.perf_counter"},
+        print(json.dumps({**base, "impl": "reference", "steps": len(times), "warmup": wu, "steps_requested": args.steps, "warmup_requested": args.warmup,
+                          "value": val, "ms_per_step": ms, "dtype": "f32",
+                          "config": {"workload": workload, "sample": f"the config's batch, {args.batch} x {vol_s} per step, computed in fp32 on the host cores",
+                                     "timing": "time.perf_counter"},
                           "cpu_baseline": {"value": val, "unit": "voxels/s", "cores": cores, "kind": "port",
-                                           "sample": f"oracle/graphs.py restatement, {steps} steps of 1 x {args.size}^3"},
+                                           "sample": f"oracle/graphs.py restatement, {len(times)} timed steps of {args.batch} x {vol_s} after {wu} warm-up"},
                           "e2e": {"value": val, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    if args.impl == "torch_gpu":
+        if rank != 0:
+            return
+        assert torch.cuda.is_available()
+        torch.cuda.set_device(local)
+        tg = torch_gpu_baseline(args.model, args.batch, vol, args.steps, args.warmup, args.norm, torch.device("cuda", local))
+        print(json.dumps({**base, "impl": "torch_gpu", "value": tg["value"], "ms_per_step": tg["ms_per_step"], "dtype": "bf16",
+                          "config": {"workload": workload}, "torch_gpu_baseline": tg}), flush=True)
         return
 
     # ------------------------------------------------------------------ our arm
@@ -194,7 +305,7 @@ def main():
     sync = (None, world) if (args.sync_bn and world > 1) else None
     net = pkg.convert(net.to(dev).train(), dtype=torch.bfloat16, sync=sync)
     opt = torch.optim.AdamW(net.parameters(), capturable=not args.eager, fused=True)
-    xh, th = synthetic_batch(args.batch, args.size, seed=rank)
+    xh, th = synthetic_batch(args.batch, vol, seed=rank)
     xh, th = xh.pin_memory(), th.pin_memory()
     xd, td = xh.to(dev), th.to(dev)
     voxels = xh.numel()
@@ -329,7 +440,7 @@ def main():
                       "traffic": traffic_tab.get(f"{dom_kernel}|" + "|".join(str(int(x)) for x in ts) + f"|n{args.batch}")}
     roofline = {"bound": "tensor", "kernel": dom_kernel, "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16_tflops"],
-                "traffic": traffic_tab.get(dom_kernel) if (args.model == "unet3d" and args.batch == 4 and args.size == 128) else None,
+                "traffic": traffic_tab.get(dom_kernel) if (args.model == "unet3d" and args.batch == 4 and vol == (128, 128, 128)) else None,
                 "traffic_unit": "bytes per launch, dram read + write averaged over the kernel's launches of one step (ncu; profiles/traffic.json)",
                 "peak_source": pk["source"] + " (sustained bf16)",
                 "launches_per_step": dom[2] / max(1, args.steps), "ms_per_launch_avg": 1e3 * dom[1] / max(1, dom[2]),
@@ -350,7 +461,7 @@ def main():
     # (zoo.Unet(literal=True): dead branch materialised, conv2 on the upsampled tensor) -- see DESIGN.md section 4
     literal = None
     if world == 1 and args.model == "unet3d" and not args.literal_graph and not args.eager and not args.no_literal_leg:
-        del step
+        step = None
         torch.cuda.empty_cache()
         torch.manual_seed(0)
         net2, _ = build_model(pkg, args.model, args.norm, True)
@@ -368,7 +479,7 @@ def main():
             dist.barrier(); dist.destroy_process_group()
         return
     out = {**base, "value": world * voxels / (ms / 1e3), "ms_per_step": ms, "dtype": "bf16",
-           "config": {"workload": workload, "network": model_desc, "volumes_per_step": args.batch * world, "volume": [args.size] * 3,
+           "config": {"workload": workload, "network": model_desc, "volumes_per_step": args.batch * world, "volume": list(vol),
                       "optimizer": "torch.optim.AdamW(fused=True)" + ("" if args.eager or world > 1 else " inside the captured step"),
                       "parallelism": f"dp{world}" + ("+syncbn" if sync else ""), "launch": "eager" if args.eager else "cuda-graph replay of the step",
                       "l2": "inputs and every activation tensor (>= 268 MB each at 16ch x 128^3 x 4) exceed the 126 MB L2; no flush needed"},
@@ -376,11 +487,19 @@ def main():
                    "h2d_bytes_per_step": xh.numel() * 4 + th.numel() * 4, "d2h_bytes_per_step": 4},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "literal_graph": literal,
            "model_tflops": FWD_BWD_FLOP_PER_VOXEL * voxels / (ms / 1e3) / 1e12 if args.model == "unet3d" else None}
+    if args.gpus == 1 and not args.no_torch_baseline:
+        # the bar SURVEY section 2 sets for every kernel: the PyTorch/cuDNN path the unmodified reference modules hit on the same B200
+        step = eager_step = net = opt = None           # release this arm's graph, activations and optimizer state first
+        torch.cuda.empty_cache()
+        tg = torch_gpu_baseline(args.model, args.batch, vol, args.steps, args.warmup, args.norm, dev)
+        if tg.get("value"):
+            tg["ours_over_torch_gpu"] = out["value"] / tg["value"]
+        out["torch_gpu_baseline"] = tg
     if args.gpus == 1 and not args.no_cpu_baseline:
-        nvox, times = cpu_reference_step(args.model, args.size, 2, 1, cores, args.norm)
+        nvox, times, _ = cpu_reference_step(args.model, vol, 2, 1, cores, args.norm)
         v = nvox / (sum(times) / len(times))
         out["cpu_baseline"] = {"value": v, "unit": "voxels/s", "cores": cores, "kind": "port",
-                               "sample": f"oracle/graphs.py (CPU restatement of the reference step), fp32, 2 timed steps of 1 x {args.size}^3 after 1 warm-up"}
+                               "sample": f"oracle/graphs.py (CPU restatement of the reference step), fp32, 2 timed steps of 1 x {vol_s} after 1 warm-up"}
     print(json.dumps(out), flush=True)
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()

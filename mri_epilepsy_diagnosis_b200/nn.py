@@ -224,7 +224,13 @@ class MaxPool2d(_MaxPoolMixin, tnn.MaxPool2d):
 
 class Upsample(_B200Mixin, tnn.Upsample):
     def forward(self, x):
-        return BF.interpolate(self._prep(x), self.size, self.scale_factor, self.mode, self.align_corners)
+        # fp32 tensors with <= 4 channels are the fp32 segmentation logits of the deep-supervision heads (unet3d.py:122-124):
+        # they stay fp32 through the interpolation (cf. `fp32_heads` in convert) instead of being rounded to the body's dtype
+        if not (x.dtype == torch.float32 and x.dim() in (4, 5) and x.shape[1] <= 4):
+            x = self._prep(x)
+        else:
+            BF.need_cuda(x, "Upsample")
+        return BF.interpolate(x, self.size, self.scale_factor, self.mode, self.align_corners)
 
 
 # torch.nn class -> replacement (exact type match only: subclasses defined by user code are left alone)

@@ -20,6 +20,68 @@ BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
 
+# --------------------------------------------------------------------------- bf16-storage mode
+# The CUDA path keeps activations and activation gradients in HBM as bf16 and feeds the tensor-core convolutions bf16
+# copies of the weights; all arithmetic in between is fp32.  `with bf16_storage(...)` makes the graphs below round at the
+# same places -- every tensor an operator STORES (conv output, norm(+residual)+activation output, upsample output) and every
+# gradient tensor an operator's backward stores -- while every operator still executes through the same fp32 ATen CPU kernels.
+# It is the reference's algorithm with the storage precision of the device path, used to show that the distance between the
+# bf16 CUDA results and the fp32 reference IS storage rounding (tests/test_gpu_models.py); with the mode off (default) the
+# graphs are the plain fp32 reference path.
+_STORE = {"on": False, "round_weight": None}
+
+
+class bf16_storage:
+    """round_weight(prefix, weight) -> bool: whether the convolution `prefix` consumes a bf16 copy of its weight (true for
+    the layers the device runs on tensor cores; the Cin=1 stems, the few-channel heads and the separable convs read fp32)."""
+
+    def __init__(self, round_weight=None):
+        self.round_weight = round_weight or (lambda pfx, w: w.shape[0] >= 8 and w.shape[1] >= 8)
+
+    def __enter__(self):
+        self.prev = dict(_STORE)
+        _STORE.update(on=True, round_weight=self.round_weight)
+        return self
+
+    def __exit__(self, *exc):
+        _STORE.update(self.prev)
+        return False
+
+
+def _r(t):
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+class _StoreFn(torch.autograd.Function):
+    """value stored as bf16 (forward) / its gradient stored as bf16 (backward)"""
+
+    @staticmethod
+    def forward(ctx, t, fwd, bwd):
+        ctx.bwd = bwd
+        return _r(t) if fwd else t.view_as(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (_r(g) if ctx.bwd else g), None, None
+
+
+def _q(t):
+    """an operator's output as the device stores it (bf16 value; the gradient arriving here is a stored bf16 tensor too)"""
+    return _StoreFn.apply(t, True, True) if _STORE["on"] else t
+
+
+def _gq(t):
+    """an operator's input: the gradient its backward writes is stored as bf16"""
+    return _StoreFn.apply(t, False, True) if _STORE["on"] and t.requires_grad else t
+
+
+def _wq(pfx, w):
+    """bf16 copy of a weight for the tensor-core layers (the fp32 master weight receives the unrounded fp32 gradient)"""
+    if _STORE["on"] and _STORE["round_weight"](pfx, w):
+        return _StoreFn.apply(w, True, False)
+    return w
+
+
 # --------------------------------------------------------------------------- helpers
 def _bn(sd, pfx, x, training):
     """nn.BatchNorm{1,2,3}d forward incl. running-stat side effects."""
@@ -34,6 +96,7 @@ def _bn(sd, pfx, x, training):
 
 def _norm(sd, pfx, x, kind, training):
     """unet3d.py:8-17 `normalization(planes, norm)`."""
+    x = _gq(x)          # (storage mode: the caller stores the result after the fused residual add / activation)
     if kind == "bn":
         return _bn(sd, pfx, x, training)
     if kind == "in":   # nn.InstanceNorm3d(planes): affine=False, no running stats
@@ -43,8 +106,10 @@ def _norm(sd, pfx, x, kind, training):
     raise ValueError(kind)
 
 
-def _conv(sd, pfx, x, stride=1, padding=0, dilation=1):
-    return F.conv3d(x, sd[pfx + ".weight"], sd.get(pfx + ".bias"), stride, padding, dilation)
+def _conv(sd, pfx, x, stride=1, padding=0, dilation=1, store=True):
+    """store=False: the layer emits fp32 (the <= 4-channel segmentation heads)"""
+    y = F.conv3d(_gq(x), _wq(pfx, sd[pfx + ".weight"]), sd.get(pfx + ".bias"), stride, padding, dilation)
+    return _q(y) if store else y
 
 
 # ----------------------------------------------------------------- unet3d.Unet (a-1)
@@ -53,41 +118,50 @@ def _convd(sd, pfx, x, first, norm, dropout, training):
     whose only effects are BN running-stat updates and RNG consumption."""
     if not first:
         x = F.max_pool3d(x, 2, 2)                                       # :41
-    x = _norm(sd, pfx + ".bn1", _conv(sd, pfx + ".conv1", x, 1, 1), norm, training)   # :42
+    x = _q(_norm(sd, pfx + ".bn1", _conv(sd, pfx + ".conv1", x, 1, 1), norm, training))   # :42
     dead = F.relu(_norm(sd, pfx + ".bn2", _conv(sd, pfx + ".conv2", x, 1, 1), norm, training))  # :43
     if dropout > 0:
         dead = F.dropout3d(dead, dropout)                               # :44-45 (always "training")
     del dead
     y = _norm(sd, pfx + ".bn3", _conv(sd, pfx + ".conv3", x, 1, 1), norm, training)   # :46
-    return F.relu(x + y)                                                # :47
+    return _q(F.relu(_gq(x) + y))                                       # :47
 
 
-def _convu(sd, pfx, x, prev, first, norm, training):
-    """unet3d.py:68-79 ConvU.forward."""
+def _up2(t):
+    return F.interpolate(_gq(t), scale_factor=2, mode="trilinear", align_corners=False)
+
+
+def _convu(sd, pfx, x, prev, first, norm, training, commute_up=False):
+    """unet3d.py:68-79 ConvU.forward.  commute_up=True evaluates :73-74 as upsample(conv2(x)) instead of conv2(upsample(x)):
+    conv2 is 1x1x1 and the interpolation is a per-channel convex combination of voxels, so both orders are the same function
+    in exact arithmetic; it only matters to the bf16-storage mode, which must round where the device graph (zoo.ConvU) stores."""
     if not first:
-        x = F.relu(_norm(sd, pfx + ".bn1", _conv(sd, pfx + ".conv1", x, 1, 1), norm, training))  # :71
-    y = F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=False)       # :73
-    y = F.relu(_norm(sd, pfx + ".bn2", _conv(sd, pfx + ".conv2", y, 1, 0), norm, training))     # :74
-    y = torch.cat([prev, y], 1)                                                        # :76
-    return F.relu(_norm(sd, pfx + ".bn3", _conv(sd, pfx + ".conv3", y, 1, 1), norm, training))  # :77
+        x = _q(F.relu(_norm(sd, pfx + ".bn1", _conv(sd, pfx + ".conv1", x, 1, 1), norm, training)))  # :71
+    if commute_up:
+        y = _q(_up2(_conv(sd, pfx + ".conv2", x, 1, 0)))
+    else:
+        y = _conv(sd, pfx + ".conv2", _q(_up2(x)), 1, 0)                                   # :73
+    y = _q(F.relu(_norm(sd, pfx + ".bn2", y, norm, training)))                             # :74
+    y = torch.cat([_gq(prev), _gq(y)], 1)                                                  # :76
+    return _q(F.relu(_norm(sd, pfx + ".bn3", _conv(sd, pfx + ".conv3", y, 1, 1), norm, training)))  # :77
 
 
-def unet3d(sd, x, norm="bn", dropout=0.5, training=False):
+def unet3d(sd, x, norm="bn", dropout=0.5, training=False, commute_up=False):
     """unet3d.py:110-126 Unet.forward.  `self.upsample` (:85, broken as written) is the
     upstream BraTS2017 nn.Upsample(scale_factor=2, trilinear, align_corners=False)."""
-    up = lambda t: F.interpolate(t, scale_factor=2, mode="trilinear", align_corners=False)
+    up = lambda t: F.interpolate(t, scale_factor=2, mode="trilinear", align_corners=False)    # fp32 heads: never stored as bf16
     x1 = _convd(sd, "convd1", x, True, norm, dropout, training)
     x2 = _convd(sd, "convd2", x1, False, norm, dropout, training)
     x3 = _convd(sd, "convd3", x2, False, norm, dropout, training)
     x4 = _convd(sd, "convd4", x3, False, norm, dropout, training)
     x5 = _convd(sd, "convd5", x4, False, norm, dropout, training)
-    y4 = _convu(sd, "convu4", x5, x4, True, norm, training)
-    y3 = _convu(sd, "convu3", y4, x3, False, norm, training)
-    y2 = _convu(sd, "convu2", y3, x2, False, norm, training)
-    y1 = _convu(sd, "convu1", y2, x1, False, norm, training)
-    s3 = _conv(sd, "seg3", y3)                                           # :122
-    s2 = _conv(sd, "seg2", y2) + up(s3)                                  # :123
-    return _conv(sd, "seg1", y1) + up(s2)                                # :124
+    y4 = _convu(sd, "convu4", x5, x4, True, norm, training, commute_up)
+    y3 = _convu(sd, "convu3", y4, x3, False, norm, training, commute_up)
+    y2 = _convu(sd, "convu2", y3, x2, False, norm, training, commute_up)
+    y1 = _convu(sd, "convu1", y2, x1, False, norm, training, commute_up)
+    s3 = _conv(sd, "seg3", y3, store=False)                              # :122
+    s2 = _conv(sd, "seg2", y2, store=False) + up(s3)                     # :123
+    return _conv(sd, "seg1", y1, store=False) + up(s2)                   # :124
 
 
 # ------------------------------------------- third-party unet.UNet (a-2, restated)

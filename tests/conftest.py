@@ -44,3 +44,35 @@ def rel_err(a, b):
     a = torch.as_tensor(np.asarray(a)).double() if not hasattr(a, "double") else a.detach().cpu().double()
     b = torch.as_tensor(np.asarray(b)).double() if not hasattr(b, "double") else b.detach().cpu().double()
     return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def tensor_core_convs(net, x):
+    """Names of the convolution modules of `net` whose forward, on input `x`, runs on the tcgen05 kernels -- i.e. the layers that
+    consume a bf16 copy of their weight (the oracle's bf16-storage mode rounds exactly those weights).  One eval-mode dry run with
+    forward pre-hooks (eval: every convolution goes through its own module, nothing is updated); asks the library
+    (b200_conv_algo), does not guess from the channel counts."""
+    import ctypes
+    import torch
+    from mri_epilepsy_diagnosis_b200 import _cabi as cabi
+    from mri_epilepsy_diagnosis_b200.nn import _ConvMixin
+    found, hooks = set(), []
+
+    def make(name):
+        def pre(mod, args):
+            xx = mod._prep(args[0])
+            cd, _ = mod._cfg().desc(xx, mod.weight, mod.out_dtype or xx.dtype)
+            fwd = cabi.lib().b200_conv_algo(ctypes.byref(cd), cabi.PASS_FWD)
+            if fwd != cabi.ALGO_SIMT:
+                found.add(name)
+        return pre
+    for name, m in net.named_modules():
+        if isinstance(m, _ConvMixin):
+            hooks.append(m.register_forward_pre_hook(make(name)))
+    was = net.training
+    net.eval()
+    with torch.no_grad():
+        net(x)
+    net.train(was)
+    for h in hooks:
+        h.remove()
+    return found
