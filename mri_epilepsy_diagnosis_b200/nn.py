@@ -281,6 +281,29 @@ functional_proxy = _FunctionalProxy("mri_epilepsy_diagnosis_b200.functional_prox
 
 
 # --------------------------------------------------------------------------- convert / patch
+def _leave_body_hook(module, args):
+    """Forward pre-hook for modules that are NOT ours but receive the convolutional body's output (Linear, Flatten -- incl.
+    user-defined ones doing `input.view(N, -1)`, cnn_model.py:8-10 -- and BatchNorm1d): hand them what stock PyTorch would have
+    produced, a contiguous (logical NCDHW order) fp32 tensor instead of a channels-last bf16 one."""
+    out = []
+    for a in args:
+        if isinstance(a, torch.Tensor) and a.is_cuda and a.is_floating_point():
+            if a.dim() in (4, 5) and not a.is_contiguous():
+                a = a.contiguous()
+            if a.dtype == torch.bfloat16:
+                a = a.float()
+        out.append(a)
+    return tuple(out)
+
+
+def _is_foreign_sink(m):
+    if isinstance(m, _B200Mixin) or next(m.children(), None) is not None:
+        return False
+    if isinstance(m, (tnn.Linear, tnn.Flatten, tnn.BatchNorm1d)):
+        return True
+    return not type(m).__module__.startswith(("torch.", "mri_epilepsy_diagnosis_b200"))      # user-defined leaf (e.g. a Flatten)
+
+
 def convert(model, dtype=torch.bfloat16, allow_umma=True, fp32_heads=True, sync=None, rebind_functional=True):
     """Re-class every torch.nn operator instance of `model` in place (parameters, buffers and hooks untouched).
 
@@ -305,6 +328,9 @@ def convert(model, dtype=torch.bfloat16, allow_umma=True, fp32_heads=True, sync=
             if isinstance(m, _ConvMixin):
                 co = m.out_channels
                 m.out_dtype = torch.float32 if (fp32_heads and co <= 4) else None
+        if _is_foreign_sink(m) and not getattr(m, "_b200_sink_hook", False):
+            m.register_forward_pre_hook(_leave_body_hook)
+            m._b200_sink_hook = True
         if rebind_functional:
             ns = sys.modules.get(type(m).__module__)
             if ns is not None and not type(m).__module__.startswith(("torch.", "mri_epilepsy_diagnosis_b200")):

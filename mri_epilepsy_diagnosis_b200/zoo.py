@@ -451,3 +451,214 @@ def fader_encoder():
 
 def config1_autoencoder(depth=6, c_base=16):
     return AE(c_in=1, is_skip=False, deapth=depth, c_base=c_base, inc_size=2, reduce_size=False, down_block_kwargs=AE_DOWN, up_block_kwargs=AE_UP)
+
+
+# ------------------------------------------------------------------ fused execution of nn.Sequential chains
+def _act_code(m):
+    if isinstance(m, tnn.LeakyReLU):
+        return cabi.ACT_LEAKY if abs(m.negative_slope - 0.01) < 1e-12 else None
+    return cabi.ACT_RELU if isinstance(m, tnn.ReLU) else None
+
+
+_NORMS = (bnn.BatchNorm3d, bnn.BatchNorm2d, bnn.InstanceNorm3d, bnn.GroupNorm)
+
+
+def run_fused(layers, x):
+    """Execute a chain of drop-in modules with the kernel-level fusions the library offers, WITHOUT changing the function:
+    conv -> BatchNorm (training) takes the statistics from the conv epilogue, norm -> ReLU/LeakyReLU(0.01) is one apply pass.
+    Modules that are not ours (Linear, Dropout, Flatten, ...) are called as they are, on a contiguous fp32 tensor once the
+    data leaves the convolutional body."""
+    layers = list(layers)
+    i = 0
+    while i < len(layers):
+        m = layers[i]
+        nxt = layers[i + 1] if i + 1 < len(layers) else None
+        nxt2 = layers[i + 2] if i + 2 < len(layers) else None
+        if isinstance(m, bnn._ConvMixin) and isinstance(nxt, _NORMS):
+            act = _act_code(nxt2)
+            x = _conv_norm(m, nxt, x, act=cabi.ACT_NONE if act is None else act)
+            i += 2 if act is None else 3
+        elif isinstance(m, _NORMS) and _act_code(nxt) is not None:
+            x = m(x, act=_act_code(nxt))
+            i += 2
+        elif isinstance(m, (tnn.Linear, tnn.Flatten, tnn.BatchNorm1d)) and x.dim() > 2:
+            x = m(x.float().contiguous())       # logical NCDHW order, as the reference's `view(N, -1)` expects
+            i += 1
+        else:
+            x = m(x)
+            i += 1
+    return x
+
+
+# ------------------------------------------------------------------ segmentation/models/modified_3dunet.py
+class Modified3DUNet(tnn.Module):
+    """segmentation/models/modified_3dunet.py:4-189 (Isensee-style U-Net: stride-2 context convolutions, InstanceNorm,
+    LeakyReLU, nearest x2 localisation path, two deep-supervision heads).  Same constructor, attribute names and state_dict
+    keys; the forward is the reference's operator sequence with norm+LeakyReLU pairs executed as one pass."""
+
+    def __init__(self, in_channels, n_classes, base_n_filter=8):
+        super().__init__()
+        self.in_channels, self.n_classes, self.base_n_filter = in_channels, n_classes, base_n_filter
+        f = base_n_filter
+        c3 = lambda ci, co, s=1: bnn.Conv3d(ci, co, kernel_size=3, stride=s, padding=1, bias=False)
+        c1 = lambda ci, co: bnn.Conv3d(ci, co, kernel_size=1, stride=1, padding=0, bias=False)
+        self.lrelu = bnn.LeakyReLU()
+        self.dropout3d = tnn.Dropout3d(p=0.6)
+        self.upsacle = bnn.Upsample(scale_factor=2, mode="nearest")          # (sic) attribute name of the reference
+        self.softmax = tnn.Softmax(dim=1)
+        # context pathway, level 1 (:17-20)
+        self.conv3d_c1_1, self.conv3d_c1_2 = c3(in_channels, f), c3(f, f)
+        self.lrelu_conv_c1 = tnn.Sequential(bnn.LeakyReLU(), c3(f, f))
+        self.inorm3d_c1 = bnn.InstanceNorm3d(f)
+        # context pathway, levels 2..5 (:23-40): stride-2 conv, a (norm, lrelu, conv) block applied twice, a norm
+        for lvl in range(2, 6):
+            w = f * 2 ** (lvl - 1)
+            setattr(self, f"conv3d_c{lvl}", c3(w // 2, w, 2))
+            setattr(self, f"norm_lrelu_conv_c{lvl}", tnn.Sequential(bnn.InstanceNorm3d(w), bnn.LeakyReLU(), c3(w, w)))
+            if lvl < 5:
+                setattr(self, f"inorm3d_c{lvl}", bnn.InstanceNorm3d(w))
+        up = lambda ci, co: tnn.Sequential(bnn.InstanceNorm3d(ci), bnn.LeakyReLU(), bnn.Upsample(scale_factor=2, mode="nearest"), c3(ci, co),
+                                           bnn.InstanceNorm3d(co), bnn.LeakyReLU())
+        cnl = lambda ci, co: tnn.Sequential(c3(ci, co), bnn.InstanceNorm3d(co), bnn.LeakyReLU())
+        self.norm_lrelu_upscale_conv_norm_lrelu_l0 = up(16 * f, 8 * f)                    # :41
+        self.conv3d_l0, self.inorm3d_l0 = c1(8 * f, 8 * f), bnn.InstanceNorm3d(8 * f)     # :43-44
+        for lvl, w in ((1, 16 * f), (2, 8 * f), (3, 4 * f)):                             # :47-59
+            setattr(self, f"conv_norm_lrelu_l{lvl}", cnl(w, w))
+            setattr(self, f"conv3d_l{lvl}", c1(w, w // 2))
+            setattr(self, f"norm_lrelu_upscale_conv_norm_lrelu_l{lvl}", up(w // 2, w // 4))
+        self.conv_norm_lrelu_l4 = cnl(2 * f, 2 * f)                                       # :62
+        self.conv3d_l4 = c1(2 * f, n_classes)
+        self.ds2_1x1_conv3d, self.ds3_1x1_conv3d = c1(8 * f, n_classes), c1(4 * f, n_classes)
+
+    def forward(self, x):
+        out = self.conv3d_c1_1(x)                                                         # :103-112
+        res = out
+        out = self.conv3d_c1_2(self.lrelu(out))
+        out = run_fused(self.lrelu_conv_c1, self.dropout3d(out))
+        out = out + res
+        context = [self.lrelu(out)]
+        out = self.inorm3d_c1(out, act=cabi.ACT_LEAKY)
+        for lvl in range(2, 6):                                                           # :115-157
+            out = getattr(self, f"conv3d_c{lvl}")(out)
+            res = out
+            block = getattr(self, f"norm_lrelu_conv_c{lvl}")
+            out = run_fused(block, self.dropout3d(run_fused(block, out)))
+            out = out + res
+            if lvl < 5:
+                out = getattr(self, f"inorm3d_c{lvl}")(out, act=cabi.ACT_LEAKY)
+                context.append(out)
+        out = run_fused(self.norm_lrelu_upscale_conv_norm_lrelu_l0, out)                  # :158
+        out = self.inorm3d_l0(self.conv3d_l0(out), act=cabi.ACT_LEAKY)                    # :160-162
+        ds = {}
+        for lvl in (1, 2, 3):                                                             # :165-183
+            out = run_fused(getattr(self, f"conv_norm_lrelu_l{lvl}"), BF.concat(out, context[4 - lvl]))
+            ds[lvl] = out
+            out = run_fused(getattr(self, f"norm_lrelu_upscale_conv_norm_lrelu_l{lvl}"), getattr(self, f"conv3d_l{lvl}")(out))
+        out = run_fused(self.conv_norm_lrelu_l4, BF.concat(out, context[0]))              # :186-188
+        pred = self.conv3d_l4(out)
+        s = self.upsacle(self.ds2_1x1_conv3d(ds[2])) + self.ds3_1x1_conv3d(ds[3])         # :190-194
+        return pred + self.upsacle(s)                                                     # :196
+
+
+# ------------------------------------------------------------------ classification/models/cnn_model.py
+class BasicBlock(tnn.Module):
+    """cnn_model.py:17-40: relu(bn2(conv2(relu(bn1(conv1(x))))) + x); the residual add and the final ReLU ride in bn2's apply pass."""
+
+    def __init__(self, inplanes, planes, stride=1):
+        super().__init__()
+        self.conv1 = bnn.Conv3d(inplanes, planes, kernel_size=3, stride=stride, padding=1, bias=False)
+        self.bn1 = bnn.BatchNorm3d(planes)
+        self.relu = bnn.ReLU(inplace=True)
+        self.conv2 = bnn.Conv3d(planes, planes, kernel_size=3, stride=1, padding=1, bias=False)
+        self.bn2 = bnn.BatchNorm3d(planes)
+        self.stride = stride
+
+    def forward(self, x):
+        out = _conv_norm(self.conv1, self.bn1, x, act=cabi.ACT_RELU)
+        return _conv_norm(self.conv2, self.bn2, out, act=cabi.ACT_RELU, residual=x)
+
+
+class _SequentialModel(tnn.Module):
+    def forward(self, x):
+        return run_fused(self.model.children(), x)
+
+
+class VoxResNet(_SequentialModel):
+    """cnn_model.py:43-101.  The reference adds `activation_6` twice (:85 inside the n_blocks >= 4 stage and :95 after
+    fully_conn_1); nn.Sequential.add_module keeps the FIRST position of a repeated name, so with n_blocks=4 there is no ReLU
+    after fully_conn_1 -- reproduced here by issuing the same add_module sequence."""
+
+    def __init__(self, input_shape=(128, 128, 128), num_classes=2, n_filters=32, stride=2, n_blocks=3, n_flatten_units=None, dropout=0, n_fc_units=128):
+        super().__init__()
+        n = n_filters
+        seq = self.model = tnn.Sequential()
+        add = seq.add_module
+        add("conv3d_1", bnn.Conv3d(1, n, kernel_size=3, padding=1, stride=stride))
+        add("batch_norm_1", bnn.BatchNorm3d(n)); add("activation_1", bnn.ReLU(inplace=True))
+        add("conv3d_2", bnn.Conv3d(n, n, kernel_size=3, padding=1))
+        add("batch_norm_2", bnn.BatchNorm3d(n)); add("activation_2", bnn.ReLU(inplace=True))
+        widths = [(n, 2 * n), (2 * n, 2 * n), (2 * n, 4 * n), (4 * n, 4 * n)]
+        for stage in range(1, 5):
+            if stage > 1 and n_blocks < stage:
+                break
+            ci, co = widths[stage - 1]
+            add(f"conv3d_{stage + 2}", bnn.Conv3d(ci, co, kernel_size=3, padding=1, stride=2))
+            add(f"block_{2 * stage - 1}", BasicBlock(co, co)); add(f"block_{2 * stage}", BasicBlock(co, co))
+            add(f"batch_norm_{stage + 2}", bnn.BatchNorm3d(co)); add(f"activation_{stage + 2}", bnn.ReLU(inplace=True))
+        if n_flatten_units is None:
+            import numpy as np
+            n_flatten_units = int(4 * n * np.prod(np.array(input_shape) // (2 ** n_blocks * stride)))
+        add("flatten_1", tnn.Flatten())
+        add("fully_conn_1", tnn.Linear(n_flatten_units, n_fc_units))
+        add("activation_6", tnn.ReLU(inplace=True))
+        add("dropout_1", tnn.Dropout(dropout))
+        add("fully_conn_2", tnn.Linear(n_fc_units, num_classes))
+
+
+class CNN(_SequentialModel):
+    """cnn_model.py:104-175: n_blocks x [conv-bn-relu, conv-bn-relu, MaxPool3d(2)], Flatten, Linear, BatchNorm1d, ReLU."""
+
+    def __init__(self, input_shape=(64, 76, 48), n_filters=16, n_blocks=3, stride=1, n_fc_units=128):
+        super().__init__()
+        seq = self.model = tnn.Sequential()
+        cin, idx = 1, 1
+        for b in range(n_blocks):
+            co = n_filters * 2 ** b
+            for j in range(2):
+                seq.add_module(f"conv3d_{idx}", bnn.Conv3d(cin, co, kernel_size=3, stride=stride if idx == 1 else 1, padding=1))
+                seq.add_module(f"batch_norm_{idx}", bnn.BatchNorm3d(co))
+                seq.add_module(f"activation_{idx}", bnn.ReLU(inplace=True))
+                cin, idx = co, idx + 1
+            seq.add_module(f"max_pool3d_{b + 1}", bnn.MaxPool3d(kernel_size=2))
+        seq.add_module("flatten_1", tnn.Flatten())
+        div = 2 ** n_blocks * stride
+        seq.add_module("fully_conn_1", tnn.Linear(cin * (input_shape[0] // div) * (input_shape[1] // div) * (input_shape[2] // div), n_fc_units))
+        seq.add_module("batch_norm_9", tnn.BatchNorm1d(n_fc_units))
+        seq.add_module("activation_9", tnn.ReLU(inplace=True))
+
+
+class DilatedCNN(_SequentialModel):
+    """cnn_model.py:207-257: dilation-3 convolutions (stride 2 / no padding and stride 1 / padding 3), MaxPool3d(4, 2)."""
+
+    def __init__(self, input_shape=(180, 180, 180), n_channels=32):
+        super().__init__()
+        c = n_channels
+        seq = self.model = tnn.Sequential()
+        #        (cin, cout, stride, padding, pool after)
+        spec = [(1, c, 2, 0, False), (c, c, 1, 3, True), (c, 2 * c, 2, 0, False), (2 * c, 2 * c, 1, 3, True), (2 * c, 4 * c, 1, 3, False),
+                (4 * c, 4 * c, 1, 0, False)]
+        pools = 0
+        for i, (ci, co, s, p, pool) in enumerate(spec, 1):
+            seq.add_module(f"conv3d_{i}", bnn.Conv3d(ci, co, kernel_size=3, stride=s, dilation=3, padding=p))
+            seq.add_module(f"batch_norm_{i}", bnn.BatchNorm3d(co))
+            seq.add_module(f"activation_{i}", bnn.LeakyReLU())
+            if pool:
+                pools += 1
+                seq.add_module(f"max_pool3d_{pools}", bnn.MaxPool3d(kernel_size=4, stride=2))
+        seq.add_module("flatten_1", tnn.Flatten())
+        seq.add_module("fully_conn_1", tnn.Linear(4 * c * ((input_shape[0] - 61) // 16 - 5) ** 3, 256))
+        seq.add_module("activation_7", tnn.LeakyReLU())
+        seq.add_module("fully_conn_2", tnn.Linear(256, 128))
+        seq.add_module("activation_8", tnn.LeakyReLU())
+        seq.add_module("fully_conn_3", tnn.Linear(128, 2))
+        seq.add_module("softmax", tnn.Softmax(dim=-1))

@@ -52,6 +52,28 @@ def _r(t):
     return t.to(torch.bfloat16).to(t.dtype)
 
 
+# optional recording of every stored intermediate (diagnostics: tools/parity_report.py compares them layer by layer)
+_TAPS = None
+
+
+class record_taps:
+    def __enter__(self):
+        global _TAPS
+        self.prev, _TAPS = _TAPS, {}
+        return _TAPS
+
+    def __exit__(self, *exc):
+        global _TAPS
+        _TAPS = self.prev
+        return False
+
+
+def _tap(name, t):
+    if _TAPS is not None:
+        _TAPS[name] = t.detach()
+    return t
+
+
 class _StoreFn(torch.autograd.Function):
     """value stored as bf16 (forward) / its gradient stored as bf16 (backward)"""
 
@@ -109,7 +131,7 @@ def _norm(sd, pfx, x, kind, training):
 def _conv(sd, pfx, x, stride=1, padding=0, dilation=1, store=True):
     """store=False: the layer emits fp32 (the <= 4-channel segmentation heads)"""
     y = F.conv3d(_gq(x), _wq(pfx, sd[pfx + ".weight"]), sd.get(pfx + ".bias"), stride, padding, dilation)
-    return _q(y) if store else y
+    return _tap(pfx, _q(y) if store else y)
 
 
 # ----------------------------------------------------------------- unet3d.Unet (a-1)
@@ -118,13 +140,13 @@ def _convd(sd, pfx, x, first, norm, dropout, training):
     whose only effects are BN running-stat updates and RNG consumption."""
     if not first:
         x = F.max_pool3d(x, 2, 2)                                       # :41
-    x = _q(_norm(sd, pfx + ".bn1", _conv(sd, pfx + ".conv1", x, 1, 1), norm, training))   # :42
+    x = _tap(pfx + ".bn1", _q(_norm(sd, pfx + ".bn1", _conv(sd, pfx + ".conv1", x, 1, 1), norm, training)))   # :42
     dead = F.relu(_norm(sd, pfx + ".bn2", _conv(sd, pfx + ".conv2", x, 1, 1), norm, training))  # :43
     if dropout > 0:
         dead = F.dropout3d(dead, dropout)                               # :44-45 (always "training")
     del dead
     y = _norm(sd, pfx + ".bn3", _conv(sd, pfx + ".conv3", x, 1, 1), norm, training)   # :46
-    return _q(F.relu(_gq(x) + y))                                       # :47
+    return _tap(pfx + ".bn3", _q(F.relu(_gq(x) + y)))                   # :47
 
 
 def _up2(t):
@@ -136,14 +158,14 @@ def _convu(sd, pfx, x, prev, first, norm, training, commute_up=False):
     conv2 is 1x1x1 and the interpolation is a per-channel convex combination of voxels, so both orders are the same function
     in exact arithmetic; it only matters to the bf16-storage mode, which must round where the device graph (zoo.ConvU) stores."""
     if not first:
-        x = _q(F.relu(_norm(sd, pfx + ".bn1", _conv(sd, pfx + ".conv1", x, 1, 1), norm, training)))  # :71
+        x = _tap(pfx + ".bn1", _q(F.relu(_norm(sd, pfx + ".bn1", _conv(sd, pfx + ".conv1", x, 1, 1), norm, training))))  # :71
     if commute_up:
         y = _q(_up2(_conv(sd, pfx + ".conv2", x, 1, 0)))
     else:
         y = _conv(sd, pfx + ".conv2", _q(_up2(x)), 1, 0)                                   # :73
-    y = _q(F.relu(_norm(sd, pfx + ".bn2", y, norm, training)))                             # :74
+    y = _tap(pfx + ".bn2", _q(F.relu(_norm(sd, pfx + ".bn2", y, norm, training))))         # :74
     y = torch.cat([_gq(prev), _gq(y)], 1)                                                  # :76
-    return _q(F.relu(_norm(sd, pfx + ".bn3", _conv(sd, pfx + ".conv3", y, 1, 1), norm, training)))  # :77
+    return _tap(pfx + ".bn3", _q(F.relu(_norm(sd, pfx + ".bn3", _conv(sd, pfx + ".conv3", y, 1, 1), norm, training))))  # :77
 
 
 def unet3d(sd, x, norm="bn", dropout=0.5, training=False, commute_up=False):
@@ -286,6 +308,109 @@ def patch_model(sd, x, training=False):
     x = F.dropout(x, 0.4, training)
     x = torch.relu(F.linear(x, sd["fc1.weight"], sd["fc1.bias"]))
     return F.linear(x, sd["fc2.weight"], sd["fc2.bias"])
+
+
+# ------------------------------------- segmentation/models/modified_3dunet.py (a-1 family)
+def _in_lrelu(x):
+    return _q(F.leaky_relu(F.instance_norm(_gq(x), eps=BN_EPS), 0.01))
+
+
+def modified_3dunet(sd, x, training=False, p_drop=0.6):
+    """modified_3dunet.py:101-196 Modified3DUNet.forward.  nn.InstanceNorm3d(affine=False) and nn.LeakyReLU() defaults;
+    every conv is bias-free; `self.dropout3d` (p=0.6) acts only in training mode."""
+    c = lambda pfx, t, stride=1, pad=1, store=True: _conv(sd, pfx, t, stride, pad, 1, store)
+    drop = lambda t: F.dropout3d(t, p_drop, True) if (training and p_drop > 0) else t
+    up = lambda t: _q(F.interpolate(_gq(t), scale_factor=2, mode="nearest"))
+    out = c("conv3d_c1_1", x)                                                 # :103
+    res = out
+    out = c("conv3d_c1_2", _q(F.leaky_relu(_gq(out), 0.01)))                  # :105-106
+    out = c("lrelu_conv_c1.1", _q(F.leaky_relu(_gq(drop(out)), 0.01)))        # :107-108
+    out = _q(_gq(out) + _gq(res))                                             # :110
+    ctx = [_q(F.leaky_relu(_gq(out), 0.01))]                                  # :111
+    out = _in_lrelu(out)                                                      # :112-113
+    for lvl in range(2, 6):                                                   # :116-157
+        out = c(f"conv3d_c{lvl}", out, 2)
+        res = out
+        blk = f"norm_lrelu_conv_c{lvl}.2"
+        out = c(blk, _in_lrelu(out))
+        out = c(blk, _in_lrelu(drop(out)))
+        out = _q(_gq(out) + _gq(res))
+        if lvl < 5:
+            out = _in_lrelu(out)
+            ctx.append(out)
+
+    def up_block(pfx, t):                                                     # norm, lrelu, nearest x2, conv, norm, lrelu (:91-99)
+        return _in_lrelu(c(pfx + ".3", up(_in_lrelu(t))))
+    out = up_block("norm_lrelu_upscale_conv_norm_lrelu_l0", out)              # :158
+    out = _in_lrelu(c("conv3d_l0", out, 1, 0))                                # :160-162
+    ds = {}
+    for lvl in (1, 2, 3):                                                     # :165-183
+        out = _in_lrelu(c(f"conv_norm_lrelu_l{lvl}.0", torch.cat([_gq(out), _gq(ctx[4 - lvl])], 1)))
+        ds[lvl] = out
+        out = up_block(f"norm_lrelu_upscale_conv_norm_lrelu_l{lvl}", c(f"conv3d_l{lvl}", out, 1, 0))
+    out = _in_lrelu(c("conv_norm_lrelu_l4.0", torch.cat([_gq(out), _gq(ctx[0])], 1)))      # :186-187
+    pred = c("conv3d_l4", out, 1, 0, store=False)                             # :188
+    up32 = lambda t: F.interpolate(t, scale_factor=2, mode="nearest")         # fp32 heads
+    s = up32(c("ds2_1x1_conv3d", ds[2], 1, 0, store=False)) + c("ds3_1x1_conv3d", ds[3], 1, 0, store=False)   # :190-194
+    return pred + up32(s)                                                     # :196
+
+
+# ------------------------------------------- classification/models/cnn_model.py (a-5)
+def _cbr(sd, conv, bn, x, training, stride=1, padding=1, dilation=1, act="relu", residual=None):
+    y = _bn(sd, bn, _gq(_conv(sd, conv, x, stride, padding, dilation)), training)
+    if residual is not None:
+        y = y + _gq(residual)
+    return _q(F.leaky_relu(y, 0.01) if act == "l_relu" else F.relu(y) if act == "relu" else y)
+
+
+def _basic_block(sd, pfx, x, training):
+    """cnn_model.py:27-40"""
+    out = _cbr(sd, pfx + ".conv1", pfx + ".bn1", x, training)
+    return _cbr(sd, pfx + ".conv2", pfx + ".bn2", out, training, residual=x)
+
+
+def voxresnet(sd, x, n_blocks=3, stride=2, training=False, dropout=0.0):
+    """cnn_model.py:43-101 VoxResNet.forward = the nn.Sequential in registration order.  `activation_6` is registered twice
+    (:85, :95): for n_blocks >= 4 the name keeps its first position, so NO ReLU follows fully_conn_1 in that case."""
+    m = "model."
+    x = _cbr(sd, m + "conv3d_1", m + "batch_norm_1", x, training, stride)
+    x = _cbr(sd, m + "conv3d_2", m + "batch_norm_2", x, training)
+    for stage in range(1, min(n_blocks, 4) + 1 if n_blocks >= 1 else 2):
+        x = _conv(sd, f"{m}conv3d_{stage + 2}", x, 2, 1)
+        x = _basic_block(sd, f"{m}block_{2 * stage - 1}", x, training)
+        x = _basic_block(sd, f"{m}block_{2 * stage}", x, training)
+        x = _q(F.relu(_bn(sd, f"{m}batch_norm_{stage + 2}", _gq(x), training)))
+    x = F.linear(x.flatten(1), sd[m + "fully_conn_1.weight"], sd[m + "fully_conn_1.bias"])
+    if n_blocks < 4:
+        x = F.relu(x)
+    x = F.dropout(x, dropout, training)
+    return F.linear(x, sd[m + "fully_conn_2.weight"], sd[m + "fully_conn_2.bias"])
+
+
+def cnn(sd, x, n_blocks=3, stride=1, training=False):
+    """cnn_model.py:104-175 CNN.forward."""
+    m, idx = "model.", 1
+    for b in range(n_blocks):
+        for _ in range(2):
+            x = _cbr(sd, f"{m}conv3d_{idx}", f"{m}batch_norm_{idx}", x, training, stride if idx == 1 else 1)
+            idx += 1
+        x = F.max_pool3d(x, 2)
+    x = F.linear(x.flatten(1), sd[m + "fully_conn_1.weight"], sd[m + "fully_conn_1.bias"])
+    return F.relu(_bn(sd, m + "batch_norm_9", x, training))
+
+
+def dilated_cnn(sd, x, training=False):
+    """cnn_model.py:207-257 DilatedCNN.forward (dilation 3 everywhere; softmax output)."""
+    m = "model."
+    spec = [(2, 0, False), (1, 3, True), (2, 0, False), (1, 3, True), (1, 3, False), (1, 0, False)]
+    for i, (s, p, pool) in enumerate(spec, 1):
+        x = _cbr(sd, f"{m}conv3d_{i}", f"{m}batch_norm_{i}", x, training, s, p, 3, act="l_relu")
+        if pool:
+            x = F.max_pool3d(x, 4, 2)
+    x = x.flatten(1)
+    for j in (1, 2):
+        x = F.leaky_relu(F.linear(x, sd[f"{m}fully_conn_{j}.weight"], sd[f"{m}fully_conn_{j}.bias"]), 0.01)
+    return F.softmax(F.linear(x, sd[m + "fully_conn_3.weight"], sd[m + "fully_conn_3.bias"]), dim=-1)
 
 
 # ------------------------------------------------------- losses on the device path

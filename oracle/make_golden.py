@@ -166,6 +166,67 @@ def fader_cases():
          **{"grad:" + k: v for k, v in grads_of(clf).items()})
 
 
+def _all_grads(net, cap=4096):
+    return {"grad:" + k: thin(p.grad, cap) for k, p in net.named_parameters() if p.grad is not None}
+
+
+def modified_unet_cases():
+    """segmentation/models/modified_3dunet.py through the REAL class: eval, and one training step's gradients with the
+    Dropout3d probability set to 0 on the instance (the CUDA path cannot replay the CPU RNG stream; source untouched)."""
+    mod = refload.modified_unet_module()
+    torch.manual_seed(0)
+    net = mod.Modified3DUNet(1, 2, 8)
+    sd = weights.seeded_like(net.state_dict(), seed=31)
+    net.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(32)
+    x = torch.randn(2, 1, 32, 32, 32, generator=g)
+    t = (torch.rand(2, 1, 32, 32, 32, generator=g) > 0.5).float()
+    net.eval()
+    with torch.no_grad():
+        ev = net(x)
+    assert torch.equal(graphs.modified_3dunet(sd, x), ev), "oracle modified_3dunet != reference (eval)"
+    net.train()
+    net.dropout3d.p = 0.0
+    logits = net(x)
+    loss = refload.seg_routine_module().get_dice_loss(torch.softmax(logits, dim=1), t).mean()
+    loss.backward()
+    save("modified3dunet", keys=np.array(list(sd.keys())), eval_logits=ev, train_logits=logits.detach(), loss=loss.detach(),
+         argmax_sha=np.array(sha16(ev.argmax(1).numpy().astype(np.uint8))), **_all_grads(net))
+
+
+def cnn_model_cases():
+    """classification/models/cnn_model.py (VoxResNet incl. the n_blocks=4 `activation_6` quirk, CNN, DilatedCNN) through the
+    REAL classes: eval probabilities/logits, train-mode logits, CrossEntropy gradients and BatchNorm running statistics."""
+    mod = refload.cnn_module()
+    cases = {
+        "voxresnet_b3": (lambda: mod.VoxResNet((32, 32, 32), 2, 16, 2, 3), (3, 1, 32, 32, 32), lambda sd, x, tr: graphs.voxresnet(sd, x, 3, 2, tr)),
+        "voxresnet_b4": (lambda: mod.VoxResNet((32, 32, 32), 2, 8, 1, 4), (2, 1, 32, 32, 32), lambda sd, x, tr: graphs.voxresnet(sd, x, 4, 1, tr)),
+        "cnn_b3": (lambda: mod.CNN((32, 40, 24), 16, 3), (4, 1, 32, 40, 24), lambda sd, x, tr: graphs.cnn(sd, x, 3, 1, tr)),
+        "dilated_cnn": (lambda: mod.DilatedCNN((180, 180, 180), 16), (2, 1, 180, 180, 180), lambda sd, x, tr: graphs.dilated_cnn(sd, x, tr)),
+    }
+    for i, (name, (ctor, shape, oracle)) in enumerate(cases.items()):
+        torch.manual_seed(0)
+        net = ctor()
+        sd = weights.seeded_like(net.state_dict(), seed=40 + i)
+        net.load_state_dict(sd, strict=True)
+        g = torch.Generator().manual_seed(50 + i)
+        x = torch.randn(*shape, generator=g)
+        y = torch.arange(shape[0]) % 2
+        net.eval()
+        with torch.no_grad():
+            ev = net(x)
+        assert torch.equal(oracle({k: v.clone() for k, v in sd.items()}, x, False), ev), f"oracle {name} != reference (eval)"
+        net.train()
+        tr = net(x)
+        assert torch.equal(oracle({k: v.clone() for k, v in sd.items()}, x, True), tr.detach()), f"oracle {name} != reference (train)"
+        loss = (torch.nn.NLLLoss()(torch.log(tr), y) if name == "dilated_cnn" else torch.nn.CrossEntropyLoss()(tr, y))
+        loss.backward()
+        bn_keys = [k for k in net.state_dict() if k.endswith("running_mean") or k.endswith("running_var")]
+        first_bn, last_bn = bn_keys[0], bn_keys[-1]
+        save(name, keys=np.array(list(sd.keys())), eval_out=ev, train_out=tr.detach(), loss=loss.detach(),
+             **{"buf:" + k: net.state_dict()[k] for k in (first_bn, last_bn)}, **_all_grads(net))
+
+
 def patch_cases():
     pu = refload.patch_utils_module()
     gm = patches.read_nifti1_f32(refload.path("detection/MNI152_T1_1mm_brain_gray.nii.gz")).astype(np.float64)
@@ -207,6 +268,31 @@ def patch_cases():
     gr = grads_of(net)
     save("patch_model", eval_logits=ev, train_logits=tr.detach(), loss=loss.detach(),
          **{"grad:" + k: gr[k] for k in ("conv_blocks.0.conv.weight", "conv_blocks.4.conv.weight", "conv_blocks.2.bn.weight", "fc2.weight")})
+
+
+def patch_model_nodrop_case():
+    """PatchModel in TRAIN mode with the Dropout probability set to 0 on the instance (a GPU run cannot replay the CPU mask):
+    logits, CrossEntropy loss, every parameter gradient and the BatchNorm running statistics, on 96 real patches."""
+    pu = refload.patch_utils_module()
+    gm = patches.read_nifti1_f32(refload.path("detection/MNI152_T1_1mm_brain_gray.nii.gz")).astype(np.float64)
+    img = np.random.default_rng(0).random((182, 218, 182))
+    plan = patches.patch_plan(gm, None, 16, 32)[:96]
+    xb = torch.from_numpy(patches.gather_patches(img, plan)).float()
+    PatchModel, _ = refload.patch_model_classes()
+    torch.manual_seed(0)
+    net = PatchModel()
+    net.load_state_dict(weights.patch_model_state(seed=9), strict=True)
+    net.train()
+    net.dropout.p = 0.0
+    tr = net(xb)
+    loss = torch.nn.CrossEntropyLoss()(tr, torch.arange(96) % 2)
+    loss.backward()
+    save("patch_model_nodrop", train_logits=tr.detach(), loss=loss.detach(), x_sha=np.array(sha16(xb.numpy())),
+         rm0=net.conv_blocks[0].bn.running_mean, rv4=net.conv_blocks[4].bn.running_var, **_all_grads(net, cap=8192))
+
+
+def rel_err_t(a, b):
+    return float((a.detach().double() - b.detach().double()).norm() / (b.detach().double().norm() + 1e-30))
 
 
 def detect_cases():
@@ -348,9 +434,9 @@ if __name__ == "__main__":
     assert refload.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["fixtures", "ops", "unet3d", "ae", "fader", "fepegar", "patches", "detect", "histstd", "metrics"]
+    which = sys.argv[1:] or ["fixtures", "ops", "unet3d", "ae", "fader", "fepegar", "patches", "detect", "histstd", "metrics", "modified_unet", "cnn_model", "patch_nodrop"]
     table = dict(fixtures=copy_fixtures, ops=op_pins, unet3d=unet3d_cases, ae=ae_cases, fader=fader_cases,
-                 fepegar=fepegar_case, patches=patch_cases, detect=detect_cases, histstd=histstd_cases, metrics=metrics_cases)
+                 fepegar=fepegar_case, patches=patch_cases, modified_unet=modified_unet_cases, cnn_model=cnn_model_cases, patch_nodrop=patch_model_nodrop_case, detect=detect_cases, histstd=histstd_cases, metrics=metrics_cases)
     for w in which:
         print(w)
         table[w]()

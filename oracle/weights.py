@@ -186,3 +186,27 @@ def synthetic_t1w(shape, seed=0):
     m = out[brain[None, None].expand_as(out) > 0]
     out = (out - m.mean()) / m.std() * brain
     return out
+
+
+def seeded_like(template, seed):
+    """Deterministic values for ANY state dict: `template` maps key -> tensor (only shape/dtype are used), e.g. the
+    `state_dict()` of a freshly constructed reference module or of its zoo mirror (identical keys and order, so both sides
+    regenerate the same tensors from the seed instead of shipping checkpoints).  Conv/Linear weights ~ N(0, 2/fan_in),
+    norm weights U(0.5, 1.5), biases N(0, 0.1), running_mean N(0, 0.1), running_var U(0.5, 1.5), counters 0."""
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+    for k, v in template.items():
+        shape = tuple(v.shape)
+        if k.endswith("num_batches_tracked"):
+            sd[k] = torch.zeros(shape, dtype=torch.int64)
+        elif k.endswith("running_var"):
+            sd[k] = torch.rand(shape, generator=g) + 0.5
+        elif k.endswith("running_mean"):
+            sd[k] = torch.randn(shape, generator=g) * 0.1
+        elif k.endswith(".bias"):
+            sd[k] = torch.randn(shape, generator=g) * 0.1
+        elif len(shape) > 1:
+            sd[k] = torch.randn(shape, generator=g) * math.sqrt(2.0 / math.prod(shape[1:]))
+        else:
+            sd[k] = torch.rand(shape, generator=g) + 0.5
+    return sd

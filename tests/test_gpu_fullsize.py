@@ -1,0 +1,234 @@
+"""GPU parity at BASELINE.json sizes, against the CPU oracle run LIVE (no golden files: the oracle finishes these in seconds).
+
+Two kinds of checks:
+
+* single layers at the exact shapes config 2 / config 3 run them (folded W=128 row kernel, linear-tiled 64^3 / 32^3 levels,
+  split-K 8^3 / 16^3 levels, Cin=1 stem, 2-class head, dual conv) -- forward, dgrad and wgrad against torch's fp32 CPU
+  convolution on the same bf16-rounded operands, rel-L2 <= 1e-2 (the north star's bf16 tolerance; the observed distance is the
+  bf16 rounding of the stored output, ~2e-3);
+* the whole unet3d step at 1 x 128^3 (bn and in) and a 192x224x192 forward.  A 40-layer network that STORES bf16 cannot stay
+  within 1e-2 of an fp32 run end to end: every stored tensor carries 2^-9 relative rounding noise, and the noise of later
+  layers is decorrelated from any other run after a few layers (one flipped rounding perturbs every downstream sum).  What
+  can be asserted, and is: (1) up to the first few layers the CUDA path reproduces the oracle's bf16-storage mode bit for bit
+  (same rounding places), and (2) at every later point -- logits, loss, every parameter gradient -- the CUDA path is no
+  further from the fp32 reference than the reference ALGORITHM itself is when only its storage is bf16
+  (oracle.graphs.bf16_storage: same fp32 ATen arithmetic, values rounded where the device stores them).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err, tensor_core_convs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def B():
+    import mri_epilepsy_diagnosis_b200 as pkg
+    pkg._cabi.lib()
+    return pkg
+
+
+LAYERS = [
+    # name, N, Ci, Co, (D,H,W), k, expected fwd algo
+    ("convd1.conv3 16->16 @128^3 (folded)", 1, 16, 16, (128, 128, 128), 3, "row"),
+    ("convu1.conv3 32->32 @128^3 (folded)", 1, 32, 32, (128, 128, 128), 3, "row"),
+    ("convd2.conv1 16->32 @64^3 (linear tiling)", 2, 16, 32, (64, 64, 64), 3, "row"),
+    ("convu1.conv1 64->32 @64^3 (streamed weights)", 1, 64, 32, (64, 64, 64), 3, "row"),
+    ("convu2.conv3 64->64 @64^3", 1, 64, 64, (64, 64, 64), 3, "row"),
+    ("convd4.conv3 128->128 @16^3 (tile kernel)", 4, 128, 128, (16, 16, 16), 3, "umma"),
+    ("convd5.conv3 256->256 @8^3 (split-K)", 4, 256, 256, (8, 8, 8), 3, "umma"),
+    ("convu1.conv2 32->16 1x1x1 @64^3", 2, 32, 16, (64, 64, 64), 1, "row"),
+    ("config 3: 16->16 @ 24x224x192", 1, 16, 16, (24, 224, 192), 3, "row"),
+    ("config 3: 32->32 @ 24x112x96", 1, 32, 32, (24, 112, 96), 3, "row"),
+]
+
+
+@pytest.mark.parametrize("case", LAYERS, ids=[c[0].split(" (")[0].replace(" ", "_") for c in LAYERS])
+def test_conv_layer_at_baseline_size_against_oracle(B, case):
+    name, N, Ci, Co, size, k, algo = case
+    g = torch.Generator().manual_seed(Ci * 7 + Co + size[2])
+    w = (torch.randn(Co, Ci, k, k, k, generator=g) * (2.0 / (Ci * k ** 3)) ** 0.5).bfloat16().float()
+    x = torch.randn(N, Ci, *size, generator=g).bfloat16().float()
+    gy = torch.randn(N, Co, *size, generator=g).bfloat16().float()
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    yr = F.conv3d(xr, wr, None, 1, k // 2)
+    yr.backward(gy)
+    mod = B.nn.Conv3d(Ci, Co, k, 1, k // 2, bias=False).cuda()
+    with torch.no_grad():
+        mod.weight.copy_(w)
+    mod.compute_dtype = torch.bfloat16
+    xg = x.cuda().bfloat16().requires_grad_(True)
+    cd, _ = mod._cfg().desc(xg, mod.weight, torch.bfloat16)
+    want = {"row": B._cabi.ALGO_ROW, "umma": B._cabi.ALGO_UMMA}[algo]
+    assert B._cabi.lib().b200_conv_algo(ctypes.byref(cd), B._cabi.PASS_FWD) == want, "case is meant to exercise this kernel"
+    yg = mod(xg)
+    yg.backward(gy.cuda().bfloat16())
+    torch.cuda.synchronize()
+    errs = rel_err(yg.float(), yr), rel_err(xg.grad.float(), xr.grad), rel_err(mod.weight.grad, wr.grad)
+    print(f"[fullsize] {name}: fwd {errs[0]:.2e} dgrad {errs[1]:.2e} wgrad {errs[2]:.2e}")
+    assert errs[0] < 1e-2 and errs[1] < 1e-2 and errs[2] < 1e-2, errs
+
+
+def test_stem_head_and_dual_conv_at_baseline_size_against_oracle(B):
+    """The CUDA-core kernels of config 2 at 128^3: the Cin=1 stem (fp32 input), the 2-class 1x1x1 head (fp32 logits), and the
+    dead/live dual convolution with statistics (unet3d.py:43-46) -- against torch's CPU convolution."""
+    g = torch.Generator().manual_seed(5)
+    size = (128, 128, 128)
+    # stem: fp32 volume in, bf16 out; fp32 weights
+    w = torch.randn(16, 1, 3, 3, 3, generator=g) * (2.0 / 27) ** 0.5
+    x = torch.randn(1, 1, *size, generator=g)
+    gy = torch.randn(1, 16, *size, generator=g).bfloat16().float()
+    wr = w.clone().requires_grad_(True)
+    yr = F.conv3d(x, wr, None, 1, 1)
+    yr.backward(gy)
+    stem = B.nn.Conv3d(1, 16, 3, 1, 1, bias=False).cuda()
+    with torch.no_grad():
+        stem.weight.copy_(w)
+    stem.compute_dtype = torch.bfloat16
+    yg = stem(x.cuda())
+    yg.backward(gy.cuda().bfloat16())
+    assert yg.dtype == torch.bfloat16
+    assert rel_err(yg.float(), yr) < 1e-2 and rel_err(stem.weight.grad, wr.grad) < 1e-2
+    # head: bf16 features in, fp32 logits out (fp32 weights + bias)
+    w = torch.randn(2, 32, 1, 1, 1, generator=g) * 0.2
+    b = torch.randn(2, generator=g) * 0.1
+    x = torch.randn(1, 32, *size, generator=g).bfloat16().float()
+    gy = torch.randn(1, 2, *size, generator=g)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.conv3d(xr, wr, br)
+    yr.backward(gy)
+    head = B.nn.Conv3d(32, 2, 1).cuda()
+    with torch.no_grad():
+        head.weight.copy_(w); head.bias.copy_(b)
+    head.compute_dtype, head.out_dtype = torch.bfloat16, torch.float32
+    xg = x.cuda().bfloat16().requires_grad_(True)
+    yg = head(xg)
+    yg.backward(gy.cuda())
+    assert yg.dtype == torch.float32
+    assert rel_err(yg, yr) < 1e-4 and rel_err(xg.grad.float(), xr.grad) < 1e-2                       # fp32 arithmetic on exact operands; dx stored bf16
+    assert rel_err(head.weight.grad, wr.grad) < 1e-3 and rel_err(head.bias.grad, br.grad) < 1e-3
+    # dual convolution 16 -> (16 dead | 16 live) with both sets of BatchNorm statistics, folded W = 128
+    wd = (torch.randn(16, 16, 3, 3, 3, generator=g) * 0.07).bfloat16().float()
+    wl = (torch.randn(16, 16, 3, 3, 3, generator=g) * 0.07).bfloat16().float()
+    x = torch.randn(1, 16, 32, 128, 128, generator=g).bfloat16().float()
+    cfg = B.functional.ConvConfig(1, 1, 1)
+    y3, part = B.functional.dual_conv(x.cuda().bfloat16(), wd.cuda(), wl.cuda(), cfg, torch.bfloat16)
+    yl, yd = F.conv3d(x, wl, None, 1, 1), F.conv3d(x, wd, None, 1, 1)
+    assert rel_err(y3.float(), yl) < 1e-2
+    s = part.double().sum(0).cpu()
+    for half, ref in ((slice(0, 16), yd), (slice(16, 32), yl)):
+        r = ref.double().permute(1, 0, 2, 3, 4).reshape(16, -1)
+        assert rel_err(s[1, half], (r * r).sum(1)) < 1e-4                       # sums of the fp32 accumulators vs the fp32 oracle
+        assert float((s[0, half] - r.sum(1)).abs().max()) < 1e-4 * float(r.abs().sum(1).max())
+
+
+def _unet_pair(B, norm, x, t, literal, hooks=False):
+    """(CUDA results, fp32-oracle results, storage-oracle results) of one unet3d training step on (x, t)"""
+    from oracle import graphs, weights
+    sd = weights.unet3d_state(1, 16, 2, norm, seed=1)
+    net = B.zoo.Unet(c=1, n=16, dropout=0.5, norm=norm, num_classes=2, literal=literal)
+    net.load_state_dict(sd, strict=True)
+    net = B.convert(net.cuda().train(), dtype=torch.bfloat16)
+    tc = tensor_core_convs(net, x.cuda())
+    acts, hs = {}, []
+    if hooks:
+        for name, m in net.named_modules():
+            if name in ("convd1.conv1", "convd1.bn1", "convd1.conv3", "convd1.bn3"):
+                hs.append(m.register_forward_hook(lambda mod, a, out, name=name: acts.__setitem__(name, (out[0] if isinstance(out, tuple) else out).detach().float().cpu())))
+    logits = net(x.cuda())
+    loss = B.functional.softmax_dice_loss(logits, t.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    for h in hs:
+        h.remove()
+    cuda = {"logits": logits.detach().float().cpu(), "loss": float(loss), "acts": acts,
+            "grads": {k: p.grad.detach().float().cpu() for k, p in net.named_parameters() if p.grad is not None}}
+
+    def run(storage):
+        osd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
+        with graphs.record_taps() as taps:
+            if storage:
+                with graphs.bf16_storage(lambda pfx, w: pfx in tc):
+                    lg = graphs.unet3d(osd, x, norm, 0.5, True, commute_up=not literal)
+                    ls = graphs.dice_loss_mean(lg, t)
+                    ls.backward()
+            else:
+                lg = graphs.unet3d(osd, x, norm, 0.5, True)
+                ls = graphs.dice_loss_mean(lg, t)
+                ls.backward()
+        return {"logits": lg.detach(), "loss": float(ls.detach()), "acts": taps, "grads": {k: v.grad for k, v in osd.items() if getattr(v, "grad", None) is not None}}
+    return cuda, run(False), run(True)
+
+
+def _assert_storage_equivalent(cuda, fp32, stor, tag):
+    e_c, e_s = rel_err(cuda["logits"], fp32["logits"]), rel_err(stor["logits"], fp32["logits"])
+    print(f"[storage-parity] {tag}: logits CUDA vs fp32 {e_c:.2e}, bf16-storage oracle vs fp32 {e_s:.2e}, CUDA vs storage oracle {rel_err(cuda['logits'], stor['logits']):.2e}; "
+          f"loss {cuda['loss']:.6f} / {fp32['loss']:.6f} / {stor['loss']:.6f}")
+    assert e_c < 1.3 * e_s + 1e-3, (tag, e_c, e_s)
+    assert e_c < 5e-2
+    assert abs(cuda["loss"] - fp32["loss"]) < max(2e-3, 3 * abs(stor["loss"] - fp32["loss"]))
+    assert sorted(cuda["grads"]) == sorted(fp32["grads"])                      # same parameters receive a gradient (dead branch: none)
+    worst = 0.0
+    for k in sorted(cuda["grads"]):
+        gc, gs = rel_err(cuda["grads"][k], fp32["grads"][k]), rel_err(stor["grads"][k], fp32["grads"][k])
+        worst = max(worst, gc / (gs + 1e-12))
+        assert gc < 1.6 * gs + 3e-3, (tag, k, gc, gs)
+    print(f"[storage-parity] {tag}: {len(cuda['grads'])} gradients, worst (CUDA vs fp32) / (storage oracle vs fp32) = {worst:.2f}")
+
+
+@pytest.mark.parametrize("norm", ["bn", "in"])
+def test_unet3d_step_at_128_cube_is_storage_equivalent(B, norm):
+    """config 2's volume, batch 1 (the oracle's fp32 + bf16-storage steps take a few seconds): folded W=128 kernels, linear tiling,
+    split-K, stem and heads inside the real graph, forward + Dice + backward, every parameter gradient."""
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(1, 1, 128, 128, 128, generator=g)
+    t = (torch.rand(1, 1, 128, 128, 128, generator=g) > 0.5).float()
+    cuda, fp32, stor = _unet_pair(B, norm, x, t, literal=False)
+    _assert_storage_equivalent(cuda, fp32, stor, f"unet3d {norm} 1x128^3")
+
+
+@pytest.mark.parametrize("literal", [True, False], ids=["literal", "rewritten"])
+def test_unet3d_rounding_places_match_the_storage_oracle(B, literal):
+    """2 x 32^3 (the golden configuration): the first stage of the network is reproduced BIT FOR BIT by the oracle's bf16-storage
+    mode (stem conv, bn1, conv3, bn3 + residual + ReLU) -- i.e. the device rounds where the storage mode says it does and
+    nowhere else; from there on single flipped roundings decorrelate the two runs (see the module docstring)."""
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 1, 32, 32, 32, generator=g)
+    t = (torch.rand(2, 1, 32, 32, 32, generator=g) > 0.5).float()
+    cuda, fp32, stor = _unet_pair(B, "bn", x, t, literal=literal, hooks=literal)
+    if literal:
+        for k, max_diff_frac in (("convd1.conv1", 1e-4), ("convd1.bn1", 1e-3), ("convd1.conv3", 2e-3), ("convd1.bn3", 1e-2)):
+            a, b = cuda["acts"][k], stor["acts"][k]
+            frac = float((a != b).float().mean())
+            print(f"[storage-parity] {k}: {frac:.5f} of the stored bf16 values differ from the storage oracle; rel {rel_err(a, b):.1e}; vs fp32 {rel_err(a, fp32['acts'][k]):.1e}")
+            assert frac <= max_diff_frac and rel_err(a, b) < 5e-4, k
+    _assert_storage_equivalent(cuda, fp32, stor, f"unet3d bn 2x32^3 {'literal' if literal else 'rewritten'}")
+
+
+def test_unet3d_forward_on_full_mni_volume(B):
+    """config 3's volume (192 x 224 x 192, the MNI152 1 mm grid padded to multiples of 32), eval-mode forward + argmax against the
+    oracle: non-cubic geometry through every kernel (W = 192 / 96 / 48 / 24 / 12 rows)."""
+    from oracle import graphs, weights
+    sd = weights.unet3d_state(1, 16, 2, "bn", seed=1)
+    net = B.zoo.Unet(c=1, n=16, norm="bn", num_classes=2)
+    net.load_state_dict(sd, strict=True)
+    net = B.convert(net.cuda().eval(), dtype=torch.bfloat16)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1, 1, 192, 224, 192, generator=g)
+    tc = tensor_core_convs(net, x.cuda())
+    with torch.no_grad():
+        logits = net(x.cuda()).float().cpu()
+        ref = graphs.unet3d(dict(sd), x, "bn", 0.5, False)
+        with graphs.bf16_storage(lambda pfx, w: pfx in tc):
+            stor = graphs.unet3d(dict(sd), x, "bn", 0.5, False, commute_up=True)
+    e_c, e_s = rel_err(logits, ref), rel_err(stor, ref)
+    print(f"[storage-parity] unet3d eval 192x224x192: logits CUDA vs fp32 {e_c:.2e}, storage oracle vs fp32 {e_s:.2e}")
+    assert e_c < 1.3 * e_s + 1e-3 and e_c < 5e-2
+    mism = logits.argmax(1) != ref.argmax(1)
+    gap = (ref[:, 0] - ref[:, 1]).abs()
+    assert float(mism.float().mean()) < 0.02 and float(gap[mism].max()) < 0.2 * float(gap.mean())      # only near-ties flip

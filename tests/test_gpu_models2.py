@@ -1,0 +1,244 @@
+"""GPU parity, model level, part 2: the model files round 1 only covered at operator level (modified_3dunet.py, cnn_model.py),
+the golden gradient vectors no GPU test consumed (fader heads, PatchModel train mode), and the drop-in path itself:
+`convert()` on stock-torch.nn models shaped like the reference's files, driven by the reference's eager training loop."""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_err, thin
+from test_gpu_models import check_grads, cosine
+
+pytestmark = pytest.mark.gpu
+TOL32, TOL16 = 1e-4, 1e-2
+
+
+@pytest.fixture(scope="module")
+def B():
+    import mri_epilepsy_diagnosis_b200 as pkg
+    pkg._cabi.lib()
+    return pkg
+
+
+def _grads_vs_golden(net, g, tol, cap=4096, f64=None):
+    gr = dict(net.named_parameters())
+    keys = [k[5:] for k in g.files if k.startswith("grad:")]
+    assert sorted(keys) == sorted(k for k, p in gr.items() if p.grad is not None)
+    got = {k: thin(gr[k].grad.detach().cpu(), cap) for k in keys}
+    want = {k: g["grad:" + k] for k in keys}
+    check_grads(got, want, tol, f64)
+    return got, want
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_modified_3dunet_against_golden(B, golden, dtype):
+    """segmentation/models/modified_3dunet.py:4-189 (zoo.Modified3DUNet, same state_dict keys) against vectors of the REAL class:
+    stride-2 context convs, InstanceNorm + LeakyReLU, nearest x2, two deep-supervision heads; eval + one train step (Dropout3d p=0)."""
+    from oracle import graphs, weights
+    g = golden("modified3dunet")
+    net = B.zoo.Modified3DUNet(1, 2, 8)
+    assert list(net.state_dict().keys()) == list(g["keys"])
+    sd = weights.seeded_like(net.state_dict(), seed=31)
+    net.load_state_dict(sd, strict=True)
+    net = B.convert(net.cuda(), dtype=dtype)
+    gen = torch.Generator().manual_seed(32)
+    x = torch.randn(2, 1, 32, 32, 32, generator=gen)
+    t = (torch.rand(2, 1, 32, 32, 32, generator=gen) > 0.5).float()
+    tol = TOL32 if dtype == torch.float32 else 3 * TOL16
+    net.eval()
+    with torch.no_grad():
+        ev = net(x.cuda())
+    assert ev.dtype == torch.float32 and rel_err(ev, g["eval_logits"]) < tol
+    mism = ev.argmax(1).cpu() != torch.from_numpy(g["eval_logits"]).argmax(1)
+    assert float(mism.float().mean()) < (1e-4 if dtype == torch.float32 else 0.03)
+    net.train()
+    net.dropout3d.p = 0.0
+    logits = net(x.cuda())
+    assert rel_err(logits, g["train_logits"]) < tol
+    loss = graphs.dice_loss_mean(logits, t.cuda())
+    assert abs(float(loss) - float(g["loss"])) < (1e-5 if dtype == torch.float32 else 5e-3)
+    loss.backward()
+    if dtype == torch.float32:
+        sd64 = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+        graphs.dice_loss_mean(graphs.modified_3dunet(sd64, x.double(), True, 0.0), t.double()).backward()
+        _grads_vs_golden(net, g, 1e-3, f64={k: thin(v.grad, 4096) for k, v in sd64.items()})
+    else:
+        gr = dict(net.named_parameters())
+        for k in (k[5:] for k in g.files if k.startswith("grad:")):
+            assert cosine(thin(gr[k].grad.cpu(), 4096), g["grad:" + k]) > 0.9, k
+        for k in ("conv3d_l4.weight", "conv_norm_lrelu_l4.0.weight"):
+            assert rel_err(thin(gr[k].grad.cpu(), 4096), g["grad:" + k]) < 5e-2, k
+
+
+CNN_CASES = {
+    "voxresnet_b3": (lambda z: z.VoxResNet((32, 32, 32), 2, 16, 2, 3), (3, 1, 32, 32, 32), 0),
+    "voxresnet_b4": (lambda z: z.VoxResNet((32, 32, 32), 2, 8, 1, 4), (2, 1, 32, 32, 32), 1),
+    "cnn_b3": (lambda z: z.CNN((32, 40, 24), 16, 3), (4, 1, 32, 40, 24), 2),
+    "dilated_cnn": (lambda z: z.DilatedCNN((180, 180, 180), 16), (2, 1, 180, 180, 180), 3),
+}
+
+
+@pytest.mark.parametrize("name", list(CNN_CASES))
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_cnn_model_family_against_golden(B, golden, name, dtype):
+    """classification/models/cnn_model.py:43-101 VoxResNet (incl. the n_blocks=4 `activation_6` quirk), :104-175 CNN,
+    :207-257 DilatedCNN (dilation 3, stride-2 unpadded convs, MaxPool3d(4, 2)) against vectors of the REAL classes."""
+    from oracle import weights
+    g = golden(name)
+    ctor, shape, seed = CNN_CASES[name]
+    net = ctor(B.zoo)
+    assert list(net.state_dict().keys()) == list(g["keys"])
+    sd = weights.seeded_like(net.state_dict(), seed=40 + seed)
+    net.load_state_dict(sd, strict=True)
+    net = B.convert(net.cuda(), dtype=dtype)
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(50 + seed)).cuda()
+    tol = TOL32 if dtype == torch.float32 else 3 * TOL16
+    net.eval()
+    with torch.no_grad():
+        ev = net(x)
+    assert rel_err(ev, g["eval_out"]) < tol
+    net.train()
+    tr = net(x)
+    assert rel_err(tr, g["train_out"]) < (tol if dtype == torch.float32 else 6 * TOL16)          # batch statistics of 2-4 samples amplify rounding
+    y = (torch.arange(shape[0]) % 2).cuda()
+    loss = torch.nn.functional.nll_loss(torch.log(tr), y) if name == "dilated_cnn" else torch.nn.functional.cross_entropy(tr, y)
+    loss.backward()
+    for k in g.files:
+        if k.startswith("buf:"):
+            assert rel_err(net.state_dict()[k[4:]], g[k]) < tol, k
+    if dtype == torch.float32:
+        assert abs(float(loss) - float(g["loss"])) < 1e-4
+        _grads_vs_golden(net, g, 5e-3)
+    else:
+        gr = dict(net.named_parameters())
+        last = [k[5:] for k in g.files if k.startswith("grad:") and "fully_conn" in k]
+        for k in last:
+            assert cosine(thin(gr[k].grad.cpu(), 4096), g["grad:" + k]) > 0.9, k
+
+
+def test_fader_heads_train_gradients(B, golden):
+    """classification/models/AE_model.py:213-312 Classificator (train) + Discriminator (eval) on a latent batch with the notebook's
+    losses (train_ENC_CLF.ipynb [cell 14]) against the REAL classes' vectors: logits, both losses, d(loss)/d(latent) and every
+    classifier gradient.  The Dropout mask the reference drew on the CPU (torch.manual_seed(5)) is replayed and applied as a fixed mask."""
+    from oracle import graphs
+    g = golden("fader_heads_train")
+    ld = lambda n: torch.load(os.path.join(GOLDEN, n), map_location="cpu", weights_only=True)
+    clf = B.zoo.Classificator(n_class=2, **B.zoo.FADER_HEAD); clf.load_state_dict(ld("clf_93_6_4.pth"), strict=True)
+    disc = B.zoo.Discriminator(n_domains=18, **B.zoo.FADER_HEAD); disc.load_state_dict(ld("disc_93_6_4.pth"), strict=True)
+    clf, disc = B.convert(clf.cuda().train(), dtype=torch.float32), B.convert(disc.cuda().eval(), dtype=torch.float32)
+    gen = torch.Generator().manual_seed(7)
+    torch.randn(4, 1, 96, 96, 96, generator=gen)            # same generator stream as make_golden
+    lat = torch.randn(6, 32, 3, 3, 3, generator=gen).cuda().requires_grad_(True)
+    y = torch.tensor([0, 1, 1, 0, 1, 0]).cuda(); dom = torch.tensor([3, 0, 17, 5, 9, 9])
+    torch.manual_seed(5)
+    mask = torch.nn.functional.dropout(torch.ones(6, 32), 0.5, True).cuda()       # first RNG draw after the seed in make_golden
+
+    class FixedMask(torch.nn.Module):
+        def forward(self, x):
+            return x * mask
+    clf.clf["8_drop"] = FixedMask()
+    pc, pd = clf(lat), disc(lat)
+    assert rel_err(pc, g["pc"]) < TOL32 and rel_err(pd, g["pd"]) < TOL32
+    ce = torch.nn.functional.cross_entropy(pc, y, weight=torch.tensor([1.0, 2.0]).cuda())
+    adv = graphs.adv_loss(dom, pd.cpu(), 18)
+    onehot = torch.zeros(6, 18).scatter_(1, dom.view(-1, 1), 1).cuda()
+    adv_dev = -torch.mean((1 - onehot) * torch.log_softmax(pd, dim=1))
+    assert abs(float(ce) - float(g["ce"])) < 1e-5 and abs(float(adv) - float(g["adv"])) < 1e-5
+    (ce + 0.05 * adv_dev).backward()
+    assert rel_err(lat.grad, g["dlat"]) < 5e-4
+    gr = dict(clf.named_parameters())
+    keys = [k[5:] for k in g.files if k.startswith("grad:")]
+    check_grads({k: gr[k].grad for k in keys}, {k: g["grad:" + k] for k in keys}, 1e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_patch_model_train_gradients(B, golden, dtype):
+    """detection/model_utils.py:19-52 in TRAIN mode (Dropout p set to 0 on the instance, like the golden): logits, loss, every
+    gradient and the BatchNorm running statistics against the REAL class, on the first 96 patches of the MNI template."""
+    from oracle import patches as OP, weights
+    g = golden("patch_model_nodrop")
+    gm = OP.read_nifti1_f32(os.path.join(GOLDEN, "MNI152_T1_1mm_brain_gray.nii.gz")).astype(np.float64)
+    img = np.random.default_rng(0).random((182, 218, 182))
+    xb = B.patches.gather(img, B.patches.patch_plan(gm)[:96], dtype=torch.float32)
+    net = B.zoo.PatchModel(); net.load_state_dict(weights.patch_model_state(seed=9), strict=True)
+    net = B.convert(net.cuda().train(), dtype=dtype)
+    net.dropout.p = 0.0
+    tr = net(xb)
+    tol = TOL32 if dtype == torch.float32 else 3 * TOL16
+    assert rel_err(tr, g["train_logits"]) < tol
+    loss = torch.nn.functional.cross_entropy(tr, (torch.arange(96) % 2).cuda())
+    assert abs(float(loss) - float(g["loss"])) < (1e-5 if dtype == torch.float32 else 1e-2)
+    loss.backward()
+    assert rel_err(net.conv_blocks[0].bn.running_mean, g["rm0"]) < tol and rel_err(net.conv_blocks[4].bn.running_var, g["rv4"]) < tol
+    if dtype == torch.float32:
+        _grads_vs_golden(net, g, 2e-3, cap=8192)
+    else:
+        gr = dict(net.named_parameters())
+        for k in (k[5:] for k in g.files if k.startswith("grad:")):
+            if float(np.linalg.norm(g["grad:" + k])) > 1e-6 * float(np.sqrt(g["grad:" + k].size)):
+                assert cosine(thin(gr[k].grad.cpu(), 8192), g["grad:" + k]) > 0.95, k
+        assert rel_err(gr["fc2.weight"].grad, g["grad:fc2.weight"]) < 5e-2
+
+
+def _dice(logits, t):
+    from oracle import graphs
+    return graphs.dice_loss_mean(logits, t)
+
+
+def test_convert_drop_in_on_reference_shaped_unet_eager_loop(B):
+    """The drop-in path proper (north star: "routine.py's training loops run as-is"): a model built from STOCK torch.nn classes
+    whose forward() calls F.upsample, F.dropout3d, torch.cat and in-place ReLU (tests/refshaped.py, the shape of unet3d.py:20-79)
+    is converted in place and driven by the reference's eager loop body (segmentation/routine.py:266-281: zero_grad -> forward ->
+    softmax/Dice -> backward -> optimizer.step) with dp.attach hooked on; losses and updated weights against the same stock model
+    on the CPU, step by step."""
+    import refshaped
+    torch.manual_seed(0)
+    ref = refshaped.RefShapedUNet(n=16).train()
+    net = copy.deepcopy(ref)
+    keys = list(ref.state_dict().keys())
+    net = B.convert(net.cuda(), dtype=torch.float32)
+    assert list(net.state_dict().keys()) == keys and refshaped.F is B.nn.functional_proxy
+    opt_r = torch.optim.AdamW(ref.parameters(), lr=1e-3)
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-3)
+    bucket = B.dp.attach(net, opt)
+    g = torch.Generator().manual_seed(1)
+    n0 = B.launch_count()
+    for step in range(3):
+        x = torch.randn(2, 1, 16, 16, 16, generator=g)
+        t = (torch.rand(2, 1, 16, 16, 16, generator=g) > 0.5).float()
+        opt_r.zero_grad(); opt.zero_grad()
+        lr_ = _dice(ref(x), t); lr_.backward(); opt_r.step()
+        lg = _dice(net(x.cuda()), t.cuda()); lg.backward(); opt.step()
+        assert abs(float(lg) - float(lr_)) < 2e-5, step
+    bucket.remove()
+    assert B.launch_count() - n0 > 300                                             # the library ran the step, not torch
+    pr, pg = dict(ref.named_parameters()), dict(net.named_parameters())
+    for k in ("d1.c1.weight", "d2.c3.weight", "u1.c3.weight", "u2.c2.weight", "head1.bias", "d3.n1.weight"):
+        assert rel_err(pg[k], pr[k]) < 5e-4, k
+    assert pg["d1.c2.weight"].grad is None and pr["d1.c2.weight"].grad is None      # dead branch: skipped by both optimizers
+    br, bg = dict(ref.named_buffers()), dict(net.named_buffers())
+    for k in ("d1.n2.running_mean", "u1.n3.running_var"):
+        assert rel_err(bg[k], br[k]) < 1e-4, k
+    assert int(bg["d2.n2.num_batches_tracked"]) == 3
+    # bf16 mode of the same converted model: runs, learns the same direction
+    net16 = B.convert(copy.deepcopy(ref).cuda(), dtype=torch.bfloat16)
+    x = torch.randn(2, 1, 16, 16, 16, generator=g)
+    assert rel_err(net16(x.cuda()), ref(x)) < 3e-2
+
+
+def test_convert_drop_in_classifier_with_view_flatten(B):
+    """cnn_model.py-shaped stock model: nn.Sequential with a user-defined Flatten doing `input.view(N, -1)` followed by Linear and
+    BatchNorm1d -- convert() hands those modules a contiguous fp32 tensor in logical NCDHW order, like stock PyTorch."""
+    import refshaped
+    torch.manual_seed(3)
+    ref = refshaped.RefShapedClassifier().train()
+    for dtype, tol in ((torch.float32, 1e-4), (torch.bfloat16, 3e-2)):
+        net = B.convert(copy.deepcopy(ref).cuda(), dtype=dtype)
+        x = torch.randn(4, 1, 16, 16, 16, generator=torch.Generator().manual_seed(4))
+        want = copy.deepcopy(ref)(x)
+        got = net(x.cuda())
+        assert got.dtype == torch.float32 and rel_err(got, want) < tol
+        torch.nn.functional.cross_entropy(got, torch.tensor([0, 1, 1, 0]).cuda()).backward()
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())

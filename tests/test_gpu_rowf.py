@@ -130,6 +130,7 @@ def test_fused_statistics_and_dual_conv(B, W, Ci):
     """conv + BatchNorm partial sums in the epilogue (b200_conv_fwd_stats) and the dead/live pair of unet3d.py:43-46 in one launch
     (b200_conv_fwd_stats_tail), in the kx-folded mode (W = 128) and the plain one: statistics against the stored outputs."""
     F_ = B.functional
+    torch.manual_seed(1000 + W + Ci)                     # the two modules below draw their weights from the global generator
     g = torch.Generator().manual_seed(W + Ci)
     x = torch.randn(2, Ci, 5, 12, W, generator=g).cuda().bfloat16()
     conv = B.nn.Conv3d(Ci, 16, 3, 1, 1, bias=False).cuda()
@@ -140,7 +141,9 @@ def test_fused_statistics_and_dual_conv(B, W, Ci):
     assert torch.equal(y, y_plain)
     s = part.double().sum(0)                                                   # sums of the fp32 accumulators, before the bf16 rounding of y
     yd = y.double().permute(1, 0, 2, 3, 4).reshape(16, -1)
-    assert rel_err(s[0], yd.sum(1)) < 2e-3 and rel_err(s[1], (yd * yd).sum(1)) < 2e-3
+    # the per-channel sums of ~15 k zero-mean values cancel to ~1 % of sum|y|, so bf16 rounding of y (2^-9 each) shows up as a
+    # few 1e-3 of the sum: 5e-3 bounds it, an indexing error would give O(1)
+    assert rel_err(s[0], yd.sum(1)) < 5e-3 and rel_err(s[1], (yd * yd).sum(1)) < 2e-3
     dead = B.nn.Conv3d(Ci, 16, 3, 1, 1, bias=False).cuda()
     assert F_.dual_conv_supported(x, dead.weight, conv.weight, conv._cfg(), torch.bfloat16)
     y3, part2 = F_.dual_conv(x, dead.weight, conv.weight, conv._cfg(), torch.bfloat16)
@@ -149,5 +152,5 @@ def test_fused_statistics_and_dual_conv(B, W, Ci):
     dead.compute_dtype = torch.bfloat16
     yd2 = dead(x).double().permute(1, 0, 2, 3, 4).reshape(16, -1)
     s2 = part2.double().sum(0)
-    assert rel_err(s2[0, :16], yd2.sum(1)) < 2e-3 and rel_err(s2[1, :16], (yd2 * yd2).sum(1)) < 2e-3
-    assert rel_err(s2[0, 16:], yd.sum(1)) < 2e-3 and rel_err(s2[1, 16:], (yd * yd).sum(1)) < 2e-3
+    assert rel_err(s2[0, :16], yd2.sum(1)) < 5e-3 and rel_err(s2[1, :16], (yd2 * yd2).sum(1)) < 2e-3
+    assert rel_err(s2[0, 16:], yd.sum(1)) < 5e-3 and rel_err(s2[1, 16:], (yd * yd).sum(1)) < 2e-3

@@ -270,3 +270,60 @@ def test_overlap_metrics(golden):
         assert iou == g[f"{name}_iou"] and np.asarray(iou).dtype == g[f"{name}_iou"].dtype, name
     z = np.zeros((4, 4, 4), np.uint8)
     assert np.isnan(M.compute_dice_coefficient(z, z))                # metrics.py:325-326 (np.NaN there)
+
+
+def test_modified_3dunet(golden):
+    """segmentation/models/modified_3dunet.py: oracle restatement vs vectors of the REAL class (eval; train step with Dropout3d p=0)."""
+    g = golden("modified3dunet")
+    import mri_epilepsy_diagnosis_b200 as pkg
+    template = pkg.zoo.Modified3DUNet(1, 2, 8).state_dict()
+    assert list(template.keys()) == list(g["keys"])            # the zoo mirror has the reference's state_dict keys, in order
+    sd = _leaf(weights.seeded_like(template, seed=31))
+    gen = torch.Generator().manual_seed(32)
+    x = torch.randn(2, 1, 32, 32, 32, generator=gen)
+    t = (torch.rand(2, 1, 32, 32, 32, generator=gen) > 0.5).float()
+    with torch.no_grad():
+        ev = graphs.modified_3dunet(sd, x)
+    assert rel_err(ev, g["eval_logits"]) < TOL and sha16(ev.argmax(1).numpy().astype(np.uint8)) == str(g["argmax_sha"])
+    logits = graphs.modified_3dunet(sd, x, training=True, p_drop=0.0)
+    assert rel_err(logits, g["train_logits"]) < TOL
+    loss = graphs.dice_loss_mean(logits, t)
+    assert abs(float(loss) - float(g["loss"])) < 1e-6
+    loss.backward()
+    for k in g.files:
+        if k.startswith("grad:"):
+            assert rel_err(thin(sd[k[5:]].grad, 4096), g[k]) < 5e-4, k
+
+
+@pytest.mark.parametrize("name", ["voxresnet_b3", "voxresnet_b4", "cnn_b3", "dilated_cnn"])
+def test_cnn_model_family(golden, name):
+    """classification/models/cnn_model.py (VoxResNet incl. the n_blocks=4 activation quirk, CNN, DilatedCNN)."""
+    import mri_epilepsy_diagnosis_b200 as pkg
+    g = golden(name)
+    ctor, shape, fn, seed = CNN_CASES[name]
+    template = ctor(pkg.zoo).state_dict()
+    assert list(template.keys()) == list(g["keys"])
+    sd = _leaf(weights.seeded_like(template, seed=40 + seed))
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(50 + seed))
+    with torch.no_grad():
+        ev = fn({k: v.detach().clone() for k, v in sd.items()}, x, False)
+    assert rel_err(ev, g["eval_out"]) < TOL
+    tr = fn(sd, x, True)
+    assert rel_err(tr, g["train_out"]) < TOL
+    y = torch.arange(shape[0]) % 2
+    loss = torch.nn.functional.nll_loss(torch.log(tr), y) if name == "dilated_cnn" else torch.nn.functional.cross_entropy(tr, y)
+    assert abs(float(loss) - float(g["loss"])) < 1e-5
+    loss.backward()
+    for k in g.files:
+        if k.startswith("grad:"):
+            assert rel_err(thin(sd[k[5:]].grad, 4096), g[k]) < 2e-3, k
+        if k.startswith("buf:"):
+            assert rel_err(sd[k[4:]], g[k]) < TOL, k
+
+
+CNN_CASES = {
+    "voxresnet_b3": (lambda z: z.VoxResNet((32, 32, 32), 2, 16, 2, 3), (3, 1, 32, 32, 32), lambda sd, x, tr: graphs.voxresnet(sd, x, 3, 2, tr), 0),
+    "voxresnet_b4": (lambda z: z.VoxResNet((32, 32, 32), 2, 8, 1, 4), (2, 1, 32, 32, 32), lambda sd, x, tr: graphs.voxresnet(sd, x, 4, 1, tr), 1),
+    "cnn_b3": (lambda z: z.CNN((32, 40, 24), 16, 3), (4, 1, 32, 40, 24), lambda sd, x, tr: graphs.cnn(sd, x, 3, 1, tr), 2),
+    "dilated_cnn": (lambda z: z.DilatedCNN((180, 180, 180), 16), (2, 1, 180, 180, 180), lambda sd, x, tr: graphs.dilated_cnn(sd, x, tr), 3),
+}

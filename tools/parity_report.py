@@ -44,21 +44,37 @@ def main():
                 net.load_state_dict(sd, strict=True)
                 net = pkg.convert(net.cuda().train(), dtype=torch.bfloat16)
                 tc = tensor_core_convs(net, x.cuda())
+                acts, hooks = {}, []
+                if literal:        # the literal graph calls every conv / norm through its module: record what each one stores
+                    for name, m in net.named_modules():
+                        if isinstance(m, (torch.nn.modules.conv._ConvNd, torch.nn.modules.batchnorm._BatchNorm, torch.nn.InstanceNorm3d)):
+                            def hook(mod, args, out, name=name):
+                                o = out[0] if isinstance(out, tuple) else out
+                                if o is not None:
+                                    acts[name] = o.detach().float().cpu()
+                            hooks.append(m.register_forward_hook(hook))
                 logits = net(x.cuda())
+                for h in hooks:
+                    h.remove()
                 loss = pkg.functional.softmax_dice_loss(logits, t.cuda())
                 loss.backward()
                 torch.cuda.synchronize()
                 grads = {k: p.grad.detach().float().cpu() for k, p in net.named_parameters() if p.grad is not None}
 
+                taps = {}
+
                 def oracle(storage):
                     osd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
                     if storage:
-                        with graphs.bf16_storage(lambda pfx, w: pfx in tc):
+                        with graphs.bf16_storage(lambda pfx, w: pfx in tc), graphs.record_taps() as tp:
                             lg = graphs.unet3d(osd, x, norm, 0.5, True, commute_up=not literal)
+                            taps["storage"] = tp
                             ls = graphs.dice_loss_mean(lg, t)
                             ls.backward()
                     else:
-                        lg = graphs.unet3d(osd, x, norm, 0.5, True)
+                        with graphs.record_taps() as tp:
+                            lg = graphs.unet3d(osd, x, norm, 0.5, True)
+                            taps["fp32"] = tp
                         ls = graphs.dice_loss_mean(lg, t)
                         ls.backward()
                     return lg.detach(), float(ls), {k: v.grad for k, v in osd.items() if getattr(v, "grad", None) is not None}
@@ -70,6 +86,13 @@ def main():
                 for k in sorted(grads):
                     row["grads"][k] = {"vs_fp32": rel(grads[k], g32[k]), "vs_storage": rel(grads[k], g16[k]), "storage_vs_fp32": rel(g16[k], g32[k]),
                                        "norm": float(g32[k].norm())}
+                row["layers"] = {}
+                for k, v in acts.items():
+                    if k in taps["storage"] and taps["storage"][k].shape == v.shape:
+                        row["layers"][k] = {"vs_fp32": rel(v, taps["fp32"][k]), "vs_storage": rel(v, taps["storage"][k]),
+                                            "mismatch_frac": float((v != taps["storage"][k]).float().mean())}
+                        print(f"    [layer] {k:22s} vs_fp32 {row['layers'][k]['vs_fp32']:.2e} vs_storage {row['layers'][k]['vs_storage']:.2e} "
+                              f"differing elements {row['layers'][k]['mismatch_frac']:.4f}")
                 worst = max(row["grads"].items(), key=lambda kv: kv[1]["vs_storage"])
                 print(f"[parity] {size}^3 x{n} norm={norm} literal={literal}: logits vs fp32 {row['logits_vs_fp32']:.2e} vs storage {row['logits_vs_storage']:.2e} "
                       f"(storage vs fp32 {row['storage_vs_fp32']:.2e}); worst grad vs storage {worst[0]} {worst[1]['vs_storage']:.2e} "
