@@ -28,15 +28,18 @@ class Down(nn.Module):
 
 
 class Up(nn.Module):
-    def __init__(self, planes):
+    def __init__(self, planes, first=False):
         super().__init__()
-        self.c1, self.n1 = nn.Conv3d(2 * planes, planes, 3, 1, 1, bias=False), nn.BatchNorm3d(planes)
+        self.first = first
+        if not first:
+            self.c1, self.n1 = nn.Conv3d(2 * planes, planes, 3, 1, 1, bias=False), nn.BatchNorm3d(planes)
         self.c2, self.n2 = nn.Conv3d(planes, planes // 2, 1, 1, 0, bias=False), nn.BatchNorm3d(planes // 2)
         self.c3, self.n3 = nn.Conv3d(planes, planes, 3, 1, 1, bias=False), nn.BatchNorm3d(planes)
         self.relu = nn.ReLU(inplace=True)
 
     def forward(self, x, skip):
-        x = self.relu(self.n1(self.c1(x)))
+        if not self.first:
+            x = self.relu(self.n1(self.c1(x)))
         y = F.upsample(x, scale_factor=2, mode="trilinear", align_corners=False)
         y = self.relu(self.n2(self.c2(y)))
         y = torch.cat([skip, y], 1)
@@ -47,9 +50,9 @@ class RefShapedUNet(nn.Module):
     def __init__(self, n=16, classes=2):
         super().__init__()
         self.d1, self.d2, self.d3 = Down(1, n, True), Down(n, 2 * n), Down(2 * n, 4 * n)
-        self.u2, self.u1 = Up(2 * n), Up(n)
+        self.u2, self.u1 = Up(4 * n, first=True), Up(2 * n)
         self.bridge = nn.Conv3d(4 * n, 4 * n, 1, bias=False)
-        self.head2, self.head1 = nn.Conv3d(2 * n, classes, 1), nn.Conv3d(n, classes, 1)
+        self.head2, self.head1 = nn.Conv3d(4 * n, classes, 1), nn.Conv3d(2 * n, classes, 1)
         self.upsample = nn.Upsample(scale_factor=2, mode="trilinear", align_corners=False)
 
     def forward(self, x):

@@ -22,6 +22,19 @@ def B():
     return pkg
 
 
+def _storage_bound(B, net, x, fn, sd, want):
+    """bf16 bound for a whole-model output: 1.3 x the distance the reference algorithm itself shows against its fp32 run when only
+    its storage is bf16 (oracle.graphs.bf16_storage with the weight rounding of exactly the layers the device runs on tensor
+    cores) + 1e-3 -- see tests/test_gpu_fullsize.py for why a fixed 1e-2 cannot hold through tens of stored bf16 tensors."""
+    from conftest import tensor_core_convs
+    from oracle import graphs
+    tc = tensor_core_convs(net, x)
+    with torch.no_grad(), graphs.bf16_storage(lambda pfx, w: pfx in tc):
+        stor = fn({k: v.clone() for k, v in sd.items()}, x.cpu())
+    e = rel_err(stor, want)
+    return 1.3 * e + 1e-3, e
+
+
 def _grads_vs_golden(net, g, tol, cap=4096, f64=None):
     gr = dict(net.named_parameters())
     keys = [k[5:] for k in g.files if k.startswith("grad:")]
@@ -46,10 +59,13 @@ def test_modified_3dunet_against_golden(B, golden, dtype):
     gen = torch.Generator().manual_seed(32)
     x = torch.randn(2, 1, 32, 32, 32, generator=gen)
     t = (torch.rand(2, 1, 32, 32, 32, generator=gen) > 0.5).float()
-    tol = TOL32 if dtype == torch.float32 else 3 * TOL16
     net.eval()
+    tol = TOL32
+    if dtype == torch.bfloat16:
+        tol, e_s = _storage_bound(B, net, x.cuda(), lambda s_, x_: graphs.modified_3dunet(s_, x_), sd, g["eval_logits"])
     with torch.no_grad():
         ev = net(x.cuda())
+    print(f"[modified3dunet {dtype}] eval logits vs reference {rel_err(ev, g['eval_logits']):.2e} (bound {tol:.2e})")
     assert ev.dtype == torch.float32 and rel_err(ev, g["eval_logits"]) < tol
     mism = ev.argmax(1).cpu() != torch.from_numpy(g["eval_logits"]).argmax(1)
     assert float(mism.float().mean()) < (1e-4 if dtype == torch.float32 else 0.03)
@@ -65,11 +81,19 @@ def test_modified_3dunet_against_golden(B, golden, dtype):
         graphs.dice_loss_mean(graphs.modified_3dunet(sd64, x.double(), True, 0.0), t.double()).backward()
         _grads_vs_golden(net, g, 1e-3, f64={k: thin(v.grad, 4096) for k, v in sd64.items()})
     else:
+        # every gradient: no further from the reference than the reference algorithm with bf16 storage is (x1.6 + 3e-3: two
+        # independent realisations of the same rounding noise), and well aligned where the storage oracle is
+        from conftest import tensor_core_convs
+        tc = tensor_core_convs(net, x.cuda())
+        osd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        with graphs.bf16_storage(lambda pfx, w: pfx in tc):
+            graphs.dice_loss_mean(graphs.modified_3dunet(osd, x, True, 0.0), t).backward()
         gr = dict(net.named_parameters())
         for k in (k[5:] for k in g.files if k.startswith("grad:")):
-            assert cosine(thin(gr[k].grad.cpu(), 4096), g["grad:" + k]) > 0.9, k
-        for k in ("conv3d_l4.weight", "conv_norm_lrelu_l4.0.weight"):
-            assert rel_err(thin(gr[k].grad.cpu(), 4096), g["grad:" + k]) < 5e-2, k
+            want, got, stor = g["grad:" + k], thin(gr[k].grad.cpu(), 4096), thin(osd[k].grad, 4096)
+            e_c, e_s = rel_err(got, want), rel_err(stor, want)
+            assert e_c < 1.6 * e_s + 3e-3, (k, e_c, e_s)
+            assert cosine(got, want) > min(0.9, cosine(stor, want) - 0.05), k
 
 
 CNN_CASES = {
@@ -93,29 +117,39 @@ def test_cnn_model_family_against_golden(B, golden, name, dtype):
     sd = weights.seeded_like(net.state_dict(), seed=40 + seed)
     net.load_state_dict(sd, strict=True)
     net = B.convert(net.cuda(), dtype=dtype)
+    from oracle import graphs
     x = torch.randn(*shape, generator=torch.Generator().manual_seed(50 + seed)).cuda()
-    tol = TOL32 if dtype == torch.float32 else 3 * TOL16
+    fn = {"voxresnet_b3": lambda s_, x_, tr=False: graphs.voxresnet(s_, x_, 3, 2, tr), "voxresnet_b4": lambda s_, x_, tr=False: graphs.voxresnet(s_, x_, 4, 1, tr),
+          "cnn_b3": lambda s_, x_, tr=False: graphs.cnn(s_, x_, 3, 1, tr), "dilated_cnn": lambda s_, x_, tr=False: graphs.dilated_cnn(s_, x_, tr)}[name]
     net.eval()
+    tol = tol_tr = TOL32
+    if dtype == torch.bfloat16:
+        tol, _ = _storage_bound(B, net, x, fn, sd, g["eval_out"])
+        tol_tr, _ = _storage_bound(B, net, x, lambda s_, x_: fn(s_, x_, True), sd, g["train_out"])
+        # the outputs are 2-4 x 2 numbers: the ratio of two realisations of the rounding noise is itself noisy -> x2 + 1e-2
+        tol, tol_tr = 2 * tol + TOL16, 2 * tol_tr + TOL16
     with torch.no_grad():
         ev = net(x)
-    assert rel_err(ev, g["eval_out"]) < tol
     net.train()
     tr = net(x)
-    assert rel_err(tr, g["train_out"]) < (tol if dtype == torch.float32 else 6 * TOL16)          # batch statistics of 2-4 samples amplify rounding
+    print(f"[{name} {dtype}] eval {rel_err(ev, g['eval_out']):.2e} (bound {tol:.2e}) train {rel_err(tr, g['train_out']):.2e} (bound {tol_tr:.2e})")
+    assert rel_err(ev, g["eval_out"]) < tol
+    assert rel_err(tr, g["train_out"]) < tol_tr                     # (batch statistics of 2-4 samples amplify rounding)
     y = (torch.arange(shape[0]) % 2).cuda()
     loss = torch.nn.functional.nll_loss(torch.log(tr), y) if name == "dilated_cnn" else torch.nn.functional.cross_entropy(tr, y)
     loss.backward()
     for k in g.files:
         if k.startswith("buf:"):
-            assert rel_err(net.state_dict()[k[4:]], g[k]) < tol, k
+            assert rel_err(net.state_dict()[k[4:]], g[k]) < max(tol, 3 * TOL16 if dtype == torch.bfloat16 else 0), k
     if dtype == torch.float32:
         assert abs(float(loss) - float(g["loss"])) < 1e-4
         _grads_vs_golden(net, g, 5e-3)
     else:
         gr = dict(net.named_parameters())
-        last = [k[5:] for k in g.files if k.startswith("grad:") and "fully_conn" in k]
-        for k in last:
-            assert cosine(thin(gr[k].grad.cpu(), 4096), g["grad:" + k]) > 0.9, k
+        scale = max(float(np.linalg.norm(g[k])) for k in g.files if k.startswith("grad:"))
+        for k in [k[5:] for k in g.files if k.startswith("grad:") and "fully_conn" in k]:
+            if float(np.linalg.norm(g["grad:" + k])) > 1e-4 * scale:             # a Linear bias in front of BatchNorm1d has an exactly-zero gradient
+                assert cosine(thin(gr[k].grad.cpu(), 4096), g["grad:" + k]) > 0.9, k
 
 
 def test_fader_heads_train_gradients(B, golden):
@@ -215,8 +249,13 @@ def test_convert_drop_in_on_reference_shaped_unet_eager_loop(B):
     bucket.remove()
     assert B.launch_count() - n0 > 300                                             # the library ran the step, not torch
     pr, pg = dict(ref.named_parameters()), dict(net.named_parameters())
-    for k in ("d1.c1.weight", "d2.c3.weight", "u1.c3.weight", "u2.c2.weight", "head1.bias", "d3.n1.weight"):
-        assert rel_err(pg[k], pr[k]) < 5e-4, k
+    # AdamW's first steps move every weight by ~lr whatever the gradient's size, so elements whose gradient is at fp32 rounding
+    # level (weights in front of a BatchNorm) may step the other way: 5e-3 of the weight norm bounds that; the losses above are tight
+    for k, p in pg.items():
+        if p.grad is not None:
+            assert rel_err(p, pr[k]) < 5e-3, k
+    for k in ("u1.c3.weight", "head1.weight", "head1.bias", "u1.n3.weight"):
+        assert rel_err(pg[k].grad, pr[k].grad) < 1e-3, k
     assert pg["d1.c2.weight"].grad is None and pr["d1.c2.weight"].grad is None      # dead branch: skipped by both optimizers
     br, bg = dict(ref.named_buffers()), dict(net.named_buffers())
     for k in ("d1.n2.running_mean", "u1.n3.running_var"):
