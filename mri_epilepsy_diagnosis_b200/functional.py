@@ -178,7 +178,30 @@ def _side_stream(device):
     return s
 
 
-def _conv_backward(cfg, cd, x, weight, dy, out_dtype, need_dx, need_dw, need_db, has_bias):
+# Deferred weight gradients (graphed.GraphedTrainStep): inside `with deferred_wgrad():` every wgrad kernel of a captured backward
+# pass goes to the side stream and ACCUMULATES into `param.grad` there; the main stream does not wait for it -- it carries on with
+# the normalisation backward / dgrad of the next layer, so the HBM-bound kernels of the main chain run next to the tensor-bound
+# wgrad kernels (different resources of the same SMs) -- and joins once, when the context exits.  Autograd gets None for those
+# parameter gradients (AccumulateGrad is not invoked), so this is only valid when `param.grad` already exists (the flat gradient
+# buffer of GraphedTrainStep) and nothing hooks the accumulation.
+_DEFER = {"on": False, "used": False}
+
+
+class deferred_wgrad:
+    def __enter__(self):
+        self.prev = dict(_DEFER)
+        _DEFER.update(on=True, used=False)
+        return self
+
+    def __exit__(self, *exc):
+        if _DEFER["used"]:
+            dev = torch.cuda.current_device()
+            torch.cuda.current_stream(dev).wait_stream(_side_stream(torch.device("cuda", dev)))
+        _DEFER.update(self.prev)
+        return False
+
+
+def _conv_backward(cfg, cd, x, weight, dy, out_dtype, need_dx, need_dw, need_db, has_bias, bias=None):
     dy = to_cl(dy)
     if dy.dtype != out_dtype:
         dy = dy.to(out_dtype)
@@ -191,7 +214,10 @@ def _conv_backward(cfg, cd, x, weight, dy, out_dtype, need_dx, need_dw, need_db,
     # Only while a CUDA graph is being captured (a fork/join in the graph): in eager mode the cross-stream lifetime tracking
     # (record_stream) keeps the GB-sized activations from being reused by the caching allocator and the step gets slower
     # (unet.UNet(first=16), 4 x 128^3: 28.6 ms without, 40-55 ms with).
-    side = _side_stream(x.device) if (OVERLAP_WGRAD and need_dx and do_w and PROFILE is None and torch.cuda.is_current_stream_capturing()) else None
+    capturing = OVERLAP_WGRAD and do_w and PROFILE is None and torch.cuda.is_current_stream_capturing()
+    defer = (capturing and _DEFER["on"] and weight.is_leaf and weight.grad is not None and weight.grad.dtype == torch.float32 and weight.grad.is_contiguous()
+             and (not need_db or (bias is not None and bias.is_leaf and bias.grad is not None and bias.grad.dtype == torch.float32)))
+    side = _side_stream(x.device) if (capturing and (need_dx or defer)) else None
     if do_w:
         dw = _tempty(weight.shape, dtype=torch.float32, device=x.device)
         db = _tempty(weight.shape[1] if cfg.transposed else weight.shape[0], dtype=torch.float32, device=x.device) if has_bias else None
@@ -212,6 +238,14 @@ def _conv_backward(cfg, cd, x, weight, dy, out_dtype, need_dx, need_dw, need_db,
         ws = _workspace(nws, x.device)
         with _Timed(cd, cabi.PASS_DGRAD):
             check(lib().b200_conv_dgrad(C.byref(cd), dy.data_ptr(), wp.data_ptr(), dx.data_ptr(), ws.data_ptr(), nws, stream()))
+    if side is not None and defer:
+        with torch.cuda.stream(side):                   # accumulate on the side stream; joined by deferred_wgrad.__exit__
+            if need_dw:
+                weight.grad.add_(dw)
+            if need_db and db is not None:
+                bias.grad.add_(db)
+        _DEFER["used"] = True
+        return dx, None, None
     if side is not None:
         cur.wait_stream(side)
     if do_w:
@@ -248,6 +282,7 @@ class _ConvFn(Function):
                 check(lib().b200_conv_fwd(C.byref(cd), x.data_ptr(), wp.data_ptr(), ptr(b), y.data_ptr(), ws.data_ptr(), nws, stream()))
         ctx.save_for_backward(x, weight)
         ctx.cfg, ctx.cd, ctx.has_bias, ctx.out_dtype = cfg, cd, bias is not None, out_dtype
+        ctx.bias_param = bias            # (not a saved tensor: only its .grad is touched, by the deferred-wgrad mode)
         if not want_stats:
             return y
         if part is None:
@@ -259,7 +294,7 @@ class _ConvFn(Function):
     def backward(ctx, dy, *unused):
         x, weight = ctx.saved_tensors
         dx, dw, db = _conv_backward(ctx.cfg, ctx.cd, x, weight, dy, ctx.out_dtype, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
-                                    ctx.has_bias and ctx.needs_input_grad[2], ctx.has_bias)
+                                    ctx.has_bias and ctx.needs_input_grad[2], ctx.has_bias, ctx.bias_param)
         return dx, dw, db, None, None, None, None
 
 

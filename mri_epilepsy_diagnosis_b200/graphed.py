@@ -16,6 +16,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
+from . import functional as BF
 from . import nn as bnn
 
 
@@ -102,7 +103,8 @@ class GraphedTrainStep:
         self.flat.zero_()
         with bnn.defer_batch_counters():
             loss = self.loss_fn(self.model(self.x), self.t)
-        loss.backward()
+        with BF.deferred_wgrad():          # wgrad kernels accumulate into the flat buffer on a side stream; one join here
+            loss.backward()
         return loss.detach()
 
     def _reduce_and_step(self):

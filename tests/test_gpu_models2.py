@@ -234,8 +234,11 @@ def test_convert_drop_in_on_reference_shaped_unet_eager_loop(B):
     keys = list(ref.state_dict().keys())
     net = B.convert(net.cuda(), dtype=torch.float32)
     assert list(net.state_dict().keys()) == keys and refshaped.F is B.nn.functional_proxy
-    opt_r = torch.optim.AdamW(ref.parameters(), lr=1e-3)
-    opt = torch.optim.AdamW(net.parameters(), lr=1e-3)
+    # (SGD + momentum rather than routine.py's AdamW: Adam's first steps move every weight by ~lr whatever the gradient's size, so
+    # parameters whose gradient sits at fp32 rounding level would make the weight comparison below meaningless; the optimizer is
+    # torch's own either way)
+    opt_r = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
+    opt = torch.optim.SGD(net.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
     bucket = B.dp.attach(net, opt)
     g = torch.Generator().manual_seed(1)
     n0 = B.launch_count()
@@ -249,11 +252,9 @@ def test_convert_drop_in_on_reference_shaped_unet_eager_loop(B):
     bucket.remove()
     assert B.launch_count() - n0 > 300                                             # the library ran the step, not torch
     pr, pg = dict(ref.named_parameters()), dict(net.named_parameters())
-    # AdamW's first steps move every weight by ~lr whatever the gradient's size, so elements whose gradient is at fp32 rounding
-    # level (weights in front of a BatchNorm) may step the other way: 5e-3 of the weight norm bounds that; the losses above are tight
     for k, p in pg.items():
         if p.grad is not None:
-            assert rel_err(p, pr[k]) < 5e-3, k
+            assert rel_err(p, pr[k]) < 1e-3 or float((p.detach().cpu() - pr[k]).abs().max()) < 1e-6, k
     for k in ("u1.c3.weight", "head1.weight", "head1.bias", "u1.n3.weight"):
         assert rel_err(pg[k].grad, pr[k].grad) < 1e-3, k
     assert pg["d1.c2.weight"].grad is None and pr["d1.c2.weight"].grad is None      # dead branch: skipped by both optimizers
