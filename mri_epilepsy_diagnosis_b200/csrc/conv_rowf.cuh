@@ -12,7 +12,7 @@
 //   * planes stream through a ring along z (one new plane per output plane; 3 live for a 3x3x3 filter);
 //   * the packed weights of ALL taps stay resident in shared memory (this kernel takes the layers where they fit);
 //   * accumulators: T tiles x Cout fp32 columns of TMEM, two sets, so the epilogue of plane z overlaps the MMAs of z+1;
-//   * warp roles (192 threads): 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue (TMEM -> bf16 -> global,
+//   * warp roles (352 threads): 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..5 and 7..10 = epilogue (TMEM -> bf16 -> global,
 //     consecutive lanes = consecutive voxels = fully coalesced stores), optionally accumulating the per-channel sum / sum of
 //     squares of the outputs for the BatchNorm that follows (fp32, per-thread partials, one atomic flush per CTA).
 #pragma once
@@ -20,9 +20,9 @@
 
 namespace b200 {
 
-constexpr int kRfThreads = 224;           // warp 6 = weight producer (streaming mode)
+constexpr int kRfThreads = 352;           // warps: 0 TMA, 1 MMA, 2..5 epilogue set 0, 6 weight producer (streaming mode), 7..10 epilogue set 1
 constexpr int kRfMaxW = 8;                // weight ring depth (streaming mode)
-constexpr int kRfRing = 4;
+constexpr int kRfRing = 8;                // deepest plane ring (barrier array size); the planner picks p.ring in [3, 8]
 constexpr int kRfMaxTiles = 16;
 constexpr int kRfMaxDynSmem = 227 * 1024 - 4096;      // 4 KB reserved for the kernel's static shared memory (barriers, statistics scratch)
 
@@ -54,6 +54,7 @@ struct RowFwdParams {
     // 9 instructions of max(32 + 3*OC/4, 3*OC/2) cycles per tile and plane instead of 27 of max(32 + OC/4, OC/2).
     int fold;
     int ncol;                    // TMEM columns per tile: OC, or 3*OC when folded
+    int dbg;                     // B200_ROWF_DBG (timing experiments only, results are WRONG): 1 = epilogue skips all work, 2 = no shifted sum
 };
 
 struct alignas(128) RowFwdBarriers {
@@ -99,6 +100,10 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ RowFwdBarriers bars;
+    // folded epilogue: [epilogue set][phase][warp][P_0 row of lane 31 | P_2 row of lane 0][channel] + a row of zeros (the x halo)
+    __shared__ __align__(16) float xch[FOLD ? 2 : 1][2][4][2][16];
+    __shared__ __align__(16) float xzero[16];
+    if (threadIdx.x < 16) xzero[threadIdx.x] = 0.f;
     uint8_t* planes = smem;
     uint8_t* wsm = smem + (size_t)p.ring * p.plane_bytes;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -107,7 +112,7 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
     if (threadIdx.x == 0) {
         for (int i = 0; i < kRfRing; ++i) { ptx::mbar_init(ptx::smem_u32(&bars.pfull[i]), 1); ptx::mbar_init(ptx::smem_u32(&bars.pempty[i]), 1); }
         for (int i = 0; i < kRfMaxW; ++i) { ptx::mbar_init(ptx::smem_u32(&bars.wfull[i]), 1); ptx::mbar_init(ptx::smem_u32(&bars.wempty[i]), 1); }
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(ptx::smem_u32(&bars.afull[i]), 1); ptx::mbar_init(ptx::smem_u32(&bars.aempty[i]), 4); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(ptx::smem_u32(&bars.afull[i]), 1); ptx::mbar_init(ptx::smem_u32(&bars.aempty[i]), 8); }
         ptx::fence_barrier_init();
         ptx::prefetch_tmap(&in_map);
     }
@@ -160,6 +165,7 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
         const bool leader = ptx::elect_one();                                   // one fixed lane issues every tcgen05 instruction of the CTA
         uint32_t cnt = 0, group = 0;
         if (!p.stream_w) {
+        const uint32_t rring = (uint32_t)p.ring;
         ptx::mbar_wait(ptx::smem_u32(&bars.wfull[0]), 0);
         for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
             const RfItem c = rf_decode(p, item);
@@ -170,13 +176,18 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
                 const int need = min(z + pd, p.D - 1);
                 for (; ready < need; ++ready) {
                     const uint32_t i = cnt + (uint32_t)(ready + 1 - first);
-                    ptx::mbar_wait(ptx::smem_u32(&bars.pfull[i % kRfRing]), (i / kRfRing) & 1);
+                    ptx::mbar_wait(ptx::smem_u32(&bars.pfull[i % rring]), (i / rring) & 1);
                 }
                 const uint32_t set = group & 1;
                 ptx::mbar_wait(ptx::smem_u32(&bars.aempty[set]), ((group >> 1) & 1) ^ 1);
                 ptx::tc_fence_after();
-                // ring slot of plane z+kz-pd is (i0 + kz) & 3 (kRfRing == 4; unsigned wrap-around keeps this right for z < pd)
-                const uint32_t i0 = cnt + (uint32_t)(z - pd - first);
+                // ring slot of plane z+kz-pd is (cnt + z-pd-first + kz) % ring.  The modulo is taken ONCE per group (first tap plane that
+                // exists) and advanced by compare-and-wrap; tile offsets and accumulator columns advance by addition: the issuing warp
+                // is a single dependent instruction stream, and integer divisions / modulos per tile showed up as idle tensor cycles
+                // once the kx-folded MMAs were no longer epilogue-bound.
+                const int j0 = z - pd - first;                                      // >= -pd
+                const int kzf = j0 < 0 ? -j0 : 0;                                   // first tap plane inside the volume
+                const uint32_t slot0 = (cnt + (uint32_t)(j0 + kzf)) % rring;
                 uint32_t hasmask = 0;
 #pragma unroll
                 for (int kz = 0; kz < KD; ++kz) { const int pl = z + kz - pd; if (pl >= 0 && pl < p.D) hasmask |= 1u << kz; }
@@ -189,15 +200,19 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
 #pragma unroll
                     for (int j = 0; j < KHW * KHW; ++j) off[j] = (uint32_t)(j / KHW) * row16 + (uint32_t)(j % KHW) * vox16;
                     const uint32_t a_flag = 1u << 16;
+                    const uint32_t colstep16 = 128u * vox16, rowstep16 = (uint32_t)p.rowstride * vox16;
+                    uint32_t d_tmem = tmem_base + (uint32_t)(set * p.T * p.ncol);
+                    uint32_t tile16 = 0, trow16 = 0;
+                    int tcol = 0;
                     for (int t = 0; t < ntiles; ++t) {
-                        const uint32_t d_tmem = tmem_base + (uint32_t)((set * p.T + t) * p.ncol);
-                        const uint32_t tile16 = (uint32_t)((t / p.tpr) * p.rowstride + (t % p.tpr) * 128) * vox16;
                         uint32_t acc = 0;
                         uint32_t bb = w16 | (FOLD ? 3u * b_lbo : b_lbo);
+                        uint32_t slot = slot0;
 #pragma unroll 1
                         for (int kz = 0; kz < KD; ++kz) {
                             if (!((hasmask >> kz) & 1)) { bb += (uint32_t)(KHW * KHW) * wtap16; continue; }
-                            const uint32_t a0 = (pl16 + ((i0 + (uint32_t)kz) & (kRfRing - 1)) * plane16 + tile16) | a_flag;
+                            const uint32_t a0 = (pl16 + slot * plane16 + tile16) | a_flag;
+                            slot = slot + 1 == rring ? 0 : slot + 1;
                             if (FOLD) {
                                 // B block of (kz, ky): [ci group][kx][oc][8 ci] -> LBO = 3*OC*16 B, next 16 ci = 2 groups further
 #pragma unroll
@@ -223,6 +238,8 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
                                 bb += wtap16;
                             }
                         }
+                        d_tmem += (uint32_t)p.ncol;
+                        if (++tcol == p.tpr) { tcol = 0; trow16 += rowstep16; tile16 = trow16; } else tile16 += colstep16;
                     }
                     if (leader) {
                         ptx::umma_commit(ptx::smem_u32(&bars.afull[set]));
@@ -230,7 +247,7 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
                         const int lo = z - pd, hi = (z + 1 == c.z1) ? last : lo;
                         for (int pl = max(lo, first); pl <= hi; ++pl) {
                             const uint32_t i = cnt + (uint32_t)(pl - first);
-                            ptx::umma_commit(ptx::smem_u32(&bars.pempty[i % kRfRing]));
+                            ptx::umma_commit(ptx::smem_u32(&bars.pempty[i % rring]));
                         }
                     }
                 }
@@ -327,6 +344,11 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
         }
     } else {
         // ===================================================== epilogue: TMEM -> (+bias) -> bf16 -> global (+ BN statistics)
+        // TWO sets of four warps (set 0 = warps 2..5, set 1 = warps 7..10; a warp reads the TMEM lane quarter warp % 4, so each set
+        // covers the 128 rows of a tile).  The sets take alternate tiles of every accumulator group: the epilogue is a long
+        // dependent chain (TMEM load -> exchange -> convert -> store), so one warp per scheduler could not hide its latencies --
+        // with the kx-folded MMAs the epilogue, not the tensor pipe, was the bound (ncu: tensor pipe 45 % busy, 71 % no eligible warp).
+        const int eset = warp >= 7 ? 1 : 0;
         const int lane_grp = warp & 3;
         const int m = lane_grp * 32 + lane;
         const bool want_stats = p.stats != nullptr;
@@ -344,52 +366,58 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
                 ptx::mbar_wait(ptx::smem_u32(&bars.afull[set]), (group >> 1) & 1);
                 ptx::tc_fence_after();
                 const int64_t plane_vox = ((int64_t)c.n * p.D + z) * p.H;
-                for (int t = 0; t < ntiles; ++t) {
-                    const int slot = (t / p.tpr) * p.rowstride + (t % p.tpr) * 128 + m;
-                    const int row = slot / p.pitchW, x = slot - row * p.pitchW;
+                for (int t = (eset ^ (int)(group & 1)); t < ntiles; t += 2) {         // (alternating start: one-tile groups still use both sets)
+                    if (p.dbg == 1) continue;
+                    int row, x;
+                    if (FOLD) { row = t; x = m; }                                   // W == 128: one tile = one whole x-row
+                    else {
+                        const int slot = (t / p.tpr) * p.rowstride + (t % p.tpr) * 128 + m;
+                        row = slot / p.pitchW; x = slot - row * p.pitchW;
+                    }
                     const bool valid = x < p.W && row < c.rows;
                     __nv_bfloat16* dst = p.out + ((plane_vox + c.y0 + row) * p.W + x) * ocs - p.store_c0;
                     const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)((set * p.T + t) * p.ncol);
                     if (FOLD) {
                         // out[x] = P_0[x-1] + P_1[x] + P_2[x+1]; the tile is one whole x-row (W == 128), so x-1 / x+1 outside the tile
-                        // are the zero halo.  Neighbour lanes by shuffle, the two warp-boundary lanes through shared memory.
-                        __shared__ __align__(16) float xch[2][4][2][16];
+                        // are the zero halo.  Neighbour lanes by a rotating shuffle; the value that crosses a warp boundary travels
+                        // through shared memory: lane 31 publishes its P_0 row and then REPLACES it by the previous warp's lane 31
+                        // (lane 0 likewise for P_2), so the rotation delivers every lane its neighbour without a per-value select.
 #pragma unroll
                         for (int ch = 0; ch < kStatCh; ++ch) {
                             if (ch * 16 < p.OC) {
                                 float v[16], l[16], r[16];
-                                ptx::tmem_ld16(taddr + (uint32_t)(ch * 16), l);
-                                ptx::tmem_ld16(taddr + (uint32_t)(p.OC + ch * 16), v);
-                                ptx::tmem_ld16(taddr + (uint32_t)(2 * p.OC + ch * 16), r);
-                                float (&buf)[4][2][16] = xch[xphase & 1];
+                                ptx::tmem_ld16x3(taddr + (uint32_t)(ch * 16), taddr + (uint32_t)(p.OC + ch * 16), taddr + (uint32_t)(2 * p.OC + ch * 16), l, v, r);
+                                float (&buf)[4][2][16] = xch[eset][xphase & 1];
+                                if (p.dbg != 2) {
                                 if (lane == 31) {
+                                    float4* d4 = reinterpret_cast<float4*>(&buf[lane_grp][0][0]);
 #pragma unroll
-                                    for (int i = 0; i < 16; ++i) buf[lane_grp][0][i] = l[i];
+                                    for (int q = 0; q < 4; ++q) d4[q] = make_float4(l[4 * q], l[4 * q + 1], l[4 * q + 2], l[4 * q + 3]);
                                 }
                                 if (lane == 0) {
+                                    float4* d4 = reinterpret_cast<float4*>(&buf[lane_grp][1][0]);
 #pragma unroll
-                                    for (int i = 0; i < 16; ++i) buf[lane_grp][1][i] = r[i];
+                                    for (int q = 0; q < 4; ++q) d4[q] = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
                                 }
-                                asm volatile("bar.sync 1, 128;" ::: "memory");
-                                // EVERY lane loads both edge rows (broadcast reads) into registers and selects: per-value
-                                // `if (lane == 0)` branches cost ~100 cycles each in branch resolution (32 per tile: 3 200 cycles)
-                                float el[16], er[16];
-                                {
-                                    const float4* pl = reinterpret_cast<const float4*>(&buf[lane_grp > 0 ? lane_grp - 1 : 0][0][0]);
-                                    const float4* pr = reinterpret_cast<const float4*>(&buf[lane_grp < 3 ? lane_grp + 1 : 3][1][0]);
-                                    const float zl = lane_grp > 0 ? 1.f : 0.f, zr = lane_grp < 3 ? 1.f : 0.f;
+                                if (eset == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+                                else asm volatile("bar.sync 2, 128;" ::: "memory");
+                                if (lane == 31) {
+                                    const float4* s4 = reinterpret_cast<const float4*>(lane_grp > 0 ? &buf[lane_grp - 1][0][0] : &xzero[0]);
 #pragma unroll
-                                    for (int q = 0; q < 4; ++q) {
-                                        const float4 a4 = pl[q], b4 = pr[q];
-                                        el[4 * q] = a4.x * zl; el[4 * q + 1] = a4.y * zl; el[4 * q + 2] = a4.z * zl; el[4 * q + 3] = a4.w * zl;
-                                        er[4 * q] = b4.x * zr; er[4 * q + 1] = b4.y * zr; er[4 * q + 2] = b4.z * zr; er[4 * q + 3] = b4.w * zr;
-                                    }
+                                    for (int q = 0; q < 4; ++q) { const float4 a4 = s4[q]; l[4 * q] = a4.x; l[4 * q + 1] = a4.y; l[4 * q + 2] = a4.z; l[4 * q + 3] = a4.w; }
                                 }
-                                const bool first = lane == 0, last = lane == 31;
+                                if (lane == 0) {
+                                    const float4* s4 = reinterpret_cast<const float4*>(lane_grp < 3 ? &buf[lane_grp + 1][1][0] : &xzero[0]);
 #pragma unroll
-                                for (int i = 0; i < 16; ++i) {
-                                    const float a = __shfl_up_sync(0xffffffffu, l[i], 1), b = __shfl_down_sync(0xffffffffu, r[i], 1);
-                                    v[i] += (first ? el[i] : a) + (last ? er[i] : b);
+                                    for (int q = 0; q < 4; ++q) { const float4 a4 = s4[q]; r[4 * q] = a4.x; r[4 * q + 1] = a4.y; r[4 * q + 2] = a4.z; r[4 * q + 3] = a4.w; }
+                                }
+                                const int from_l = (lane + 31) & 31, from_r = (lane + 1) & 31;
+#pragma unroll
+                                for (int i = 0; i < 16; ++i)
+                                    v[i] += __shfl_sync(0xffffffffu, l[i], from_l) + __shfl_sync(0xffffffffu, r[i], from_r);
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) v[i] += l[i] + r[i];
                                 }
                                 ++xphase;
                                 if (p.bias != nullptr) {
@@ -442,22 +470,27 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
             }
         }
         if (want_stats) {
-            // per-CTA partial: lanes -> warp (shuffle), 4 warps -> CTA in a fixed order (deterministic); summed over CTAs by
-            // norm_stats_finalize_kernel in double
-            __shared__ float red[4][2][16 * kStatCh];
+            // per-CTA partial: lanes -> warp (shuffle), 8 warps -> CTA in a fixed order (deterministic); summed over CTAs by
+            // norm_stats_finalize_kernel in double.  The scratch aliases the plane ring: every MMA that reads it has retired (the
+            // last accumulator group was waited for above) and no TMA load is in flight.
+            float* red = reinterpret_cast<float*>(smem);                 // [8 warps][2][16 * kStatCh]
+            const int w8 = eset * 4 + lane_grp;
 #pragma unroll
             for (int i = 0; i < 16 * kStatCh; ++i) {
                 if (i < p.OC) {
                     float a = ssum[i], b = ssq[i];
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-                    if (lane == 0) { red[lane_grp][0][i] = a; red[lane_grp][1][i] = b; }
+                    if (lane == 0) { red[(w8 * 2 + 0) * 16 * kStatCh + i] = a; red[(w8 * 2 + 1) * 16 * kStatCh + i] = b; }
                 }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (m < 2 * p.OC) {
+            asm volatile("bar.sync 3, 256;" ::: "memory");
+            if (eset == 0 && m < 2 * p.OC) {
                 const int which = m / p.OC, ch = m - which * p.OC;
-                p.stats[((size_t)blockIdx.x * 2 + which) * p.OC + ch] = (red[0][which][ch] + red[1][which][ch]) + (red[2][which][ch] + red[3][which][ch]);
+                float acc = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) acc += red[(w * 2 + which) * 16 * kStatCh + ch];
+                p.stats[((size_t)blockIdx.x * 2 + which) * p.OC + ch] = acc;
             }
         }
     }
@@ -541,9 +574,9 @@ inline int row_fwd_plan_mode(const RowFwdGeom& g, int N, RowFwdParams* p, size_t
     double mma_cyc = 32.0 + p->ncol / 4.0;
     if (mma_cyc < 48.0) mma_cyc = 48.0;
     if (mma_cyc < p->ncol / 2.0) mma_cyc = p->ncol / 2.0;
-    int best = 0, best_zs = 1, best_nw = 1, best_stream = 0; double best_cost = 1e30;
+    int best = 0, best_zs = 1, best_nw = 1, best_stream = 0, best_ring = 4; double best_cost = 1e30;
+    static const int ring_cap = [] { const char* e = getenv("B200_ROWF_RING"); const int v = e == nullptr ? kRfRing : atoi(e); return v < 4 ? 4 : (v > kRfRing ? kRfRing : v); }();
     for (int stream_w = 0; stream_w <= (p->fold ? 0 : 1); ++stream_w) {
-        const int ring = stream_w ? 3 : kRfRing;
         const int nw_lo = stream_w ? 2 : 1, nw_hi = stream_w ? kRfMaxW : 1;
         for (int nw = nw_lo; nw <= nw_hi; ++nw) {
             const size_t wsm_bytes = stream_w ? (size_t)nw * p->wtap_bytes : (size_t)p->w_bytes;
@@ -555,6 +588,13 @@ inline int row_fwd_plan_mode(const RowFwdGeom& g, int N, RowFwdParams* p, size_t
                 const size_t pb = (((size_t)(YB + 2 * ph) * p->pitchW * g.IC * 2) + 1023) & ~(size_t)1023;
                 const size_t reach = ((size_t)T * 128 + (size_t)(g.khw - 1) * (p->pitchW + 1)) * g.IC * 2;
                 const size_t tail = reach > pb ? reach - pb : 0;
+                // plane ring: 2*pd + 1 planes are live while a group runs, every further slot is one plane of TMA lookahead.  With a
+                // single spare slot the load of plane z+2 has exactly one group time to arrive, and a TMA round trip under load
+                // (~2 k cycles + transfer) is LONGER than the MMAs of a kx-folded group: measured 32->32 @128^3 with the epilogue
+                // switched off, 0.367 ms against 0.23 ms of MMA time.  Resident mode takes the deepest ring that fits (<= 8);
+                // streaming mode keeps 3 (it releases the kz = 0 plane early, see the MMA loop).
+                int ring = stream_w ? 3 : ring_cap;
+                while (ring > (stream_w ? 3 : 4) && (size_t)ring * pb + (tail > wsm_bytes ? tail - wsm_bytes : 0) > budget) --ring;
                 if ((size_t)ring * pb + (tail > wsm_bytes ? tail - wsm_bytes : 0) > budget) continue;
                 const int yblocks = (g.H + YB - 1) / YB;
                 const double g_mma = (double)T * (p->fold ? taps / 3 : taps) * nks * mma_cyc;
@@ -564,8 +604,11 @@ inline int row_fwd_plan_mode(const RowFwdGeom& g, int N, RowFwdParams* p, size_t
                 const double g_w = stream_w ? (double)p->w_bytes / w_bw : 0.0;
                 // streaming pays a full-barrier wait + commit per tap and cannot run ahead of the weight ring: measured ~1.5x the
                 // MMA time of the resident mode on the layers where both fit
-                const double group = stream_w ? 1.5 * (g_mma > g_w ? g_mma : g_w) + 150.0 * taps + 400.0 : g_mma + 400.0;
+                double group = stream_w ? 1.5 * (g_mma > g_w ? g_mma : g_w) + 150.0 * taps + 400.0 : g_mma + 400.0;
                 const double plane_cyc = (double)pb / 20.0;
+                const int lookahead = stream_w ? 1 : ring - (2 * pd + 1);
+                const double feed = (2000.0 + (double)pb / 16.0) / (lookahead > 0 ? lookahead : 1);      // one plane per group must arrive
+                if (!stream_w && group < feed) group = feed;
                 for (int zs = g.D; zs >= 1; zs = (zs > 4 ? (zs + 1) / 2 : zs - 1)) {
                     if (g.kd == 1 && zs != 1) continue;
                     const int zsegs = (g.D + zs - 1) / zs;
@@ -573,13 +616,13 @@ inline int row_fwd_plan_mode(const RowFwdGeom& g, int N, RowFwdParams* p, size_t
                     const double rounds = (double)((items + kNumSMs - 1) / kNumSMs);
                     // resident weights are loaded once per CTA (w_bytes / 10 B/clk)
                     const double cost = rounds * (zs * group + 2 * pd * plane_cyc + 1500.0) + (stream_w ? 0.0 : (double)p->w_bytes / 10.0);
-                    if (cost < best_cost) { best_cost = cost; best = YB; best_zs = zs; best_nw = nw; best_stream = stream_w; }
+                    if (cost < best_cost) { best_cost = cost; best = YB; best_zs = zs; best_nw = nw; best_stream = stream_w; best_ring = ring; }
                 }
             }
         }
     }
     p->stream_w = best_stream;
-    p->ring = best_stream ? 3 : kRfRing;
+    p->ring = best_stream ? 3 : best_ring;
     p->nw = best_nw;
     B200_REQUIRE(best >= 1, "row fwd: a row block does not fit shared memory / TMEM");
     p->YB = best;
@@ -653,6 +696,8 @@ inline int row_fwd_run(const b200_conv_desc* d, int pass, const void* in, const 
     size_t smem_bytes = 0;
     if (row_fwd_plan(g, d->N, &p, &smem_bytes)) return 1;
     p.w = (const __nv_bfloat16*)w_packed; p.bias = bias; p.out = (__nv_bfloat16*)out; p.stats = stats; p.store_c0 = store_c0;
+    static const int dbg = [] { const char* e = getenv("B200_ROWF_DBG"); return e == nullptr ? 0 : atoi(e); }();
+    p.dbg = dbg;
     static const bool debug = [] { const char* e = getenv("B200_ROWF_DEBUG"); return e != nullptr && e[0] == '1'; }();
     if (debug)
         fprintf(stderr, "[row_fwd] N=%d %dx%dx%d IC=%d OC=%d k=%d,%d: YB=%d T=%d zs=%d items=%d ring=%d stream=%d nw=%d plane=%dB smem=%zuB tmem=%d fold=%d\n", d->N,
