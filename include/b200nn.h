@@ -215,6 +215,19 @@ int b200_copy_channels(int dtype, int64_t V, int32_t C, const void* src, int32_t
 int b200_to_channels_last(int src_dtype, int dst_dtype, int32_t N, int32_t C, int64_t S, const void* src, void* dst, void* stream);
 int b200_from_channels_last(int src_dtype, int dst_dtype, int32_t N, int32_t C, int64_t S, const void* src, void* dst, void* stream);
 
+/* ------------------------------------------------------------------ sliding-grid patch inference / random-patch sampling (row f-3)
+ * torchio.inference.GridSampler / GridAggregator and torchio.Queue(ImageSampler) as called at
+ * segmentation/pretraining_3d_unet.ipynb [cell 26, 35] and segmentation/routine.py:150-178 (third-party torchio, version
+ * unpinned: the host side restates its published <= 0.16 algorithm, see mri_epilepsy_diagnosis_b200/grid.py).
+ * b200_grid_gather:    out[l][c][:,:,:] = vol[c][z0:z0+pd, y0:y0+ph, x0:x0+pw] for the L windows loc[l] = (z0,y0,x0,z1,y1,x1).
+ * b200_grid_aggregate: vol (D,H,W) receives, voxel by voxel, the value of the LAST window (in `loc` order) whose box cropped by
+ *                      `border` on every side contains it (== the reference's sequential overwrites); other voxels are untouched.
+ * elem_bytes: 1, 2, 4 or 8 (plain copies: bit-exact for every dtype). */
+int b200_grid_gather(int elem_bytes, const void* vol, const int32_t* loc, int64_t L, int C, int D, int H, int W, int pd, int ph, int pw,
+                     void* out, void* stream);
+int b200_grid_aggregate(int elem_bytes, const void* labels, const int32_t* loc, int L, int D, int H, int W, int pd, int ph, int pw,
+                        int bd, int bh, int bw, void* vol, void* stream);
+
 /* ------------------------------------------------------------------ sliding-window patch gather
  * detection/patch_utils.py: get_only_patches :142-191, get_all_patches_and_labels :17-140.
  * Volumes are C-order (X,Y,Z) float64 exactly as the reference holds them.  Two steps:

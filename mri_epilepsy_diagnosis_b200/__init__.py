@@ -8,7 +8,7 @@ Everything computes in libb200nn.so (hand-written CUDA, C ABI in include/b200nn.
 no cuDNN dispatch and no Triton.  Importing the package does not load the library; the first operator call does,
 and raises RuntimeError if it is missing.
 """
-from . import _cabi, functional, nn, patches, zoo, dp, graphed, detect, preprocess, metrics  # noqa: F401
+from . import _cabi, functional, nn, patches, zoo, dp, graphed, detect, preprocess, metrics, grid  # noqa: F401
 from .nn import convert, patch  # noqa: F401
 
 __version__ = "0.1.0"

@@ -94,6 +94,8 @@ _SIGS = {
     "b200_patch_max_rows": (i64, [P(PatchDesc)]),
     "b200_patch_plan": (C.c_int, [P(PatchDesc), vp, vp, vp, vp, vp, vp, sz, vp]),
     "b200_patch_gather": (C.c_int, [P(PatchDesc), vp, vp, i64, C.c_int, vp, vp]),
+    "b200_grid_gather": (C.c_int, [C.c_int, vp, vp, i64, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "b200_grid_aggregate": (C.c_int, [C.c_int, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
     "b200_overlap_counts": (C.c_int, [vp, vp, i64, vp, vp]),
     "b200_histstd_workspace_bytes": (sz, []),
     "b200_histstd_normalize": (C.c_int, [P(HistStdDesc), vp, vp, i64, vp, vp, vp, sz, vp]),

@@ -12,6 +12,7 @@
 #include "loss.cuh"
 #include "norm.cuh"
 #include "patches.cuh"
+#include "grid.cuh"
 #include "pool_upsample.cuh"
 #include "preprocess.cuh"
 #include "metrics.cuh"
@@ -793,6 +794,41 @@ int b200_patch_gather(const b200_patch_desc* d, const double* target, const int3
     const int64_t total = rows * 2 * g.h * g.w;
     if (out_is_f32) B200_LAUNCH(patch_gather_kernel<float>, stream_grid(total, 256), 256, 0, stream, g, target, plan, rows, (float*)out);
     else B200_LAUNCH(patch_gather_kernel<double>, stream_grid(total, 256), 256, 0, stream, g, target, plan, rows, (double*)out);
+    return 0;
+}
+
+// ============================================================================ sliding-grid patches (f-3)
+int b200_grid_gather(int elem_bytes, const void* vol, const int32_t* loc, int64_t L, int C, int D, int H, int W, int pd, int ph, int pw,
+                     void* out, void* stream) {
+    B200_REQUIRE(L >= 0 && C > 0 && D > 0 && H > 0 && W > 0 && pd > 0 && ph > 0 && pw > 0, "grid_gather: non-positive size");
+    B200_REQUIRE(pd <= D && ph <= H && pw <= W, "grid_gather: patch (%d,%d,%d) larger than the volume (%d,%d,%d)", pd, ph, pw, D, H, W);
+    if (L == 0) return 0;
+    B200_REQUIRE(vol && loc && out, "grid_gather: null pointer");
+    const int64_t total = L * C * pd * ph * pw;
+#define B200_GRID_G(T) B200_LAUNCH(grid_gather_kernel<T>, stream_grid(total, 256), 256, 0, stream, (const T*)vol, loc, L, C, D, H, W, pd, ph, pw, (T*)out)
+    if (elem_bytes == 1) { B200_GRID_G(uint8_t); }
+    else if (elem_bytes == 2) { B200_GRID_G(uint16_t); }
+    else if (elem_bytes == 4) { B200_GRID_G(uint32_t); }
+    else if (elem_bytes == 8) { B200_GRID_G(uint64_t); }
+    else return fail("grid_gather: elem_bytes must be 1, 2, 4 or 8");
+#undef B200_GRID_G
+    return 0;
+}
+
+int b200_grid_aggregate(int elem_bytes, const void* labels, const int32_t* loc, int L, int D, int H, int W, int pd, int ph, int pw,
+                        int bd, int bh, int bw, void* vol, void* stream) {
+    B200_REQUIRE(L >= 0 && D > 0 && H > 0 && W > 0 && pd > 0 && ph > 0 && pw > 0, "grid_aggregate: non-positive size");
+    B200_REQUIRE(bd >= 0 && bh >= 0 && bw >= 0 && 2 * bd < pd && 2 * bh < ph && 2 * bw < pw, "grid_aggregate: border (%d,%d,%d) leaves nothing of the patch", bd, bh, bw);
+    if (L == 0) return 0;
+    B200_REQUIRE(labels && loc && vol, "grid_aggregate: null pointer");
+    const int64_t total = (int64_t)D * H * W;
+#define B200_GRID_A(T) B200_LAUNCH(grid_aggregate_kernel<T>, stream_grid(total, 256), 256, 0, stream, (const T*)labels, loc, L, D, H, W, pd, ph, pw, bd, bh, bw, (T*)vol)
+    if (elem_bytes == 1) { B200_GRID_A(uint8_t); }
+    else if (elem_bytes == 2) { B200_GRID_A(uint16_t); }
+    else if (elem_bytes == 4) { B200_GRID_A(uint32_t); }
+    else if (elem_bytes == 8) { B200_GRID_A(uint64_t); }
+    else return fail("grid_aggregate: elem_bytes must be 1, 2, 4 or 8");
+#undef B200_GRID_A
     return 0;
 }
 

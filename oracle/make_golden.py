@@ -295,6 +295,23 @@ def rel_err_t(a, b):
     return float((a.detach().double() - b.detach().double()).norm() / (b.detach().double().norm() + 1e-30))
 
 
+def grid_case():
+    """Row f-3 (sliding-grid inference).  torchio is third-party and absent: this vector comes from the oracle restatement of its
+    published <= 0.16 algorithm (oracle/grid.py) -- a REGRESSION anchor, 'parity unpinned' -- on the MNI-sized volume of config 3
+    with the notebook's arguments (64^3 windows, overlap 4)."""
+    from oracle import grid
+    shape = (192, 224, 192)
+    loc = grid.grid_spatial_coordinates(shape, (64, 64, 64), (4, 4, 4))
+    rng = np.random.default_rng(6)
+    labels = rng.integers(0, 2, (len(loc), 1, 64, 64, 64)).astype(np.uint8)
+    out = grid.aggregate(np.zeros(shape, np.uint8), labels, loc, (4, 4, 4))
+    vol = rng.integers(0, 255, (1,) + shape).astype(np.uint8)
+    patches_ = grid.extract_patches(vol, loc)
+    save("grid_kat6_UNPINNED", locations=loc, n=np.array(len(loc)), agg_sha=np.array(sha16(out)), agg_sum=np.array(int(out.sum())),
+         written=np.array(int((grid.aggregate(np.zeros(shape, np.uint8), np.ones_like(labels), loc, (4, 4, 4)) > 0).sum())),
+         patches_sha=np.array(sha16(patches_)), small_locations=grid.grid_spatial_coordinates((100, 70, 130), (64, 64, 64), (4, 4, 4)))
+
+
 def detect_cases():
     """FCD mask generation (detection/model_utils.py:118-228) run through the REFERENCE class with a deterministic stand-in
     classifier (best_model.pth is not shipped): pins the patch map, the post-processing quirk and the painted mask."""
@@ -434,9 +451,9 @@ if __name__ == "__main__":
     assert refload.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["fixtures", "ops", "unet3d", "ae", "fader", "fepegar", "patches", "detect", "histstd", "metrics", "modified_unet", "cnn_model", "patch_nodrop"]
+    which = sys.argv[1:] or ["fixtures", "ops", "unet3d", "ae", "fader", "fepegar", "patches", "detect", "histstd", "metrics", "modified_unet", "cnn_model", "patch_nodrop", "grid"]
     table = dict(fixtures=copy_fixtures, ops=op_pins, unet3d=unet3d_cases, ae=ae_cases, fader=fader_cases,
-                 fepegar=fepegar_case, patches=patch_cases, modified_unet=modified_unet_cases, cnn_model=cnn_model_cases, patch_nodrop=patch_model_nodrop_case, detect=detect_cases, histstd=histstd_cases, metrics=metrics_cases)
+                 fepegar=fepegar_case, patches=patch_cases, modified_unet=modified_unet_cases, cnn_model=cnn_model_cases, patch_nodrop=patch_model_nodrop_case, grid=grid_case, detect=detect_cases, histstd=histstd_cases, metrics=metrics_cases)
     for w in which:
         print(w)
         table[w]()
