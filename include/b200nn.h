@@ -215,6 +215,20 @@ int b200_copy_channels(int dtype, int64_t V, int32_t C, const void* src, int32_t
 int b200_to_channels_last(int src_dtype, int dst_dtype, int32_t N, int32_t C, int64_t S, const void* src, void* dst, void* stream);
 int b200_from_channels_last(int src_dtype, int dst_dtype, int32_t N, int32_t C, int64_t S, const void* src, void* dst, void* stream);
 
+/* ------------------------------------------------------------------ surface distances (row f-2, the surface half)
+ * compute_surface_distances, segmentation/metrics.py:25-178 (neighbour-code correlate :123-130, borders :133-135, exact Euclidean
+ * distance transform :139-149, surfel lists :157-160), called from segmentation/routine.py:206-214.  All arrays live on the corner
+ * grid (D+1, H+1, W+1) of a (D, H, W) mask volume; voxels != 0 are inside.
+ * b200_surface_codes:   code u8 per corner + the number of border corners (code != 0 && != 255) added to *nborder (zero it first).
+ * b200_surface_edt:     exact squared distance of every corner to the nearest border corner of `code`; spacing == NULL: int32
+ *                       result in voxel units (exact), else fp64 with the three spacings; `scratch` has the result's size.
+ * b200_surface_collect: for every border corner of `code`: its code and dist2_other[corner], appended at out[atomic counter++]
+ *                       (unordered; *counter must be zeroed first; outputs sized by the b200_surface_codes count). */
+int b200_surface_codes(const uint8_t* mask, int D, int H, int W, uint8_t* code, uint32_t* nborder, void* stream);
+int b200_surface_edt(const uint8_t* code, int D1, int H1, int W1, const double* spacing, void* dist2, void* scratch, void* stream);
+int b200_surface_collect(const uint8_t* code, const void* dist2_other, int is_f64, int64_t corners, void* out_dist2, uint8_t* out_code,
+                         uint32_t* counter, void* stream);
+
 /* ------------------------------------------------------------------ sliding-grid patch inference / random-patch sampling (row f-3)
  * torchio.inference.GridSampler / GridAggregator and torchio.Queue(ImageSampler) as called at
  * segmentation/pretraining_3d_unet.ipynb [cell 26, 35] and segmentation/routine.py:150-178 (third-party torchio, version

@@ -97,6 +97,9 @@ _SIGS = {
     "b200_grid_gather": (C.c_int, [C.c_int, vp, vp, i64, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
     "b200_grid_aggregate": (C.c_int, [C.c_int, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
     "b200_overlap_counts": (C.c_int, [vp, vp, i64, vp, vp]),
+    "b200_surface_codes": (C.c_int, [vp, i32, i32, i32, vp, vp, vp]),
+    "b200_surface_edt": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, vp]),
+    "b200_surface_collect": (C.c_int, [vp, vp, C.c_int, i64, vp, vp, vp, vp]),
     "b200_histstd_workspace_bytes": (sz, []),
     "b200_histstd_normalize": (C.c_int, [P(HistStdDesc), vp, vp, i64, vp, vp, vp, sz, vp]),
 }

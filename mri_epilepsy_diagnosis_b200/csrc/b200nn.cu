@@ -16,6 +16,7 @@
 #include "pool_upsample.cuh"
 #include "preprocess.cuh"
 #include "metrics.cuh"
+#include "surface.cuh"
 
 using namespace b200;
 
@@ -835,6 +836,31 @@ int b200_grid_aggregate(int elem_bytes, const void* labels, const int32_t* loc, 
 // ============================================================================ validation overlap counts (f-2, counting part)
 int b200_overlap_counts(const uint8_t* pred, const uint8_t* gt, int64_t n, uint64_t* counts5, void* stream) {
     return overlap_counts_run(pred, gt, n, counts5, stream);
+}
+
+// ============================================================================ surface distances (f-2, surface half)
+int b200_surface_codes(const uint8_t* mask, int D, int H, int W, uint8_t* code, uint32_t* nborder, void* stream) {
+    B200_REQUIRE(mask && code && nborder && D > 0 && H > 0 && W > 0, "surface_codes: bad arguments");
+    const int64_t total = (int64_t)(D + 1) * (H + 1) * (W + 1);
+    B200_LAUNCH(sd_code_kernel, stream_grid(total, 256), 256, 0, stream, mask, D, H, W, code, nborder);
+    return 0;
+}
+
+int b200_surface_edt(const uint8_t* code, int D1, int H1, int W1, const double* spacing, void* dist2, void* scratch, void* stream) {
+    B200_REQUIRE(code && dist2 && scratch && D1 > 1 && H1 > 1 && W1 > 1, "surface_edt: bad arguments");
+    B200_REQUIRE(D1 <= 4096 && H1 <= 4096 && W1 <= 4096, "surface_edt: volume too large for the int32 distance range");
+    if (spacing == nullptr) return surface_edt_run<int32_t>(code, D1, H1, W1, 1, 1, 1, (int32_t*)dist2, (int32_t*)scratch, stream);
+    B200_REQUIRE(spacing[0] > 0 && spacing[1] > 0 && spacing[2] > 0, "surface_edt: spacing must be positive");
+    return surface_edt_run<double>(code, D1, H1, W1, spacing[0] * spacing[0], spacing[1] * spacing[1], spacing[2] * spacing[2], (double*)dist2,
+                                   (double*)scratch, stream);
+}
+
+int b200_surface_collect(const uint8_t* code, const void* dist2_other, int is_f64, int64_t corners, void* out_dist2, uint8_t* out_code,
+                         uint32_t* counter, void* stream) {
+    B200_REQUIRE(code && dist2_other && out_dist2 && out_code && counter && corners > 0, "surface_collect: bad arguments");
+    if (is_f64) B200_LAUNCH(sd_collect_kernel<double>, stream_grid(corners, 256), 256, 0, stream, code, (const double*)dist2_other, corners, (double*)out_dist2, out_code, counter);
+    else B200_LAUNCH(sd_collect_kernel<int32_t>, stream_grid(corners, 256), 256, 0, stream, code, (const int32_t*)dist2_other, corners, (int32_t*)out_dist2, out_code, counter);
+    return 0;
 }
 
 // ============================================================================ intensity preprocessing (f-1)

@@ -312,6 +312,82 @@ def grid_case():
          patches_sha=np.array(sha16(patches_)), small_locations=grid.grid_spatial_coordinates((100, 70, 130), (64, 64, 64), (4, 4, 4)))
 
 
+def surface_cases():
+    """Row f-2, surface half: `compute_surface_distances` and the statistics built on it through the REFERENCE's own functions
+    (segmentation/metrics.py:25-309) on synthetic label volumes (ellipsoids, a hollow shell, touching the volume faces, random blobs,
+    disjoint far-apart objects, one empty mask).  Also writes the package's data asset: the 256-entry normal table that
+    metrics.py:333-600 vendors from Google's surface-distance library (Apache-2.0), as a structured .npy (data, not source)."""
+    from oracle import metrics as M
+    ref = refload._load("_ref_metrics", "segmentation/metrics.py")
+    table = ref.neighbour_code_to_normals
+    asset = np.zeros(256, dtype=[("count", np.int32), ("normals", np.float64, (4, 3))])
+    for code, normals in enumerate(table):
+        arr = np.array(normals, dtype=np.float64).reshape(-1, 3)
+        asset["count"][code] = len(arr)
+        asset["normals"][code][:len(arr)] = arr
+    dst = os.path.join(ROOT, "mri_epilepsy_diagnosis_b200", "data", "neighbour_code_normals.npy")
+    os.makedirs(os.path.dirname(dst), exist_ok=True)
+    np.save(dst, asset)
+    print("  wrote", os.path.relpath(dst, ROOT))
+    rng = np.random.default_rng(12)
+    zz, yy, xx = np.meshgrid(np.arange(48), np.arange(56), np.arange(40), indexing="ij")
+    ell = lambda c, r: (((zz - c[0]) / r[0]) ** 2 + ((yy - c[1]) / r[1]) ** 2 + ((xx - c[2]) / r[2]) ** 2 < 1)
+    blobs = lambda thr: ndimage_blobs(rng, (48, 56, 40), thr)
+    cases = {
+        "ellipsoids": (ell((24, 25, 20), (10, 15, 9)), ell((25, 27, 21), (9.5, 14, 10))),
+        "shell": (ell((24, 28, 20), (14, 16, 12)) & ~ell((24, 28, 20), (8, 9, 6)), ell((24, 28, 20), (13, 16, 12))),
+        "faces": (ell((2, 28, 20), (10, 12, 8)), ell((44, 30, 36), (12, 10, 9))),          # cut by the volume faces, far apart
+        "blobs": (blobs(0.62), blobs(0.6)),
+        "single_voxel": (np.pad(np.ones((1, 1, 1), bool), ((5, 42), (7, 48), (9, 30))), ell((24, 25, 20), (6, 6, 6))),
+        "identical": (ell((24, 25, 20), (10, 15, 9)), ell((24, 25, 20), (10, 15, 9))),
+    }
+    out = {}
+    for name, (gt, pred) in cases.items():
+        gt8, pr8 = gt.astype(np.uint8), pred.astype(np.uint8)                                 # validate_dsc_asd passes uint8 0/1 volumes
+        for sp_name, spacing in (("", (1, 1, 1)), ("_aniso", (1.0, 0.8, 2.5))):
+            if sp_name and name not in ("ellipsoids", "blobs"):
+                continue
+            sd = ref.compute_surface_distances(gt8, pr8, spacing)
+            mine = M.compute_surface_distances(gt8, pr8, spacing, table)
+            for k in sd:
+                assert np.array_equal(sd[k], mine[k]), (name, k)
+            key = name + sp_name
+            out[key + ":gt"], out[key + ":pred"] = gt8, pr8
+            for k, v in sd.items():
+                out[f"{key}:{k}"] = v
+            out[key + ":asd"] = np.array(ref.compute_average_surface_distance(sd))
+            out[key + ":hd95"] = np.array(ref.compute_robust_hausdorff(sd, 95))
+            out[key + ":overlap1"] = np.array(ref.compute_surface_overlap_at_tolerance(sd, 1.0))
+            out[key + ":sdice1"] = np.array(ref.compute_surface_dice_at_tolerance(sd, 1.0))
+            print(f"  {key}: {len(sd['distances_gt_to_pred'])} / {len(sd['distances_pred_to_gt'])} surfels, asd {out[key + ':asd']}, hd95 {float(out[key + ':hd95']):.4f}")
+    out["area_table_111"] = M_area(ref, (1, 1, 1))
+    save("surface_distances", **out)
+
+
+def M_area(ref, spacing):
+    """the reference's surfel-area table for `spacing`, by running its own code on a one-voxel mask and reading the table back
+    through the areas it reports is not possible for all 256 codes -- so evaluate metrics.py:58-71's expression on its table"""
+    area = np.zeros([256])
+    for code in range(256):
+        normals = np.array(ref.neighbour_code_to_normals[code])
+        s = 0
+        for i in range(normals.shape[0]):
+            n = np.zeros([3])
+            n[0] = normals[i, 0] * spacing[1] * spacing[2]
+            n[1] = normals[i, 1] * spacing[0] * spacing[2]
+            n[2] = normals[i, 2] * spacing[0] * spacing[1]
+            s += np.linalg.norm(n)
+        area[code] = s
+    return area
+
+
+def ndimage_blobs(rng, shape, thr):
+    from scipy import ndimage
+    f = ndimage.gaussian_filter(rng.random(shape), 2.5)
+    f = (f - f.min()) / (f.max() - f.min())
+    return f > thr
+
+
 def detect_cases():
     """FCD mask generation (detection/model_utils.py:118-228) run through the REFERENCE class with a deterministic stand-in
     classifier (best_model.pth is not shipped): pins the patch map, the post-processing quirk and the painted mask."""
@@ -451,9 +527,9 @@ if __name__ == "__main__":
     assert refload.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["fixtures", "ops", "unet3d", "ae", "fader", "fepegar", "patches", "detect", "histstd", "metrics", "modified_unet", "cnn_model", "patch_nodrop", "grid"]
+    which = sys.argv[1:] or ["fixtures", "ops", "unet3d", "ae", "fader", "fepegar", "patches", "detect", "histstd", "metrics", "modified_unet", "cnn_model", "patch_nodrop", "grid", "surface"]
     table = dict(fixtures=copy_fixtures, ops=op_pins, unet3d=unet3d_cases, ae=ae_cases, fader=fader_cases,
-                 fepegar=fepegar_case, patches=patch_cases, modified_unet=modified_unet_cases, cnn_model=cnn_model_cases, patch_nodrop=patch_model_nodrop_case, grid=grid_case, detect=detect_cases, histstd=histstd_cases, metrics=metrics_cases)
+                 fepegar=fepegar_case, patches=patch_cases, modified_unet=modified_unet_cases, cnn_model=cnn_model_cases, patch_nodrop=patch_model_nodrop_case, grid=grid_case, surface=surface_cases, detect=detect_cases, histstd=histstd_cases, metrics=metrics_cases)
     for w in which:
         print(w)
         table[w]()
