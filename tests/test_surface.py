@@ -64,7 +64,12 @@ def test_surface_distances_against_reference_vectors(M, golden, case):
         want = g[f"{case}:{k}"]
         assert sd[k].dtype == np.float64 and sd[k].shape == want.shape, k
         if case.endswith("_aniso"):
-            assert np.allclose(sd[k], want, rtol=1e-14, atol=0), k                  # fp64 products with non-unit spacing: last-bit freedom
+            # fp64 products with non-unit spacing: last-bit freedom in a distance, which may also swap two surfels whose distances
+            # tie in exact arithmetic -- distances element-wise, areas as a multiset (the statistics below are order-independent)
+            if k.startswith("distances"):
+                assert np.allclose(sd[k], want, rtol=1e-14, atol=0), k
+            else:
+                assert np.array_equal(np.sort(sd[k]), np.sort(want)), k
         else:
             assert np.array_equal(sd[k], want), k                                   # exact integer squared distances + one fp64 sqrt
     tol = dict(rtol=1e-13, atol=0) if case.endswith("_aniso") else dict(rtol=0, atol=0)
