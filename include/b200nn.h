@@ -215,6 +215,22 @@ int b200_copy_channels(int dtype, int64_t V, int32_t C, const void* src, int32_t
 int b200_to_channels_last(int src_dtype, int dst_dtype, int32_t N, int32_t C, int64_t S, const void* src, void* dst, void* stream);
 int b200_from_channels_last(int src_dtype, int dst_dtype, int32_t N, int32_t C, int64_t S, const void* src, void* dst, void* stream);
 
+/* min-max normalisation of get_image_patches (detection/patch_utils.py:196): out = (x - min(x)) / (max(x) - min(x)), float64,
+ * the same two correctly rounded operations per element as numpy (bit-exact).  workspace: b200_minmax_workspace_bytes() bytes. */
+size_t b200_minmax_workspace_bytes(void);
+int b200_minmax_normalize(const double* x, int64_t n, double* out, void* workspace, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ FCD mask post-processing (row f-4)
+ * FCDMaskGenerator (detection/model_utils.py:118-228) around the batched patch classifier: `plan` is the (rows, 5) int32 output of
+ * b200_patch_plan for the template; patch_map is the reference's (4, Y/h, Z) int64 array, mask its (X, Y, Z) int64 result.
+ * b200_fcd_scatter_labels  :160-178   patch_map[slot][row0/h][slice] = labels[row] (patch_map must be zeroed by the caller)
+ * b200_fcd_vote            :182-193   out-of-place 4-neighbour vote; fixed = 0 reproduces the reference's int-array-as-index
+ *                                     behaviour (slabs 0 / 1 overwritten), fixed = 1 the boolean-mask vote; flags4: 4 zeroed int32
+ * b200_fcd_paint           :195-216   paints the patch labels back (mask must be zeroed by the caller) */
+int b200_fcd_scatter_labels(const int32_t* plan, int64_t rows, const int64_t* labels, int X, int Y, int Z, int h, int w, int64_t* patch_map, void* stream);
+int b200_fcd_vote(const int64_t* patch_map, int ny, int Z, int fixed, int64_t* out, int32_t* flags4, void* stream);
+int b200_fcd_paint(const int32_t* plan, int64_t rows, const int64_t* patch_map, int X, int Y, int Z, int h, int w, int64_t* mask, void* stream);
+
 /* ------------------------------------------------------------------ surface distances (row f-2, the surface half)
  * compute_surface_distances, segmentation/metrics.py:25-178 (neighbour-code correlate :123-130, borders :133-135, exact Euclidean
  * distance transform :139-149, surfel lists :157-160), called from segmentation/routine.py:206-214.  All arrays live on the corner

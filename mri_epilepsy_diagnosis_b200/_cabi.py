@@ -97,6 +97,11 @@ _SIGS = {
     "b200_grid_gather": (C.c_int, [C.c_int, vp, vp, i64, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
     "b200_grid_aggregate": (C.c_int, [C.c_int, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
     "b200_overlap_counts": (C.c_int, [vp, vp, i64, vp, vp]),
+    "b200_minmax_workspace_bytes": (sz, []),
+    "b200_minmax_normalize": (C.c_int, [vp, i64, vp, vp, sz, vp]),
+    "b200_fcd_scatter_labels": (C.c_int, [vp, i64, vp, i32, i32, i32, i32, i32, vp, vp]),
+    "b200_fcd_vote": (C.c_int, [vp, i32, i32, C.c_int, vp, vp, vp]),
+    "b200_fcd_paint": (C.c_int, [vp, i64, vp, i32, i32, i32, i32, i32, vp, vp]),
     "b200_surface_codes": (C.c_int, [vp, i32, i32, i32, vp, vp, vp]),
     "b200_surface_edt": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, vp]),
     "b200_surface_collect": (C.c_int, [vp, vp, C.c_int, i64, vp, vp, vp, vp]),

@@ -17,6 +17,7 @@
 #include "preprocess.cuh"
 #include "metrics.cuh"
 #include "surface.cuh"
+#include "detect.cuh"
 
 using namespace b200;
 
@@ -836,6 +837,46 @@ int b200_grid_aggregate(int elem_bytes, const void* labels, const int32_t* loc, 
 // ============================================================================ validation overlap counts (f-2, counting part)
 int b200_overlap_counts(const uint8_t* pred, const uint8_t* gt, int64_t n, uint64_t* counts5, void* stream) {
     return overlap_counts_run(pred, gt, n, counts5, stream);
+}
+
+// ============================================================================ min-max normalisation (get_image_patches)
+size_t b200_minmax_workspace_bytes(void) { return (size_t)kNumSMs * 4 * 2 * sizeof(double); }
+
+int b200_minmax_normalize(const double* x, int64_t n, double* out, void* workspace, size_t ws_bytes, void* stream) {
+    B200_REQUIRE(x && out && workspace && n > 0, "minmax_normalize: bad arguments");
+    B200_REQUIRE(ws_bytes >= b200_minmax_workspace_bytes(), "minmax_normalize: workspace too small");
+    int parts = (int)ceil_div(n, 256 * 8);
+    if (parts > kNumSMs * 4) parts = kNumSMs * 4;
+    B200_LAUNCH(minmax_partial_kernel, parts, 256, 0, stream, x, n, (double*)workspace);
+    B200_LAUNCH(minmax_apply_kernel, stream_grid(n, 256), 256, 0, stream, x, n, (const double*)workspace, parts, out);
+    return 0;
+}
+
+// ============================================================================ FCD mask post-processing (f-4)
+int b200_fcd_scatter_labels(const int32_t* plan, int64_t rows, const int64_t* labels, int X, int Y, int Z, int h, int w, int64_t* patch_map, void* stream) {
+    B200_REQUIRE(rows >= 0 && X > 0 && Y > 0 && Z > 0 && h > 0 && w > 0 && Y / h > 0, "fcd_scatter_labels: bad geometry");
+    if (rows == 0) return 0;
+    B200_REQUIRE(plan && labels && patch_map, "fcd_scatter_labels: null pointer");
+    B200_LAUNCH(fcd_scatter_kernel, (int)ceil_div(rows, 256), 256, 0, stream, plan, rows, labels, X, h, w, Y / h, Z, patch_map);
+    return 0;
+}
+
+int b200_fcd_vote(const int64_t* patch_map, int ny, int Z, int fixed, int64_t* out, int32_t* flags4, void* stream) {
+    B200_REQUIRE(patch_map && out && flags4 && ny > 0 && Z > 0 && patch_map != out, "fcd_vote: bad arguments");
+    const int64_t total = (int64_t)4 * ny * Z;
+    B200_LAUNCH(fcd_vote_kernel, stream_grid(total, 256), 256, 0, stream, patch_map, ny, Z, fixed, out, flags4);
+    if (!fixed) B200_LAUNCH(fcd_vote_quirk_kernel, stream_grid(2 * (int64_t)ny * Z, 256), 256, 0, stream, ny, Z, (const int*)flags4, out);
+    return 0;
+}
+
+int b200_fcd_paint(const int32_t* plan, int64_t rows, const int64_t* patch_map, int X, int Y, int Z, int h, int w, int64_t* mask, void* stream) {
+    B200_REQUIRE(rows >= 0 && X > 0 && Y > 0 && Z > 0 && h > 0 && w > 0 && Y / h > 0, "fcd_paint: bad geometry");
+    if (rows == 0) return 0;
+    B200_REQUIRE(plan && patch_map && mask, "fcd_paint: null pointer");
+    const int order[4] = {0, 3, 1, 2};                    // the reference's assignment order inside a strip: later boxes overwrite earlier ones
+    for (int s = 0; s < 4; ++s)
+        B200_LAUNCH(fcd_paint_kernel, stream_grid(rows * w * h, 256), 256, 0, stream, plan, rows, patch_map, X, Y, Z, h, w, Y / h, order[s], mask);
+    return 0;
 }
 
 // ============================================================================ surface distances (f-2, surface half)

@@ -173,3 +173,40 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(PatchGeom g, const do
 }
 
 }  // namespace b200
+
+// ------------------------------------------------------------------------------------------------ min-max normalisation
+// get_image_patches (detection/patch_utils.py:193-205): target = (target - target.min()) / (target.max() - target.min()) in float64,
+// evaluated per element with the same two correctly rounded operations as numpy -> bit-exact.
+namespace b200 {
+
+__global__ void __launch_bounds__(256) minmax_partial_kernel(const double* __restrict__ x, int64_t n, double* __restrict__ partial /* [grid][2] */) {
+    double lo = INFINITY, hi = -INFINITY;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = x[i];
+        lo = fmin(lo, v); hi = fmax(hi, v);
+    }
+    __shared__ double slo[8], shi[8];
+    for (int o = 16; o > 0; o >>= 1) { lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    if ((threadIdx.x & 31) == 0) { slo[threadIdx.x >> 5] = lo; shi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { lo = fmin(lo, slo[w]); hi = fmax(hi, shi[w]); }
+        partial[2 * blockIdx.x] = lo; partial[2 * blockIdx.x + 1] = hi;
+    }
+}
+
+__global__ void __launch_bounds__(256) minmax_apply_kernel(const double* __restrict__ x, int64_t n, const double* __restrict__ partial, int nparts,
+                                                           double* __restrict__ out) {
+    __shared__ double s[2];
+    if (threadIdx.x < 32) {
+        double lo = INFINITY, hi = -INFINITY;
+        for (int i = threadIdx.x; i < nparts; i += 32) { lo = fmin(lo, partial[2 * i]); hi = fmax(hi, partial[2 * i + 1]); }
+        for (int o = 16; o > 0; o >>= 1) { lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+        if (threadIdx.x == 0) { s[0] = lo; s[1] = hi - lo; }
+    }
+    __syncthreads();
+    const double lo = s[0], range = s[1];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (x[i] - lo) / range;
+}
+
+}  // namespace b200

@@ -3,6 +3,7 @@
 Same names, argument meaning, output order/dtype and error behaviour as the reference:
   get_only_patches(target_np, gmpm, h=16, w=32)                      patch_utils.py:142-191
   get_all_patches_and_labels(target_np, gmpm, mask_np, h=16, w=32)   patch_utils.py:17-140
+  get_image_patches(input_img, input_mask=None, h=16, w=32, gmpm=...) patch_utils.py:193-205 (min-max normalisation + either of the above)
 Inputs may be numpy arrays (copied to the GPU) or CUDA tensors of shape (X,Y,Z); outputs are CUDA tensors
 ((P,2,h,w) float64, labels bool).  `patch_plan` exposes the integer decisions (bit-exact with the reference).
 """
@@ -73,3 +74,52 @@ def get_only_patches(target_np, gmpm, h=16, w=32, device="cuda"):
 def get_all_patches_and_labels(target_np, gmpm, mask_np, h=16, w=32, device="cuda"):
     plan = patch_plan(gmpm, mask_np, h, w, device=device)
     return gather(target_np, plan, h, w), plan[:, 4].bool()
+
+
+def load_nifti(path):
+    """float64 array of a NIfTI-1 file (.nii / .nii.gz), what `nib.load(path).get_fdata()` returns for the files the reference reads:
+    single-file NIfTI-1, little endian, scl_slope / scl_inter applied when set.  (nibabel is not a dependency of this package.)"""
+    import gzip
+    import struct
+    with (gzip.open(path, "rb") if str(path).endswith(".gz") else open(path, "rb")) as f:
+        raw = f.read()
+    if struct.unpack("<i", raw[0:4])[0] != 348:
+        raise ValueError(f"{path}: not a little-endian NIfTI-1 file")
+    dim = struct.unpack("<8h", raw[40:56])
+    datatype = struct.unpack("<h", raw[70:72])[0]
+    vox_offset = int(struct.unpack("<f", raw[108:112])[0])
+    slope, inter = struct.unpack("<2f", raw[112:120])
+    dtypes = {2: "<u1", 4: "<i2", 8: "<i4", 16: "<f4", 64: "<f8", 256: "<i1", 512: "<u2", 768: "<u4"}
+    if datatype not in dtypes:
+        raise ValueError(f"{path}: unsupported NIfTI datatype {datatype}")
+    shape = dim[1:1 + dim[0]]
+    data = np.frombuffer(raw, dtype=dtypes[datatype], count=int(np.prod(shape)), offset=vox_offset).reshape(shape, order="F").astype(np.float64)
+    if slope not in (0.0, 1.0) or inter != 0.0:
+        if slope != 0.0 and np.isfinite(slope) and np.isfinite(inter):
+            data = data * np.float64(slope) + np.float64(inter)
+    return data
+
+
+def minmax_normalize(target, device="cuda"):
+    """(t - t.min()) / (t.max() - t.min()) in float64 on the device -- patch_utils.py:196, bit-exact with numpy"""
+    t = _dev(target if not isinstance(target, str) else load_nifti(target), torch.float64, device)
+    out = torch.empty_like(t)
+    nws = lib().b200_minmax_workspace_bytes()
+    ws = torch.empty(nws, dtype=torch.uint8, device=t.device)
+    check(lib().b200_minmax_normalize(t.data_ptr(), t.numel(), out.data_ptr(), ws.data_ptr(), nws, stream()))
+    return out
+
+
+def get_image_patches(input_img_name, input_mask_name=None, h=16, w=32, gmpm=None, device="cuda"):
+    """detection/patch_utils.py:193-205.  `input_img_name` / `input_mask_name`: NIfTI paths (as in the reference) or arrays / tensors
+    already in memory; `gmpm`: the grey-matter template the reference reads from a notebook global.  Returns (patches (P,2,h,w)
+    float64, labels (P,) bool) as CUDA tensors."""
+    if gmpm is None:
+        raise ValueError("get_image_patches: pass the grey-matter template as gmpm= (a module-level global in the reference)")
+    target = minmax_normalize(input_img_name, device)
+    if input_mask_name is not None:
+        m = load_nifti(input_mask_name) if isinstance(input_mask_name, str) else input_mask_name
+        m = (m > 0) if not torch.is_tensor(m) else (m > 0)
+        return get_all_patches_and_labels(target, gmpm, m, h=h, w=w, device=device)
+    patches = get_only_patches(target, gmpm, h=h, w=w, device=device)
+    return patches, torch.zeros(patches.shape[0], dtype=torch.bool, device=patches.device)

@@ -635,3 +635,41 @@ def test_upsample_concat_rejects_mismatched_skip(B):
     for bad in ((1, 3, 9, 8, 8), (1, 3, 8, 8, 7), (2, 3, 8, 8, 8)):
         with pytest.raises(RuntimeError):
             B.functional.upsample_concat(torch.randn(*bad).cuda(), x)
+
+
+def test_get_image_patches_minmax_and_labels(B, template, tmp_path):
+    """detection/patch_utils.py:193-205: min-max normalisation (float64, bit-exact with numpy) in front of the patch extraction, from
+    arrays and from NIfTI files, with and without a lesion mask."""
+    import gzip
+    import struct
+    from oracle import patches as OP
+    rng = np.random.default_rng(4)
+    img = rng.normal(300.0, 90.0, (182, 218, 182))
+    norm = (img - img.min()) / (img.max() - img.min())
+    got = B.patches.minmax_normalize(img)
+    assert np.array_equal(got.cpu().numpy(), norm)
+    pt, lb = B.patches.get_image_patches(img, gmpm=template)
+    plan = OP.patch_plan(template, None, 16, 32)
+    assert np.array_equal(pt.cpu().numpy(), OP.gather_patches(norm, plan)) and lb.dtype == torch.bool and not bool(lb.any())
+    xx, yy, zz = np.meshgrid(np.arange(182), np.arange(218), np.arange(182), indexing="ij")
+    mask = (((xx - 60) / 9.0) ** 2 + ((yy - 120) / 11.0) ** 2 + ((zz - 90) / 7.0) ** 2 < 1).astype(np.float32)
+
+    def write_nifti(path, arr):                          # minimal single-file NIfTI-1, float32, like the shipped template
+        hdr = bytearray(352)
+        struct.pack_into("<i", hdr, 0, 348)
+        struct.pack_into("<8h", hdr, 40, 3, *arr.shape, 1, 1, 1, 1)
+        struct.pack_into("<h", hdr, 70, 16)
+        struct.pack_into("<h", hdr, 72, 32)
+        struct.pack_into("<f", hdr, 108, 352.0)
+        hdr[344:348] = b"n+1\x00"
+        with gzip.open(path, "wb", compresslevel=1) as f:
+            f.write(bytes(hdr) + np.asfortranarray(arr.astype("<f4")).tobytes(order="F"))
+    write_nifti(tmp_path / "img.nii.gz", img)
+    write_nifti(tmp_path / "mask.nii.gz", mask)
+    img32 = img.astype(np.float32).astype(np.float64)    # what get_fdata() returns for a float32 file
+    assert np.array_equal(B.patches.load_nifti(str(tmp_path / "img.nii.gz")), img32)
+    norm32 = (img32 - img32.min()) / (img32.max() - img32.min())
+    pt2, lb2 = B.patches.get_image_patches(str(tmp_path / "img.nii.gz"), str(tmp_path / "mask.nii.gz"), gmpm=template)
+    plan2 = OP.patch_plan(template, mask > 0, 16, 32)
+    assert np.array_equal(pt2.cpu().numpy(), OP.gather_patches(norm32, plan2))
+    assert np.array_equal(lb2.cpu().numpy(), plan2[:, OP.LABEL].astype(bool)) and int(lb2.sum()) > 0
