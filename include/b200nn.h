@@ -124,6 +124,12 @@ int b200_norm_stats_from_partial(const b200_norm_desc* d, const float* partial, 
 /* eval-mode BatchNorm: mean/rstd derived from the running statistics */
 int b200_norm_stats_from_running(const b200_norm_desc* d, const float* running_mean, const float* running_var,
                                  float* mean, float* rstd, void* stream);
+/* SyncBN (data parallel): packed[2C] = (mean, var + mean^2) of this rank's statistics -> the caller all-reduces
+ * `packed` with AVG over the ranks -> finalize writes the global (mean, rstd) and updates the running statistics with the unbiased
+ * variance for `count_global` = world x N x S elements. */
+int b200_syncbn_pack(int C, float eps, const float* mean, const float* rstd, float* packed, void* stream);
+int b200_syncbn_finalize(int C, float eps, float momentum, double count_global, const float* packed, float* mean, float* rstd,
+                         float* running_mean, float* running_var, void* stream);
 int b200_norm_apply(const b200_norm_desc* d, const void* x, const float* mean, const float* rstd,
                     const float* gamma, const float* beta, const void* residual, void* y, void* stream);
 /* training=1: batch statistics take part in the gradient; 0: eval-mode BN (mean/rstd are constants).

@@ -69,6 +69,8 @@ _SIGS = {
     "b200_norm_stats": (C.c_int, [P(NormDesc), vp, vp, vp, vp, vp, vp, sz, vp]),
     "b200_norm_stats_from_partial": (C.c_int, [P(NormDesc), vp, C.c_int, vp, vp, vp, vp, vp]),
     "b200_norm_stats_from_running": (C.c_int, [P(NormDesc), vp, vp, vp, vp, vp]),
+    "b200_syncbn_pack": (C.c_int, [i32, f32, vp, vp, vp, vp]),
+    "b200_syncbn_finalize": (C.c_int, [i32, f32, f32, C.c_double, vp, vp, vp, vp, vp, vp]),
     "b200_norm_apply": (C.c_int, [P(NormDesc), vp, vp, vp, vp, vp, vp, vp, vp]),
     "b200_norm_bwd": (C.c_int, [P(NormDesc), C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "b200_norm_bwd_reduce": (C.c_int, [P(NormDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),

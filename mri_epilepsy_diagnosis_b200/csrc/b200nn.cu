@@ -356,6 +356,20 @@ int b200_norm_stats_from_running(const b200_norm_desc* d, const float* running_m
     return 0;
 }
 
+int b200_syncbn_pack(int C, float eps, const float* mean, const float* rstd, float* packed, void* stream) {
+    B200_REQUIRE(C > 0 && mean && rstd && packed, "syncbn_pack: bad arguments");
+    B200_LAUNCH(syncbn_pack_kernel, (int)ceil_div(C, 128), 128, 0, stream, C, eps, mean, rstd, packed);
+    return 0;
+}
+
+int b200_syncbn_finalize(int C, float eps, float momentum, double count_global, const float* packed, float* mean, float* rstd,
+                         float* running_mean, float* running_var, void* stream) {
+    B200_REQUIRE(C > 0 && packed && mean && rstd && count_global > 0, "syncbn_finalize: bad arguments");
+    B200_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "syncbn_finalize: running_mean / running_var must come together");
+    B200_LAUNCH(syncbn_finalize_kernel, (int)ceil_div(C, 128), 128, 0, stream, C, eps, momentum, count_global, packed, mean, rstd, running_mean, running_var);
+    return 0;
+}
+
 static int apply_grid(const NormGeom& g, int64_t S) {
     // gx*256 must be a multiple of CV so every thread keeps fixed channels
     int m = g.CV;

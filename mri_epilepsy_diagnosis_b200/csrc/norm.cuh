@@ -439,3 +439,36 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T* __restrict
 }
 
 }  // namespace b200
+
+// ------------------------------------------------------------------------------------------------ SyncBN glue (data parallel)
+// N ranks x local batch == one device x global batch: every rank reduces its own (mean, rstd), packs
+// (mean, E[x^2]) = (mean, var + mean^2), ONE all-reduce(AVG) over the ranks (equal per-rank counts), and the finalize kernel turns
+// the averages back into (mean, rstd) and performs the running-statistics update with the GLOBAL element count.
+namespace b200 {
+
+__global__ void syncbn_pack_kernel(int C, float eps, const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ packed) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float m = mean[c], r = rstd[c];
+    const float var = 1.f / (r * r) - eps;
+    packed[c] = m;
+    packed[C + c] = var + m * m;
+}
+
+__global__ void syncbn_finalize_kernel(int C, float eps, float momentum, double count_global, const float* __restrict__ packed, float* __restrict__ mean,
+                                       float* __restrict__ rstd, float* __restrict__ running_mean, float* __restrict__ running_var) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float m = packed[c];
+    float var = packed[C + c] - m * m;
+    var = var > 0.f ? var : 0.f;
+    mean[c] = m;
+    rstd[c] = rsqrtf(var + eps);
+    if (running_mean != nullptr) {
+        const double unbiased = (double)var * (count_global / (count_global > 1.0 ? count_global - 1.0 : 1.0));
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * m;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+
+}  // namespace b200

@@ -184,13 +184,17 @@ def _side_stream(device):
 # wgrad kernels (different resources of the same SMs) -- and joins once, when the context exits.  Autograd gets None for those
 # parameter gradients (AccumulateGrad is not invoked), so this is only valid when `param.grad` already exists (the flat gradient
 # buffer of GraphedTrainStep) and nothing hooks the accumulation.
-_DEFER = {"on": False, "used": False}
+_DEFER = {"on": False, "used": False, "notify": None, "count": None}
 
 
 class deferred_wgrad:
+    def __init__(self, notify=None):
+        """notify(param): called after a deferred gradient of `param` has been enqueued (GraphedTrainStep's gradient buckets)"""
+        self.notify = notify
+
     def __enter__(self):
         self.prev = dict(_DEFER)
-        _DEFER.update(on=True, used=False)
+        _DEFER.update(on=True, used=False, notify=self.notify)
         return self
 
     def __exit__(self, *exc):
@@ -238,6 +242,10 @@ def _conv_backward(cfg, cd, x, weight, dy, out_dtype, need_dx, need_dw, need_db,
         ws = _workspace(nws, x.device)
         with _Timed(cd, cabi.PASS_DGRAD):
             check(lib().b200_conv_dgrad(C.byref(cd), dy.data_ptr(), wp.data_ptr(), dx.data_ptr(), ws.data_ptr(), nws, stream()))
+    if _DEFER["count"] is not None and do_w:              # counting pass: gradient contributions per parameter and backward
+        for t_, need in ((weight, need_dw), (bias, need_db)):
+            if need and t_ is not None:
+                _DEFER["count"][t_] = _DEFER["count"].get(t_, 0) + 1
     if side is not None and defer:
         with torch.cuda.stream(side):                   # accumulate on the side stream; joined by deferred_wgrad.__exit__
             if need_dw:
@@ -245,6 +253,11 @@ def _conv_backward(cfg, cd, x, weight, dy, out_dtype, need_dx, need_dw, need_db,
             if need_db and db is not None:
                 bias.grad.add_(db)
         _DEFER["used"] = True
+        if _DEFER["notify"] is not None:
+            if need_dw:
+                _DEFER["notify"](weight)
+            if need_db and db is not None:
+                _DEFER["notify"](bias)
         return dx, None, None
     if side is not None:
         cur.wait_stream(side)
@@ -399,18 +412,14 @@ class _NormFn(Function):
             if sync is not None and kind == cabi.NORM_BATCH:
                 import torch.distributed as dist
                 pg, world = sync
+                # local statistics -> (mean, E[x^2]) -> ONE all-reduce(AVG) -> global (mean, rstd) + running statistics: two small
+                # kernels and one collective per layer and direction
                 check(lib().b200_norm_stats(C.byref(nd), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), None, None, ws.data_ptr(), nws, stream()))
-                var = rstd.pow(-2) - eps
-                packed = torch.stack([mean, var + mean * mean])
-                dist.all_reduce(packed, group=pg)
-                packed /= world
-                mean = packed[0].contiguous()
-                var = (packed[1] - mean * mean).clamp_min_(0)
-                rstd = (var + eps).rsqrt()
-                if running_mean is not None:
-                    cnt = nd.N * nd.S * world
-                    running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
-                    running_var.mul_(1 - momentum).add_(var * (cnt / max(cnt - 1, 1)), alpha=momentum)
+                packed = _tempty(2 * nd.C, dtype=torch.float32, device=x.device)
+                check(lib().b200_syncbn_pack(nd.C, float(eps), mean.data_ptr(), rstd.data_ptr(), packed.data_ptr(), stream()))
+                dist.all_reduce(packed, op=dist.ReduceOp.AVG, group=pg)
+                check(lib().b200_syncbn_finalize(nd.C, float(eps), float(momentum if momentum is not None else 0.0), float(nd.N * nd.S * world),
+                                                 packed.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ptr(running_mean), ptr(running_var), stream()))
             elif stats_partial is not None and kind == cabi.NORM_BATCH:
                 check(lib().b200_norm_stats_from_partial(C.byref(nd), stats_partial.data_ptr(), stats_partial.shape[0], mean.data_ptr(), rstd.data_ptr(),
                                                          ptr(running_mean), ptr(running_var), stream()))

@@ -7,9 +7,10 @@ removes the host from the loop.  Every library call only enqueues kernels on the
 buffers, so the C ABI is capture-safe as it stands (tensor maps are built on the host and passed by value).
 
 Single GPU: the graph holds zero_grad + forward + loss + backward + optimizer.step (the optimizer must be constructed with
-`capturable=True`).  Data parallel: the graph holds zero_grad + forward + loss + backward; gradients accumulate directly into
-one flat fp32 buffer (each `p.grad` is a view of it), which is all-reduced over NCCL after the replay, followed by the
-optimizer step (eager or its own graph) -- one collective per step, no per-parameter copies.
+`capturable=True`).  Data parallel: gradients accumulate directly into one flat fp32 buffer (each `p.grad` is a view of it),
+cut into a few contiguous buckets; the NCCL all-reduce (AVG) of a bucket is captured INSIDE the graph on a communication
+stream, forked as soon as the backward pass has produced the bucket's last gradient (late layers first), so it overlaps the
+rest of the backward pass; the optimizer step is captured too when the optimizer is capturable.  No per-parameter copies.
 """
 from __future__ import annotations
 
@@ -34,8 +35,9 @@ class GraphedTrainStep:
     dampening=0) state; an optimizer whose fresh state is not all zeros must be stepped once by the caller before construction.
     """
 
-    def __init__(self, model, loss_fn, optimizer, x_example, t_example, process_group=None, warmup=3):
+    def __init__(self, model, loss_fn, optimizer, x_example, t_example, process_group=None, warmup=3, buckets=3):
         self.model, self.loss_fn, self.opt = model, loss_fn, optimizer
+        self._bucketing = False
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         dev = next(model.parameters()).device
@@ -56,17 +58,22 @@ class GraphedTrainStep:
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
-        self.capture_opt = self.world == 1
-        if self.capture_opt:
-            for g in optimizer.param_groups:
-                if "capturable" in g and not g["capturable"]:
-                    raise RuntimeError("GraphedTrainStep: construct the optimizer with capturable=True so optimizer.step() can be captured")
+        capturable = all(g.get("capturable", False) for g in optimizer.param_groups)
+        self.capture_opt = self.world == 1 or capturable
+        if self.world == 1 and not capturable:
+            raise RuntimeError("GraphedTrainStep: construct the optimizer with capturable=True so optimizer.step() can be captured")
+        if self.world > 1:
+            self._make_buckets(max(1, int(buckets)), dev)
 
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            for _ in range(max(1, warmup)):
+            for i in range(max(1, warmup)):
+                if i == 0 and self.world > 1:          # counting pass: how many gradient contributions each parameter gets per backward
+                    BF._DEFER["count"] = {}
                 self._body(eager=True)
+                if i == 0 and self.world > 1:
+                    self._uses, BF._DEFER["count"] = BF._DEFER["count"], None
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self._restore(snap, dev)
@@ -99,27 +106,86 @@ class GraphedTrainStep:
         torch.set_rng_state(snap["cpu_rng"])
         torch.cuda.set_rng_state(snap["cuda_rng"], dev)
 
-    def _fwd_bwd(self):
+    # ---- gradient buckets (data parallel): contiguous slices of the flat buffer in parameter order; the backward pass finishes them
+    # from the last one to the first
+    def _make_buckets(self, n, dev):
+        total = self.flat.numel()
+        per = -(-total // n)
+        self._bucket_of, self._bucket_range, self._members = {}, [], []
+        off = lo = 0
+        cur = []
+        for p in self.params:
+            cur.append(p)
+            off += p.numel()
+            if off - lo >= per:
+                self._bucket_range.append((lo, off)); self._members.append(cur)
+                lo, cur = off, []
+        if cur:
+            self._bucket_range.append((lo, off)); self._members.append(cur)
+        for b, ps in enumerate(self._members):
+            for p in ps:
+                self._bucket_of[p] = b
+        self._uses = {}
+        self.comm = torch.cuda.Stream(device=dev)
+        self._hooks = [p.register_post_accumulate_grad_hook(self._notify) for p in self.params]
+
+    def _notify(self, p):
+        if not self._bucketing:
+            return
+        b = self._bucket_of.get(p)
+        if b is None or self._launched[b]:
+            return
+        self._remaining[b] -= 1
+        if self._remaining[b] <= 0:
+            self._launch_bucket(b)
+
+    def _launch_bucket(self, b):
+        dev = self.flat.device
+        cur = torch.cuda.current_stream(dev)
+        self.comm.wait_stream(cur)
+        self.comm.wait_stream(BF._side_stream(dev))            # deferred weight gradients are accumulated on the side stream
+        lo, hi = self._bucket_range[b]
+        with torch.cuda.stream(self.comm):
+            dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.AVG, group=self.pg)
+        self._launched[b] = True
+
+    def _fwd_bwd(self, bucketing=False):
         self.flat.zero_()
         with bnn.defer_batch_counters():
             loss = self.loss_fn(self.model(self.x), self.t)
-        with BF.deferred_wgrad():          # wgrad kernels accumulate into the flat buffer on a side stream; one join here
-            loss.backward()
+        if bucketing:
+            # a deferred conv gradient notifies once per use, every other parameter once per backward (AccumulateGrad hook)
+            self._remaining = [sum(max(1, self._uses.get(p, 1)) for p in ps) for ps in self._members]
+            self._launched = [False] * len(self._members)
+            self._bucketing = True
+        try:
+            with BF.deferred_wgrad(self._notify if bucketing else None):     # wgrad kernels accumulate into the flat buffer on a side stream; one join here
+                loss.backward()
+        finally:
+            self._bucketing = False
         return loss.detach()
 
     def _reduce_and_step(self):
         if self.world > 1:
-            dist.all_reduce(self.flat, group=self.pg)
-            self.flat.div_(self.world)
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.pg)
         self.opt.step()
 
     def _body(self, eager):
-        loss = self._fwd_bwd()
-        if eager or self.capture_opt:
+        if eager or self.world == 1:
+            loss = self._fwd_bwd()
             if eager:
                 self._reduce_and_step()
             else:
                 self.opt.step()
+            return loss
+        # data parallel, captured: bucketed all-reduce overlapped with the backward pass, then (capturable optimizers) the step
+        loss = self._fwd_bwd(bucketing=True)
+        for b in reversed(range(len(self._members))):
+            if not self._launched[b]:
+                self._launch_bucket(b)
+        torch.cuda.current_stream(self.flat.device).wait_stream(self.comm)
+        if self.capture_opt:
+            self.opt.step()
         return loss
 
     def __call__(self, x, t):
@@ -127,7 +193,7 @@ class GraphedTrainStep:
         self.t.copy_(t, non_blocking=True)
         self.graph.replay()
         if not self.capture_opt:
-            self._reduce_and_step()
+            self.opt.step()
         return self.loss
 
     # ---- host-fed steps with the next batch's H2D copy overlapped with the current step (what a pin_memory DataLoader with
@@ -165,5 +231,5 @@ class GraphedTrainStep:
         self._consumed[s] = ev
         self.graph.replay()
         if not self.capture_opt:
-            self._reduce_and_step()
+            self.opt.step()
         return self.loss
