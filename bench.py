@@ -227,6 +227,9 @@ def torch_gpu_baseline(model_name, batch, size, steps, warmup, norm, dev):
 
 
 def main():
+    if os.environ.get("B200_BENCH_WATCHDOG"):            # debugging aid: dump every thread's stack if the run has not finished in time
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["B200_BENCH_WATCHDOG"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -474,14 +477,27 @@ def main():
         literal = {"ms_per_step": ms2, "value": voxels / (ms2 / 1e3), "unit": "voxels/s",
                    "what": "same step, reference operator sequence executed one to one (no graph-level rewrites)"}
         del step2, net2, opt2
+    def shutdown():
+        """CUDA graphs that hold captured NCCL kernels must be gone before the communicator is torn down (destroy_process_group
+        otherwise never returns); a watchdog ends the process if the teardown stalls anyway -- every result is printed by then."""
+        if dist is None:
+            return
+        import gc
+        dist.barrier()
+        torch.cuda.synchronize()
+        gc.collect()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        dist.destroy_process_group()
+        os._exit(0)
     if rank != 0:
-        if dist is not None:
-            dist.barrier(); dist.destroy_process_group()
+        step = eager_step = net = opt = None
+        shutdown()
         return
     out = {**base, "value": world * voxels / (ms / 1e3), "ms_per_step": ms, "dtype": "bf16",
            "config": {"workload": workload, "network": model_desc, "volumes_per_step": args.batch * world, "volume": list(vol),
-                      "optimizer": "torch.optim.AdamW(fused=True)" + ("" if args.eager or world > 1 else " inside the captured step"),
-                      "parallelism": f"dp{world}" + ("+syncbn" if sync else ""), "launch": "eager" if args.eager else "cuda-graph replay of the step",
+                      "optimizer": "torch.optim.AdamW(fused=True)" + ("" if args.eager else " inside the captured step"),
+                      "parallelism": f"dp{world}" + ("+syncbn" if sync else ""),
+                      "launch": "eager" if args.eager else "cuda-graph replay of the step" + (" (bucketed NCCL all-reduce captured inside, overlapping the backward pass)" if world > 1 else ""),
                       "l2": "inputs and every activation tensor (>= 268 MB each at 16ch x 128^3 x 4) exceed the 126 MB L2; no flush needed"},
            "e2e": {"value": world * voxels / (ms_e2e / 1e3), "unit": "voxels/s", "ms_per_step": ms_e2e,
                    "h2d_bytes_per_step": xh.numel() * 4 + th.numel() * 4, "d2h_bytes_per_step": 4},
@@ -501,8 +517,8 @@ def main():
         out["cpu_baseline"] = {"value": v, "unit": "voxels/s", "cores": cores, "kind": "port",
                                "sample": f"oracle/graphs.py (CPU restatement of the reference step), fp32, 2 timed steps of 1 x {vol_s} after 1 warm-up"}
     print(json.dumps(out), flush=True)
-    if dist is not None:
-        dist.barrier(); dist.destroy_process_group()
+    step = eager_step = net = opt = None
+    shutdown()
 
 
 if __name__ == "__main__":

@@ -136,7 +136,9 @@ class GraphedTrainStep:
         if b is None or self._launched[b]:
             return
         self._remaining[b] -= 1
-        if self._remaining[b] <= 0:
+        # bucket 0 holds the first layers: the backward pass finishes them last, nothing is left to overlap with, and it is
+        # reduced after the side stream has been joined (see _body)
+        if self._remaining[b] <= 0 and b > 0:
             self._launch_bucket(b)
 
     def _launch_bucket(self, b):
