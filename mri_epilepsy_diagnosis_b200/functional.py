@@ -182,19 +182,16 @@ def _side_stream(device):
 # pass goes to the side stream and ACCUMULATES into `param.grad` there; the main stream does not wait for it -- it carries on with
 # the normalisation backward / dgrad of the next layer, so the HBM-bound kernels of the main chain run next to the tensor-bound
 # wgrad kernels (different resources of the same SMs) -- and joins once, when the context exits.  Autograd gets None for those
-# parameter gradients (AccumulateGrad is not invoked), so this is only valid when `param.grad` already exists (the flat gradient
-# buffer of GraphedTrainStep) and nothing hooks the accumulation.
-_DEFER = {"on": False, "used": False, "notify": None, "count": None}
+# parameter gradients, so this is only valid when `param.grad` already exists (the flat gradient buffer of GraphedTrainStep).
+# Post-accumulate-grad hooks still fire for such a parameter (torch >= 2.1 runs them even when the incoming gradient is None), after
+# the node that enqueued the side-stream accumulation has returned -- GraphedTrainStep's gradient buckets rely on exactly that.
+_DEFER = {"on": False, "used": False}
 
 
 class deferred_wgrad:
-    def __init__(self, notify=None):
-        """notify(param): called after a deferred gradient of `param` has been enqueued (GraphedTrainStep's gradient buckets)"""
-        self.notify = notify
-
     def __enter__(self):
         self.prev = dict(_DEFER)
-        _DEFER.update(on=True, used=False, notify=self.notify)
+        _DEFER.update(on=True, used=False)
         return self
 
     def __exit__(self, *exc):
@@ -242,10 +239,6 @@ def _conv_backward(cfg, cd, x, weight, dy, out_dtype, need_dx, need_dw, need_db,
         ws = _workspace(nws, x.device)
         with _Timed(cd, cabi.PASS_DGRAD):
             check(lib().b200_conv_dgrad(C.byref(cd), dy.data_ptr(), wp.data_ptr(), dx.data_ptr(), ws.data_ptr(), nws, stream()))
-    if _DEFER["count"] is not None and do_w:              # counting pass: gradient contributions per parameter and backward
-        for t_, need in ((weight, need_dw), (bias, need_db)):
-            if need and t_ is not None:
-                _DEFER["count"][t_] = _DEFER["count"].get(t_, 0) + 1
     if side is not None and defer:
         with torch.cuda.stream(side):                   # accumulate on the side stream; joined by deferred_wgrad.__exit__
             if need_dw:
@@ -253,11 +246,6 @@ def _conv_backward(cfg, cd, x, weight, dy, out_dtype, need_dx, need_dw, need_db,
             if need_db and db is not None:
                 bias.grad.add_(db)
         _DEFER["used"] = True
-        if _DEFER["notify"] is not None:
-            if need_dw:
-                _DEFER["notify"](weight)
-            if need_db and db is not None:
-                _DEFER["notify"](bias)
         return dx, None, None
     if side is not None:
         cur.wait_stream(side)

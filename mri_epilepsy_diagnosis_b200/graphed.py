@@ -68,12 +68,8 @@ class GraphedTrainStep:
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            for i in range(max(1, warmup)):
-                if i == 0 and self.world > 1:          # counting pass: how many gradient contributions each parameter gets per backward
-                    BF._DEFER["count"] = {}
+            for _ in range(max(1, warmup)):
                 self._body(eager=True)
-                if i == 0 and self.world > 1:
-                    self._uses, BF._DEFER["count"] = BF._DEFER["count"], None
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self._restore(snap, dev)
@@ -125,8 +121,10 @@ class GraphedTrainStep:
         for b, ps in enumerate(self._members):
             for p in ps:
                 self._bucket_of[p] = b
-        self._uses = {}
         self.comm = torch.cuda.Stream(device=dev)
+        # one notification per parameter and backward pass: autograd runs the post-accumulate-grad hook of a leaf once all of its
+        # gradient contributions have been produced -- also when they were None because the deferred-wgrad path accumulated them
+        # itself on the side stream (the hook then fires after that accumulation has been enqueued)
         self._hooks = [p.register_post_accumulate_grad_hook(self._notify) for p in self.params]
 
     def _notify(self, p):
@@ -156,12 +154,11 @@ class GraphedTrainStep:
         with bnn.defer_batch_counters():
             loss = self.loss_fn(self.model(self.x), self.t)
         if bucketing:
-            # a deferred conv gradient notifies once per use, every other parameter once per backward (AccumulateGrad hook)
-            self._remaining = [sum(max(1, self._uses.get(p, 1)) for p in ps) for ps in self._members]
+            self._remaining = [len(ps) for ps in self._members]
             self._launched = [False] * len(self._members)
             self._bucketing = True
         try:
-            with BF.deferred_wgrad(self._notify if bucketing else None):     # wgrad kernels accumulate into the flat buffer on a side stream; one join here
+            with BF.deferred_wgrad():     # wgrad kernels accumulate into the flat buffer on a side stream; one join here
                 loss.backward()
         finally:
             self._bucketing = False
