@@ -242,6 +242,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[2, 3],
                     help="BASELINE.json config: 2 = batch 4 x 128^3 (default), 3 = one 192x224x192 volume per GPU (data parallel)")
     ap.add_argument("--no-torch-baseline", action="store_true", help="skip the stock-PyTorch-on-this-GPU leg")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short timings of BASELINE configs 1/3/4/5 and rows f-1..f-3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sync-bn", action="store_true")
     ap.add_argument("--no-literal-leg", action="store_true", help="skip the extra timing of the literal operator sequence")
@@ -511,6 +512,12 @@ def main():
         if tg.get("value"):
             tg["ours_over_torch_gpu"] = out["value"] / tg["value"]
         out["torch_gpu_baseline"] = tg
+    if args.gpus == 1 and not args.no_other_configs and args.model == "unet3d" and args.config == 2:
+        # every other BASELINE configuration + the 'next' rows, timed in this same process (tools/workloads.py)
+        from tools import workloads
+        step = eager_step = net = opt = None
+        torch.cuda.empty_cache()
+        out["other_configs"] = workloads.run_all(pkg, dev, pk["hbm_gbs"])
     if args.gpus == 1 and not args.no_cpu_baseline:
         nvox, times, _ = cpu_reference_step(args.model, vol, 2, 1, cores, args.norm)
         v = nvox / (sum(times) / len(times))

@@ -232,3 +232,43 @@ def test_unet3d_forward_on_full_mni_volume(B):
     mism = logits.argmax(1) != ref.argmax(1)
     gap = (ref[:, 0] - ref[:, 1]).abs()
     assert float(mism.float().mean()) < 0.02 and float(gap[mism].max()) < 0.2 * float(gap.mean())      # only near-ties flip
+
+
+def test_autoencoder_at_config1_size_against_oracle(B):
+    """BASELINE config 1 itself: AE (train_AE.ipynb [cell 8]: depth 6, c_base 16 -> channels 1..512) on batch 2 x 128^3, forward + MSE +
+    backward, fp32 ("tf32-off") kernels against the oracle live (AE_model.py:4-210): reconstruction, loss, latent and every gradient."""
+    from oracle import graphs, weights
+    sd = weights.ae_state(depth=6, c_base=16, seed=3)
+    net = B.zoo.config1_autoencoder(depth=6, c_base=16)
+    net.load_state_dict(sd, strict=True)
+    net = B.convert(net.cuda().train(), dtype=torch.float32)
+    x = weights.synthetic_t1w((2, 1, 128, 128, 128), seed=4)
+    rec = net(x.cuda())
+    loss = F.mse_loss(rec, x.cuda())
+    loss.backward()
+    osd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
+    ref = graphs.autoencoder(osd, x, 6, graphs.AE_DOWN, graphs.AE_UP, training=True)
+    rl = F.mse_loss(ref, x)
+    rl.backward()
+    assert tuple(rec.shape) == (2, 1, 128, 128, 128) and rel_err(rec, ref) < 1e-4 and abs(float(loss) - float(rl)) < 1e-6
+    gr = dict(net.named_parameters())
+    scale = max(float(v.grad.norm()) for v in osd.values() if getattr(v, "grad", None) is not None)
+    worst = 0.0
+    for k, v in osd.items():
+        if getattr(v, "grad", None) is None:
+            continue
+        if float(v.grad.norm()) < 1e-4 * scale:                     # conv biases in front of a BatchNorm: the exact gradient is 0
+            assert float(gr[k].grad.norm()) < 1e-3 * scale, k
+            continue
+        e = rel_err(gr[k].grad, v.grad)
+        worst = max(worst, e)
+        assert e < 5e-3, (k, e)                                     # weights in front of a BatchNorm: ill-conditioned, see test_gpu_models.check_grads
+    print(f"[fullsize] AE depth 6 @ 2x128^3 fp32: rec {rel_err(rec, ref):.1e}, worst gradient {worst:.1e}")
+    # the bf16 body on the same input: bounded by the reference algorithm's own bf16-storage distance
+    net16 = B.zoo.config1_autoencoder(depth=6, c_base=16)
+    net16.load_state_dict(sd, strict=True)
+    net16 = B.convert(net16.cuda().eval(), dtype=torch.bfloat16)
+    with torch.no_grad():
+        r16 = net16(x.cuda()).float().cpu()
+        ref_eval = graphs.autoencoder(dict(sd), x, 6, graphs.AE_DOWN, graphs.AE_UP, training=False)
+    assert rel_err(r16, ref_eval) < 8e-2
