@@ -242,6 +242,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[2, 3],
                     help="BASELINE.json config: 2 = batch 4 x 128^3 (default), 3 = one 192x224x192 volume per GPU (data parallel)")
     ap.add_argument("--no-torch-baseline", action="store_true", help="skip the stock-PyTorch-on-this-GPU leg")
+    ap.add_argument("--no-dropin-leg", action="store_true", help="skip the timing of the drop-in path (convert() of a stock model + eager loop)")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short timings of BASELINE configs 1/3/4/5 and rows f-1..f-3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sync-bn", action="store_true")
@@ -512,6 +513,35 @@ def main():
         if tg.get("value"):
             tg["ours_over_torch_gpu"] = out["value"] / tg["value"]
         out["torch_gpu_baseline"] = tg
+    if args.gpus == 1 and args.model == "unet3d" and not args.no_dropin_leg:
+        # the drop-in path as a reference user runs it: a STOCK torch.nn model with unet3d.py's graph (tests/refshaped.StockUnet3d:
+        # F.upsample, F.dropout3d, torch.cat, in-place ReLU) -> nn.convert() -> the eager loop body of segmentation/routine.py:266-281
+        # (zero_grad, forward, torch softmax + Dice, backward, optimizer.step) with dp.attach hooked on; no graph capture, no zoo rewrite
+        step = eager_step = net = opt = None
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import refshaped
+        torch.manual_seed(0)
+        stock = refshaped.StockUnet3d(c=1, n=16, dropout=0.5, norm=args.norm, num_classes=2)
+        dnet = pkg.convert(stock.to(dev).train(), dtype=torch.bfloat16)
+        dopt = torch.optim.AdamW(dnet.parameters())
+        dbucket = pkg.dp.attach(dnet, dopt)
+
+        def dropin_step():
+            dopt.zero_grad()
+            loss = dice_loss_mean(dnet(xd), td)
+            loss.backward()
+            dopt.step()
+            return loss
+        for _ in range(3):
+            dropin_step()
+        msd, _, _ = timed(dropin_step, args.steps)
+        dbucket.remove()
+        out["dropin_eager"] = {"ms_per_step": msd, "value": voxels / (msd / 1e3), "unit": "voxels/s",
+                               "what": "nn.convert() of a stock torch.nn unet3d-shaped model, eager routine.py loop body (torch softmax + Dice, torch AdamW), "
+                                       "no CUDA graph and no graph-level rewrites: the reference's op sequence incl. the dead branch"}
+        dnet = dopt = stock = None
+        torch.cuda.empty_cache()
     if args.gpus == 1 and not args.no_other_configs and args.model == "unet3d" and args.config == 2:
         # every other BASELINE configuration + the 'next' rows, timed in this same process (tools/workloads.py)
         from tools import workloads

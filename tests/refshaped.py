@@ -87,3 +87,84 @@ class RefShapedClassifier(nn.Module):
 
     def forward(self, x):
         return self.model(x)
+
+
+# ------------------------------------------------------------------------------------------------ full-size stock restatement of unet3d.Unet
+def _norm(planes, kind):
+    if kind == "bn":
+        return nn.BatchNorm3d(planes)
+    if kind == "gn":
+        return nn.GroupNorm(4, planes)
+    if kind == "in":
+        return nn.InstanceNorm3d(planes)
+    raise ValueError(kind)
+
+
+class StockConvD(nn.Module):
+    def __init__(self, cin, cout, dropout, norm, first=False):
+        super().__init__()
+        self.first, self.dropout = first, dropout
+        self.maxpool = nn.MaxPool3d(2, 2)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv1, self.bn1 = nn.Conv3d(cin, cout, 3, 1, 1, bias=False), _norm(cout, norm)
+        self.conv2, self.bn2 = nn.Conv3d(cout, cout, 3, 1, 1, bias=False), _norm(cout, norm)
+        self.conv3, self.bn3 = nn.Conv3d(cout, cout, 3, 1, 1, bias=False), _norm(cout, norm)
+
+    def forward(self, x):
+        if not self.first:
+            x = self.maxpool(x)
+        x = self.bn1(self.conv1(x))
+        y = self.relu(self.bn2(self.conv2(x)))
+        if self.dropout > 0:
+            y = F.dropout3d(y, self.dropout)
+        y = self.bn3(self.conv3(x))
+        return self.relu(x + y)
+
+
+class StockConvU(nn.Module):
+    def __init__(self, planes, norm, first=False):
+        super().__init__()
+        self.first = first
+        if not first:
+            self.conv1, self.bn1 = nn.Conv3d(2 * planes, planes, 3, 1, 1, bias=False), _norm(planes, norm)
+        self.conv2, self.bn2 = nn.Conv3d(planes, planes // 2, 1, 1, 0, bias=False), _norm(planes // 2, norm)
+        self.conv3, self.bn3 = nn.Conv3d(planes, planes, 3, 1, 1, bias=False), _norm(planes, norm)
+        self.relu = nn.ReLU(inplace=True)
+
+    def forward(self, x, prev):
+        if not self.first:
+            x = self.relu(self.bn1(self.conv1(x)))
+        y = F.upsample(x, scale_factor=2, mode="trilinear", align_corners=False)
+        y = self.relu(self.bn2(self.conv2(y)))
+        y = torch.cat([prev, y], 1)
+        return self.relu(self.bn3(self.conv3(y)))
+
+
+class StockUnet3d(nn.Module):
+    """A stock-torch.nn model with the operator graph, attribute names and state_dict keys of the reference's
+    segmentation/models/unet3d.py `Unet` (written for the tests and the bench's drop-in leg, where /root/reference does not exist):
+    what a reference user holds before calling `nn.convert()`."""
+
+    def __init__(self, c=4, n=16, dropout=0.5, norm="gn", num_classes=5):
+        super().__init__()
+        self.upsample = nn.Upsample(scale_factor=2, mode="trilinear", align_corners=False)
+        w = [c, n, 2 * n, 4 * n, 8 * n, 16 * n]
+        for i in range(1, 6):
+            setattr(self, f"convd{i}", StockConvD(w[i - 1], w[i], dropout, norm, first=(i == 1)))
+        self.convu4 = StockConvU(16 * n, norm, True)
+        self.convu3, self.convu2, self.convu1 = StockConvU(8 * n, norm), StockConvU(4 * n, norm), StockConvU(2 * n, norm)
+        self.seg3, self.seg2, self.seg1 = nn.Conv3d(8 * n, num_classes, 1), nn.Conv3d(4 * n, num_classes, 1), nn.Conv3d(2 * n, num_classes, 1)
+
+    def forward(self, x):
+        x1 = self.convd1(x)
+        x2 = self.convd2(x1)
+        x3 = self.convd3(x2)
+        x4 = self.convd4(x3)
+        x5 = self.convd5(x4)
+        y4 = self.convu4(x5, x4)
+        y3 = self.convu3(y4, x3)
+        y2 = self.convu2(y3, x2)
+        y1 = self.convu1(y2, x1)
+        y3 = self.seg3(y3)
+        y2 = self.seg2(y2) + self.upsample(y3)
+        return self.seg1(y1) + self.upsample(y2)

@@ -285,3 +285,35 @@ def test_convert_drop_in_classifier_with_view_flatten(B):
         assert got.dtype == torch.float32 and rel_err(got, want) < tol
         torch.nn.functional.cross_entropy(got, torch.tensor([0, 1, 1, 0]).cuda()).backward()
         assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+
+
+@pytest.mark.parametrize("norm", ["bn", "in"])
+def test_convert_on_full_stock_unet3d_matches_golden(B, golden, norm):
+    """`convert()` on a STOCK torch.nn model with unet3d.py's graph and state_dict keys (tests/refshaped.StockUnet3d: F.upsample,
+    F.dropout3d on the dead branch, torch.cat, in-place ReLU) against the vectors of the REAL reference module: the drop-in path
+    gives what zoo.Unet gives -- logits, Dice loss, gradients, the dead branch's running statistics and its missing gradients."""
+    import refshaped
+    from oracle import graphs, weights
+    g = golden(f"unet3d_{norm}_train")
+    net = refshaped.StockUnet3d(c=1, n=16, dropout=0.5, norm=norm, num_classes=2)
+    net.load_state_dict(weights.unet3d_state(1, 16, 2, norm, seed=1), strict=True)
+    net = B.convert(net.cuda().train(), dtype=torch.float32)
+    gen = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 1, 32, 32, 32, generator=gen)
+    t = (torch.rand(2, 1, 32, 32, 32, generator=gen) > 0.5).float()
+    n0 = B.launch_count()
+    logits = net(x.cuda())
+    assert rel_err(logits, g["logits"]) < TOL32
+    loss = graphs.dice_loss_mean(logits, t.cuda())
+    assert abs(float(loss) - float(g["loss"])) < 1e-5
+    loss.backward()
+    assert B.launch_count() - n0 > 200
+    gr = dict(net.named_parameters())
+    assert sorted(k for k, p in gr.items() if p.grad is None) == list(g["none_grads"])
+    keys = [k[5:] for k in g.files if k.startswith("grad:")]
+    sd64 = {k: (v.double().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.double() if v.is_floating_point() else v.clone())
+            for k, v in weights.unet3d_state(1, 16, 2, norm, seed=1).items()}
+    graphs.dice_loss_mean(graphs.unet3d(sd64, x.double(), norm, 0.5, True), t.double()).backward()
+    check_grads({k: thin(gr[k].grad.cpu()) for k in keys}, {k: g["grad:" + k] for k in keys}, 1e-3, {k: thin(sd64[k].grad) for k in keys})
+    if norm == "bn":
+        assert rel_err(net.convd1.bn2.running_mean, g["rm:convd1.bn2"]) < TOL32 and rel_err(net.convu1.bn3.running_var, g["rv:convu1.bn3"]) < TOL32
