@@ -252,18 +252,16 @@ def test_autoencoder_at_config1_size_against_oracle(B):
     rl.backward()
     assert tuple(rec.shape) == (2, 1, 128, 128, 128) and rel_err(rec, ref) < 1e-4 and abs(float(loss) - float(rl)) < 1e-6
     gr = dict(net.named_parameters())
-    scale = max(float(v.grad.norm()) for v in osd.values() if getattr(v, "grad", None) is not None)
-    worst = 0.0
-    for k, v in osd.items():
-        if getattr(v, "grad", None) is None:
-            continue
-        if float(v.grad.norm()) < 1e-4 * scale:                     # conv biases in front of a BatchNorm: the exact gradient is 0
-            assert float(gr[k].grad.norm()) < 1e-3 * scale, k
-            continue
-        e = rel_err(gr[k].grad, v.grad)
-        worst = max(worst, e)
-        assert e < 5e-3, (k, e)                                     # weights in front of a BatchNorm: ill-conditioned, see test_gpu_models.check_grads
-    print(f"[fullsize] AE depth 6 @ 2x128^3 fp32: rec {rel_err(rec, ref):.1e}, worst gradient {worst:.1e}")
+    # conditioning-aware bound (tests/test_gpu_models.check_grads): conv weights / biases in front of a BatchNorm have gradients that
+    # are small differences of large terms, so two correct fp32 implementations differ by more than 1e-4 there -- the bound is
+    # max(2e-3, 4 x the fp32 oracle's own distance from an fp64 run of the oracle)
+    from test_gpu_models import check_grads
+    sd64 = {k: (v.double().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.double() if v.is_floating_point() else v.clone())
+            for k, v in sd.items()}
+    F.mse_loss(graphs.autoencoder(sd64, x.double(), 6, graphs.AE_DOWN, graphs.AE_UP, training=True), x.double()).backward()
+    keys = [k for k, v in osd.items() if getattr(v, "grad", None) is not None]
+    check_grads({k: gr[k].grad for k in keys}, {k: osd[k].grad for k in keys}, 2e-3, {k: sd64[k].grad for k in keys})
+    print(f"[fullsize] AE depth 6 @ 2x128^3 fp32: rec {rel_err(rec, ref):.1e}, {len(keys)} gradients within the conditioning-aware bound")
     # the bf16 body on the same input: bounded by the reference algorithm's own bf16-storage distance
     net16 = B.zoo.config1_autoencoder(depth=6, c_base=16)
     net16.load_state_dict(sd, strict=True)
