@@ -5,6 +5,7 @@
 #include "conv_simt.cuh"
 #include "conv_small.cuh"
 #include "conv_axis.cuh"
+#include "conv_tiny.cuh"
 #include "conv_umma.cuh"
 #include "conv_row.cuh"
 #include "conv_rowf.cuh"
@@ -117,6 +118,31 @@ int dispatch_gather(const ConvPlan& p, const void* in, const float* w, const flo
     return launch_gather<float, __nv_bfloat16>(p, in, w, bias, out, stream);
 }
 
+template <typename TI, typename TO>
+int launch_tiny(const ConvPlan& p, const void* in, const float* w, const float* bias, void* out, void* stream) {
+    const GatherGeom& g = p.g;
+    const int64_t V = (int64_t)g.N * g.OD * g.OH * g.OW;
+    dim3 grid((unsigned)ceil_div(V, kTinyVT), (unsigned)ceil_div(g.OC, 128));
+    B200_LAUNCH((conv_tiny_kernel<TI, TO>), grid, 128, (size_t)kTinyVT * g.IC * sizeof(float), stream, g, (const TI*)in, w, bias, (TO*)out);
+    return 0;
+}
+
+int dispatch_tiny(const ConvPlan& p, const void* in, const float* w, const float* bias, void* out, void* stream) {
+    if (p.in_dtype == B200_F32 && p.out_dtype == B200_F32) return launch_tiny<float, float>(p, in, w, bias, out, stream);
+    if (p.in_dtype == B200_BF16 && p.out_dtype == B200_BF16) return launch_tiny<__nv_bfloat16, __nv_bfloat16>(p, in, w, bias, out, stream);
+    if (p.in_dtype == B200_BF16 && p.out_dtype == B200_F32) return launch_tiny<__nv_bfloat16, float>(p, in, w, bias, out, stream);
+    return launch_tiny<float, __nv_bfloat16>(p, in, w, bias, out, stream);
+}
+
+template <typename TX, typename TG>
+int launch_tiny_wgrad(const ConvPlan& p, const void* x, const void* dy, float* dw, float* dbias, void* stream) {
+    const GatherGeom& g = p.g;
+    const int64_t V = (int64_t)g.N * g.OD * g.OH * g.OW;
+    dim3 grid((unsigned)(p.taps * g.IC), (unsigned)ceil_div(g.OC, 128));
+    B200_LAUNCH((conv_tiny_wgrad_kernel<TX, TG>), grid, 128, (size_t)V * sizeof(float), stream, g, (const TX*)x, (const TG*)dy, dw, dbias);
+    return 0;
+}
+
 struct WgradSplit { int splits; int64_t vox_per_split; int bias_chunks; int64_t bias_rows_per_chunk; size_t partial_bytes, bias_bytes; };
 
 WgradSplit wgrad_split(const b200_conv_desc* d, const ConvPlan& p) {
@@ -213,6 +239,7 @@ int b200_conv_fwd(const b200_conv_desc* d, const void* x, const void* w_packed, 
     if (head_supported(d)) return head_fwd_run(d, x, (const float*)w_packed, bias, y, stream);
     if (axis_conv_supported(d, B200_PASS_FWD)) return axis_gather_run(d, B200_PASS_FWD, x, (const float*)w_packed, bias, y, stream);
     const ConvPlan p = conv_plan(d, B200_PASS_FWD);
+    if (conv_tiny_supported(d, B200_PASS_FWD)) return dispatch_tiny(p, x, (const float*)w_packed, bias, y, stream);
     return dispatch_gather(p, x, (const float*)w_packed, bias, y, stream);
 }
 
@@ -250,6 +277,7 @@ int b200_conv_dgrad(const b200_conv_desc* d, const void* dy, const void* w_packe
     if (head_supported(d)) return head_dgrad_run(d, dy, (const float*)w_packed_dgrad, dx, stream);
     if (axis_conv_supported(d, B200_PASS_DGRAD)) return axis_gather_run(d, B200_PASS_DGRAD, dy, (const float*)w_packed_dgrad, nullptr, dx, stream);
     const ConvPlan p = conv_plan(d, B200_PASS_DGRAD);
+    if (conv_tiny_supported(d, B200_PASS_DGRAD)) return dispatch_tiny(p, dy, (const float*)w_packed_dgrad, nullptr, dx, stream);
     return dispatch_gather(p, dy, (const float*)w_packed_dgrad, nullptr, dx, stream);
 }
 
@@ -264,6 +292,12 @@ int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const void* dy, floa
     if (head_supported(d)) return head_wgrad_run(d, x, dy, dw, dbias, workspace, stream);
     if (axis_conv_supported(d, B200_PASS_WGRAD)) return axis_wgrad_run(d, x, dy, dw, dbias, workspace, stream);
     const ConvPlan p = conv_plan(d, B200_PASS_WGRAD);
+    if (conv_tiny_supported(d, B200_PASS_WGRAD)) {
+        if (d->x_dtype == B200_F32 && d->y_dtype == B200_F32) return launch_tiny_wgrad<float, float>(p, x, dy, dw, dbias, stream);
+        if (d->x_dtype == B200_BF16 && d->y_dtype == B200_BF16) return launch_tiny_wgrad<__nv_bfloat16, __nv_bfloat16>(p, x, dy, dw, dbias, stream);
+        if (d->x_dtype == B200_BF16 && d->y_dtype == B200_F32) return launch_tiny_wgrad<__nv_bfloat16, float>(p, x, dy, dw, dbias, stream);
+        return launch_tiny_wgrad<float, __nv_bfloat16>(p, x, dy, dw, dbias, stream);
+    }
     const WgradSplit s = wgrad_split(d, p);
     float* partial = (float*)workspace;
     const void* gathered = d->transposed ? dy : x;

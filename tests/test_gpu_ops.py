@@ -49,6 +49,11 @@ CONV_CASES = [
     ("k3s2p0", 1, 8, 12, (11, 13, 15), 3, 2, 0, 1, True),
     ("k4s4", 1, 1, 1, (16, 16, 16), 4, 4, 0, 1, True),
     ("odd_c", 1, 5, 7, (6, 7, 9), 3, 1, 1, 1, True),
+    # tiny volumes (conv_tiny.cuh): the deep autoencoder levels of config 1 and friends
+    ("tiny_512_k311", 2, 512, 512, (2, 2, 2), (3, 1, 1), 1, (1, 0, 0), 1, True),
+    ("tiny_256_128_k3", 2, 256, 128, (4, 4, 4), 3, 1, 1, 1, False),
+    ("tiny_64_48_k113", 3, 64, 48, (3, 5, 4), (1, 1, 3), 1, (0, 0, 1), 1, True),
+    ("tiny_40_72_s2", 2, 40, 72, (7, 6, 5), 3, 2, 1, 1, True),
 ]
 
 

@@ -58,7 +58,13 @@ def config1_autoencoder(pkg, dev, hbm_gbs):
     x = torch.randn(2, 1, 128, 128, 128, device=dev)
     opt = torch.optim.Adam(net.parameters(), lr=1e-4, capturable=True)
     io = _layer_io_bytes(net, x)
-    step = pkg.graphed.GraphedTrainStep(net, lambda y, t: torch.nn.functional.mse_loss(y.float(), t), opt, x, x)
+    if os.environ.get("B200_WORKLOAD_EAGER") == "1":           # for ncu launch lists: plain eager launches
+        def step(a, b):
+            opt.zero_grad()
+            torch.nn.functional.mse_loss(net(a).float(), b).backward()
+            opt.step()
+    else:
+        step = pkg.graphed.GraphedTrainStep(net, lambda y, t: torch.nn.functional.mse_loss(y.float(), t), opt, x, x)
     ms = _timeit(lambda: step(x, x))
     gbs = 3 * io / ms / 1e6
     return {"workload": "AE depth 6 c_base 16, batch 2 x 128^3, fwd + MSE + bwd + Adam, bf16 body, cuda-graph replay", "ms_per_step": ms,
