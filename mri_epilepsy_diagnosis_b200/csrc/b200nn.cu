@@ -122,8 +122,13 @@ template <typename TI, typename TO>
 int launch_tiny(const ConvPlan& p, const void* in, const float* w, const float* bias, void* out, void* stream) {
     const GatherGeom& g = p.g;
     const int64_t V = (int64_t)g.N * g.OD * g.OH * g.OW;
-    dim3 grid((unsigned)ceil_div(V, kTinyVT), (unsigned)ceil_div(g.OC, 128));
-    B200_LAUNCH((conv_tiny_kernel<TI, TO>), grid, 128, (size_t)kTinyVT * g.IC * sizeof(float), stream, g, (const TI*)in, w, bias, (TO*)out);
+    if (V < 1024) {
+        dim3 grid((unsigned)ceil_div(V, 4), (unsigned)ceil_div(g.OC, 128));
+        B200_LAUNCH((conv_tiny_kernel<TI, TO, 4>), grid, 128, (size_t)4 * g.IC * sizeof(float), stream, g, (const TI*)in, w, bias, (TO*)out);
+    } else {
+        dim3 grid((unsigned)ceil_div(V, 16), (unsigned)ceil_div(g.OC, 128));
+        B200_LAUNCH((conv_tiny_kernel<TI, TO, 16>), grid, 128, (size_t)16 * g.IC * sizeof(float), stream, g, (const TI*)in, w, bias, (TO*)out);
+    }
     return 0;
 }
 

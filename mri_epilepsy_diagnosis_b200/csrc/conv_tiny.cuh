@@ -1,4 +1,4 @@
-// Convolutions on TINY volumes (< 4096 output voxels in the whole batch): the deep levels of the autoencoder of BASELINE config 1
+// Convolutions on TINY volumes (< 16384 output voxels in the whole batch; wgrad: <= 4096): the deep levels of the autoencoder of BASELINE config 1
 // (AE_model.py:4-120, channels up to 512 on 2^3 / 4^3 / 8^3 volumes, separable (3,1,1) kernels) and the fader heads.
 // They are too small for a tensor-core tile grid, and the generic implicit-GEMM kernel (conv_simt.cuh) ran them as a handful of CTAs
 // walking K = taps * Cin in 16-wide chunks with two barriers each: latency-bound, ~0.3 ms for 25 MFLOP (ncu, round 2).
@@ -14,10 +14,9 @@
 
 namespace b200 {
 
-constexpr int kTinyVT = 4;
-constexpr int kTinyMaxVox = 4096;
+constexpr int kTinyMaxVox = 16384;        // VT = 4 voxels per block below 1024 voxels, 16 above (fewer re-reads of the weights through L2)
 
-template <typename TI, typename TO>
+template <typename TI, typename TO, int kTinyVT>
 __global__ void __launch_bounds__(128) conv_tiny_kernel(GatherGeom g, const TI* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
                                                         TO* __restrict__ out) {
     extern __shared__ float xs[];                              // [VT][IC]
@@ -117,7 +116,8 @@ inline bool conv_tiny_supported(const b200_conv_desc* d, int pass) {
     const int64_t V = pass == B200_PASS_DGRAD ? Vx : Vy;        // voxels of the produced tensor (fwd: y, dgrad: x) / of dy (wgrad)
     const int OC = pass == B200_PASS_DGRAD ? d->Ci : d->Co, IC = pass == B200_PASS_DGRAD ? d->Co : d->Ci;
     if (V >= kTinyMaxVox || Vx >= 8 * kTinyMaxVox || Vy >= 8 * kTinyMaxVox) return false;
-    if (OC < 32 || IC > 2048) return false;                     // coalescing needs a few warps of output channels; xs fits shared memory
+    if (pass == B200_PASS_WGRAD && V > 4096) return false;      // the per-block x table lives in shared memory
+    if (OC < 32 || IC > 2048 || (V >= 1024 && IC > 512)) return false;                     // coalescing needs a few warps of output channels; xs fits shared memory
     return true;
 }
 

@@ -54,6 +54,7 @@ CONV_CASES = [
     ("tiny_256_128_k3", 2, 256, 128, (4, 4, 4), 3, 1, 1, 1, False),
     ("tiny_64_48_k113", 3, 64, 48, (3, 5, 4), (1, 1, 3), 1, (0, 0, 1), 1, True),
     ("tiny_40_72_s2", 2, 40, 72, (7, 6, 5), 3, 2, 1, 1, True),
+    ("tiny_vt16_k131", 2, 64, 128, (16, 16, 16), (1, 3, 1), 1, (0, 1, 0), 1, True),
 ]
 
 
