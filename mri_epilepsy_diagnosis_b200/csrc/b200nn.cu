@@ -148,6 +148,28 @@ int launch_tiny_wgrad(const ConvPlan& p, const void* x, const void* dy, float* d
     return 0;
 }
 
+// stem wgrad through the tcgen05 row_wgrad kernel (see conv_small.cuh): the derived 16 -> Co (1,3,3) problem, or false when the
+// geometry does not fit it (the FFMA kernel is used then).  B200_STEM_TC=0 disables.
+bool stem_tc_desc(const b200_conv_desc* d, b200_conv_desc* d2) {
+    static const bool on = [] { const char* e = getenv("B200_STEM_TC"); return e == nullptr || e[0] != '0'; }();
+    if (!on || !stem3_supported(d) || !d->allow_umma || d->Co % 16 != 0) return false;
+    *d2 = *d;
+    d2->x_dtype = B200_BF16; d2->y_dtype = B200_BF16;
+    d2->Ci = 16;
+    d2->kd = 1; d2->pd = 0;
+    return row_wgrad_supported(d2);
+}
+struct StemTcWs { size_t x16, dw16, inner, total; };
+StemTcWs stem_tc_ws(const b200_conv_desc* d, const b200_conv_desc* d2) {
+    StemTcWs w;
+    const size_t V = (size_t)d->N * d->Di * d->Hi * d->Wi;
+    w.x16 = (V * 16 * 2 + 255) & ~(size_t)255;
+    w.dw16 = ((size_t)d->Co * 16 * 9 * 4 + 255) & ~(size_t)255;
+    w.inner = row_wgrad_workspace_bytes(d2);
+    w.total = w.x16 + w.dw16 + w.inner + 256;
+    return w;
+}
+
 struct WgradSplit { int splits; int64_t vox_per_split; int bias_chunks; int64_t bias_rows_per_chunk; size_t partial_bytes, bias_bytes; };
 
 WgradSplit wgrad_split(const b200_conv_desc* d, const ConvPlan& p) {
@@ -226,7 +248,12 @@ size_t b200_conv_workspace_bytes(const b200_conv_desc* d, int pass) {
     if (b200_conv_algo(d, pass) == B200_ALGO_ROW) return pass == B200_PASS_WGRAD ? row_wgrad_workspace_bytes(d) : 0;
     if (b200_conv_algo(d, pass) == B200_ALGO_UMMA) return umma_workspace_bytes(d, pass);
     if (pass != B200_PASS_WGRAD) return 0;
-    if (stem3_supported(d)) return stem3_wgrad_ws_bytes(d) + 256;
+    if (stem3_supported(d)) {
+        b200_conv_desc d2;
+        const size_t plain = stem3_wgrad_ws_bytes(d) + 256;
+        if (stem_tc_desc(d, &d2)) { const size_t tc = stem_tc_ws(d, &d2).total; return tc > plain ? tc : plain; }
+        return plain;
+    }
     if (head_supported(d)) return head_wgrad_ws_bytes(d) + 256;
     if (axis_conv_supported(d, pass)) return axis_wgrad_ws_bytes(d) + 256;
     const ConvPlan p = conv_plan(d, pass);
@@ -293,7 +320,22 @@ int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const void* dy, floa
     B200_REQUIRE(ws_bytes >= b200_conv_workspace_bytes(d, B200_PASS_WGRAD) && workspace != nullptr, "conv_wgrad: workspace too small");
     if (b200_conv_algo(d, B200_PASS_WGRAD) == B200_ALGO_ROW) return row_wgrad_run(d, x, dy, dw, dbias, workspace, ws_bytes, stream);
     if (b200_conv_algo(d, B200_PASS_WGRAD) == B200_ALGO_UMMA) return umma_wgrad_run(d, x, dy, dw, dbias, workspace, ws_bytes, stream);
-    if (stem3_supported(d)) return stem3_wgrad_run(d, x, dy, dw, dbias, workspace, stream);
+    if (stem3_supported(d)) {
+        b200_conv_desc d2;
+        if (stem_tc_desc(d, &d2)) {
+            const StemTcWs w = stem_tc_ws(d, &d2);
+            __nv_bfloat16* x16 = (__nv_bfloat16*)workspace;
+            float* dw16 = (float*)((char*)workspace + w.x16);
+            void* inner = (char*)workspace + w.x16 + w.dw16;
+            const int64_t V = (int64_t)d->N * d->Di * d->Hi * d->Wi;
+            if (d->x_dtype == B200_F32) B200_LAUNCH(stem3_expand_kernel<float>, stream_grid(V, 256), 256, 0, stream, (const float*)x, d->N, d->Di, d->Hi, d->Wi, x16);
+            else B200_LAUNCH(stem3_expand_kernel<__nv_bfloat16>, stream_grid(V, 256), 256, 0, stream, (const __nv_bfloat16*)x, d->N, d->Di, d->Hi, d->Wi, x16);
+            if (row_wgrad_run(&d2, x16, dy, dw16, dbias, inner, w.inner, stream)) return 1;
+            B200_LAUNCH(stem3_combine_kernel, (int)ceil_div(d->Co * 27, 128), 128, 0, stream, (const float*)dw16, d->Co, dw);
+            return 0;
+        }
+        return stem3_wgrad_run(d, x, dy, dw, dbias, workspace, stream);
+    }
     if (head_supported(d)) return head_wgrad_run(d, x, dy, dw, dbias, workspace, stream);
     if (axis_conv_supported(d, B200_PASS_WGRAD)) return axis_wgrad_run(d, x, dy, dw, dbias, workspace, stream);
     const ConvPlan p = conv_plan(d, B200_PASS_WGRAD);

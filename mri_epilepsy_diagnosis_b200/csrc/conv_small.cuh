@@ -302,6 +302,47 @@ __global__ void __launch_bounds__(256) head_wgrad_reduce_kernel(const float* __r
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+// ------------------------------------------------------------------------------------------------ stem wgrad on tensor cores
+// The FFMA kernel above is bound by its 432 multiply-adds per voxel (0.64 ms on 4 x 128^3, 16 % of the fp32 FMA rate, ~7 % of the
+// HBM peak).  The same gradient is a (1,3,3) weight gradient over a 16-channel tensor whose channels are the three z-shifted copies
+// of x -- each split into a bf16 "hi" and a bf16 "lo" part so that the fp32 volume loses nothing that matters (|x - hi - lo| <=
+// 2^-17 |x|) -- which is exactly the shape the tcgen05 row_wgrad_kernel runs at its best:
+//     X16[v][kz] = hi(x[z + kz - 1]),  X16[v][3 + kz] = lo(x[z + kz - 1]),  channels 6..15 = 0
+//     dW[co][kz][ky][kx] = dW16[co][kz][ky][kx] + dW16[co][3 + kz][ky][kx]
+// Cost: one expansion pass (read 4 B, write 32 B per voxel) + a 9-tap 16 -> Co tcgen05 wgrad + a 432-element combine.
+template <typename TX>
+__global__ void __launch_bounds__(256) stem3_expand_kernel(const TX* __restrict__ x, int N, int D, int H, int W, __nv_bfloat16* __restrict__ x16) {
+    const int64_t plane = (int64_t)H * W, total = (int64_t)N * D * plane;
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
+        const int z = (int)((v / plane) % D);
+        float val[3];
+        val[0] = z > 0 ? ldg_f<TX>(x + v - plane) : 0.f;
+        val[1] = ldg_f<TX>(x + v);
+        val[2] = z + 1 < D ? ldg_f<TX>(x + v + plane) : 0.f;
+        __nv_bfloat16 hi[3], lo[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            hi[k] = __float2bfloat16_rn(val[k]);
+            lo[k] = __float2bfloat16_rn(val[k] - __bfloat162float(hi[k]));
+        }
+        uint4 a, b = make_uint4(0u, 0u, 0u, 0u);
+        a.x = (uint32_t)__bfloat16_as_ushort(hi[0]) | ((uint32_t)__bfloat16_as_ushort(hi[1]) << 16);
+        a.y = (uint32_t)__bfloat16_as_ushort(hi[2]) | ((uint32_t)__bfloat16_as_ushort(lo[0]) << 16);
+        a.z = (uint32_t)__bfloat16_as_ushort(lo[1]) | ((uint32_t)__bfloat16_as_ushort(lo[2]) << 16);
+        a.w = 0u;
+        uint4* dst = reinterpret_cast<uint4*>(x16 + v * 16);
+        dst[0] = a;
+        dst[1] = b;
+    }
+}
+
+__global__ void stem3_combine_kernel(const float* __restrict__ dw16 /* [Co][16][9] */, int Co, float* __restrict__ dw /* [Co][1][27] */) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= Co * 27) return;
+    const int co = e / 27, t = e - co * 27, kz = t / 9, r = t - kz * 9;
+    dw[e] = dw16[(co * 16 + kz) * 9 + r] + dw16[(co * 16 + 3 + kz) * 9 + r];
+}
+
 inline bool stem3_supported(const b200_conv_desc* d) {
     return !d->transposed && d->Ci == 1 && (d->Co == 8 || d->Co == 16 || d->Co == 32) && d->kd == 3 && d->kh == 3 && d->kw == 3 && d->sd == 1 &&
            d->sh == 1 && d->sw == 1 && d->pd == 1 && d->ph == 1 && d->pw == 1 && d->dd == 1 && d->dh == 1 && d->dw == 1 && d->y_dtype == B200_BF16;
