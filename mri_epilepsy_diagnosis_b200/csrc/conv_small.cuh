@@ -183,27 +183,38 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __re
         for (int k = 0; k < 8; ++k) wr[c][k] = __ldg(w + (int64_t)(j * 8 + k) * OCp + c);
     }
     const int64_t total = V * LPV;               // one 16-byte chunk per thread and step
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i - lane < total; i += (int64_t)gridDim.x * 256) {
-        float xv[8];
-        const bool ok = i < total;
-        if (ok) Pack<__nv_bfloat16, 8>::load(x + i * 8, xv);
-        else {
+    const int sh = 31 - __clz(LPV);              // LPV is a power of two
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    constexpr int U = 4;                         // independent 16-byte loads in flight per thread (the kernel is a pure stream)
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i - lane < total; i += U * stride) {
+        float xv[U][8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) xv[k] = 0.f;
+        for (int u = 0; u < U; ++u) {
+            const int64_t idx = i + u * stride;
+            if (idx < total) Pack<__nv_bfloat16, 8>::load(x + idx * 8, xv[u]);
+            else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) xv[u][k] = 0.f;
+            }
         }
-        float s[CO];
 #pragma unroll
-        for (int c = 0; c < CO; ++c) {
-            float a = 0.f;
+        for (int u = 0; u < U; ++u) {
+            const int64_t idx = i + u * stride;
+            if (idx - lane >= total) break;                                      // warp-uniform
+            float s[CO];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) a = fmaf(xv[k], wr[c][k], a);
-            for (int o = 1; o < LPV; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            s[c] = a + bv[c];
-        }
-        if (ok && j == 0) {
-            TY* dst = y + (i / LPV) * CO;
+            for (int c = 0; c < CO; ++c) {
+                float a = 0.f;
 #pragma unroll
-            for (int c = 0; c < CO; ++c) dst[c] = from_f<TY>(s[c]);
+                for (int k = 0; k < 8; ++k) a = fmaf(xv[u][k], wr[c][k], a);
+                for (int o = 1; o < LPV; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                s[c] = a + bv[c];
+            }
+            if (idx < total && j == 0) {
+                TY* dst = y + (idx >> sh) * CO;
+#pragma unroll
+                for (int c = 0; c < CO; ++c) dst[c] = from_f<TY>(s[c]);
+            }
         }
     }
 }
@@ -220,18 +231,30 @@ __global__ void __launch_bounds__(256) head_dgrad_kernel(const TY* __restrict__ 
 #pragma unroll
         for (int k = 0; k < 8; ++k) wr[c][k] = __ldg(w + (int64_t)c * OCp + j * 8 + k);
     const int64_t total = V * LPV;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-        const int64_t v = i / LPV;
-        float o[8];
+    const int sh = 31 - __clz(LPV);
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    constexpr int U = 4;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += U * stride) {
+        float g[U][CO];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = 0.f;
+        for (int u = 0; u < U; ++u) {
+            const int64_t idx = i + u * stride;
 #pragma unroll
-        for (int c = 0; c < CO; ++c) {
-            const float g = to_f<TY>(dy[v * CO + c]);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) o[k] = fmaf(g, wr[c][k], o[k]);
+            for (int c = 0; c < CO; ++c) g[u][c] = idx < total ? to_f<TY>(dy[(idx >> sh) * CO + c]) : 0.f;
         }
-        Pack<__nv_bfloat16, 8>::store(dx + i * 8, o);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t idx = i + u * stride;
+            if (idx >= total) break;
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = 0.f;
+#pragma unroll
+            for (int c = 0; c < CO; ++c)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = fmaf(g[u][c], wr[c][k], o[k]);
+            Pack<__nv_bfloat16, 8>::store(dx + idx * 8, o);
+        }
     }
 }
 
@@ -251,17 +274,33 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(const __nv_bfloat16* __
         for (int k = 0; k < 8; ++k) acc[c][k] = 0.f;
     }
     const int64_t total = V * LPV;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-        const int64_t v = i / LPV;
-        float xv[8];
-        Pack<__nv_bfloat16, 8>::load(x + i * 8, xv);
+    const int sh = 31 - __clz(LPV);
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    constexpr int U = 4;                         // (the order of the additions per thread is unchanged: u ascending = i ascending)
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += U * stride) {
+        float xv[U][8], g[U][CO];
 #pragma unroll
-        for (int c = 0; c < CO; ++c) {
-            const float g = to_f<TY>(dy[v * CO + c]);
-            accb[c] += g;
+        for (int u = 0; u < U; ++u) {
+            const int64_t idx = i + u * stride;
+            if (idx < total) {
+                Pack<__nv_bfloat16, 8>::load(x + idx * 8, xv[u]);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc[c][k] = fmaf(g, xv[k], acc[c][k]);
+                for (int c = 0; c < CO; ++c) g[u][c] = to_f<TY>(dy[(idx >> sh) * CO + c]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) xv[u][k] = 0.f;
+#pragma unroll
+                for (int c = 0; c < CO; ++c) g[u][c] = 0.f;
+            }
         }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int c = 0; c < CO; ++c) {
+                accb[c] += g[u][c];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[c][k] = fmaf(g[u][c], xv[u][k], acc[c][k]);
+            }
     }
     // lanes j, j+LPV, ... hold the same channels
 #pragma unroll

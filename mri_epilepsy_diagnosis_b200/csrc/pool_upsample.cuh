@@ -88,14 +88,17 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(b200_pool_desc d, con
                                                            T* __restrict__ dx, const T* __restrict__ add = nullptr, int add_ctot = 0) {
     const int CV = d.C / V;
     const int rows = d.N * d.Di * d.Hi, per_row = d.Wi * CV;
-    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int tpr = per_row < 256 ? per_row : 256, rpb = 256 / tpr;          // narrow rows share a block (see the forward kernel)
+    const int sub = threadIdx.x / tpr, lane_e = threadIdx.x - sub * tpr;
+    if (sub >= rpb) return;
+    for (int row = blockIdx.x * rpb + sub; row < rows; row += gridDim.x * rpb) {
         const int yi = row % d.Hi, zi = (row / d.Hi) % d.Di, n = row / (d.Hi * d.Di);
         const int zo = zi >> 1, yo = yi >> 1;
         const bool row_in = zo < d.Do && yo < d.Ho;                   // floor mode: a trailing odd plane/row is in no window
         const int64_t orow = (((int64_t)n * d.Do + zo) * d.Ho + yo) * d.Wo;
         const int lzy = ((zi & 1) * 2 + (yi & 1)) * 2;
         T* xr = dx + (int64_t)row * d.Wi * d.C;
-        for (int e = threadIdx.x; e < per_row; e += 256) {
+        for (int e = lane_e; e < per_row; e += tpr) {
             const int xi = e / CV, cv = e - xi * CV;
             const int xo = xi >> 1;
             float acc[V];
@@ -260,7 +263,12 @@ template <typename T, int V>
 __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(b200_up_desc d, const T* __restrict__ x, T* __restrict__ y) {
     const int CV = d.C / V;
     const int rows = d.N * d.Do * d.Ho, per_row = d.Wi * CV;
-    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    // narrow rows (the 2-channel fp32 logits of the deep-supervision heads: 64 work items per row) share a block: 256 / per_row rows
+    // per block pass, so no thread idles
+    const int tpr = per_row < 256 ? per_row : 256, rpb = 256 / tpr;
+    const int sub = threadIdx.x / tpr, lane_e = threadIdx.x - sub * tpr;
+    if (sub >= rpb) return;
+    for (int row = blockIdx.x * rpb + sub; row < rows; row += gridDim.x * rpb) {
         const int yo = row % d.Ho, zo = (row / d.Ho) % d.Do, n = row / (d.Ho * d.Do);
         const Lin2 lz = lin2(zo, d.Di), ly = lin2(yo, d.Hi);
         const T* xn = x + (int64_t)n * d.Di * d.Hi * d.Wi * d.C;
@@ -270,7 +278,7 @@ __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(b200_up_desc d, con
         const T* r11 = xn + ((int64_t)lz.i1 * d.Hi + ly.i1) * d.Wi * d.C;
         const float w00 = lz.w0 * ly.w0, w01 = lz.w0 * ly.w1, w10 = lz.w1 * ly.w0, w11 = lz.w1 * ly.w1;
         T* yr = y + (int64_t)row * d.Wo * d.Ctot + d.c_off;
-        for (int e = threadIdx.x; e < per_row; e += 256) {
+        for (int e = lane_e; e < per_row; e += tpr) {
             const int xi = e / CV, cv = e - xi * CV;
             const int xm = max(xi - 1, 0), xp = min(xi + 1, d.Wi - 1);
             const int om = xm * d.C + cv * V, oc = xi * d.C + cv * V, op = xp * d.C + cv * V;
@@ -542,12 +550,15 @@ template <typename T, int V>
 __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(b200_up_desc d, const T* __restrict__ dy, T* __restrict__ dx) {
     const int CV = d.C / V;
     const int rows = d.N * d.Di * d.Hi, per_row = d.Wi * CV;
-    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int tpr = per_row < 256 ? per_row : 256, rpb = 256 / tpr;          // narrow rows share a block (see the forward kernel)
+    const int sub = threadIdx.x / tpr, lane_e = threadIdx.x - sub * tpr;
+    if (sub >= rpb) return;
+    for (int row = blockIdx.x * rpb + sub; row < rows; row += gridDim.x * rpb) {
         const int yi = row % d.Hi, zi = (row / d.Hi) % d.Di, n = row / (d.Hi * d.Di);
         const Touch2 tz = touch2(zi, d.Di), ty = touch2(yi, d.Hi);
         const T* gn = dy + (int64_t)n * d.Do * d.Ho * d.Wo * d.Ctot + d.c_off;
         T* xr = dx + (int64_t)row * d.Wi * d.C;
-        for (int e = threadIdx.x; e < per_row; e += 256) {
+        for (int e = lane_e; e < per_row; e += tpr) {
             const int xi = e / CV, cv = e - xi * CV;
             const Touch2 tx = touch2(xi, d.Wi);
             float acc[V];
@@ -555,7 +566,7 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(b200_up_desc d, con
             for (int k = 0; k < V; ++k) acc[k] = 0.f;
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
-                if (tz.w[a] == 0.f) continue;                                   // warp-uniform (the whole block shares zi)
+                if (tz.w[a] == 0.f) continue;                                   // uniform per row
                 float g[4][4][V];
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
