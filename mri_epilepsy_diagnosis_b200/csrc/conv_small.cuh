@@ -443,16 +443,19 @@ inline int stem3_wgrad_run(const b200_conv_desc* d, const void* x, const void* d
     return 0;
 }
 
-inline int head_grid(int64_t V, int lpv) {
+inline int head_grid(int64_t V, int lpv, int cap = kSmallBlocks) {
     int64_t need = ceil_div(V * lpv, 256 * 4);
-    if (need > kSmallBlocks) need = kSmallBlocks;
+    if (need > cap) need = cap;
     if (need < 1) need = 1;
     return (int)need;                            // 256 threads per block is a multiple of every lpv (power of two <= 32)
 }
+// fwd / dgrad keep no per-block partials: a fine grid (one 4-chunk pass per thread, up to 32 blocks per SM in flight over the run)
+// instead of a persistent one whose block count (4 per SM) did not match the 3 blocks per SM the registers allow (1.33 waves)
+constexpr int kHeadStreamBlocks = kNumSMs * 32;
 
 inline int head_fwd_run(const b200_conv_desc* d, const void* x, const float* w, const float* bias, void* y, void* stream) {
     const int64_t V = (int64_t)d->N * d->Di * d->Hi * d->Wi;
-    const int grid = head_grid(V, d->Ci / 8);
+    const int grid = head_grid(V, d->Ci / 8, kHeadStreamBlocks);
     B200_HEAD_CO(d->Co, {
         if (d->y_dtype == B200_F32) B200_LAUNCH((head_fwd_kernel<float, CO>), grid, 256, 0, stream, (const __nv_bfloat16*)x, w, bias, (float*)y, V, d->Ci);
         else B200_LAUNCH((head_fwd_kernel<__nv_bfloat16, CO>), grid, 256, 0, stream, (const __nv_bfloat16*)x, w, bias, (__nv_bfloat16*)y, V, d->Ci);
@@ -462,7 +465,7 @@ inline int head_fwd_run(const b200_conv_desc* d, const void* x, const float* w, 
 
 inline int head_dgrad_run(const b200_conv_desc* d, const void* dy, const float* w, void* dx, void* stream) {
     const int64_t V = (int64_t)d->N * d->Di * d->Hi * d->Wi;
-    const int grid = head_grid(V, d->Ci / 8);
+    const int grid = head_grid(V, d->Ci / 8, kHeadStreamBlocks);
     const int OCp = (d->Ci + 3) & ~3;
     B200_HEAD_CO(d->Co, {
         if (d->y_dtype == B200_F32) B200_LAUNCH((head_dgrad_kernel<float, CO>), grid, 256, 0, stream, (const float*)dy, w, (__nv_bfloat16*)dx, V, d->Ci, OCp);
