@@ -144,7 +144,7 @@ int launch_tiny_wgrad(const ConvPlan& p, const void* x, const void* dy, float* d
     const GatherGeom& g = p.g;
     const int64_t V = (int64_t)g.N * g.OD * g.OH * g.OW;
     dim3 grid((unsigned)(p.taps * g.IC), (unsigned)ceil_div(g.OC, 128));
-    B200_LAUNCH((conv_tiny_wgrad_kernel<TX, TG>), grid, 128, (size_t)V * sizeof(float), stream, g, (const TX*)x, (const TG*)dy, dw, dbias);
+    B200_LAUNCH((conv_tiny_wgrad_kernel<TX, TG>), grid, dim3(128, kTinyWgSlices), (size_t)V * sizeof(float), stream, g, (const TX*)x, (const TG*)dy, dw, dbias);
     return 0;
 }
 
@@ -255,6 +255,7 @@ size_t b200_conv_workspace_bytes(const b200_conv_desc* d, int pass) {
         return plain;
     }
     if (head_supported(d)) return head_wgrad_ws_bytes(d) + 256;
+    if (c1k3_supported(d)) return c1k3_wgrad_ws_bytes() + 256;
     if (axis_conv_supported(d, pass)) return axis_wgrad_ws_bytes(d) + 256;
     const ConvPlan p = conv_plan(d, pass);
     const WgradSplit s = wgrad_split(d, p);
@@ -269,6 +270,7 @@ int b200_conv_fwd(const b200_conv_desc* d, const void* x, const void* w_packed, 
     if (b200_conv_algo(d, B200_PASS_FWD) == B200_ALGO_UMMA) return umma_conv_run(d, B200_PASS_FWD, x, w_packed, bias, y, workspace, ws_bytes, stream);
     if (stem3_supported(d)) return stem3_fwd_run(d, x, (const float*)w_packed, bias, y, stream);
     if (head_supported(d)) return head_fwd_run(d, x, (const float*)w_packed, bias, y, stream);
+    if (c1k3_supported(d)) return c1k3_gather_run(d, B200_PASS_FWD, x, (const float*)w_packed, bias, y, stream);
     if (axis_conv_supported(d, B200_PASS_FWD)) return axis_gather_run(d, B200_PASS_FWD, x, (const float*)w_packed, bias, y, stream);
     const ConvPlan p = conv_plan(d, B200_PASS_FWD);
     if (conv_tiny_supported(d, B200_PASS_FWD)) return dispatch_tiny(p, x, (const float*)w_packed, bias, y, stream);
@@ -307,6 +309,7 @@ int b200_conv_dgrad(const b200_conv_desc* d, const void* dy, const void* w_packe
     if (b200_conv_algo(d, B200_PASS_DGRAD) == B200_ALGO_UMMA)
         return umma_conv_run(d, B200_PASS_DGRAD, dy, w_packed_dgrad, nullptr, dx, workspace, ws_bytes, stream);
     if (head_supported(d)) return head_dgrad_run(d, dy, (const float*)w_packed_dgrad, dx, stream);
+    if (c1k3_supported(d)) return c1k3_gather_run(d, B200_PASS_DGRAD, dy, (const float*)w_packed_dgrad, nullptr, dx, stream);
     if (axis_conv_supported(d, B200_PASS_DGRAD)) return axis_gather_run(d, B200_PASS_DGRAD, dy, (const float*)w_packed_dgrad, nullptr, dx, stream);
     const ConvPlan p = conv_plan(d, B200_PASS_DGRAD);
     if (conv_tiny_supported(d, B200_PASS_DGRAD)) return dispatch_tiny(p, dy, (const float*)w_packed_dgrad, nullptr, dx, stream);
@@ -337,6 +340,7 @@ int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const void* dy, floa
         return stem3_wgrad_run(d, x, dy, dw, dbias, workspace, stream);
     }
     if (head_supported(d)) return head_wgrad_run(d, x, dy, dw, dbias, workspace, stream);
+    if (c1k3_supported(d)) return c1k3_wgrad_run(d, x, dy, dw, dbias, workspace, stream);
     if (axis_conv_supported(d, B200_PASS_WGRAD)) return axis_wgrad_run(d, x, dy, dw, dbias, workspace, stream);
     const ConvPlan p = conv_plan(d, B200_PASS_WGRAD);
     if (conv_tiny_supported(d, B200_PASS_WGRAD)) {

@@ -382,6 +382,100 @@ __global__ void stem3_combine_kernel(const float* __restrict__ dw16 /* [Co][16][
     dw[e] = dw16[(co * 16 + kz) * 9 + r] + dw16[(co * 16 + 3 + kz) * 9 + r];
 }
 
+// ------------------------------------------------------------------------------------------------ 1 -> 1 channel 3x3x3 convolution
+// The autoencoder's final `vox` layer (AE_model.py:160-164: Conv3d(1, 1, 3, padding=1) on the full-resolution volume).  27 MACs per
+// voxel: the generic implicit-GEMM kernel spent > 1 ms per pass on it (128 x 16 tiles with one useful column); these are plain
+// streaming kernels.  `flip` = 1 evaluates the transposed geometry (dgrad): src = v + 1 - k instead of v - 1 + k.
+// w: the SIMT packing [27][4] fp32 (column 0).
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(256) c1k3_gather_kernel(const TX* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                          TY* __restrict__ y, int N, int D, int H, int W, int flip) {
+    __shared__ float ws[27];
+    if (threadIdx.x < 27) ws[threadIdx.x] = w[threadIdx.x * 4];
+    __syncthreads();
+    const float b = bias != nullptr ? bias[0] : 0.f;
+    const int64_t total = (int64_t)N * D * H * W;
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = v;
+        const int xq = (int)(r % W); r /= W;
+        const int yq = (int)(r % H); r /= H;
+        const int zq = (int)(r % D);
+        float acc = b;
+#pragma unroll
+        for (int kz = 0; kz < 3; ++kz) {
+            const int z = zq + (flip ? 1 - kz : kz - 1);
+            if ((unsigned)z >= (unsigned)D) continue;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int yy = yq + (flip ? 1 - ky : ky - 1);
+                if ((unsigned)yy >= (unsigned)H) continue;
+                const TX* row = x + v + ((int64_t)(z - zq) * H + (yy - yq)) * W;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int xx = xq + (flip ? 1 - kx : kx - 1);
+                    if ((unsigned)xx < (unsigned)W) acc = fmaf(ldg_f<TX>(row + (xx - xq)), ws[(kz * 3 + ky) * 3 + kx], acc);
+                }
+            }
+        }
+        y[v] = from_f<TY>(acc);
+    }
+}
+
+// partial[block][1][28]: dw[tap] = sum_v dy[v] * x[v + tap - 1], [27] = sum_v dy[v]   (reduced by stem3_wgrad_reduce_kernel, CO = 1)
+template <typename TX, typename TG>
+__global__ void __launch_bounds__(256) c1k3_wgrad_kernel(const TX* __restrict__ x, const TG* __restrict__ dy, float* __restrict__ partial, int N, int D,
+                                                         int H, int W) {
+    float acc[28];
+#pragma unroll
+    for (int i = 0; i < 28; ++i) acc[i] = 0.f;
+    const int64_t total = (int64_t)N * D * H * W;
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = v;
+        const int xq = (int)(r % W); r /= W;
+        const int yq = (int)(r % H); r /= H;
+        const int zq = (int)(r % D);
+        const float g = to_f<TG>(dy[v]);
+        acc[27] += g;
+#pragma unroll
+        for (int kz = 0; kz < 3; ++kz) {
+            const int z = zq + kz - 1;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int yy = yq + ky - 1;
+                const bool rok = (unsigned)z < (unsigned)D && (unsigned)yy < (unsigned)H;
+                const TX* row = x + v + ((int64_t)(kz - 1) * H + (ky - 1)) * W;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int xx = xq + kx - 1;
+                    const float xv = (rok && (unsigned)xx < (unsigned)W) ? ldg_f<TX>(row + (kx - 1)) : 0.f;
+                    acc[(kz * 3 + ky) * 3 + kx] = fmaf(g, xv, acc[(kz * 3 + ky) * 3 + kx]);
+                }
+            }
+        }
+    }
+    __shared__ float red[8][28];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < 28; ++i) {
+        float a = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) red[warp][i] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x < 28) {
+        float a = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < 8; ++wq) a += red[wq][threadIdx.x];
+        partial[(int64_t)blockIdx.x * 28 + threadIdx.x] = a;
+    }
+}
+
+inline bool c1k3_supported(const b200_conv_desc* d) {
+    return !d->transposed && d->Ci == 1 && d->Co == 1 && d->kd == 3 && d->kh == 3 && d->kw == 3 && d->sd == 1 && d->sh == 1 && d->sw == 1 && d->pd == 1 &&
+           d->ph == 1 && d->pw == 1 && d->dd == 1 && d->dh == 1 && d->dw == 1;
+}
+
 inline bool stem3_supported(const b200_conv_desc* d) {
     return !d->transposed && d->Ci == 1 && (d->Co == 8 || d->Co == 16 || d->Co == 32) && d->kd == 3 && d->kh == 3 && d->kw == 3 && d->sd == 1 &&
            d->sh == 1 && d->sw == 1 && d->pd == 1 && d->ph == 1 && d->pw == 1 && d->dd == 1 && d->dh == 1 && d->dw == 1 && d->y_dtype == B200_BF16;
@@ -440,6 +534,37 @@ inline int stem3_wgrad_run(const b200_conv_desc* d, const void* x, const void* d
                         d->Di, d->Hi, d->Wi);
         B200_LAUNCH(stem3_wgrad_reduce_kernel, (int)ceil_div(CO * 28, 8), 256, 0, stream, partial, grid, CO, dw, dbias);
     });
+    return 0;
+}
+
+#define B200_C1K3_DT(in_dt, out_dt, TI, TO, ...)                                                     \
+    do {                                                                                             \
+        if ((in_dt) == B200_F32 && (out_dt) == B200_BF16) { using TI = float; using TO = __nv_bfloat16; __VA_ARGS__; }           \
+        else if ((in_dt) == B200_BF16 && (out_dt) == B200_BF16) { using TI = __nv_bfloat16; using TO = __nv_bfloat16; __VA_ARGS__; } \
+        else if ((in_dt) == B200_BF16 && (out_dt) == B200_F32) { using TI = __nv_bfloat16; using TO = float; __VA_ARGS__; }       \
+        else { using TI = float; using TO = float; __VA_ARGS__; }                                    \
+    } while (0)
+
+// pass: B200_PASS_FWD (x -> y) or B200_PASS_DGRAD (dy -> dx, flipped taps)
+inline int c1k3_gather_run(const b200_conv_desc* d, int pass, const void* in, const float* w, const float* bias, void* out, void* stream) {
+    const int64_t V = (int64_t)d->N * d->Di * d->Hi * d->Wi;
+    const int in_dt = pass == B200_PASS_DGRAD ? d->y_dtype : d->x_dtype, out_dt = pass == B200_PASS_DGRAD ? d->x_dtype : d->y_dtype;
+    B200_C1K3_DT(in_dt, out_dt, TI, TO, {
+        B200_LAUNCH((c1k3_gather_kernel<TI, TO>), stream_grid(V, 256, 16), 256, 0, stream, (const TI*)in, w, bias, (TO*)out, d->N, d->Di, d->Hi, d->Wi,
+                    pass == B200_PASS_DGRAD ? 1 : 0);
+    });
+    return 0;
+}
+inline size_t c1k3_wgrad_ws_bytes() { return (size_t)kSmallBlocks * 28 * 4; }
+inline int c1k3_wgrad_run(const b200_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias, void* workspace, void* stream) {
+    const int64_t V = (int64_t)d->N * d->Di * d->Hi * d->Wi;
+    const int64_t need = ceil_div(V, 256 * 8);
+    const int grid = (int)(need < kSmallBlocks ? (need < 1 ? 1 : need) : kSmallBlocks);
+    float* partial = (float*)workspace;
+    B200_C1K3_DT(d->x_dtype, d->y_dtype, TX, TG, {
+        B200_LAUNCH((c1k3_wgrad_kernel<TX, TG>), grid, 256, 0, stream, (const TX*)x, (const TG*)dy, partial, d->N, d->Di, d->Hi, d->Wi);
+    });
+    B200_LAUNCH(stem3_wgrad_reduce_kernel, (int)ceil_div(28, 8), 256, 0, stream, partial, grid, 1, dw, dbias);
     return 0;
 }
 

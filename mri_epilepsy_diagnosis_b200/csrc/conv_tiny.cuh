@@ -74,15 +74,19 @@ __global__ void __launch_bounds__(128) conv_tiny_kernel(GatherGeom g, const TI* 
 
 // dw[co][ci][tap] (param_is_ci_major = 0) = sum_v x[src(v, tap)][ci] * dy[v][co];  dbias[co] = sum_v dy[v][co]
 // grid (taps * IC, ceil(OC / 128)); v walks the (OD,OH,OW) grid of dy (g is the WGRAD plan: gathered = x, second = dy)
+constexpr int kTinyWgSlices = 4;         // the voxel loop of the wgrad kernel is split over threadIdx.y (fixed-order combine: deterministic)
+
 template <typename TX, typename TG>
-__global__ void __launch_bounds__(128) conv_tiny_wgrad_kernel(GatherGeom g, const TX* __restrict__ x, const TG* __restrict__ gy, float* __restrict__ dw,
-                                                              float* __restrict__ dbias) {
+__global__ void __launch_bounds__(128 * kTinyWgSlices) conv_tiny_wgrad_kernel(GatherGeom g, const TX* __restrict__ x, const TG* __restrict__ gy,
+                                                                              float* __restrict__ dw, float* __restrict__ dbias) {
     extern __shared__ float xv[];                               // [V] x value of this block's (tap, ic) at every output voxel (0 where padded)
+    __shared__ float red[2][kTinyWgSlices][128];
     const int V = g.N * g.OD * g.OH * g.OW;
     const int tap = blockIdx.x / g.IC, ic = blockIdx.x - tap * g.IC;
     const int taps_hw = g.kh * g.kw, taps = g.kd * taps_hw;
     const int kz = tap / taps_hw, kr = tap - kz * taps_hw, ky = kr / g.kw, kx = kr - ky * g.kw;
-    for (int v = threadIdx.x; v < V; v += 128) {
+    const int tid = threadIdx.y * 128 + threadIdx.x;
+    for (int v = tid; v < V; v += 128 * kTinyWgSlices) {
         int r = v;
         const int xo = r % g.OW; r /= g.OW;
         const int yo = r % g.OH; r /= g.OH;
@@ -96,18 +100,25 @@ __global__ void __launch_bounds__(128) conv_tiny_wgrad_kernel(GatherGeom g, cons
     }
     __syncthreads();
     const int co = blockIdx.y * 128 + threadIdx.x;
-    if (co >= g.OC) return;
     float acc = 0.f, accb = 0.f;
-    const bool want_b = dbias != nullptr && blockIdx.x == 0;
-    const TG* gp = gy + co;
+    if (co < g.OC) {
+        const TG* gp = gy + co;
 #pragma unroll 4
-    for (int v = 0; v < V; ++v) {
-        const float gv = to_f<TG>(gp[(int64_t)v * g.OC]);
-        acc = fmaf(xv[v], gv, acc);
-        accb += gv;
+        for (int v = threadIdx.y; v < V; v += kTinyWgSlices) {
+            const float gv = to_f<TG>(gp[(int64_t)v * g.OC]);
+            acc = fmaf(xv[v], gv, acc);
+            accb += gv;
+        }
     }
-    dw[((int64_t)co * g.IC + ic) * taps + tap] = acc;
-    if (want_b) dbias[co] = accb;
+    red[0][threadIdx.y][threadIdx.x] = acc;
+    red[1][threadIdx.y][threadIdx.x] = accb;
+    __syncthreads();
+    if (threadIdx.y != 0 || co >= g.OC) return;
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int q = 0; q < kTinyWgSlices; ++q) { a += red[0][q][threadIdx.x]; b += red[1][q][threadIdx.x]; }
+    dw[((int64_t)co * g.IC + ic) * taps + tap] = a;
+    if (dbias != nullptr && blockIdx.x == 0) dbias[co] = b;
 }
 
 inline bool conv_tiny_supported(const b200_conv_desc* d, int pass) {

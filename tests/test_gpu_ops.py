@@ -49,6 +49,7 @@ CONV_CASES = [
     ("k3s2p0", 1, 8, 12, (11, 13, 15), 3, 2, 0, 1, True),
     ("k4s4", 1, 1, 1, (16, 16, 16), 4, 4, 0, 1, True),
     ("odd_c", 1, 5, 7, (6, 7, 9), 3, 1, 1, 1, True),
+    ("vox_1_1_k3", 2, 1, 1, (9, 10, 33), 3, 1, 1, 1, True),            # AE_model.py:160-164 (c1k3 kernels)
     # tiny volumes (conv_tiny.cuh): the deep autoencoder levels of config 1 and friends
     ("tiny_512_k311", 2, 512, 512, (2, 2, 2), (3, 1, 1), 1, (1, 0, 0), 1, True),
     ("tiny_256_128_k3", 2, 256, 128, (4, 4, 4), 3, 1, 1, 1, False),

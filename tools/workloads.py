@@ -56,7 +56,7 @@ def config1_autoencoder(pkg, dev, hbm_gbs):
     torch.manual_seed(0)
     net = pkg.convert(pkg.zoo.config1_autoencoder(depth=6, c_base=16).to(dev).train(), dtype=torch.bfloat16)
     x = torch.randn(2, 1, 128, 128, 128, device=dev)
-    opt = torch.optim.Adam(net.parameters(), lr=1e-4, capturable=True)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, capturable=True, fused=True)
     io = _layer_io_bytes(net, x)
     if os.environ.get("B200_WORKLOAD_EAGER") == "1":           # for ncu launch lists: plain eager launches
         def step(a, b):
