@@ -102,87 +102,6 @@ __global__ void __launch_bounds__(256) axis_gather_kernel(AxisGeom g, const TI* 
     }
 }
 
-// Forward variant with a SLIDING WINDOW along the convolution axis (round 2).  ncu on the kernel above (fader stem, 8 x 192^3,
-// k = 6, s = 2): 279 instructions per output voxel -- six strided loads with their index arithmetic, two integer divisions, the
-// generic transposed / bounds logic -- and 48 % issue utilisation: instruction-bound at 1.5 TB/s.  Here one thread owns a column
-// (outer, inner position) and walks a segment of the axis: the K input taps live in registers, every step shifts them by the
-// stride and loads only S new ones (2 instead of 6 loads per output; all index arithmetic is one add per step).
-template <typename TI, typename TO, int IC, int OC, int K, int S>
-__global__ void __launch_bounds__(256) axis_slide_fwd_kernel(AxisGeom g, const TI* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
-                                                             TO* __restrict__ out, int seg_len) {
-    extern __shared__ float ws[];                         // [K][IC][OC]
-    for (int i = threadIdx.x; i < K * IC * OC; i += 256) ws[i] = w[(int64_t)(i / OC) * g.OCp + i % OC];
-    __syncthreads();
-    const int64_t cols = g.outer * g.inner;
-    const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (c >= cols) return;
-    const int64_t ou = c / g.inner, in_ = c - ou * g.inner;
-    const int o0 = blockIdx.y * seg_len, o1 = min(g.out_len, o0 + seg_len);
-    if (o0 >= o1) return;
-    const int64_t istep = g.inner * IC, ostep = g.inner * OC;                  // element strides along the axis
-    const TI* ibase = in + (ou * g.in_len * g.inner + in_) * IC;
-    TO* optr = out + ((ou * g.out_len + o0) * g.inner + in_) * OC;
-    float bv[OC];
-#pragma unroll
-    for (int q = 0; q < OC; ++q) bv[q] = bias != nullptr ? __ldg(bias + q) : 0.f;
-    float win[K][IC];
-    int i0 = o0 * S - g.p;                                                      // axis index of win[0]
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const int i = i0 + k;
-        if ((unsigned)i < (unsigned)g.in_len) load_vec<TI, IC>(ibase + (int64_t)i * istep, win[k]);
-        else {
-#pragma unroll
-            for (int ci = 0; ci < IC; ++ci) win[k][ci] = 0.f;
-        }
-    }
-    for (int o = o0; o < o1; ++o) {
-        // the weights are re-read from shared memory (broadcast loads) every step: without this barrier the compiler hoists all
-        // K*IC*OC of them into registers and spills (255 registers + 2.4 KB of stack for 8 -> 8 channels, k = 6)
-        asm volatile("" ::: "memory");
-        float acc[OC];
-#pragma unroll
-        for (int q = 0; q < OC; ++q) acc[q] = bv[q];
-#pragma unroll
-        for (int k = 0; k < K; ++k)
-#pragma unroll
-            for (int ci = 0; ci < IC; ++ci) {
-                const float xv = win[k][ci];
-                const float* wk = ws + (k * IC + ci) * OC;
-                if constexpr (OC % 4 == 0) {
-#pragma unroll
-                    for (int q = 0; q < OC / 4; ++q) {
-                        const float4 f = *reinterpret_cast<const float4*>(wk + 4 * q);
-                        acc[4 * q + 0] = fmaf(xv, f.x, acc[4 * q + 0]);
-                        acc[4 * q + 1] = fmaf(xv, f.y, acc[4 * q + 1]);
-                        acc[4 * q + 2] = fmaf(xv, f.z, acc[4 * q + 2]);
-                        acc[4 * q + 3] = fmaf(xv, f.w, acc[4 * q + 3]);
-                    }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < OC; ++q) acc[q] = fmaf(xv, wk[q], acc[q]);
-                }
-            }
-        store_vec<TO, OC>(optr, acc);
-        optr += ostep;
-        // slide: drop S taps, load S new ones
-        i0 += S;
-#pragma unroll
-        for (int k = 0; k + S < K; ++k)
-#pragma unroll
-            for (int ci = 0; ci < IC; ++ci) win[k][ci] = win[k + S][ci];
-#pragma unroll
-        for (int k = (K - S > 0 ? K - S : 0); k < K; ++k) {
-            const int i = i0 + k;
-            if ((unsigned)i < (unsigned)g.in_len) load_vec<TI, IC>(ibase + (int64_t)i * istep, win[k]);
-            else {
-#pragma unroll
-                for (int ci = 0; ci < IC; ++ci) win[k][ci] = 0.f;
-            }
-        }
-    }
-}
-
 // partial[block][K][IC*OC + OC]: dw[k][ic][oc] = sum_v G[v][oc] * X[src(v,k)][ic]; the trailing OC entries of tap 0 hold sum_v G[v][oc]
 template <typename TX, typename TG, int IC, int OC>
 __global__ void __launch_bounds__(256) axis_wgrad_kernel(AxisGeom g, const TX* __restrict__ x, const TG* __restrict__ gy, float* __restrict__ partial) {
@@ -345,26 +264,6 @@ inline int axis_gather_run(const b200_conv_desc* d, int pass, const void* in, co
     const int grid = (int)(ceil_div(total, 256) < (int64_t)kNumSMs * 16 ? ceil_div(total, 256) : (int64_t)kNumSMs * 16);
     const size_t smem = (size_t)g.K * ICv * OCv * sizeof(float);
     B200_REQUIRE(aligned16(in) && aligned16(out), "axis conv: pointers must be 16-byte aligned");
-    // forward with (K, stride) = (3, 1) or (6, 2) -- every separable conv of the AE / fader encoder: sliding-window kernel
-    static const bool slide_on = [] { const char* e = getenv("B200_AXIS_SLIDE"); return e == nullptr || e[0] != '0'; }();
-    const bool slide = slide_on && pass != B200_PASS_DGRAD && ((g.K == 3 && g.s == 1) || (g.K == 6 && g.s == 2)) && ICv * OCv <= 128;
-    if (slide) {
-        const int64_t cols = g.outer * g.inner;
-        // enough threads to fill the GPU: split the axis into segments when there are few columns
-        int segs = 1;
-        while (segs < 16 && cols * segs < (int64_t)kNumSMs * 2048 && g.out_len / (segs * 2) >= 8) segs *= 2;
-        const int seg_len = (int)ceil_div(g.out_len, segs);
-        dim3 sgrid((unsigned)ceil_div(cols, 256), (unsigned)ceil_div(g.out_len, seg_len));
-        B200_AXIS_CH(ICv, OCv, {
-            if constexpr (IC * OC <= 128) {
-                B200_AXIS_DT(in_dt, out_dt, TI, TO, {
-                    if (g.K == 3) B200_LAUNCH((axis_slide_fwd_kernel<TI, TO, IC, OC, 3, 1>), sgrid, 256, smem, stream, g, (const TI*)in, w, bias, (TO*)out, seg_len);
-                    else B200_LAUNCH((axis_slide_fwd_kernel<TI, TO, IC, OC, 6, 2>), sgrid, 256, smem, stream, g, (const TI*)in, w, bias, (TO*)out, seg_len);
-                });
-            }
-        });
-        return 0;
-    }
     B200_AXIS_CH(ICv, OCv, {
         B200_AXIS_DT(in_dt, out_dt, TI, TO, {
             B200_LAUNCH((axis_gather_kernel<TI, TO, IC, OC>), grid, 256, smem, stream, g, (const TI*)in, w, bias, (TO*)out);
