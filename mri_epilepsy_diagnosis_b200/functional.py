@@ -400,14 +400,24 @@ class _NormFn(Function):
             if sync is not None and kind == cabi.NORM_BATCH:
                 import torch.distributed as dist
                 pg, world = sync
-                # local statistics -> (mean, E[x^2]) -> ONE all-reduce(AVG) -> global (mean, rstd) + running statistics: two small
-                # kernels and one collective per layer and direction
-                check(lib().b200_norm_stats(C.byref(nd), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), None, None, ws.data_ptr(), nws, stream()))
-                packed = _tempty(2 * nd.C, dtype=torch.float32, device=x.device)
-                check(lib().b200_syncbn_pack(nd.C, float(eps), mean.data_ptr(), rstd.data_ptr(), packed.data_ptr(), stream()))
-                dist.all_reduce(packed, op=dist.ReduceOp.AVG, group=pg)
-                check(lib().b200_syncbn_finalize(nd.C, float(eps), float(momentum if momentum is not None else 0.0), float(nd.N * nd.S * world),
-                                                 packed.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ptr(running_mean), ptr(running_var), stream()))
+                if stats_partial is not None:
+                    # the conv epilogue already produced per-CTA (sum, sum^2) partials of the fp32 accumulators: ONE all-reduce(SUM) of that
+                    # small buffer, then the ordinary finalize kernel with the GLOBAL batch size -- no extra pass over the activation
+                    stats_partial = stats_partial.contiguous()
+                    dist.all_reduce(stats_partial, group=pg)
+                    ndg = _norm_desc(x, kind, groups, eps, momentum if momentum is not None else 0.0, act, slope)
+                    ndg.N = nd.N * world
+                    check(lib().b200_norm_stats_from_partial(C.byref(ndg), stats_partial.data_ptr(), stats_partial.shape[0], mean.data_ptr(),
+                                                             rstd.data_ptr(), ptr(running_mean), ptr(running_var), stream()))
+                else:
+                    # local statistics -> (mean, E[x^2]) -> ONE all-reduce(AVG) -> global (mean, rstd) + running statistics: two small
+                    # kernels and one collective per layer and direction
+                    check(lib().b200_norm_stats(C.byref(nd), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), None, None, ws.data_ptr(), nws, stream()))
+                    packed = _tempty(2 * nd.C, dtype=torch.float32, device=x.device)
+                    check(lib().b200_syncbn_pack(nd.C, float(eps), mean.data_ptr(), rstd.data_ptr(), packed.data_ptr(), stream()))
+                    dist.all_reduce(packed, op=dist.ReduceOp.AVG, group=pg)
+                    check(lib().b200_syncbn_finalize(nd.C, float(eps), float(momentum if momentum is not None else 0.0), float(nd.N * nd.S * world),
+                                                     packed.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ptr(running_mean), ptr(running_var), stream()))
             elif stats_partial is not None and kind == cabi.NORM_BATCH:
                 check(lib().b200_norm_stats_from_partial(C.byref(nd), stats_partial.data_ptr(), stats_partial.shape[0], mean.data_ptr(), rstd.data_ptr(),
                                                          ptr(running_mean), ptr(running_var), stream()))
@@ -476,13 +486,21 @@ def norm(x, gamma, beta, *, kind, groups=0, running_mean=None, running_var=None,
                          stats_partial)
 
 
-def batchnorm_update_running(x, running_mean, running_var, momentum, eps, stats_partial=None):
+def batchnorm_update_running(x, running_mean, running_var, momentum, eps, stats_partial=None, sync=None):
     """Only the side effect of a training-mode BatchNorm whose OUTPUT is discarded (unet3d.py:43-46: bn2 feeds a dead branch):
-    batch statistics -> running_mean / running_var.  No normalised tensor is written."""
+    batch statistics -> running_mean / running_var.  No normalised tensor is written.  `sync` = (process_group, world): the
+    per-CTA partials are all-reduced first (SyncBN; needs stats_partial)."""
     need_cuda(x, "norm")
     nd = _norm_desc(x, cabi.NORM_BATCH, 0, eps, momentum, cabi.ACT_NONE, 0.0)
     mean = _tempty(nd.C, dtype=torch.float32, device=x.device)
     rstd = _tempty_like(mean)
+    if sync is not None:
+        if stats_partial is None:
+            raise RuntimeError("batchnorm_update_running: SyncBN needs the conv epilogue's partial statistics")
+        import torch.distributed as dist
+        stats_partial = stats_partial.contiguous()
+        dist.all_reduce(stats_partial, group=sync[0])
+        nd.N = nd.N * sync[1]
     if stats_partial is not None:
         check(lib().b200_norm_stats_from_partial(C.byref(nd), stats_partial.data_ptr(), stats_partial.shape[0], mean.data_ptr(), rstd.data_ptr(),
                                                  ptr(running_mean), ptr(running_var), stream()))

@@ -152,14 +152,14 @@ class _BatchNormMixin(_B200Mixin):
         rv = self.running_var if (not self.training or self.track_running_stats) else None
         sync = self.sync if self.training else None
         if stats_only:
-            if use_batch and rm is not None and sync is None:
-                BF.batchnorm_update_running(x, rm, rv, factor, self.eps, stats_partial)
+            if use_batch and rm is not None and (sync is None or stats_partial is not None):
+                BF.batchnorm_update_running(x, rm, rv, factor, self.eps, stats_partial, sync=sync)
                 return None
             if not use_batch or rm is None:
                 return None             # eval mode / no running statistics: a discarded BatchNorm output has no side effect at all
         return BF.norm(x, self.weight, self.bias, kind=cabi.NORM_BATCH, running_mean=rm, running_var=rv, use_batch_stats=use_batch,
                        momentum=factor, eps=self.eps, act=self.fused_act if act is None else act, slope=self.fused_slope, residual=residual,
-                       sync=sync, stats_partial=stats_partial if sync is None else None)
+                       sync=sync, stats_partial=stats_partial)
 
 
 class BatchNorm3d(_BatchNormMixin, tnn.BatchNorm3d):

@@ -42,7 +42,7 @@ def _conv_norm(conv, norm, x, act=cabi.ACT_NONE, residual=None, stats_only=False
     """act(norm(conv(x)) [+ residual]) as two kernels + one finalize: the convolution's epilogue also accumulates the batch
     statistics of its own output (BatchNorm, training), the apply pass folds the residual add and the activation."""
     part = None
-    if isinstance(norm, bnn.BatchNorm3d) and norm.training and norm.sync is None:
+    if isinstance(norm, bnn.BatchNorm3d) and norm.training:          # (SyncBN all-reduces these partials, functional._NormFn)
         y, part = conv(x, want_stats=True)
     else:
         y = conv(x)
@@ -76,7 +76,7 @@ class ConvD(tnn.Module):
             return _conv_norm(self.conv3, self.bn3, x, act=cabi.ACT_RELU, residual=x)        # :46-47
         # unet3d.py:43-45: y = relu(bn2(conv2(x))); y = dropout3d(y) is overwritten at :46.  Its only observable effects are
         # bn2's running statistics (BatchNorm, training) and the RNG draw of dropout3d; exactly those are performed.
-        bn_train = isinstance(self.bn2, bnn.BatchNorm3d) and self.bn2.training and self.bn2.sync is None
+        bn_train = isinstance(self.bn2, bnn.BatchNorm3d) and self.bn2.training
         if self.dropout > 0:                       # F.dropout3d is always in training mode there: one Bernoulli draw per (n, c)
             x.new_empty((x.shape[0], self.conv2.out_channels, 1, 1, 1)).bernoulli_(1 - self.dropout)
         if bn_train and self.conv2.bias is None and self.conv3.bias is None and x.dtype == torch.bfloat16 and \

@@ -12,11 +12,11 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _make(B, norm, sync=None):
+def _make(B, norm, sync=None, dtype=torch.float32):
     from oracle import weights
     net = B.zoo.Unet(c=1, n=16, dropout=0.0, norm=norm, num_classes=2)
     net.load_state_dict(weights.unet3d_state(1, 16, 2, norm, seed=5), strict=True)
-    return B.convert(net.cuda().train(), dtype=torch.float32, sync=sync)
+    return B.convert(net.cuda().train(), dtype=dtype, sync=sync)
 
 
 def _batches(steps):
@@ -60,6 +60,14 @@ def _worker(rank, world, port, q):
     out["dp_bn_params"] = {k: v.detach().cpu() for k, v in net.named_parameters() if v.grad is not None}
     out["dp_bn_buffers"] = {k: v.detach().cpu() for k, v in net.named_buffers() if k in ("convd1.bn1.running_mean", "convu1.bn3.running_var", "convd1.bn2.running_var")}
     out["dead_grad_none"] = net.convd1.conv2.weight.grad is None
+    # ---- bf16 SyncBN: the conv-epilogue partial statistics are all-reduced (no extra pass over the activations)
+    net = _make(B, "bn", sync=(None, world), dtype=torch.bfloat16)
+    x, t = data[0]
+    loss = B.functional.softmax_dice_loss(net(x[lo:hi].cuda()), t[lo:hi].cuda())
+    loss.backward()
+    out["bf16_sync_loss"] = float(loss)
+    out["bf16_sync_buffers"] = {k: v.detach().float().cpu() for k, v in net.named_buffers() if k in ("convd1.bn1.running_mean", "convd1.bn2.running_var", "convu1.bn3.running_var", "convd3.bn3.running_mean")}
+    out["bf16_sync_grad"] = net.convu1.conv3.weight.grad.detach().cpu()
     q.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()
@@ -111,4 +119,16 @@ def test_two_ranks_equal_one_device_on_the_global_batch():
             for k, v in res[0]["dp_bn_buffers"].items():
                 assert rel_err(v, bufs[k]) < 1e-4, k
             assert res[0]["dead_grad_none"] and res[1]["dead_grad_none"]
+    # bf16 DP + SyncBN (statistics from the all-reduced conv-epilogue partials) against one GPU on the global batch, bf16 tolerances
+    net = _make(B, "bn", dtype=torch.bfloat16)
+    x, t = data[0]
+    loss = B.functional.softmax_dice_loss(net(x.cuda()), t.cuda())
+    loss.backward()
+    assert abs(0.5 * (res[0]["bf16_sync_loss"] + res[1]["bf16_sync_loss"]) - float(loss)) < 3e-3
+    bufs = dict(net.named_buffers())
+    for k, v in res[0]["bf16_sync_buffers"].items():
+        assert torch.equal(v, res[1]["bf16_sync_buffers"][k]), k                   # both ranks hold the same global statistics
+        assert rel_err(v, bufs[k].float()) < 2e-2, k
+    g = 0.5 * (res[0]["bf16_sync_grad"] + res[1]["bf16_sync_grad"])
+    assert rel_err(g, net.convu1.conv3.weight.grad) < 6e-2
     assert res[0]["graph_buckets"] >= 2
