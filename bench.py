@@ -226,6 +226,71 @@ def torch_gpu_baseline(model_name, batch, size, steps, warmup, norm, dev):
             "best_variant": best[0], "value": best[1].get("value"), "ms_per_step": best[1].get("ms_per_step"), "unit": "voxels/s", "variants": out}
 
 
+def other_config(pkg, args, rank, world, local, base):
+    """BASELINE configs 1 and 4 through the same contract as the headline: W warm-up steps, K timed steps between barriers, max over
+    ranks, one JSON line; HBM roofline = layer-I/O bytes of the step (tools/workloads.py) / time against the measured copy bandwidth."""
+    from tools import workloads
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    w = (workloads.make_config1 if args.config == 1 else workloads.make_config4)(pkg, dev, world)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / n
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+    l0 = pkg.launch_count()
+    for _ in range(max(3, args.warmup)):
+        w["step"](*w["x_dev"])
+    per_step = (pkg.launch_count() - l0) // max(3, args.warmup)
+    sampler = ClockSampler(local) if rank == 0 else None
+    time.sleep(0.3)
+    t0 = time.time()
+    ms = timed(lambda: w["step"](*w["x_dev"]), args.steps)
+    ms_e2e = timed(lambda: float(w["step"](*[h.to(dev, non_blocking=True) for h in w["x_host"]])), args.steps)
+    clocks = sampler.summary(t0, time.time()) if sampler else None
+    pk = peaks()
+    if rank == 0:
+        gbs = w["bytes_per_step"] / ms / 1e6
+        print(json.dumps({**base, "metric": "conv3d autoencoder train voxels/s" if args.config == 1 else "fader encoder+classifier+discriminator step voxels/s",
+                          "value": world * w["voxels"] / (ms / 1e3), "ms_per_step": ms, "dtype": "bf16",
+                          "config": {"workload": w["workload"], "baseline_config": args.config, "parallelism": f"dp{world}",
+                                     "l2": "every 128^3 / 192^3 activation tensor exceeds the 126 MB L2"},
+                          "e2e": {"value": world * w["voxels"] / (ms_e2e / 1e3), "unit": "voxels/s", "ms_per_step": ms_e2e,
+                                  "h2d_bytes_per_step": sum(h.numel() * h.element_size() for h in w["x_host"]), "d2h_bytes_per_step": 4},
+                          "gpu_launches": int(per_step * args.steps), "clocks": clocks,
+                          "roofline": {"bound": "hbm", "kernel": "whole step (axis_gather / axis_wgrad dominate, profiles/r2_config*_kernel_table.md)",
+                                       "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": None,
+                                       "note": "achieved = bytes every layer of the step has to read + write once (forward layer I/O measured with hooks, "
+                                               "x3 for forward + backward; x4 for the fader step's two encoder forwards) / step time"}}), flush=True)
+    if dist is not None:
+        import gc
+        w = None
+        dist.barrier(); torch.cuda.synchronize(); gc.collect()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        dist.destroy_process_group()
+        os._exit(0)
+
+
 def main():
     if os.environ.get("B200_BENCH_WATCHDOG"):            # debugging aid: dump every thread's stack if the run has not finished in time
         import faulthandler
@@ -239,8 +304,10 @@ def main():
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--volume", default=None, help="D,H,W of a non-cubic volume (overrides --size), e.g. 192,224,192")
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3],
-                    help="BASELINE.json config: 2 = batch 4 x 128^3 (default), 3 = one 192x224x192 volume per GPU (data parallel)")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4],
+                    help="BASELINE.json config: 2 = unet3d batch 4 x 128^3 (default, the headline), 3 = one 192x224x192 volume per GPU (data parallel), "
+                         "1 = conv3d autoencoder batch 2 x 128^3, 4 = fader encoder+classifier+discriminator step, batch 8 x 192^3 per GPU (HBM-bound: "
+                         "their roofline block is bytes, not FLOPs)")
     ap.add_argument("--no-torch-baseline", action="store_true", help="skip the stock-PyTorch-on-this-GPU leg")
     ap.add_argument("--no-dropin-leg", action="store_true", help="skip the timing of the drop-in path (convert() of a stock model + eager loop)")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short timings of BASELINE configs 1/3/4/5 and rows f-1..f-3")
@@ -297,6 +364,8 @@ def main():
     # ------------------------------------------------------------------ our arm
     import __graft_entry__
     pkg = __graft_entry__.build()
+    if args.config in (1, 4):
+        return other_config(pkg, args, rank, world, local, base)
     from mri_epilepsy_diagnosis_b200 import functional as BF
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path)"
     torch.cuda.set_device(local)

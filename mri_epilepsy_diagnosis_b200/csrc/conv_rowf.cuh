@@ -521,13 +521,13 @@ inline bool row_fwd_geom(const b200_conv_desc* d, int pass, RowFwdGeom* g) {
 
 // kx-folded mode (see RowFwdParams::fold): one whole x-row per tile, small Cout, resident weights.  B200_ROWF_FOLD=0 disables.
 inline bool row_fwd_fold_geom(const RowFwdGeom& g) {
-    // Measured on B200, 4 x 128^3 forward: 32->32 0.684 -> 0.512 ms (907 TFLOP/s), 16->16 0.378 -> 0.338 ms, but 16->32
-    // 0.395 -> 0.500 ms (two 16-channel epilogue passes per tile against only nine K = 16 instructions): the epilogue, three TMEM
-    // loads + the shifted sum per 16 channels, is the new bound, so folding pays when there is enough K per epilogue pass.
-    // B200_ROWF_FOLD: 0 = never, 1 = that rule (default), 2 = whenever the geometry allows.
+    // Measured on B200, 4 x 128^3 forward.  Round 1 (one epilogue warp set): 32->32 0.684 -> 0.512 ms, 16->16 0.378 -> 0.338 ms, but
+    // 16->32 0.395 -> 0.500 ms (two 16-channel epilogue passes per tile against only nine K = 16 instructions), so 16->32 stayed
+    // unfolded.  Round 2 (two epilogue sets, cheaper shifted sum): 32->32 0.41 ms, 16->16 0.23 ms and 16->32 0.366 against 0.390 ms
+    // unfolded -- folding now pays whenever the geometry allows it.
+    // B200_ROWF_FOLD: 0 = never, 1 (default) = whenever the geometry allows.
     static const int mode = [] { const char* e = getenv("B200_ROWF_FOLD"); return e == nullptr ? 1 : atoi(e); }();
-    if (mode == 0 || g.khw != 3 || g.W != 128 || g.OC > 32) return false;
-    return mode >= 2 || g.IC >= 32 || g.OC == 16;
+    return mode != 0 && g.khw == 3 && g.W == 128 && g.OC <= 32;
 }
 inline int row_fwd_plan_mode(const RowFwdGeom& g, int N, RowFwdParams* p, size_t* smem_bytes, bool fold);
 // the folded plan when the geometry allows it and it fits, the plain one otherwise

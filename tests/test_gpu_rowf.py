@@ -53,7 +53,7 @@ CASES = [
     ("f64_32_w128", 1, 64, 32, (4, 9, 128), 3, 1, True),
     ("f133_w128", 2, 16, 16, (6, 10, 128), (1, 3, 3), (0, 1, 1), True),
     ("f16_16_w128_tall", 1, 16, 16, (3, 37, 128), 3, 1, False),
-    ("f16_32_w128", 1, 16, 32, (4, 9, 128), 3, 1, True),          # NOT folded by the default rule (Cin = 16, Cout = 32)
+    ("f16_32_w128", 1, 16, 32, (4, 9, 128), 3, 1, True),          # folded since round 2 (two 16-channel epilogue passes per tile)
 ]
 
 

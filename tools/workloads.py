@@ -51,24 +51,39 @@ def _layer_io_bytes(net, *inputs):
     return total[0]
 
 
-def config1_autoencoder(pkg, dev, hbm_gbs):
-    """BASELINE config 1: conv3d autoencoder (train_AE.ipynb [cell 8]: depth 6, c_base 16) fwd + MSE + bwd + Adam, batch 2 x 128^3"""
+def make_config1(pkg, dev, world=1):
+    """BASELINE config 1: conv3d autoencoder (train_AE.ipynb [cell 8]: depth 6, c_base 16) fwd + MSE + bwd + Adam, batch 2 x 128^3.
+    Returns the pieces bench.py and the timing wrapper below share: step(x_dev) -> loss tensor, the pinned host batch, voxel and
+    layer-I/O byte counts."""
     torch.manual_seed(0)
     net = pkg.convert(pkg.zoo.config1_autoencoder(depth=6, c_base=16).to(dev).train(), dtype=torch.bfloat16)
-    x = torch.randn(2, 1, 128, 128, 128, device=dev)
+    xh = torch.randn(2, 1, 128, 128, 128).pin_memory()
+    x = xh.to(dev)
     opt = torch.optim.Adam(net.parameters(), lr=1e-4, capturable=True, fused=True)
     io = _layer_io_bytes(net, x)
+    if world > 1:
+        pkg.dp.broadcast_parameters(net)
     if os.environ.get("B200_WORKLOAD_EAGER") == "1":           # for ncu launch lists: plain eager launches
-        def step(a, b):
+        def step(a):
             opt.zero_grad()
-            torch.nn.functional.mse_loss(net(a).float(), b).backward()
+            loss = torch.nn.functional.mse_loss(net(a).float(), a)
+            loss.backward()
             opt.step()
+            return loss.detach()
     else:
-        step = pkg.graphed.GraphedTrainStep(net, lambda y, t: torch.nn.functional.mse_loss(y.float(), t), opt, x, x)
-    ms = _timeit(lambda: step(x, x))
-    gbs = 3 * io / ms / 1e6
-    return {"workload": "AE depth 6 c_base 16, batch 2 x 128^3, fwd + MSE + bwd + Adam, bf16 body, cuda-graph replay", "ms_per_step": ms,
-            "value": x.numel() / ms * 1e3, "unit": "voxels/s", "layer_io_bytes_fwd": io, "hbm_gbs_achieved": gbs, "hbm_frac": gbs / hbm_gbs}
+        g = pkg.graphed.GraphedTrainStep(net, lambda y, t: torch.nn.functional.mse_loss(y.float(), t), opt, x, x)
+        step = lambda a: g(a, a)
+    return {"step": step, "x_host": (xh,), "x_dev": (x,), "voxels": x.numel(), "layer_io_bytes_fwd": io, "bytes_per_step": 3 * io,
+            "workload": "AE depth 6 c_base 16, batch 2 x 128^3 per GPU, fwd + MSE + bwd + Adam, bf16 body, cuda-graph replay",
+            "keep": (net, opt)}
+
+
+def config1_autoencoder(pkg, dev, hbm_gbs):
+    w = make_config1(pkg, dev)
+    ms = _timeit(lambda: w["step"](*w["x_dev"]))
+    gbs = w["bytes_per_step"] / ms / 1e6
+    return {"workload": w["workload"], "ms_per_step": ms, "value": w["voxels"] / ms * 1e3, "unit": "voxels/s",
+            "layer_io_bytes_fwd": w["layer_io_bytes_fwd"], "hbm_gbs_achieved": gbs, "hbm_frac": gbs / hbm_gbs}
 
 
 def config3_full_volume(pkg, dev, hbm_gbs):
@@ -85,16 +100,17 @@ def config3_full_volume(pkg, dev, hbm_gbs):
             "value": x.numel() / ms * 1e3, "unit": "voxels/s", "model_tflops": 518186.0 * x.numel() / ms / 1e9}
 
 
-def config4_fader(pkg, dev, hbm_gbs):
+def make_config4(pkg, dev, world=1):
     """BASELINE config 4, the per-GPU share: fader encoder + classifier + discriminator step (train_ENC_CLF.ipynb [cell 14, 16], n_d = 1),
-    batch 8 x 192^3, shapes of the shipped *_93_6_4.pth"""
+    batch 8 x 192^3 per GPU (global batch 64 on 8 GPUs), shapes of the shipped *_93_6_4.pth.  Data parallel: dp.attach on both optimizers."""
     torch.manual_seed(0)
     BF16 = torch.bfloat16
     enc = pkg.convert(pkg.zoo.fader_encoder().to(dev), dtype=BF16)
     clf = pkg.convert(pkg.zoo.Classificator(n_class=2, **pkg.zoo.FADER_HEAD).to(dev), dtype=BF16)
     disc = pkg.convert(pkg.zoo.Discriminator(n_domains=18, **pkg.zoo.FADER_HEAD).to(dev), dtype=BF16)
     B = 8
-    x = torch.randn(B, 1, 192, 192, 192, device=dev)
+    xh = torch.randn(B, 1, 192, 192, 192).pin_memory()
+    x = xh.to(dev)
     y = torch.randint(0, 2, (B,), device=dev)
     dom = torch.randint(0, 18, (B,), device=dev)
     opt_e = torch.optim.Adam(list(enc.parameters()) + list(clf.parameters()), lr=7e-4, weight_decay=1e-4)
@@ -102,11 +118,17 @@ def config4_fader(pkg, dev, hbm_gbs):
     ce_y = torch.nn.CrossEntropyLoss(weight=torch.tensor([1.0, 2.0], device=dev))
     ce_d = torch.nn.CrossEntropyLoss()
     io = _layer_io_bytes(enc, x)
+    buckets = []
+    if world > 1:
+        for m in (enc, clf, disc):
+            pkg.dp.broadcast_parameters(m)
+        buckets = [pkg.dp.GradientBucket(list(enc.parameters()) + list(clf.parameters()), opt_e, buckets=1),
+                   pkg.dp.GradientBucket(list(disc.parameters()), opt_d, buckets=1)]
 
-    def step(lam=0.1):
+    def step(xb, lam=0.1):
         enc.eval(); disc.train()
         with torch.no_grad():
-            lat = enc(x)[0]
+            lat = enc(xb)[0]
         opt_d.zero_grad()
         ce_d(disc(lat), dom).backward()
         opt_d.step()
@@ -114,17 +136,26 @@ def config4_fader(pkg, dev, hbm_gbs):
         for p in disc.parameters():
             p.requires_grad = False
         opt_e.zero_grad()
-        lat = enc(x)[0]
+        lat = enc(xb)[0]
         logp = torch.log_softmax(disc(lat), dim=1)
         adv = -(torch.ones_like(logp) / 18.0 * logp).sum(1).mean()
-        (ce_y(clf(lat), y) + lam * adv).backward()
+        loss = ce_y(clf(lat), y) + lam * adv
+        loss.backward()
         opt_e.step()
         for p in disc.parameters():
             p.requires_grad = True
-    ms = _timeit(step, iters=4)
-    gbs = 4 * io / ms / 1e6               # 2 encoder forwards + 1 encoder backward (~2 forwards' worth of bytes) per step
-    return {"workload": "fader enc+clf+disc step (n_d=1), batch 8 x 192^3, bf16 body, eager launches", "ms_per_step": ms, "value": x.numel() / ms * 1e3,
-            "unit": "voxels/s", "layer_io_bytes_fwd": io, "hbm_gbs_achieved": gbs, "hbm_frac": gbs / hbm_gbs}
+        return loss.detach()
+    # 2 encoder forwards + 1 encoder backward (~2 forwards' worth of bytes) per step
+    return {"step": step, "x_host": (xh,), "x_dev": (x,), "voxels": x.numel(), "layer_io_bytes_fwd": io, "bytes_per_step": 4 * io,
+            "workload": "fader enc+clf+disc step (n_d=1), batch 8 x 192^3 per GPU, bf16 body, eager launches", "keep": (enc, clf, disc, opt_e, opt_d, buckets)}
+
+
+def config4_fader(pkg, dev, hbm_gbs):
+    w = make_config4(pkg, dev)
+    ms = _timeit(lambda: w["step"](*w["x_dev"]), iters=4)
+    gbs = w["bytes_per_step"] / ms / 1e6
+    return {"workload": w["workload"], "ms_per_step": ms, "value": w["voxels"] / ms * 1e3, "unit": "voxels/s",
+            "layer_io_bytes_fwd": w["layer_io_bytes_fwd"], "hbm_gbs_achieved": gbs, "hbm_frac": gbs / hbm_gbs}
 
 
 def config5_detection(pkg, dev, hbm_gbs):
