@@ -73,6 +73,7 @@ def make_config1(pkg, dev, world=1):
     else:
         g = pkg.graphed.GraphedTrainStep(net, lambda y, t: torch.nn.functional.mse_loss(y.float(), t), opt, x, x)
         step = lambda a: g(a, a)
+        step.graph = g
     return {"step": step, "x_host": (xh,), "x_dev": (x,), "voxels": x.numel(), "layer_io_bytes_fwd": io, "bytes_per_step": 3 * io,
             "workload": "AE depth 6 c_base 16, batch 2 x 128^3 per GPU, fwd + MSE + bwd + Adam, bf16 body, cuda-graph replay",
             "keep": (net, opt)}
