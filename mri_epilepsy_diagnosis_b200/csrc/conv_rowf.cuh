@@ -48,11 +48,13 @@ struct RowFwdParams {
     __nv_bfloat16* out;          // [N][D][H][W][OC]
     float* stats;                // [grid][2][OC] fp32 per-CTA (sum, sum of squares) of the outputs (OC <= 64); or null
     int store_c0;                // only channels [store_c0, OC) are stored (out has OC - store_c0 channels); statistics cover all
-    // kx-folded mode (small Cout, W == 128): ONE tcgen05.mma per (kz, ky) with the UNSHIFTED voxel rows as A and the three kx
+    // kx-folded mode (small Cout, W = 32 / 64 / 128): ONE tcgen05.mma per (kz, ky) with the UNSHIFTED voxel rows as A and the three kx
     // weight blocks side by side as B (N = 3*OC): TMEM holds P_kx[x] = x[x] . W[kx] in three column blocks per tile and the
     // epilogue forms out[x] = P_0[x-1] + P_1[x] + P_2[x+1] (lane shuffles; warp-boundary lanes through shared memory).
     // 9 instructions of max(32 + 3*OC/4, 3*OC/2) cycles per tile and plane instead of 27 of max(32 + OC/4, OC/2).
+    // Folded planes carry NO x halo (pitchW == W, W in {32, 64, 128}): a tile is 128 consecutive slots = 128 / W whole rows.
     int fold;
+    int wshift;                  // log2(W) (folded mode)
     int ncol;                    // TMEM columns per tile: OC, or 3*OC when folded
     int dbg;                     // B200_ROWF_DBG (timing experiments only, results are WRONG): 1 = epilogue skips all work, 2 = no shifted sum
 };
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
                     ptx::mbar_wait(ptx::smem_u32(&bars.pempty[s]), phs ^ 1);
                     const uint32_t full = ptx::smem_u32(&bars.pfull[s]);
                     ptx::mbar_expect_tx(full, (uint32_t)p.plane_tx);
-                    ptx::tma_load_4d(ptx::smem_u32(planes + (size_t)s * p.plane_bytes), &in_map, full, 0, -ph, c.y0 - ph, c.n * p.D + pl);
+                    ptx::tma_load_4d(ptx::smem_u32(planes + (size_t)s * p.plane_bytes), &in_map, full, 0, FOLD ? 0 : -ph, c.y0 - ph, c.n * p.D + pl);
                 }
             }
         }
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
                                 // B block of (kz, ky): [ci group][kx][oc][8 ci] -> LBO = 3*OC*16 B, next 16 ci = 2 groups further
 #pragma unroll
                                 for (int ky = 0; ky < KHW; ++ky) {
-                                    uint32_t a = a0 + (uint32_t)ky * row16 + (uint32_t)(KHW / 2) * vox16, b2 = bb;
+                                    uint32_t a = a0 + (uint32_t)ky * row16, b2 = bb;             // unshifted rows (the image has no x halo)
 #pragma unroll
                                     for (int ks = 0; ks < nks; ++ks) {
                                         if (leader) ptx::umma_bf16_lohi(d_tmem, a, a_hi, b2, b_hi, idesc, acc);
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
                 const uint32_t set = group & 1;
                 ptx::mbar_wait(ptx::smem_u32(&bars.aempty[set]), ((group >> 1) & 1) ^ 1);
                 ptx::tc_fence_after();
-                const uint32_t d_set = tmem_base + (uint32_t)(set * p.T * p.OC);
+                const uint32_t d_set = tmem_base + (uint32_t)(set * p.T * p.ncol);
                 uint32_t acc = 0;
                 bool released = false;
 #pragma unroll 1
@@ -283,21 +285,21 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
                     if (pl < 0 || pl >= p.D) continue;                                  // the weight producer skips the same taps
                     const uint32_t a_pl = (pl16 + ((cnt + (uint32_t)(pl - first)) % ring) * plane16) | (1u << 16);
 #pragma unroll 1
-                    for (int j = 0; j < KHW * KHW; ++j) {
+                    for (int j = 0; j < (FOLD ? KHW : KHW * KHW); ++j) {              // folded: one stage = the three kx blocks of (kz, ky)
                         ptx::mbar_wait(ptx::smem_u32(&bars.wfull[ws]), wph);
                         ptx::tc_fence_after();
                         {
-                            const uint32_t a_tap = a_pl + (uint32_t)(j / KHW) * row16 + (uint32_t)(j % KHW) * vox16;
-                            const uint32_t b0 = (w16 + ws * wstage16) | b_lbo;
+                            const uint32_t a_tap = FOLD ? a_pl + (uint32_t)j * row16 : a_pl + (uint32_t)(j / KHW) * row16 + (uint32_t)(j % KHW) * vox16;
+                            const uint32_t b0 = (w16 + ws * wstage16) | (FOLD ? 3u * b_lbo : b_lbo);
                             uint32_t d = d_set;
                             for (int t = 0; t < ntiles; ++t) {
                                 uint32_t a = a_tap + (uint32_t)((t / p.tpr) * p.rowstride + (t % p.tpr) * 128) * vox16, b2 = b0;
 #pragma unroll
                                 for (int ks = 0; ks < nks; ++ks) {
                                     if (leader) ptx::umma_bf16_lohi(d, a, a_hi, b2, b_hi, idesc, ks == 0 ? acc : 1u);
-                                    a += 2; b2 += wks16;
+                                    a += 2; b2 += FOLD ? 3u * wks16 : wks16;
                                 }
-                                d += (uint32_t)p.OC;
+                                d += (uint32_t)p.ncol;
                             }
                             if (leader) ptx::umma_commit(ptx::smem_u32(&bars.wempty[ws]));           // stage free once these MMAs retire
                         }
@@ -331,12 +333,13 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
                     for (int kz = 0; kz < KD; ++kz) {
                         const int pl = z + kz - pd;
                         if (pl < 0 || pl >= p.D) continue;
-                        for (int j = 0; j < KHW * KHW; ++j) {
+                        constexpr int stages = FOLD ? KHW : KHW * KHW;             // wtap_bytes = one stage (three taps when folded)
+                        for (int j = 0; j < stages; ++j) {
                             ptx::mbar_wait(ptx::smem_u32(&bars.wempty[s]), ph ^ 1);
                             const uint32_t full = ptx::smem_u32(&bars.wfull[s]);
                             ptx::mbar_expect_tx(full, (uint32_t)p.wtap_bytes);
                             ptx::bulk_load(ptx::smem_u32(wsm + (size_t)s * p.wtap_bytes),
-                                           reinterpret_cast<const uint8_t*>(p.w) + (size_t)(kz * KHW * KHW + j) * p.wtap_bytes, (uint32_t)p.wtap_bytes, full);
+                                           reinterpret_cast<const uint8_t*>(p.w) + (size_t)(kz * stages + j) * p.wtap_bytes, (uint32_t)p.wtap_bytes, full);
                             if (++s == (uint32_t)p.nw) { s = 0; ph ^= 1; }
                         }
                     }
@@ -357,6 +360,8 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
 #pragma unroll
         for (int i = 0; i < 16 * kStatCh; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
         const int ocs = p.OC - p.store_c0;                       // stored channels per voxel
+        const bool lzero = ((lane_grp * 32) & (p.W - 1)) == 0;          // folded: this warp's lane 0 is x == 0 / its lane 31 is x == W-1
+        const bool rzero = (((lane_grp + 1) * 32) & (p.W - 1)) == 0;
         uint32_t group = 0, xphase = 0;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
             const RfItem c = rf_decode(p, item);
@@ -369,7 +374,7 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
                 for (int t = (eset ^ (int)(group & 1)); t < ntiles; t += 2) {         // (alternating start: one-tile groups still use both sets)
                     if (p.dbg == 1) continue;
                     int row, x;
-                    if (FOLD) { row = t; x = m; }                                   // W == 128: one tile = one whole x-row
+                    if (FOLD) { const int slot = t * 128 + m; row = slot >> p.wshift; x = slot & (p.W - 1); }   // 128 / W whole rows per tile
                     else {
                         const int slot = (t / p.tpr) * p.rowstride + (t % p.tpr) * 128 + m;
                         row = slot / p.pitchW; x = slot - row * p.pitchW;
@@ -378,8 +383,8 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
                     __nv_bfloat16* dst = p.out + ((plane_vox + c.y0 + row) * p.W + x) * ocs - p.store_c0;
                     const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)((set * p.T + t) * p.ncol);
                     if (FOLD) {
-                        // out[x] = P_0[x-1] + P_1[x] + P_2[x+1]; the tile is one whole x-row (W == 128), so x-1 / x+1 outside the tile
-                        // are the zero halo.  Neighbour lanes by a rotating shuffle; the value that crosses a warp boundary travels
+                        // out[x] = P_0[x-1] + P_1[x] + P_2[x+1]; the tile is 128 / W whole x-rows whose ends fall on warp boundaries
+                        // (W = 32, 64, 128), where the neighbour is the zero halo (lzero / rzero).  Neighbour lanes by a rotating shuffle; the value that crosses a warp boundary travels
                         // through shared memory: lane 31 publishes its P_0 row and then REPLACES it by the previous warp's lane 31
                         // (lane 0 likewise for P_2), so the rotation delivers every lane its neighbour without a per-value select.
 #pragma unroll
@@ -402,12 +407,12 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
                                 if (eset == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
                                 else asm volatile("bar.sync 2, 128;" ::: "memory");
                                 if (lane == 31) {
-                                    const float4* s4 = reinterpret_cast<const float4*>(lane_grp > 0 ? &buf[lane_grp - 1][0][0] : &xzero[0]);
+                                    const float4* s4 = reinterpret_cast<const float4*>(!lzero ? &buf[lane_grp - 1][0][0] : &xzero[0]);
 #pragma unroll
                                     for (int q = 0; q < 4; ++q) { const float4 a4 = s4[q]; l[4 * q] = a4.x; l[4 * q + 1] = a4.y; l[4 * q + 2] = a4.z; l[4 * q + 3] = a4.w; }
                                 }
                                 if (lane == 0) {
-                                    const float4* s4 = reinterpret_cast<const float4*>(lane_grp < 3 ? &buf[lane_grp + 1][1][0] : &xzero[0]);
+                                    const float4* s4 = reinterpret_cast<const float4*>(!rzero ? &buf[lane_grp + 1][1][0] : &xzero[0]);
 #pragma unroll
                                     for (int q = 0; q < 4; ++q) { const float4 a4 = s4[q]; r[4 * q] = a4.x; r[4 * q + 1] = a4.y; r[4 * q + 2] = a4.z; r[4 * q + 3] = a4.w; }
                                 }
@@ -519,7 +524,7 @@ inline bool row_fwd_geom(const b200_conv_desc* d, int pass, RowFwdGeom* g) {
     return true;
 }
 
-// kx-folded mode (see RowFwdParams::fold): one whole x-row per tile, small Cout, resident weights.  B200_ROWF_FOLD=0 disables.
+// kx-folded mode (see RowFwdParams::fold): 128 / W whole x-rows per tile, small Cout, resident or streamed weights.  B200_ROWF_FOLD=0 disables.
 inline bool row_fwd_fold_geom(const RowFwdGeom& g) {
     // Measured on B200, 4 x 128^3 forward.  Round 1 (one epilogue warp set): 32->32 0.684 -> 0.512 ms, 16->16 0.378 -> 0.338 ms, but
     // 16->32 0.395 -> 0.500 ms (two 16-channel epilogue passes per tile against only nine K = 16 instructions), so 16->32 stayed
@@ -527,7 +532,7 @@ inline bool row_fwd_fold_geom(const RowFwdGeom& g) {
     // unfolded -- folding now pays whenever the geometry allows it.
     // B200_ROWF_FOLD: 0 = never, 1 (default) = whenever the geometry allows.
     static const int mode = [] { const char* e = getenv("B200_ROWF_FOLD"); return e == nullptr ? 1 : atoi(e); }();
-    return mode != 0 && g.khw == 3 && g.W == 128 && g.OC <= 32;
+    return mode != 0 && g.khw == 3 && (g.W == 128 || g.W == 64 || g.W == 32) && g.OC <= 32;
 }
 inline int row_fwd_plan_mode(const RowFwdGeom& g, int N, RowFwdParams* p, size_t* smem_bytes, bool fold);
 // the folded plan when the geometry allows it and it fits, the plain one otherwise
@@ -553,12 +558,13 @@ inline int row_fwd_plan_mode(const RowFwdGeom& g, int N, RowFwdParams* p, size_t
     memset(p, 0, sizeof *p);
     p->N = N; p->D = g.D; p->H = g.H; p->W = g.W; p->IC = g.IC; p->OC = g.OC; p->kd = g.kd; p->khw = g.khw;
     const int ph = g.khw / 2, pd = g.kd / 2;
-    p->pitchW = g.W + 2 * ph;
-    const bool per_row = (g.W % 128) == 0;
+    p->pitchW = fold ? g.W : g.W + 2 * ph;
+    p->wshift = g.W == 128 ? 7 : g.W == 64 ? 6 : 5;
+    const bool per_row = !fold && (g.W % 128) == 0;
     p->tpr = per_row ? g.W / 128 : (1 << 30);
     p->rowstride = per_row ? p->pitchW : 0;
     p->w_bytes = g.kd * g.khw * g.khw * g.IC * g.OC * 2;
-    p->wtap_bytes = g.IC * g.OC * 2;
+    p->wtap_bytes = (fold ? 3 : 1) * g.IC * g.OC * 2;                     // one streamed stage
     // weights: RESIDENT (every tap in shared memory next to a 4-deep plane ring) or STREAMED tap by tap through a ring (the
     // plane ring then shrinks to 3: the kz = 0 plane is released after its pass, see the MMA loop).  Both modes are costed.
     p->fold = fold ? 1 : 0;
@@ -576,7 +582,8 @@ inline int row_fwd_plan_mode(const RowFwdGeom& g, int N, RowFwdParams* p, size_t
     if (mma_cyc < p->ncol / 2.0) mma_cyc = p->ncol / 2.0;
     int best = 0, best_zs = 1, best_nw = 1, best_stream = 0, best_ring = 4; double best_cost = 1e30;
     static const int ring_cap = [] { const char* e = getenv("B200_ROWF_RING"); const int v = e == nullptr ? kRfRing : atoi(e); return v < 4 ? 4 : (v > kRfRing ? kRfRing : v); }();
-    for (int stream_w = 0; stream_w <= (p->fold ? 0 : 1); ++stream_w) {
+    const int stages = fold ? taps / 3 : taps;
+    for (int stream_w = 0; stream_w <= 1; ++stream_w) {
         const int nw_lo = stream_w ? 2 : 1, nw_hi = stream_w ? kRfMaxW : 1;
         for (int nw = nw_lo; nw <= nw_hi; ++nw) {
             const size_t wsm_bytes = stream_w ? (size_t)nw * p->wtap_bytes : (size_t)p->w_bytes;
@@ -604,7 +611,7 @@ inline int row_fwd_plan_mode(const RowFwdGeom& g, int N, RowFwdParams* p, size_t
                 const double g_w = stream_w ? (double)p->w_bytes / w_bw : 0.0;
                 // streaming pays a full-barrier wait + commit per tap and cannot run ahead of the weight ring: measured ~1.5x the
                 // MMA time of the resident mode on the layers where both fit
-                double group = stream_w ? 1.5 * (g_mma > g_w ? g_mma : g_w) + 150.0 * taps + 400.0 : g_mma + 400.0;
+                double group = stream_w ? 1.5 * (g_mma > g_w ? g_mma : g_w) + 150.0 * stages + 400.0 : g_mma + 400.0;
                 const double plane_cyc = (double)pb / 20.0;
                 const int lookahead = stream_w ? 1 : ring - (2 * pd + 1);
                 const double feed = (2000.0 + (double)pb / 16.0) / (lookahead > 0 ? lookahead : 1);      // one plane per group must arrive
