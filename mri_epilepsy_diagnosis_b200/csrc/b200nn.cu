@@ -455,6 +455,10 @@ int b200_syncbn_finalize(int C, float eps, float momentum, double count_global, 
     return 0;
 }
 
+// rows in flight per thread in the three streaming norm kernels (tools/bench_norm.py, 4 x {16,32} x 128^3 bf16: apply 2 > 4;
+// bwd_partial 4 > 2 by 5-6 %; bwd_apply 4 > 2 by 2-4 %)
+constexpr int kNormApplyU = 2, kNormBwdPartialU = 4, kNormBwdApplyU = 4;
+
 static int apply_grid(const NormGeom& g, int64_t S) {
     // gx*256 must be a multiple of CV so every thread keeps fixed channels
     int m = g.CV;
@@ -475,9 +479,9 @@ int b200_norm_apply(const b200_norm_desc* d, const void* x, const float* mean, c
     B200_REQUIRE(x && y && mean && rstd, "norm_apply: null pointer");
     dim3 grid(apply_grid(g, d->S), d->N);
     B200_DISPATCH_T(d->dtype, T, {
-        if (g.V == 1) B200_LAUNCH((norm_apply_kernel<T, 1>), grid, 256, 0, stream, (const T*)x, mean, rstd, gamma, beta, (const T*)residual, (T*)y,
+        if (g.V == 1) B200_LAUNCH((norm_apply_kernel<T, 1>), grid, 256, (size_t)2 * d->C * sizeof(float), stream, (const T*)x, mean, rstd, gamma, beta, (const T*)residual, (T*)y,
                                   d->C, d->S, d->kind, d->G, d->act, d->slope);
-        else B200_LAUNCH((norm_apply_kernel<T, Vec16<T>::N>), grid, 256, 0, stream, (const T*)x, mean, rstd, gamma, beta, (const T*)residual, (T*)y,
+        else B200_LAUNCH((norm_apply_kernel<T, Vec16<T>::N, kNormApplyU>), grid, 256, (size_t)2 * d->C * sizeof(float), stream, (const T*)x, mean, rstd, gamma, beta, (const T*)residual, (T*)y,
                          d->C, d->S, d->kind, d->G, d->act, d->slope);
     });
     return 0;
@@ -507,7 +511,7 @@ int b200_norm_bwd_reduce(const b200_norm_desc* d, const void* x, const void* y, 
     B200_DISPATCH_T(d->dtype, T, {
         if (g.V == 1) B200_LAUNCH((norm_bwd_partial_kernel<T, 1>), grid, 256, smem, stream, (const T*)x, (const T*)y, (const T*)dy, mean, rstd, gamma,
                                   beta, d->C, g.R, g.rows_per_chunk, d->kind, d->G, d->act, d->slope, w.partial);
-        else B200_LAUNCH((norm_bwd_partial_kernel<T, Vec16<T>::N>), grid, 256, smem, stream, (const T*)x, (const T*)y, (const T*)dy, mean, rstd, gamma,
+        else B200_LAUNCH((norm_bwd_partial_kernel<T, Vec16<T>::N, kNormBwdPartialU>), grid, 256, smem, stream, (const T*)x, (const T*)y, (const T*)dy, mean, rstd, gamma,
                          beta, d->C, g.R, g.rows_per_chunk, d->kind, d->G, d->act, d->slope, w.partial);
     });
     B200_LAUNCH(norm_bwd_sum_kernel, (int)ceil_div((int64_t)g.NB * d->C, 8), 256, 0, stream, g.NB, d->C, g.chunks, w.partial, sums);
@@ -527,9 +531,9 @@ int b200_norm_bwd_apply(const b200_norm_desc* d, int training, int world, const 
     B200_LAUNCH(norm_bwd_coef_kernel, (int)ceil_div((int64_t)g.NB * d->C, 128), 128, 0, stream, d->N, d->C, d->S, d->kind, d->G, training, world,
                 sums, mean, rstd, gamma, beta, w.coef, dgamma, dbeta);
     B200_DISPATCH_T(d->dtype, T, {
-        if (g.V == 1) B200_LAUNCH((norm_bwd_apply_kernel<T, 1>), agrid, 256, 0, stream, (const T*)x, (const T*)y, (const T*)dy, w.coef, (T*)dx,
+        if (g.V == 1) B200_LAUNCH((norm_bwd_apply_kernel<T, 1>), agrid, 256, (size_t)5 * d->C * sizeof(float), stream, (const T*)x, (const T*)y, (const T*)dy, w.coef, (T*)dx,
                                   (T*)dresidual, d->C, d->S, per_sample, d->act, d->slope);
-        else B200_LAUNCH((norm_bwd_apply_kernel<T, Vec16<T>::N>), agrid, 256, 0, stream, (const T*)x, (const T*)y, (const T*)dy, w.coef, (T*)dx,
+        else B200_LAUNCH((norm_bwd_apply_kernel<T, Vec16<T>::N, kNormBwdApplyU>), agrid, 256, (size_t)5 * d->C * sizeof(float), stream, (const T*)x, (const T*)y, (const T*)dy, w.coef, (T*)dx,
                          (T*)dresidual, d->C, d->S, per_sample, d->act, d->slope);
     });
     return 0;
@@ -552,16 +556,16 @@ int b200_norm_bwd(const b200_norm_desc* d, int training, const void* x, const vo
         B200_DISPATCH_T(d->dtype, T, {
             if (g.V == 1) B200_LAUNCH((norm_bwd_partial_kernel<T, 1>), grid, 256, smem, stream, (const T*)x, (const T*)y, (const T*)dy, mean, rstd, gamma,
                                       beta, d->C, g.R, g.rows_per_chunk, d->kind, d->G, d->act, d->slope, w.partial);
-            else B200_LAUNCH((norm_bwd_partial_kernel<T, Vec16<T>::N>), grid, 256, smem, stream, (const T*)x, (const T*)y, (const T*)dy, mean, rstd, gamma,
+            else B200_LAUNCH((norm_bwd_partial_kernel<T, Vec16<T>::N, kNormBwdPartialU>), grid, 256, smem, stream, (const T*)x, (const T*)y, (const T*)dy, mean, rstd, gamma,
                              beta, d->C, g.R, g.rows_per_chunk, d->kind, d->G, d->act, d->slope, w.partial);
         });
         B200_LAUNCH(norm_bwd_sum_coef_bn_kernel, (int)ceil_div(d->C, 8), 256, 0, stream, d->N, d->C, d->S, g.chunks, training, w.partial, mean, rstd, gamma,
                     beta, w.coef, dgamma, dbeta);
         dim3 agrid(apply_grid(g, d->S), d->N);
         B200_DISPATCH_T(d->dtype, T, {
-            if (g.V == 1) B200_LAUNCH((norm_bwd_apply_kernel<T, 1>), agrid, 256, 0, stream, (const T*)x, (const T*)y, (const T*)dy, w.coef, (T*)dx,
+            if (g.V == 1) B200_LAUNCH((norm_bwd_apply_kernel<T, 1>), agrid, 256, (size_t)5 * d->C * sizeof(float), stream, (const T*)x, (const T*)y, (const T*)dy, w.coef, (T*)dx,
                                       (T*)dresidual, d->C, d->S, 0, d->act, d->slope);
-            else B200_LAUNCH((norm_bwd_apply_kernel<T, Vec16<T>::N>), agrid, 256, 0, stream, (const T*)x, (const T*)y, (const T*)dy, w.coef, (T*)dx,
+            else B200_LAUNCH((norm_bwd_apply_kernel<T, Vec16<T>::N, kNormBwdApplyU>), agrid, 256, (size_t)5 * d->C * sizeof(float), stream, (const T*)x, (const T*)y, (const T*)dy, w.coef, (T*)dx,
                              (T*)dresidual, d->C, d->S, 0, d->act, d->slope);
         });
         return 0;

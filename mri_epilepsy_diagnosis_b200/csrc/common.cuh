@@ -62,7 +62,12 @@ template <typename T> struct Vec16 { static constexpr int N = 16 / sizeof(T); };
 
 template <typename T, int V> struct Pack;   // V elements of T moved as one transaction when V == 16/sizeof(T)
 
+// `raw` / ldraw / unpack: the packed form of one transaction -- streaming kernels issue the loads of several rows first and unpack
+// row by row, so the loads in flight cost 4 registers each instead of V
 template <> struct Pack<float, 4> {
+    using raw = float4;
+    static __device__ __forceinline__ raw ldraw(const float* p) { return *reinterpret_cast<const float4*>(p); }
+    static __device__ __forceinline__ void unpack(const raw& v, float (&o)[4]) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
     static __device__ __forceinline__ void load(const float* p, float (&o)[4]) {
         float4 v = *reinterpret_cast<const float4*>(p);
         o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
@@ -72,6 +77,9 @@ template <> struct Pack<float, 4> {
     }
 };
 template <> struct Pack<float, 2> {
+    using raw = float2;
+    static __device__ __forceinline__ raw ldraw(const float* p) { return *reinterpret_cast<const float2*>(p); }
+    static __device__ __forceinline__ void unpack(const raw& v, float (&o)[2]) { o[0] = v.x; o[1] = v.y; }
     static __device__ __forceinline__ void load(const float* p, float (&o)[2]) {
         float2 v = *reinterpret_cast<const float2*>(p);
         o[0] = v.x; o[1] = v.y;
@@ -79,10 +87,20 @@ template <> struct Pack<float, 2> {
     static __device__ __forceinline__ void store(float* p, const float (&o)[2]) { *reinterpret_cast<float2*>(p) = make_float2(o[0], o[1]); }
 };
 template <> struct Pack<float, 1> {
+    using raw = float;
+    static __device__ __forceinline__ raw ldraw(const float* p) { return *p; }
+    static __device__ __forceinline__ void unpack(const raw& v, float (&o)[1]) { o[0] = v; }
     static __device__ __forceinline__ void load(const float* p, float (&o)[1]) { o[0] = *p; }
     static __device__ __forceinline__ void store(float* p, const float (&o)[1]) { *p = o[0]; }
 };
 template <> struct Pack<__nv_bfloat16, 8> {
+    using raw = uint4;
+    static __device__ __forceinline__ raw ldraw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+    static __device__ __forceinline__ void unpack(const raw& v, float (&o)[8]) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { o[2 * i] = __uint_as_float(w[i] << 16); o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+    }
     static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&o)[8]) {
         uint4 v = *reinterpret_cast<const uint4*>(p);
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
@@ -101,9 +119,27 @@ template <> struct Pack<__nv_bfloat16, 8> {
     }
 };
 template <> struct Pack<__nv_bfloat16, 1> {
+    using raw = __nv_bfloat16;
+    static __device__ __forceinline__ raw ldraw(const __nv_bfloat16* p) { return *p; }
+    static __device__ __forceinline__ void unpack(const raw& v, float (&o)[1]) { o[0] = __bfloat162float(v); }
     static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&o)[1]) { o[0] = __bfloat162float(*p); }
     static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&o)[1]) { *p = __float2bfloat16_rn(o[0]); }
 };
+
+// V per-channel coefficients from shared memory, re-read at every use (volatile: the compiler must not hoist them into registers
+// for the whole loop -- with 3..5 coefficient vectors of V = 8 channels that cost 24..40 registers and held the streaming kernels
+// at 2-3 blocks per SM, too few loads in flight to cover the HBM latency)
+template <int V> __device__ __forceinline__ void lds_coef(const float* p, float (&o)[V]) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    if constexpr (V % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < V / 4; ++q)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[4 * q]), "=f"(o[4 * q + 1]), "=f"(o[4 * q + 2]), "=f"(o[4 * q + 3]) : "r"(a + 16u * q));
+    } else {
+#pragma unroll
+        for (int k = 0; k < V; ++k) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o[k]) : "r"(a + 4u * k));
+    }
+}
 
 __device__ __forceinline__ float act_apply(float v, int act, float slope) {
     if (act == B200_ACT_RELU) return v < 0.f ? 0.f : v;           // NaN stays NaN, like at::relu (clamp_min)

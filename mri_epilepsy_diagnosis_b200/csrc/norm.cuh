@@ -165,68 +165,81 @@ __device__ __forceinline__ void norm_scale_shift(float mean, float rstd, float g
     sh = be - mean * sc;
 }
 
-// y = act((x - mean) * rstd * gamma + beta [+ residual]); grid (gx, N); gx*256 is a multiple of CV so each thread owns fixed channels
-template <typename T, int V>
-__global__ void __launch_bounds__(256) norm_apply_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
+// y = act((x - mean) * rstd * gamma + beta [+ residual]); grid (gx, N); gx*256 is a multiple of CV so each thread owns fixed channels.
+// Dynamic shared memory: 2*C floats (scale, shift of this sample's channels, see lds_coef).
+template <typename T, int V, int U = 2>
+__global__ void __launch_bounds__(256, U == 2 ? 4 : 3) norm_apply_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          const T* __restrict__ res, T* __restrict__ y,
                                                          int C, int64_t S, int kind, int G, int act, float slope) {
+    extern __shared__ __align__(16) float cf[];
+    using P = Pack<T, V>;
     const int CV = C / V, n = blockIdx.y;
+    for (int c = threadIdx.x; c < C; c += 256) {
+        const int g = norm_group_index(kind, n, c, C, G);
+        norm_scale_shift(mean[g], rstd[g], gamma ? gamma[c] : 1.f, beta ? beta[c] : 0.f, cf[c], cf[C + c]);
+    }
+    __syncthreads();
     const int64_t i0 = (int64_t)blockIdx.x * 256 + threadIdx.x;
     const int cv = (int)(i0 % CV);
-    float sc[V], sh[V];
-#pragma unroll
-    for (int k = 0; k < V; ++k) {
-        const int c = cv * V + k;
-        const int g = norm_group_index(kind, n, c, C, G);
-        const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
-        norm_scale_shift(mean[g], rstd[g], ga, be, sc[k], sh[k]);
-    }
+    const float* csc = cf + cv * V;
+    const float* csh = cf + C + cv * V;
     const int64_t total = S * CV, stride = (int64_t)gridDim.x * 256, base = (int64_t)n * total;
     int64_t i = i0;
-    for (; i + stride < total; i += 2 * stride) {            // two independent 16-byte streams per tensor in flight
-        float v[2][V], r[2][V];
+    for (; i + (U - 1) * stride < total; i += U * stride) {            // U independent 16-byte streams per tensor in flight
+        typename P::raw xr[U], rr[U];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            Pack<T, V>::load(x + (base + i + u * stride) * V, v[u]);
-            if (res != nullptr) Pack<T, V>::load(res + (base + i + u * stride) * V, r[u]);
+        for (int u = 0; u < U; ++u) {
+            xr[u] = P::ldraw(x + (base + i + u * stride) * V);
+            if (res != nullptr) rr[u] = P::ldraw(res + (base + i + u * stride) * V);
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
+            float v[V], r[V], sc[V], sh[V];
+            P::unpack(xr[u], v);
+            if (res != nullptr) P::unpack(rr[u], r);
+            lds_coef<V>(csc, sc);
+            lds_coef<V>(csh, sh);
 #pragma unroll
             for (int k = 0; k < V; ++k) {
-                const float t = fmaf(v[u][k], sc[k], sh[k]);
-                v[u][k] = act_apply(res != nullptr ? t + r[u][k] : t, act, slope);
+                const float t = fmaf(v[k], sc[k], sh[k]);
+                v[k] = act_apply(res != nullptr ? t + r[k] : t, act, slope);
             }
-            Pack<T, V>::store(y + (base + i + u * stride) * V, v[u]);
+            P::store(y + (base + i + u * stride) * V, v);
         }
     }
     for (; i < total; i += stride) {
-        float v[V];
-        Pack<T, V>::load(x + (base + i) * V, v);
+        float v[V], sc[V], sh[V];
+        P::load(x + (base + i) * V, v);
+        lds_coef<V>(csc, sc);
+        lds_coef<V>(csh, sh);
         if (res != nullptr) {
             float r[V];
-            Pack<T, V>::load(res + (base + i) * V, r);
+            P::load(res + (base + i) * V, r);
 #pragma unroll
             for (int k = 0; k < V; ++k) v[k] = act_apply(fmaf(v[k], sc[k], sh[k]) + r[k], act, slope);
         } else {
 #pragma unroll
             for (int k = 0; k < V; ++k) v[k] = act_apply(fmaf(v[k], sc[k], sh[k]), act, slope);
         }
-        Pack<T, V>::store(y + (base + i) * V, v);
+        P::store(y + (base + i) * V, v);
     }
 }
 
 // partial[((nb*chunks+chunk)*2+{0,1})*C + c] = sum dy', sum dy' * xhat, with dy' = dy * act'(y).
 // The gate act'(.) comes from the saved output y when given; with y == nullptr (fused activation WITHOUT residual) it is
 // recomputed from x through the same affine form as the forward pass -- one tensor read less.  Two rows are in flight per thread.
-template <typename T, int V>
-__global__ void __launch_bounds__(256) norm_bwd_partial_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ dy,
-                                                               const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                               int C, int64_t R, int64_t rows_per_chunk, int kind, int G, int act, float slope,
-                                                               float* __restrict__ partial) {
-    extern __shared__ float sm[];
+// U rows in flight per thread, loaded in packed form.  The per-channel constants stay in REGISTERS here (measured: re-reading four
+// coefficient vectors per row from shared memory made this kernel slower, 4.1 -> 3.3 TB/s, while it helped the two apply kernels).
+// Dynamic shared memory: 2*rpi*C floats (block reduction).
+template <typename T, int V, int U = 2>
+__global__ void __launch_bounds__(256, 2) norm_bwd_partial_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ dy,
+                                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  int C, int64_t R, int64_t rows_per_chunk, int kind, int G, int act, float slope,
+                                                                  float* __restrict__ partial) {
+    extern __shared__ __align__(16) float sm[];
+    using P = Pack<T, V>;
     const int CV = C / V, rpi = 256 / CV;
     const int t = threadIdx.x, cv = t % CV, rr = t / CV;
     const bool active = rr < rpi;
@@ -244,33 +257,7 @@ __global__ void __launch_bounds__(256) norm_bwd_partial_kernel(const T* __restri
             mu[k] = mean[g]; rs[k] = rstd[g];
             norm_scale_shift(mu[k], rs[k], gamma ? gamma[c] : 1.f, beta ? beta[c] : 0.f, sc[k], sh[k]);
         }
-        const int64_t r_end = min(R, (int64_t)(chunk + 1) * rows_per_chunk);
-        int64_t r = (int64_t)chunk * rows_per_chunk + rr;
-        for (; r + rpi < r_end; r += 2 * rpi) {
-            float xv[2][V], gv[2][V], ov[2][V];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int64_t p = off + (r + u * rpi) * C + cv * V;
-                Pack<T, V>::load(x + p, xv[u]);
-                Pack<T, V>::load(dy + p, gv[u]);
-                if (gate_y) Pack<T, V>::load(y + p, ov[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < 2; ++u)
-#pragma unroll
-                for (int k = 0; k < V; ++k) {
-                    float g = gv[u][k];
-                    if (gate_y) g *= act_gate(ov[u][k], act, slope);
-                    else if (gate_x) g *= act_gate(fmaf(xv[u][k], sc[k], sh[k]), act, slope);
-                    a[k] += g; b[k] += g * (xv[u][k] - mu[k]) * rs[k];
-                }
-        }
-        for (; r < r_end; r += rpi) {
-            float xv[V], gv[V], ov[V];
-            const int64_t p = off + r * C + cv * V;
-            Pack<T, V>::load(x + p, xv);
-            Pack<T, V>::load(dy + p, gv);
-            if (gate_y) Pack<T, V>::load(y + p, ov);
+        auto row = [&](const float (&xv)[V], const float (&gv)[V], const float (&ov)[V]) {
 #pragma unroll
             for (int k = 0; k < V; ++k) {
                 float g = gv[k];
@@ -278,6 +265,34 @@ __global__ void __launch_bounds__(256) norm_bwd_partial_kernel(const T* __restri
                 else if (gate_x) g *= act_gate(fmaf(xv[k], sc[k], sh[k]), act, slope);
                 a[k] += g; b[k] += g * (xv[k] - mu[k]) * rs[k];
             }
+        };
+        const int64_t r_end = min(R, (int64_t)(chunk + 1) * rows_per_chunk);
+        int64_t r = (int64_t)chunk * rows_per_chunk + rr;
+        for (; r + (U - 1) * rpi < r_end; r += U * rpi) {
+            typename P::raw xr[U], gr[U], orr[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t p = off + (r + u * rpi) * C + cv * V;
+                xr[u] = P::ldraw(x + p);
+                gr[u] = P::ldraw(dy + p);
+                if (gate_y) orr[u] = P::ldraw(y + p);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                float xv[V], gv[V], ov[V];
+                P::unpack(xr[u], xv);
+                P::unpack(gr[u], gv);
+                if (gate_y) P::unpack(orr[u], ov);
+                row(xv, gv, ov);
+            }
+        }
+        for (; r < r_end; r += rpi) {
+            float xv[V], gv[V], ov[V];
+            const int64_t p = off + r * C + cv * V;
+            P::load(x + p, xv);
+            P::load(dy + p, gv);
+            if (gate_y) P::load(y + p, ov);
+            row(xv, gv, ov);
         }
 #pragma unroll
         for (int k = 0; k < V; ++k) {
@@ -379,62 +394,74 @@ __global__ void norm_bwd_coef_kernel(int N, int C, int64_t S, int kind, int G, i
 }
 
 // gsc/gsh (optional, [NBg*C] each, per_sample-indexed like coef): affine form for recomputing the gate from x when y == nullptr
-template <typename T, int V>
-__global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ dy,
+// Dynamic shared memory: 5*C floats (k1, k4, k5, scale, shift per channel, see lds_coef).
+template <typename T, int V, int U = 2>
+__global__ void __launch_bounds__(256, U == 2 ? 3 : 2) norm_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ dy,
                                                              const float* __restrict__ coef, T* __restrict__ dx, T* __restrict__ dres,
                                                              int C, int64_t S, int per_sample, int act, float slope) {
+    extern __shared__ __align__(16) float cf[];
+    using P = Pack<T, V>;
     const int CV = C / V, n = blockIdx.y;
+    for (int e = threadIdx.x; e < 5 * C; e += 256) {
+        const int c = e / 5, j = e - c * 5;
+        cf[j * C + c] = coef[((int64_t)(per_sample ? n : 0) * C) * 5 + e];
+    }
+    __syncthreads();
     const int64_t i0 = (int64_t)blockIdx.x * 256 + threadIdx.x;
     const int cv = (int)(i0 % CV);
+    const float* ck = cf + cv * V;
     const bool gate_y = act != B200_ACT_NONE && y != nullptr, gate_x = act != B200_ACT_NONE && y == nullptr;
-    float k1[V], k4[V], k5[V], sc[V], sh[V];
+    constexpr int W = V % 4 == 0 ? 4 : V;                     // channels per pass: bounds the live coefficient registers
+    auto row = [&](float (&xv)[V], float (&gv)[V], const float (&ov)[V], int64_t p) {
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-        const int64_t e = ((int64_t)(per_sample ? n : 0) * C + cv * V + k) * 5;
-        k1[k] = coef[e]; k4[k] = coef[e + 1]; k5[k] = coef[e + 2]; sc[k] = coef[e + 3]; sh[k] = coef[e + 4];
-    }
+        for (int h = 0; h < V; h += W) {
+            if (gate_y) {
+#pragma unroll
+                for (int k = h; k < h + W; ++k) gv[k] *= act_gate(ov[k], act, slope);
+            } else if (gate_x) {
+                float sc[W], sh[W];
+                lds_coef<W>(ck + 3 * C + h, sc);
+                lds_coef<W>(ck + 4 * C + h, sh);
+#pragma unroll
+                for (int k = 0; k < W; ++k) gv[h + k] *= act_gate(fmaf(xv[h + k], sc[k], sh[k]), act, slope);
+            }
+            float k1[W], k4[W], k5[W];
+            lds_coef<W>(ck + h, k1);
+            lds_coef<W>(ck + C + h, k4);
+            lds_coef<W>(ck + 2 * C + h, k5);
+#pragma unroll
+            for (int k = 0; k < W; ++k) xv[h + k] = fmaf(k1[k], gv[h + k], fmaf(k4[k], xv[h + k], k5[k]));
+        }
+        if (dres != nullptr) P::store(dres + p, gv);
+        P::store(dx + p, xv);
+    };
     const int64_t total = S * CV, stride = (int64_t)gridDim.x * 256, base = (int64_t)n * total;
     int64_t i = i0;
-    for (; i + stride < total; i += 2 * stride) {
-        float xv[2][V], gv[2][V], ov[2][V];
+    for (; i + (U - 1) * stride < total; i += U * stride) {
+        typename P::raw xr[U], gr[U], orr[U];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int64_t p = (base + i + u * stride) * V;
-            Pack<T, V>::load(x + p, xv[u]);
-            Pack<T, V>::load(dy + p, gv[u]);
-            if (gate_y) Pack<T, V>::load(y + p, ov[u]);
+            xr[u] = P::ldraw(x + p);
+            gr[u] = P::ldraw(dy + p);
+            if (gate_y) orr[u] = P::ldraw(y + p);
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int64_t p = (base + i + u * stride) * V;
-#pragma unroll
-            for (int k = 0; k < V; ++k) {
-                if (gate_y) gv[u][k] *= act_gate(ov[u][k], act, slope);
-                else if (gate_x) gv[u][k] *= act_gate(fmaf(xv[u][k], sc[k], sh[k]), act, slope);
-            }
-            if (dres != nullptr) Pack<T, V>::store(dres + p, gv[u]);
-#pragma unroll
-            for (int k = 0; k < V; ++k) xv[u][k] = fmaf(k1[k], gv[u][k], fmaf(k4[k], xv[u][k], k5[k]));
-            Pack<T, V>::store(dx + p, xv[u]);
+        for (int u = 0; u < U; ++u) {
+            float xv[V], gv[V], ov[V];
+            P::unpack(xr[u], xv);
+            P::unpack(gr[u], gv);
+            if (gate_y) P::unpack(orr[u], ov);
+            row(xv, gv, ov, (base + i + u * stride) * V);
         }
     }
     for (; i < total; i += stride) {
-        float xv[V], gv[V];
-        Pack<T, V>::load(x + (base + i) * V, xv);
-        Pack<T, V>::load(dy + (base + i) * V, gv);
-        if (gate_y) {
-            float ov[V];
-            Pack<T, V>::load(y + (base + i) * V, ov);
-#pragma unroll
-            for (int k = 0; k < V; ++k) gv[k] *= act_gate(ov[k], act, slope);
-        } else if (gate_x) {
-#pragma unroll
-            for (int k = 0; k < V; ++k) gv[k] *= act_gate(fmaf(xv[k], sc[k], sh[k]), act, slope);
-        }
-        if (dres != nullptr) Pack<T, V>::store(dres + (base + i) * V, gv);
-#pragma unroll
-        for (int k = 0; k < V; ++k) xv[k] = fmaf(k1[k], gv[k], fmaf(k4[k], xv[k], k5[k]));
-        Pack<T, V>::store(dx + (base + i) * V, xv);
+        float xv[V], gv[V], ov[V];
+        const int64_t p = (base + i) * V;
+        P::load(x + p, xv);
+        P::load(dy + p, gv);
+        if (gate_y) P::load(y + p, ov);
+        row(xv, gv, ov, p);
     }
 }
 
