@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "conv_simt.cuh"
 #include "conv_small.cuh"
+#include "conv_stem_mma.cuh"
 #include "conv_axis.cuh"
 #include "conv_tiny.cuh"
 #include "conv_umma.cuh"
@@ -150,6 +151,12 @@ int launch_tiny_wgrad(const ConvPlan& p, const void* x, const void* dy, float* d
 
 // stem wgrad through the tcgen05 row_wgrad kernel (see conv_small.cuh): the derived 16 -> Co (1,3,3) problem, or false when the
 // geometry does not fit it (the FFMA kernel is used then).  B200_STEM_TC=0 disables.
+// B200_STEM_MMA=0: fall back to the FFMA forward / tcgen05-expansion wgrad kernels (A/B measurements)
+static bool stem_mma_enabled() {
+    static const bool on = [] { const char* e = getenv("B200_STEM_MMA"); return e == nullptr || e[0] != '0'; }();
+    return on;
+}
+
 bool stem_tc_desc(const b200_conv_desc* d, b200_conv_desc* d2) {
     static const bool on = [] { const char* e = getenv("B200_STEM_TC"); return e == nullptr || e[0] != '0'; }();
     if (!on || !stem3_supported(d) || !d->allow_umma || d->Co % 16 != 0) return false;
@@ -268,6 +275,7 @@ int b200_conv_fwd(const b200_conv_desc* d, const void* x, const void* w_packed, 
     B200_REQUIRE(x && w_packed && y, "conv_fwd: null pointer");
     if (b200_conv_algo(d, B200_PASS_FWD) == B200_ALGO_ROW) return row_fwd_run(d, B200_PASS_FWD, x, w_packed, bias, y, nullptr, stream);
     if (b200_conv_algo(d, B200_PASS_FWD) == B200_ALGO_UMMA) return umma_conv_run(d, B200_PASS_FWD, x, w_packed, bias, y, workspace, ws_bytes, stream);
+    if (stem3_mma_supported(d) && stem_mma_enabled()) return stem3_mma_fwd_run(d, x, (const float*)w_packed, bias, y, stream);
     if (stem3_supported(d)) return stem3_fwd_run(d, x, (const float*)w_packed, bias, y, stream);
     if (head_supported(d)) return head_fwd_run(d, x, (const float*)w_packed, bias, y, stream);
     if (c1k3_supported(d)) return c1k3_gather_run(d, B200_PASS_FWD, x, (const float*)w_packed, bias, y, stream);
@@ -323,6 +331,7 @@ int b200_conv_wgrad(const b200_conv_desc* d, const void* x, const void* dy, floa
     B200_REQUIRE(ws_bytes >= b200_conv_workspace_bytes(d, B200_PASS_WGRAD) && workspace != nullptr, "conv_wgrad: workspace too small");
     if (b200_conv_algo(d, B200_PASS_WGRAD) == B200_ALGO_ROW) return row_wgrad_run(d, x, dy, dw, dbias, workspace, ws_bytes, stream);
     if (b200_conv_algo(d, B200_PASS_WGRAD) == B200_ALGO_UMMA) return umma_wgrad_run(d, x, dy, dw, dbias, workspace, ws_bytes, stream);
+    if (stem3_mma_supported(d) && stem_mma_enabled()) return stem3_mma_wgrad_run(d, x, dy, dw, dbias, workspace, stream);
     if (stem3_supported(d)) {
         b200_conv_desc d2;
         if (stem_tc_desc(d, &d2)) {

@@ -20,7 +20,7 @@ def B():
 
 @pytest.mark.parametrize("co", [8, 16, 32])
 @pytest.mark.parametrize("xdtype", [torch.float32, torch.bfloat16], ids=["x_fp32", "x_bf16"])
-@pytest.mark.parametrize("size", [(5, 7, 9), (4, 16, 33), (3, 6, 128)], ids=["odd", "w33", "w128"])
+@pytest.mark.parametrize("size", [(5, 7, 9), (4, 16, 33), (3, 6, 128), (3, 11, 200)], ids=["odd", "w33", "w128", "w200"])
 def test_stem_fwd_wgrad(B, co, xdtype, size):
     g = torch.Generator().manual_seed(co + size[2])
     ref = torch.nn.Conv3d(1, co, 3, 1, 1, bias=True)
