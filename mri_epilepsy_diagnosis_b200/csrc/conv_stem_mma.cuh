@@ -72,7 +72,7 @@ __device__ __forceinline__ void stem_fill_halo(float* tile, const TX* __restrict
             *dstp = ok ? ldg_f<TX>(src) : 0.f;
         }
     };
-#pragma unroll
+#pragma unroll 3
     for (int p = 0; p < NR / 2; ++p) put(2 * p + (tid >> 7), tid & 127);
     if (tid < 2 * NR) put(tid >> 1, kSmTX + (tid & 1));
 }

@@ -22,6 +22,7 @@ def B():
 @pytest.mark.parametrize("xdtype", [torch.float32, torch.bfloat16], ids=["x_fp32", "x_bf16"])
 @pytest.mark.parametrize("size", [(5, 7, 9), (4, 16, 33), (3, 6, 128), (3, 11, 200)], ids=["odd", "w33", "w128", "w200"])
 def test_stem_fwd_wgrad(B, co, xdtype, size):
+    """Cin = 1 stems: FFMA forward, warp-MMA weight gradient (Co = 16; hi/lo bf16 split of the fp32 volume) or the FFMA one."""
     g = torch.Generator().manual_seed(co + size[2])
     ref = torch.nn.Conv3d(1, co, 3, 1, 1, bias=True)
     mod = B.nn.Conv3d(1, co, 3, 1, 1, bias=True).cuda()
@@ -45,6 +46,37 @@ def test_stem_fwd_wgrad(B, co, xdtype, size):
     mod.zero_grad()
     mod(x.cuda().to(xdtype)).backward(gy.cuda().bfloat16())
     assert torch.equal(first, mod.weight.grad), "wgrad must be run-to-run deterministic"
+
+
+def test_stem_mma_forward_opt_in():
+    """The warp-MMA stem FORWARD kernel is opt-in (B200_STEM_MMA_FWD=1, read once per process): run it in a child process against
+    torch's fp32 convolution -- fp32 and bf16 volumes, ragged rows, two x chunks."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, torch
+sys.path.insert(0, %r)
+import mri_epilepsy_diagnosis_b200 as B
+for xdtype, size in ((torch.float32, (3, 11, 200)), (torch.bfloat16, (4, 16, 33)), (torch.float32, (2, 8, 128))):
+    g = torch.Generator().manual_seed(size[2])
+    ref = torch.nn.Conv3d(1, 16, 3, 1, 1, bias=True)
+    mod = B.nn.Conv3d(1, 16, 3, 1, 1, bias=True).cuda()
+    mod.load_state_dict(ref.state_dict())
+    mod.compute_dtype = torch.bfloat16
+    x = torch.randn(2, 1, *size, generator=g)
+    if xdtype == torch.bfloat16:
+        x = x.bfloat16().float()
+    yr = ref(x)
+    y = mod(x.cuda().to(xdtype)).float().cpu()
+    err = float((y - yr).norm() / yr.norm())
+    exact = float((y == yr.bfloat16().float()).float().mean())
+    assert err < 3e-3 and exact > 0.98, (err, exact)
+print("ok")
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, B200_STEM_MMA_FWD="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
 
 
 @pytest.mark.parametrize("ci", [8, 16, 32, 64, 128, 256])
