@@ -643,6 +643,21 @@ def main():
         out["dropin_eager"] = {"ms_per_step": msd, "value": voxels / (msd / 1e3), "unit": "voxels/s",
                                "what": "nn.convert() of a stock torch.nn unet3d-shaped model, eager routine.py loop body (torch softmax + Dice, torch AdamW), "
                                        "no CUDA graph and no graph-level rewrites: the reference's op sequence incl. the dead branch"}
+        # the same converted stock model, loop body captured: ONE extra line for the user (graphed.GraphedTrainStep around the model,
+        # the loss and a capturable optimizer); still no zoo rewrite -- the stock graph incl. the dead branch and F.dropout3d is replayed
+        try:
+            dbucket = None
+            torch.manual_seed(0)
+            dopt2 = torch.optim.AdamW(dnet.parameters(), capturable=True, fused=True)
+            gstep = pkg.graphed.GraphedTrainStep(dnet, dice_loss_mean, dopt2, xd, td)
+            for _ in range(3):
+                gstep(xd, td)
+            msg, _, _ = timed(lambda: gstep(xd, td), args.steps)
+            out["dropin_graphed"] = {"ms_per_step": msg, "value": voxels / (msg / 1e3), "unit": "voxels/s",
+                                     "what": "the same converted stock model inside graphed.GraphedTrainStep (CUDA-graph replay of the eager loop body)"}
+        except Exception as e:      # a stock op that cannot be captured is reported, not hidden
+            out["dropin_graphed"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+        gstep = dopt2 = None
         dnet = dopt = stock = None
         torch.cuda.empty_cache()
     if args.gpus == 1 and not args.no_other_configs and args.model == "unet3d" and args.config == 2:
