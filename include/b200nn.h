@@ -69,6 +69,24 @@ int b200_conv_algo(const b200_conv_desc* d, int pass);
 size_t b200_conv_packed_bytes(const b200_conv_desc* d, int pass);
 /* Pack the fp32 PyTorch-layout parameter (Conv: Co,Ci,kd,kh,kw; ConvTranspose: Ci,Co,kd,kh,kw). */
 int b200_conv_pack_weights(const b200_conv_desc* d, int pass, const float* w, void* packed, void* stream);
+
+/* Batched re-pack of many (layer, pass) weight copies in ONE launch.  Each entry gathers `count` packed elements through a
+ * precomputed permutation: dst[i] = idx[i] < 0 ? 0 : src[idx[i]], src = src0 (n0 elements) followed by src1 (may be null), dst bf16
+ * or fp32.  The host derives idx once per (descriptor, pass) by running b200_conv_pack_weights on index-coded weights
+ * (mri_epilepsy_diagnosis_b200/functional.py:PackPlan).  Entries live in DEVICE memory; entry k owns blocks
+ * [first_block, first_block + ceil(count / 2048)).  Replaces the per-module re-pack the reference gets for free from cuDNN reading
+ * nn.Conv3d.weight in place (segmentation/models/unet3d.py:20-79: every conv of the step). */
+typedef struct {
+    const float* src0;
+    const float* src1;
+    const int32_t* idx;
+    void* dst;
+    int64_t count;
+    int64_t first_block;
+    int32_t n0;
+    int32_t dst_bf16;
+} b200_pack_entry;
+int b200_pack_batched(const b200_pack_entry* entries_dev, int n_entries, int64_t total_blocks, void* stream);
 size_t b200_conv_workspace_bytes(const b200_conv_desc* d, int pass);
 /* y = conv(x, w) + bias.  `bias` is fp32 [Co] or NULL. */
 int b200_conv_fwd(const b200_conv_desc* d, const void* x, const void* w_packed, const float* bias, void* y,

@@ -25,6 +25,10 @@ class ConvDesc(C.Structure):
                                    "sd", "sh", "sw", "pd", "ph", "pw", "dd", "dh", "dw", "transposed", "allow_umma")]
 
 
+class PackEntry(C.Structure):
+    _fields_ = [("src0", vp), ("src1", vp), ("idx", vp), ("dst", vp), ("count", i64), ("first_block", i64), ("n0", i32), ("dst_bf16", i32)]
+
+
 class NormDesc(C.Structure):
     _fields_ = [("dtype", i32), ("N", i32), ("C", i32), ("S", i64), ("kind", i32), ("G", i32), ("eps", f32), ("momentum", f32),
                 ("act", i32), ("slope", f32)]
@@ -58,6 +62,7 @@ _SIGS = {
     "b200_conv_algo": (C.c_int, [P(ConvDesc), C.c_int]),
     "b200_conv_packed_bytes": (sz, [P(ConvDesc), C.c_int]),
     "b200_conv_pack_weights": (C.c_int, [P(ConvDesc), C.c_int, vp, vp, vp]),
+    "b200_pack_batched": (C.c_int, [vp, C.c_int, i64, vp]),
     "b200_conv_workspace_bytes": (sz, [P(ConvDesc), C.c_int]),
     "b200_conv_fwd": (C.c_int, [P(ConvDesc), vp, vp, vp, vp, vp, sz, vp]),
     "b200_conv_stats_chunks": (C.c_int, [P(ConvDesc)]),

@@ -137,8 +137,8 @@ class ConvConfig:
         shape = (N, Co) + (tuple(out) if dims == 5 else tuple(out[1:]))
         return cd, shape
 
-    def packed(self, cd, weight, which, fresh):
-        """Packed copy of `weight` for pass `which`.
+    def packed(self, cd, weight, which, fresh, second=None):
+        """Packed copy of `weight` (or of torch.cat([weight, second], 0): the fused dead/live pair) for pass `which`.
 
         `fresh=True` (every call that takes part in autograd, forward and backward): always re-derived.  The parameter's
         version counter cannot be trusted to announce an update -- fused optimizers (`AdamW(fused=True)`) and `p.data`
@@ -149,21 +149,135 @@ class ConvConfig:
         # the packed layout depends on the GEOMETRY too (the kx-folded row kernel packs the three kx blocks side by side and is
         # chosen per input shape), so the whole descriptor is the key: one module called at W=128 and then at W=64 packs twice
         key = (which, algo) + tuple(getattr(cd, f) for f, _ in ConvDesc._fields_)
+        if _PACK_SERVE is not None:                 # inside PackPlan.serving(): every copy of this step was packed by ONE launch
+            hit = _PACK_SERVE.get((id(self), key))
+            if hit is not None and hit[1] == (weight.data_ptr(), 0 if second is None else second.data_ptr()):
+                return hit[0]
         tag = (weight.data_ptr(), weight._version, weight.device)
         if fresh:
             self._packed.clear()
-        hit = self._packed.get(key)
+        hit = self._packed.get(key) if second is None else None
         if hit is not None and hit[0] == tag:
             return hit[1]
         nbytes = lib().b200_conv_packed_bytes(C.byref(cd), which)
         buf = _tempty(max(nbytes, 16), dtype=torch.uint8, device=weight.device)
-        w = weight.detach()
+        w = weight.detach() if second is None else torch.cat([weight.detach(), second.detach()], 0)
         if w.dtype != torch.float32 or not w.is_contiguous():
             w = w.float().contiguous()
         check(lib().b200_conv_pack_weights(C.byref(cd), which, w.data_ptr(), buf.data_ptr(), stream()))
-        if not fresh:
+        if not fresh and second is None:
             self._packed[key] = (tag, buf)
+        if _PACK_RECORD is not None:
+            _PACK_RECORD.append((self, key, ConvDesc.from_buffer_copy(cd), which, weight, second))
         return buf
+
+
+# --------------------------------------------------------------------------- batched weight pack (one launch per step)
+_PACK_RECORD = None        # list while PackPlan.recording() is active
+_PACK_SERVE = None         # {(id(cfg), key): (buffer, (ptr0, ptr1))} while PackPlan.serving() is active
+
+
+class PackPlan:
+    """All packed weight copies of one training step, re-derived by ONE kernel launch (b200_pack_batched).
+
+        with PackPlan.recording() as rec:  <one eager forward + backward>
+        plan = PackPlan(rec)               # derives every layout's permutation by packing index-coded weights, checks it bit for bit
+        plan.run();  with plan.serving():  <forward + backward>      # no pack launches inside
+
+    Only fp32, contiguous parameters take part; everything else keeps its own pack launch.  The plan holds the parameters by
+    address: it belongs to one model whose parameter storage does not move (the same contract as CUDA-graph capture)."""
+
+    class recording:
+        def __enter__(self):
+            global _PACK_RECORD
+            self.prev, _PACK_RECORD = _PACK_RECORD, []
+            return _PACK_RECORD
+
+        def __exit__(self, *exc):
+            global _PACK_RECORD
+            _PACK_RECORD = self.prev
+
+    def __init__(self, records):
+        self.entries, self.lookup, seen = [], {}, set()
+        dev = None
+        for cfg, key, cd, which, w0, w1 in records:
+            k = (id(cfg), key)
+            ok = all(w is None or (w.dtype == torch.float32 and w.is_contiguous() and w.is_cuda) for w in (w0, w1))
+            if k in seen or not ok:
+                continue
+            seen.add(k)
+            dev = w0.device
+            ent = self._derive(cd, which, w0, w1)
+            if ent is not None:
+                self.entries.append(ent + (w0, w1, cfg))
+                self.lookup[k] = (ent[1], (w0.data_ptr(), 0 if w1 is None else w1.data_ptr()))
+        self.table = None
+        if self.entries:
+            arr = (cabi.PackEntry * len(self.entries))()
+            blk = 0
+            for i, (idx, dst, bf16, w0, w1, _) in enumerate(self.entries):
+                count = idx.numel()
+                arr[i] = cabi.PackEntry(w0.data_ptr(), 0 if w1 is None else w1.data_ptr(), idx.data_ptr(), dst.data_ptr(), count, blk, w0.numel(), int(bf16))
+                blk += -(-count // 2048)
+            self.blocks = blk
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            self.table = host.to(dev)
+
+    @staticmethod
+    def _derive(cd, which, w0, w1):
+        """(idx int32 [count], dst buffer, dst_is_bf16) or None when the layout is not a pure permutation (checked on the real weights)."""
+        dev = w0.device
+        algo = lib().b200_conv_algo(C.byref(cd), which)
+        bf16 = algo != cabi.ALGO_SIMT
+        nbytes = lib().b200_conv_packed_bytes(C.byref(cd), which)
+        count = nbytes // (2 if bf16 else 4)
+        n = w0.numel() + (0 if w1 is None else w1.numel())
+        if count == 0 or n >= (1 << 24):
+            return None
+        ar = torch.arange(n, device=dev, dtype=torch.int64)
+        tmp = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+
+        def coded(vals):        # pack a tensor whose VALUES are small integer codes; read the codes back out of the packed copy
+            check(lib().b200_conv_pack_weights(C.byref(cd), which, vals.float().contiguous().data_ptr(), tmp.data_ptr(), stream()))
+            out = tmp[:nbytes].view(torch.bfloat16 if bf16 else torch.float32)[:count]
+            return out.float().round().to(torch.int64)
+        if bf16:                # bf16 holds the integers 0..256 exactly: three 8-bit digits, each stored as digit + 1 (0 = padding)
+            d = [coded(((ar >> (8 * k)) & 0xFF) + 1) for k in range(3)]
+            idx = torch.where(d[0] == 0, torch.full_like(d[0], -1), (d[0] - 1) + ((d[1] - 1) << 8) + ((d[2] - 1) << 16))
+        else:
+            idx = coded(ar + 1) - 1
+        idx = idx.to(torch.int32)
+        dst = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+        # bit-for-bit check against the regular pack on the real weights
+        w = w0.detach() if w1 is None else torch.cat([w0.detach(), w1.detach()], 0)
+        check(lib().b200_conv_pack_weights(C.byref(cd), which, w.contiguous().data_ptr(), tmp.data_ptr(), stream()))
+        flat = w.reshape(-1)
+        ref = torch.where(idx < 0, torch.zeros((), device=dev), flat[idx.clamp(min=0).long()])
+        ref = ref.bfloat16() if bf16 else ref
+        got = tmp[:nbytes].view(torch.bfloat16 if bf16 else torch.float32)[:count]
+        if not torch.equal(ref, got):
+            return None
+        return idx, dst, bf16
+
+    def run(self):
+        if self.table is not None:
+            check(lib().b200_pack_batched(self.table.data_ptr(), len(self.entries), self.blocks, stream()))
+
+    class _Serving:
+        def __init__(self, lookup):
+            self.lookup = lookup
+
+        def __enter__(self):
+            global _PACK_SERVE
+            self.prev, _PACK_SERVE = _PACK_SERVE, self.lookup
+            return self
+
+        def __exit__(self, *exc):
+            global _PACK_SERVE
+            _PACK_SERVE = self.prev
+
+    def serving(self):
+        return PackPlan._Serving(self.lookup)
 
 
 _SIDE_STREAMS = {}
@@ -308,15 +422,13 @@ class _DualConvFn(Function):
         need_cuda(x, "dual_conv")
         x = to_cl(x)
         cdead = w_dead.shape[0]
-        wcat = torch.cat([w_dead.detach(), w_live.detach()], 0)
+        wcat = torch.empty((cdead + w_live.shape[0],) + tuple(w_dead.shape[1:]), device="meta")      # shape only: desc() reads no values
         cd, shape = cfg.desc(x, wcat, out_dtype)
         chunks = lib().b200_conv_stats_chunks(C.byref(cd))
         if chunks <= 0 or cdead % 16 != 0:
             raise RuntimeError("b200nn.dual_conv: shape not supported (check dual_conv_supported)")
         # packed on every call (training-only path; see ConvConfig.packed on why the version counter is not trusted)
-        wp = _tempty(max(lib().b200_conv_packed_bytes(C.byref(cd), cabi.PASS_FWD), 16), dtype=torch.uint8, device=x.device)
-        wf = wcat if wcat.dtype == torch.float32 else wcat.float()
-        check(lib().b200_conv_pack_weights(C.byref(cd), cabi.PASS_FWD, wf.contiguous().data_ptr(), wp.data_ptr(), stream()))
+        wp = cfg.packed(cd, w_dead, cabi.PASS_FWD, True, second=w_live)
         y = _empty_cl((shape[0], shape[1] - cdead) + tuple(shape[2:]), out_dtype, x.device)
         part = _tempty((chunks, 2, cd.Co), dtype=torch.float32, device=x.device)
         ws = _workspace(0, x.device)

@@ -14,6 +14,9 @@ rest of the backward pass; the optimizer step is captured too when the optimizer
 """
 from __future__ import annotations
 
+import contextlib
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -65,14 +68,22 @@ class GraphedTrainStep:
         if self.world > 1:
             self._make_buckets(max(1, int(buckets)), dev)
 
+        self.pack_plan = None
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            for _ in range(max(1, warmup)):
+            with BF.PackPlan.recording() as packs:       # which (layer, pass) weight copies one step derives
+                self._body(eager=True)
+            for _ in range(max(1, warmup) - 1):
                 self._body(eager=True)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self._restore(snap, dev)
+        if os.environ.get("B200_PACK_BATCHED", "1") != "0":
+            # every packed weight copy of the step from ONE launch at its start instead of one launch per layer and pass
+            plan = BF.PackPlan(packs)
+            torch.cuda.synchronize(dev)
+            self.pack_plan = plan if plan.table is not None else None
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = self._body(eager=False)
@@ -151,17 +162,21 @@ class GraphedTrainStep:
 
     def _fwd_bwd(self, bucketing=False):
         self.flat.zero_()
-        with bnn.defer_batch_counters():
-            loss = self.loss_fn(self.model(self.x), self.t)
-        if bucketing:
-            self._remaining = [len(ps) for ps in self._members]
-            self._launched = [False] * len(self._members)
-            self._bucketing = True
-        try:
-            with BF.deferred_wgrad():     # wgrad kernels accumulate into the flat buffer on a side stream; one join here
-                loss.backward()
-        finally:
-            self._bucketing = False
+        plan = self.pack_plan
+        if plan is not None:
+            plan.run()
+        with (plan.serving() if plan is not None else contextlib.nullcontext()):
+            with bnn.defer_batch_counters():
+                loss = self.loss_fn(self.model(self.x), self.t)
+            if bucketing:
+                self._remaining = [len(ps) for ps in self._members]
+                self._launched = [False] * len(self._members)
+                self._bucketing = True
+            try:
+                with BF.deferred_wgrad():     # wgrad kernels accumulate into the flat buffer on a side stream; one join here
+                    loss.backward()
+            finally:
+                self._bucketing = False
         return loss.detach()
 
     def _reduce_and_step(self):

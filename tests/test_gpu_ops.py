@@ -680,3 +680,49 @@ def test_get_image_patches_minmax_and_labels(B, template, tmp_path):
     plan2 = OP.patch_plan(template, mask > 0, 16, 32)
     assert np.array_equal(pt2.cpu().numpy(), OP.gather_patches(norm32, plan2))
     assert np.array_equal(lb2.cpu().numpy(), plan2[:, OP.LABEL].astype(bool)) and int(lb2.sum()) > 0
+
+
+def test_batched_weight_pack_plan(B):
+    """functional.PackPlan: every packed weight copy of a training step (tcgen05 row / tile layouts, the kx-folded layout, the fused
+    dead/live pair, fp32 SIMT layouts, forward and dgrad) re-derived by ONE b200_pack_batched launch, bit for bit equal to the
+    per-layer b200_conv_pack_weights, also after the weights changed."""
+    import ctypes
+    BF = B.functional
+    torch.manual_seed(5)
+    net = B.convert(B.zoo.Unet(c=1, n=16, dropout=0.5, norm="bn", num_classes=2).cuda().train(), dtype=torch.bfloat16)
+    x = torch.randn(1, 1, 32, 32, 128, device="cuda")
+    t = (torch.rand(1, 1, 32, 32, 128, device="cuda") > 0.5).float()
+    with BF.PackPlan.recording() as rec:
+        BF.softmax_dice_loss(net(x), t).backward()
+    plan = BF.PackPlan(rec)
+    uniq = {(id(r[0]), r[1]) for r in rec}
+    assert len(rec) >= 40 and len(plan.lookup) == len(uniq), (len(rec), len(plan.lookup), len(uniq))
+    assert any(r[5] is not None for r in rec), "the fused dead/live pair must be part of the plan"
+    with torch.no_grad():
+        for p in net.parameters():
+            p.add_(torch.randn_like(p) * 0.01)
+    plan.run()
+    torch.cuda.synchronize()
+    lib = B._cabi.lib()
+    for cfg, key, cd, which, w0, w1 in rec:
+        buf = plan.lookup[(id(cfg), key)][0]
+        n = lib.b200_conv_packed_bytes(ctypes.byref(cd), which)
+        ref = torch.empty(max(n, 16), dtype=torch.uint8, device="cuda")
+        w = w0.detach() if w1 is None else torch.cat([w0.detach(), w1.detach()], 0)
+        B._cabi.check(lib.b200_conv_pack_weights(ctypes.byref(cd), which, w.contiguous().data_ptr(), ref.data_ptr(), B._cabi.stream()))
+        assert torch.equal(buf[:n], ref[:n]), key
+    # served: a forward + backward inside plan.serving() launches no pack kernel and gives the same loss and gradients
+    net.zero_grad()
+    l0 = BF.softmax_dice_loss(net(x), t)
+    l0.backward()
+    g0 = [p.grad.clone() for p in net.parameters() if p.grad is not None]
+    net.zero_grad()
+    n_before = len(rec)
+    with BF.PackPlan.recording() as rec2:
+        plan.run()
+        with plan.serving():
+            l1 = BF.softmax_dice_loss(net(x), t)
+            l1.backward()
+    assert len(rec2) == 0, "served steps must not pack per layer"
+    g1 = [p.grad for p in net.parameters() if p.grad is not None]
+    assert torch.equal(l0, l1) and all(torch.equal(a, b) for a, b in zip(g0, g1))
