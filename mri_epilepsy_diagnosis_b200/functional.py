@@ -184,8 +184,12 @@ class PackPlan:
         plan = PackPlan(rec)               # derives every layout's permutation by packing index-coded weights, checks it bit for bit
         plan.run();  with plan.serving():  <forward + backward>      # no pack launches inside
 
-    Only fp32, contiguous parameters take part; everything else keeps its own pack launch.  The plan holds the parameters by
-    address: it belongs to one model whose parameter storage does not move (the same contract as CUDA-graph capture)."""
+    Only fp32, contiguous parameters take part, and only copies of at most `max_count` packed elements: the small layers' packs are
+    launch-bound and gain from sharing one launch, the large ones are bandwidth-bound and their own kernels read the parameters
+    in a better order than a generic gather (measured: batching the 512-channel layers of the autoencoder cost 1 ms per step).
+    Everything else keeps its own pack launch.  The plan holds the parameters by address: it belongs to one model whose parameter
+    storage does not move (the same contract as CUDA-graph capture)."""
+    MAX_COUNT = int(os.environ.get("B200_PACK_BATCHED_MAX", str(320 * 1024)))
 
     class recording:
         def __enter__(self):
@@ -197,12 +201,14 @@ class PackPlan:
             global _PACK_RECORD
             _PACK_RECORD = self.prev
 
-    def __init__(self, records):
+    def __init__(self, records, max_count=MAX_COUNT):
         self.entries, self.lookup, seen = [], {}, set()
         dev = None
         for cfg, key, cd, which, w0, w1 in records:
             k = (id(cfg), key)
             ok = all(w is None or (w.dtype == torch.float32 and w.is_contiguous() and w.is_cuda) for w in (w0, w1))
+            if max_count is not None and w0.numel() + (0 if w1 is None else w1.numel()) > max_count:
+                ok = False
             if k in seen or not ok:
                 continue
             seen.add(k)

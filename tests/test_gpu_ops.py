@@ -694,9 +694,11 @@ def test_batched_weight_pack_plan(B):
     t = (torch.rand(1, 1, 32, 32, 128, device="cuda") > 0.5).float()
     with BF.PackPlan.recording() as rec:
         BF.softmax_dice_loss(net(x), t).backward()
-    plan = BF.PackPlan(rec)
+    plan = BF.PackPlan(rec, max_count=None)                          # every layer, whatever its size
     uniq = {(id(r[0]), r[1]) for r in rec}
     assert len(rec) >= 40 and len(plan.lookup) == len(uniq), (len(rec), len(plan.lookup), len(uniq))
+    small = BF.PackPlan(rec)                                         # default: only the launch-bound (small) copies share the launch
+    assert 0 < len(small.lookup) < len(uniq)
     assert any(r[5] is not None for r in rec), "the fused dead/live pair must be part of the plan"
     with torch.no_grad():
         for p in net.parameters():

@@ -17,6 +17,9 @@ ap = argparse.ArgumentParser()
 ap.add_argument("csv")
 ap.add_argument("--traffic-json")
 ap.add_argument("--hbm-peak", type=float, default=6544.7)
+ap.add_argument("--step-marker", default=None,
+                help="a kernel launched exactly once at the start of every step (pack_batched_kernel): keep only the launches of the LAST "
+                     "complete step, i.e. from the last-but-one marker launch up to the last one")
 a = ap.parse_args()
 
 per_launch = defaultdict(dict)
@@ -38,6 +41,12 @@ def short(name):
     return name.replace("b200::", "")
 
 
+if a.step_marker:
+    ids = sorted(per_launch, key=int)
+    marks = [i for i in ids if a.step_marker in names[i]]
+    if len(marks) >= 2:
+        lo, hi = int(marks[-2]), int(marks[-1])
+        per_launch = {i: m for i, m in per_launch.items() if lo <= int(i) < hi}
 agg = defaultdict(lambda: [0, 0.0, 0.0])
 for i, m in per_launch.items():
     k = short(names[i])
