@@ -360,6 +360,10 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
 #pragma unroll
         for (int i = 0; i < 16 * kStatCh; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
         const int ocs = p.OC - p.store_c0;                       // stored channels per voxel
+        // folded with 64 output channels (N = 192, one tile per accumulator set): the two epilogue sets split the CHANNELS of every
+        // tile (set s takes [32 s, 32 s + 32)) instead of alternating tiles, so each thread still carries 32 channels of statistics
+        const bool csplit = FOLD && p.OC > 32;
+        const int cbase = csplit ? eset * 32 : 0;
         const bool lzero = ((lane_grp * 32) & (p.W - 1)) == 0;          // folded: this warp's lane 0 is x == 0 / its lane 31 is x == W-1
         const bool rzero = (((lane_grp + 1) * 32) & (p.W - 1)) == 0;
         uint32_t group = 0, xphase = 0;
@@ -371,7 +375,7 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
                 ptx::mbar_wait(ptx::smem_u32(&bars.afull[set]), (group >> 1) & 1);
                 ptx::tc_fence_after();
                 const int64_t plane_vox = ((int64_t)c.n * p.D + z) * p.H;
-                for (int t = (eset ^ (int)(group & 1)); t < ntiles; t += 2) {         // (alternating start: one-tile groups still use both sets)
+                for (int t = csplit ? 0 : (eset ^ (int)(group & 1)); t < ntiles; t += csplit ? 1 : 2) {   // (alternating start: one-tile groups still use both sets)
                     if (p.dbg == 1) continue;
                     int row, x;
                     if (FOLD) { const int slot = t * 128 + m; row = slot >> p.wshift; x = slot & (p.W - 1); }   // 128 / W whole rows per tile
@@ -389,9 +393,10 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
                         // (lane 0 likewise for P_2), so the rotation delivers every lane its neighbour without a per-value select.
 #pragma unroll
                         for (int ch = 0; ch < kStatCh; ++ch) {
-                            if (ch * 16 < p.OC) {
+                            const int c0 = cbase + ch * 16;                         // first channel of this pass
+                            if (c0 < p.OC) {
                                 float v[16], l[16], r[16];
-                                ptx::tmem_ld16x3(taddr + (uint32_t)(ch * 16), taddr + (uint32_t)(p.OC + ch * 16), taddr + (uint32_t)(2 * p.OC + ch * 16), l, v, r);
+                                ptx::tmem_ld16x3(taddr + (uint32_t)c0, taddr + (uint32_t)(p.OC + c0), taddr + (uint32_t)(2 * p.OC + c0), l, v, r);
                                 float (&buf)[4][2][16] = xch[eset][xphase & 1];
                                 if (p.dbg != 2) {
                                 if (lane == 31) {
@@ -427,10 +432,10 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
                                 ++xphase;
                                 if (p.bias != nullptr) {
 #pragma unroll
-                                    for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + ch * 16 + i);
+                                    for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + c0 + i);
                                 }
                                 if (valid) {
-                                    if (ch * 16 >= p.store_c0) rf_store16(dst + ch * 16, v);
+                                    if (c0 >= p.store_c0) rf_store16(dst + c0, v);
                                     if (want_stats) {
 #pragma unroll
                                         for (int i = 0; i < 16; ++i) { ssum[ch * 16 + i] += v[i]; ssq[ch * 16 + i] = fmaf(v[i], v[i], ssq[ch * 16 + i]); }
@@ -482,7 +487,7 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
             const int w8 = eset * 4 + lane_grp;
 #pragma unroll
             for (int i = 0; i < 16 * kStatCh; ++i) {
-                if (i < p.OC) {
+                if (cbase + i < p.OC) {
                     float a = ssum[i], b = ssq[i];
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
@@ -493,8 +498,13 @@ __global__ void __launch_bounds__(kRfThreads, 1) row_fwd_kernel(const __grid_con
             if (eset == 0 && m < 2 * p.OC) {
                 const int which = m / p.OC, ch = m - which * p.OC;
                 float acc = 0.f;
+                if (csplit) {                                       // channel ch was accumulated by the four warps of set ch / 32
 #pragma unroll
-                for (int w = 0; w < 8; ++w) acc += red[(w * 2 + which) * 16 * kStatCh + ch];
+                    for (int w = 0; w < 4; ++w) acc += red[(((ch >> 5) * 4 + w) * 2 + which) * 16 * kStatCh + (ch & 31)];
+                } else {
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) acc += red[(w * 2 + which) * 16 * kStatCh + ch];
+                }
                 p.stats[((size_t)blockIdx.x * 2 + which) * p.OC + ch] = acc;
             }
         }
@@ -532,7 +542,10 @@ inline bool row_fwd_fold_geom(const RowFwdGeom& g) {
     // unfolded -- folding now pays whenever the geometry allows it.
     // B200_ROWF_FOLD: 0 = never, 1 (default) = whenever the geometry allows.
     static const int mode = [] { const char* e = getenv("B200_ROWF_FOLD"); return e == nullptr ? 1 : atoi(e); }();
-    return mode != 0 && g.khw == 3 && (g.W == 128 || g.W == 64 || g.W == 32) && g.OC <= 32;
+    // Cout = 64 (N = 192 = the full MMA rate, ONE tile per accumulator set) only with resident weights (Cin <= 32): streamed, its
+    // weights would pass once per 128 voxels.  B200_ROWF_FOLD=2 keeps Cout = 64 unfolded.
+    const bool oc_ok = g.OC <= 32 || (g.OC == 64 && g.IC <= 32 && mode != 2);
+    return mode != 0 && g.khw == 3 && (g.W == 128 || g.W == 64 || g.W == 32) && oc_ok;
 }
 inline int row_fwd_plan_mode(const RowFwdGeom& g, int N, RowFwdParams* p, size_t* smem_bytes, bool fold);
 // the folded plan when the geometry allows it and it fits, the plain one otherwise

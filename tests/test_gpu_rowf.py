@@ -58,6 +58,10 @@ CASES = [
     ("f32_32_w64", 2, 32, 32, (5, 13, 64), 3, 1, True),
     ("f16_16_w32", 1, 16, 16, (6, 23, 32), 3, 1, False),
     ("f133_w64", 2, 32, 16, (6, 10, 64), (1, 3, 3), (0, 1, 1), True),
+    # folded with Cout = 64 (N = 192, Cin <= 32): the two epilogue warp sets split the channels of every tile
+    ("f32_64_w64", 2, 32, 64, (6, 13, 64), 3, 1, True),
+    ("f16_64_w128", 2, 16, 64, (3, 9, 128), 3, 1, False),
+    ("f32_64_w32", 2, 32, 64, (5, 22, 32), 3, 1, True),
     # folded with streamed weights (Cin = 64: the nine folded blocks do not fit next to a plane ring)
     ("fs64_32_w64", 2, 64, 32, (6, 18, 64), 3, 1, True),
     ("fs64_16_w32", 1, 64, 16, (9, 21, 32), 3, 1, False),
@@ -161,3 +165,31 @@ def test_fused_statistics_and_dual_conv(B, W, Ci):
     s2 = part2.double().sum(0)
     assert rel_err(s2[0, :16], yd2.sum(1)) < 5e-3 and rel_err(s2[1, :16], (yd2 * yd2).sum(1)) < 2e-3
     assert rel_err(s2[0, 16:], yd.sum(1)) < 5e-3 and rel_err(s2[1, 16:], (yd * yd).sum(1)) < 2e-3
+
+
+def test_fused_statistics_folded_64_channels(B):
+    """Cout = 64 in the kx-folded mode (each epilogue warp set owns 32 channels of every tile): fused BatchNorm sums and the dead/live
+    pair with 32 + 32 channels (the 64^3 level of unet3d.py:43-46), statistics against the stored outputs."""
+    F_ = B.functional
+    torch.manual_seed(77)
+    g = torch.Generator().manual_seed(78)
+    x = torch.randn(2, 32, 5, 12, 64, generator=g).cuda().bfloat16()
+    conv = B.nn.Conv3d(32, 64, 3, 1, 1, bias=False).cuda()
+    conv.compute_dtype = torch.bfloat16
+    y, part = F_.conv(x, conv.weight, None, conv._cfg(), torch.bfloat16, want_stats=True)
+    assert part is not None and torch.equal(y, conv(x))
+    ref = torch.nn.functional.conv3d(x.float().cpu(), conv.weight.detach().bfloat16().float().cpu(), padding=1)
+    assert rel_err(y.float(), ref) < 1e-2
+    s = part.double().sum(0)
+    yd = y.double().permute(1, 0, 2, 3, 4).reshape(64, -1)
+    assert rel_err(s[0], yd.sum(1)) < 5e-3 and rel_err(s[1], (yd * yd).sum(1)) < 2e-3
+    live, dead = B.nn.Conv3d(32, 32, 3, 1, 1, bias=False).cuda(), B.nn.Conv3d(32, 32, 3, 1, 1, bias=False).cuda()
+    live.compute_dtype = dead.compute_dtype = torch.bfloat16
+    assert F_.dual_conv_supported(x, dead.weight, live.weight, live._cfg(), torch.bfloat16)
+    y3, part2 = F_.dual_conv(x, dead.weight, live.weight, live._cfg(), torch.bfloat16)
+    yl, ydd = live(x), dead(x)
+    assert torch.equal(y3, yl) or rel_err(y3.float(), yl.float()) < 2e-3
+    s2 = part2.double().sum(0)
+    for half, yy in ((slice(0, 32), ydd), (slice(32, 64), yl)):
+        yv = yy.double().permute(1, 0, 2, 3, 4).reshape(32, -1)
+        assert rel_err(s2[0, half], yv.sum(1)) < 5e-3 and rel_err(s2[1, half], (yv * yv).sum(1)) < 2e-3
