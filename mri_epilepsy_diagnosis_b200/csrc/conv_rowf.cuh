@@ -10,11 +10,13 @@
 // the image of plane z+kz-pd: 27 descriptor start addresses, no im2col, every input byte staged once per plane block.
 // Slots that fall into the x halo produce garbage rows of D that are simply not stored.
 //   * planes stream through a ring along z (one new plane per output plane; 3 live for a 3x3x3 filter);
-//   * the packed weights of ALL taps stay resident in shared memory (this kernel takes the layers where they fit);
+//   * the packed weights of ALL taps stay resident in shared memory, or stream tap by tap through a ring where they do not fit;
+//   * kx-folded mode (RowFwdParams::fold): planes WITHOUT the x halo, a tile = 128 / W whole rows, one MMA per (kz, ky) with the
+//     three kx weight blocks side by side (N = 3*Cout), the x shift applied to the accumulators in the epilogue;
 //   * accumulators: T tiles x Cout fp32 columns of TMEM, two sets, so the epilogue of plane z overlaps the MMAs of z+1;
 //   * warp roles (352 threads): 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..5 and 7..10 = epilogue (TMEM -> bf16 -> global,
 //     consecutive lanes = consecutive voxels = fully coalesced stores), optionally accumulating the per-channel sum / sum of
-//     squares of the outputs for the BatchNorm that follows (fp32, per-thread partials, one atomic flush per CTA).
+//     squares of the outputs for the BatchNorm that follows (fp32, per-thread partials, one deterministic per-CTA partial; no atomics).
 #pragma once
 #include "conv_row.cuh"
 

@@ -46,7 +46,7 @@ CASES = [
     ("s64_64_d2", 2, 64, 64, (2, 27, 40), 3, 1, False),
     ("d1", 4, 32, 32, (1, 33, 64), 3, 1, False),                  # single plane: both z neighbours are padding
     ("d2", 2, 16, 16, (2, 17, 128), 3, 1, False),
-    # kx-folded mode (W == 128, Cout <= 32, see row_fwd_fold_geom): one MMA per (kz, ky) with N = 3*Cout, shifted sum in the epilogue
+    # kx-folded mode (see row_fwd_fold_geom): one MMA per (kz, ky) with N = 3*Cout, shifted sum in the epilogue; W = 128 cases first
     ("f32_32_w128", 2, 32, 32, (3, 9, 128), 3, 1, True),
     ("f32_16_w128", 2, 32, 16, (3, 8, 128), 3, 1, False),
     ("f64_16_w128", 1, 64, 16, (4, 9, 128), 3, 1, False),
