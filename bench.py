@@ -265,7 +265,9 @@ def other_config(pkg, args, rank, world, local, base):
         per_step = pkg.launch_count() - l0
     for _ in range(max(3, args.warmup)):
         w["step"](*w["x_dev"])
-    if graph is None:
+    if w.get("launches_per_step"):          # a workload that captured its own step reports the launches of one replay
+        per_step = w["launches_per_step"]
+    elif graph is None:
         per_step = (pkg.launch_count() - l0) // max(3, args.warmup)
     copy = torch.cuda.Stream()
 
