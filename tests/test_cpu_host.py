@@ -187,3 +187,35 @@ def test_data_parallel_bucket_matches_single_process_gloo():
         for a, b in zip(r[1], net.parameters()):
             assert torch.allclose(torch.tensor(a), b.detach(), atol=1e-6)
         assert all(r[2])
+
+
+def test_ctypes_descriptors_match_the_header_layout(tmp_path):
+    """Every POD descriptor of include/b200nn.h against its ctypes mirror in _cabi.py: same size and the same offset for every field
+    (a C program compiled with gcc prints sizeof / offsetof; a silent mismatch would hand the kernels garbage geometry)."""
+    import ctypes
+    import shutil
+    import subprocess
+    from mri_epilepsy_diagnosis_b200 import _cabi as cabi
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    pairs = {"b200_conv_desc": cabi.ConvDesc, "b200_pack_entry": cabi.PackEntry, "b200_norm_desc": cabi.NormDesc, "b200_dice_desc": cabi.DiceDesc,
+             "b200_pool_desc": cabi.PoolDesc, "b200_up_desc": cabi.UpDesc, "b200_patch_desc": cabi.PatchDesc, "b200_histstd_desc": cabi.HistStdDesc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200nn.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    seen = 0
+    for line in out.splitlines():
+        cname, field, value = line.split()
+        cls = pairs[cname]
+        expect = ctypes.sizeof(cls) if field == "size" else getattr(cls, field).offset
+        assert int(value) == expect, f"{cname}.{field}: header {value}, ctypes {expect}"
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in pairs.values())
