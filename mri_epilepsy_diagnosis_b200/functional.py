@@ -153,7 +153,7 @@ class ConvConfig:
             hit = _PACK_SERVE.get((id(self), key))
             if hit is not None and hit[1] == (weight.data_ptr(), 0 if second is None else second.data_ptr()):
                 return hit[0]
-        tag = (weight.data_ptr(), weight._version, weight.device)
+        tag = (weight.data_ptr(), weight._version, weight.device, _PACK_EPOCH[0])
         if fresh:
             self._packed.clear()
         hit = self._packed.get(key) if second is None else None
@@ -173,6 +173,16 @@ class ConvConfig:
 
 
 # --------------------------------------------------------------------------- batched weight pack (one launch per step)
+# Inference-cache epoch: a CUDA-graph replay updates the parameters without running any Python, so neither the version counter nor a
+# `fresh` call can announce it; graphed.GraphedTrainStep bumps the epoch on every step and every cached packed copy goes stale with it.
+_PACK_EPOCH = [0]
+
+
+def invalidate_packed_weights():
+    """Drop every cached (inference) packed weight copy: call after updating parameters behind PyTorch's back."""
+    _PACK_EPOCH[0] += 1
+
+
 _PACK_RECORD = None        # list while PackPlan.recording() is active
 _PACK_SERVE = None         # {(id(cfg), key): (buffer, (ptr0, ptr1))} while PackPlan.serving() is active
 

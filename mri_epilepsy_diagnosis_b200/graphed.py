@@ -206,6 +206,7 @@ class GraphedTrainStep:
         self.x.copy_(x, non_blocking=True)
         self.t.copy_(t, non_blocking=True)
         self.graph.replay()
+        BF.invalidate_packed_weights()            # the replay changed the parameters without any Python running (inference caches)
         if not self.capture_opt:
             self.opt.step()
         return self.loss
@@ -244,6 +245,7 @@ class GraphedTrainStep:
         ev.record(cur)
         self._consumed[s] = ev
         self.graph.replay()
+        BF.invalidate_packed_weights()            # the replay changed the parameters without any Python running (inference caches)
         if not self.capture_opt:
             self.opt.step()
         return self.loss

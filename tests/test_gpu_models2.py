@@ -317,3 +317,31 @@ def test_convert_on_full_stock_unet3d_matches_golden(B, golden, norm):
     check_grads({k: thin(gr[k].grad.cpu()) for k in keys}, {k: g["grad:" + k] for k in keys}, 1e-3, {k: thin(sd64[k].grad) for k in keys})
     if norm == "bn":
         assert rel_err(net.convd1.bn2.running_mean, g["rm:convd1.bn2"]) < TOL32 and rel_err(net.convu1.bn3.running_var, g["rv:convu1.bn3"]) < TOL32
+
+
+def test_eval_after_graphed_training_sees_the_new_weights(B):
+    """train (CUDA-graph replays) -> validate -> train -> validate, the loop of segmentation/routine.py:262-300: a replay updates the
+    parameters without running Python, so the packed-weight cache of the inference path must not survive it."""
+    torch.manual_seed(11)
+    net = B.convert(torch.nn.Sequential(torch.nn.Conv3d(16, 16, 3, 1, 1, bias=False), torch.nn.ReLU(), torch.nn.Conv3d(16, 16, 3, 1, 1, bias=False)).cuda(),
+                    dtype=torch.bfloat16)
+    x = torch.randn(2, 16, 8, 16, 128, device="cuda")
+    t = torch.randn(2, 16, 8, 16, 128, device="cuda")
+    opt = torch.optim.Adam(net.parameters(), lr=5e-2, capturable=True)
+    step = B.graphed.GraphedTrainStep(net, lambda y, tt: torch.nn.functional.mse_loss(y.float(), tt), opt, x, t)
+
+    def validate():
+        net.eval()
+        with torch.no_grad():
+            y = net(x).float()
+        net.train()
+        w0, w1 = (m.weight.detach().bfloat16().float() for m in (net[0], net[2]))
+        h = torch.relu(torch.nn.functional.conv3d(x.bfloat16().float(), w0, padding=1)).bfloat16().float()
+        return y, torch.nn.functional.conv3d(h, w1, padding=1)
+    y0, r0 = validate()
+    assert rel_err(y0, r0) < 1e-2
+    for _ in range(3):
+        step(x, t)
+    y1, r1 = validate()
+    assert rel_err(r1, r0) > 5e-2, "three Adam steps at lr 5e-2 must have moved the function"
+    assert rel_err(y1, r1) < 1e-2, "validation after graph replays ran on stale packed weights"
